@@ -1,0 +1,359 @@
+// Contexts, host-buffer entry points and the reference's InitQueryProxy entry.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+
+#include "internal.h"
+
+namespace eu {
+
+__global__ void k_seed(EuRngState* r, unsigned long long seed) {
+  // std::minstd_rand0::seed(s): x = s mod m, 1 if that is 0
+  unsigned long long x = seed % 2147483647ull;
+  r->x = x == 0 ? 1u : (uint32_t)x;
+  r->draws = 0;
+  r->calls = 0;
+  r->blocks_done = 0;
+}
+
+template <typename T>
+static int regrow(T** p, int64_t count) {
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  void* q = nullptr;
+  size_t bytes = (size_t)(count > 0 ? count : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&q, bytes);
+  if (e != cudaSuccess) { set_error("cudaMalloc(%zu) -> %s", bytes, cudaGetErrorString(e)); return EU_ERR_CUDA; }
+  *p = (T*)q;
+  return EU_OK;
+}
+
+int ctx_reserve(eu_ctx* c, int64_t rows) {
+  if (rows <= c->cap_rows) return EU_OK;
+  // growing while the stream still uses the old buffers would be a race
+  EU_CUDA(cudaStreamSynchronize(c->stream));
+  int64_t cap = 64;
+  while (cap < rows * 2) cap <<= 1;
+  int rc;
+  if ((rc = regrow(&c->d_dedup, cap + 1))) return rc;
+  c->dedup_cap = cap;
+  if ((rc = regrow(&c->d_first, rows))) return rc;
+  if ((rc = regrow(&c->d_rowof, rows))) return rc;
+  if ((rc = regrow(&c->d_elig, rows))) return rc;
+  if ((rc = regrow(&c->d_state, rows))) return rc;
+  if ((rc = regrow(&c->d_front[0], rows))) return rc;
+  if ((rc = regrow(&c->d_front[1], rows))) return rc;
+  c->cap_rows = rows;
+  return EU_OK;
+}
+
+int ctx_misc(eu_ctx* c, int64_t bytes) {
+  if (bytes <= c->misc_bytes) return EU_OK;
+  EU_CUDA(cudaStreamSynchronize(c->stream));
+  char* p = (char*)c->d_misc;
+  int rc = regrow(&p, bytes);
+  c->d_misc = p;
+  if (rc) { c->misc_bytes = 0; return rc; }
+  c->misc_bytes = bytes;
+  return EU_OK;
+}
+
+int ctx_stage(eu_ctx* c, int64_t host_bytes, int64_t dev_bytes) {
+  if (host_bytes > c->pin_bytes) {
+    if (c->h_pin) cudaFreeHost(c->h_pin);
+    c->h_pin = nullptr; c->pin_bytes = 0;
+    EU_CUDA(cudaHostAlloc(&c->h_pin, (size_t)host_bytes, cudaHostAllocDefault));
+    c->pin_bytes = host_bytes;
+  }
+  if (dev_bytes > c->stage_bytes) {
+    EU_CUDA(cudaStreamSynchronize(c->stream));
+    char* p = (char*)c->d_stage;
+    int rc = regrow(&p, dev_bytes);
+    c->d_stage = p;
+    if (rc) { c->stage_bytes = 0; return rc; }
+    c->stage_bytes = dev_bytes;
+  }
+  return EU_OK;
+}
+
+static inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+// Bump allocator over the ctx staging buffers: the same offsets are used on the pinned host
+// side and on the device side.
+struct Stage {
+  int64_t off = 0;
+  int64_t take(int64_t bytes) { int64_t o = off; off += align256(bytes); return o; }
+};
+
+static std::mutex g_default_mu;
+static eu_graph* g_default_graph = nullptr;
+static eu_ctx* g_default_ctx = nullptr;
+
+}  // namespace eu
+
+using namespace eu;
+
+extern "C" {
+
+int eu_ctx_create(eu_graph* g, eu_rng_kind rng, uint64_t seed, void* stream, eu_ctx** out) {
+  if (!g || !out || (rng != EU_RNG_MINSTD && rng != EU_RNG_PHILOX)) { set_error("eu_ctx_create: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(g->device));
+  eu_ctx* c = new eu_ctx();
+  c->g = g; c->rng = rng; c->seed = seed; c->stream = (cudaStream_t)stream;
+  cudaError_t e = cudaMalloc(&c->d_rng, sizeof(EuRngState));
+  if (e != cudaSuccess) { set_error("cudaMalloc rng -> %s", cudaGetErrorString(e)); delete c; return EU_ERR_CUDA; }
+  k_seed<<<1, 1, 0, c->stream>>>(c->d_rng, seed);
+  g_launches++;
+  *out = c;
+  return EU_OK;
+}
+
+int eu_ctx_destroy(eu_ctx* c) {
+  if (!c) return EU_OK;
+  cudaSetDevice(c->g->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_rng); cudaFree(c->d_dedup); cudaFree(c->d_first); cudaFree(c->d_rowof);
+  cudaFree(c->d_elig); cudaFree(c->d_state); cudaFree(c->d_front[0]); cudaFree(c->d_front[1]);
+  cudaFree(c->d_misc); cudaFree(c->d_stage);
+  if (c->h_pin) cudaFreeHost(c->h_pin);
+  delete c;
+  return EU_OK;
+}
+
+int eu_ctx_set_stream(eu_ctx* c, void* stream) {
+  if (!c) { set_error("null ctx"); return EU_ERR_INVALID; }
+  c->stream = (cudaStream_t)stream;
+  return EU_OK;
+}
+
+int eu_ctx_seed(eu_ctx* c, uint64_t seed) {
+  if (!c) { set_error("null ctx"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  c->seed = seed;
+  k_seed<<<1, 1, 0, c->stream>>>(c->d_rng, seed);
+  EU_LAUNCHED();
+  return EU_OK;
+}
+
+int eu_ctx_reserve(eu_ctx* c, int64_t max_rows) {
+  if (!c || max_rows < 0) { set_error("eu_ctx_reserve: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  int rc = ctx_reserve(c, max_rows);
+  if (rc) return rc;
+  return ctx_misc(c, 256 + 4 * max_rows);
+}
+
+int eu_ctx_sync(eu_ctx* c) {
+  if (!c) { set_error("null ctx"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  EU_CUDA(cudaStreamSynchronize(c->stream));
+  return EU_OK;
+}
+
+int eu_ctx_draws(eu_ctx* c, uint64_t* draws) {
+  if (!c || !draws) { set_error("eu_ctx_draws: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  EuRngState h;
+  EU_CUDA(cudaMemcpyAsync(&h, c->d_rng, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  EU_CUDA(cudaStreamSynchronize(c->stream));
+  *draws = h.draws;
+  return EU_OK;
+}
+
+// ------------------------------------------------------------------------------ host variants
+// Pattern: copy inputs into pinned memory, H2D on the ctx stream, run the device op, D2H into
+// pinned memory, synchronise, copy out.  The pinned hop keeps the copies asynchronous-capable
+// (pageable cudaMemcpyAsync would serialise against the host).
+
+int eu_sample_fanout_host(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes,
+                          int32_t K, const int32_t* counts, int32_t L, int64_t default_node,
+                          int64_t* const* out_ids, float* const* out_w, int32_t* const* out_t) {
+  if (!c || B < 0 || L < 0 || L > 16 || !counts || (B > 0 && !nodes)) { set_error("eu_sample_fanout_host: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  Stage st;
+  const int64_t o_nodes = st.take(8 * B);
+  int64_t o_ids[16], o_w[16], o_t[16], n_l[16];
+  int64_t rows = B;
+  for (int l = 0; l < L; ++l) {
+    rows *= counts[l];
+    n_l[l] = rows;
+    o_ids[l] = st.take(8 * rows); o_w[l] = st.take(4 * rows); o_t[l] = st.take(4 * rows);
+  }
+  int rc = ctx_stage(c, st.off, st.off);
+  if (rc) return rc;
+  char* hp = (char*)c->h_pin;
+  char* dp = (char*)c->d_stage;
+  cudaStream_t s = c->stream;
+  memcpy(hp + o_nodes, nodes, 8 * (size_t)B);
+  EU_CUDA(cudaMemcpyAsync(dp + o_nodes, hp + o_nodes, 8 * (size_t)B, cudaMemcpyHostToDevice, s));
+  int64_t* d_ids[16]; float* d_w[16]; int32_t* d_t[16];
+  for (int l = 0; l < L; ++l) { d_ids[l] = (int64_t*)(dp + o_ids[l]); d_w[l] = (float*)(dp + o_w[l]); d_t[l] = (int32_t*)(dp + o_t[l]); }
+  rc = eu_sample_fanout(c, (const int64_t*)(dp + o_nodes), B, etypes, K, counts, L, default_node, d_ids, d_w, d_t);
+  if (rc) return rc;
+  if (L > 0) {
+    // outputs are contiguous in the stage: one D2H
+    const int64_t first = o_ids[0], bytes = st.off - first;
+    EU_CUDA(cudaMemcpyAsync(hp + first, dp + first, (size_t)bytes, cudaMemcpyDeviceToHost, s));
+  }
+  EU_CUDA(cudaStreamSynchronize(s));
+  for (int l = 0; l < L; ++l) {
+    if (out_ids && out_ids[l]) memcpy(out_ids[l], hp + o_ids[l], 8 * (size_t)n_l[l]);
+    if (out_w && out_w[l]) memcpy(out_w[l], hp + o_w[l], 4 * (size_t)n_l[l]);
+    if (out_t && out_t[l]) memcpy(out_t[l], hp + o_t[l], 4 * (size_t)n_l[l]);
+  }
+  return EU_OK;
+}
+
+int eu_sample_neighbor_host(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes,
+                            int32_t K, int32_t count, int64_t default_node, int64_t* out_ids,
+                            float* out_w, int32_t* out_t) {
+  return eu_sample_fanout_host(c, nodes, B, etypes, K, &count, 1, default_node, &out_ids, &out_w, &out_t);
+}
+
+int eu_sample_node_host(eu_ctx* c, int32_t count, const int32_t* types, int32_t n_types, int64_t* out) {
+  if (!c || count < 0 || (count > 0 && !out)) { set_error("eu_sample_node_host: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  int rc = ctx_stage(c, 8 * (int64_t)count + 256, 8 * (int64_t)count + 256);
+  if (rc) return rc;
+  rc = eu_sample_node(c, count, types, n_types, (int64_t*)c->d_stage);
+  if (rc) return rc;
+  EU_CUDA(cudaMemcpyAsync(c->h_pin, c->d_stage, 8 * (size_t)count, cudaMemcpyDeviceToHost, c->stream));
+  EU_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(out, c->h_pin, 8 * (size_t)count);
+  return EU_OK;
+}
+
+int eu_random_walk_host(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes,
+                        int32_t K, int32_t L, float p, float q, int64_t default_node, int64_t* out) {
+  if (!c || B < 0 || L < 0 || (B > 0 && (!nodes || !out))) { set_error("eu_random_walk_host: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  Stage st;
+  const int64_t o_nodes = st.take(8 * B), o_out = st.take(8 * B * (L + 1));
+  int rc = ctx_stage(c, st.off, st.off);
+  if (rc) return rc;
+  char* hp = (char*)c->h_pin; char* dp = (char*)c->d_stage;
+  memcpy(hp + o_nodes, nodes, 8 * (size_t)B);
+  EU_CUDA(cudaMemcpyAsync(dp + o_nodes, hp + o_nodes, 8 * (size_t)B, cudaMemcpyHostToDevice, c->stream));
+  rc = eu_random_walk(c, (const int64_t*)(dp + o_nodes), B, etypes, K, L, p, q, default_node, (int64_t*)(dp + o_out));
+  if (rc) return rc;
+  EU_CUDA(cudaMemcpyAsync(hp + o_out, dp + o_out, 8 * (size_t)(B * (L + 1)), cudaMemcpyDeviceToHost, c->stream));
+  EU_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(out, hp + o_out, 8 * (size_t)(B * (L + 1)));
+  return EU_OK;
+}
+
+int eu_get_dense_feature_host(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid, int32_t dim, float* out) {
+  if (!c || M < 0 || dim < 0 || (M > 0 && (!nodes || !out))) { set_error("eu_get_dense_feature_host: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  Stage st;
+  const int64_t o_nodes = st.take(8 * M), o_out = st.take(4 * M * dim);
+  int rc = ctx_stage(c, st.off, st.off);
+  if (rc) return rc;
+  char* hp = (char*)c->h_pin; char* dp = (char*)c->d_stage;
+  memcpy(hp + o_nodes, nodes, 8 * (size_t)M);
+  EU_CUDA(cudaMemcpyAsync(dp + o_nodes, hp + o_nodes, 8 * (size_t)M, cudaMemcpyHostToDevice, c->stream));
+  rc = eu_get_dense_feature(c, (const int64_t*)(dp + o_nodes), M, fid, dim, (float*)(dp + o_out));
+  if (rc) return rc;
+  EU_CUDA(cudaMemcpyAsync(hp + o_out, dp + o_out, 4 * (size_t)(M * dim), cudaMemcpyDeviceToHost, c->stream));
+  EU_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(out, hp + o_out, 4 * (size_t)(M * dim));
+  return EU_OK;
+}
+
+int eu_gather_host(eu_ctx* c, const float* params, int64_t N, int64_t D, const int32_t* idx, int64_t E, float* out) {
+  if (!c || N < 0 || D <= 0 || E < 0) { set_error("eu_gather_host: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  Stage st;
+  const int64_t o_p = st.take(4 * N * D), o_i = st.take(4 * E), o_o = st.take(4 * E * D);
+  int rc = ctx_stage(c, st.off, st.off);
+  if (rc) return rc;
+  char* hp = (char*)c->h_pin; char* dp = (char*)c->d_stage;
+  memcpy(hp + o_p, params, 4 * (size_t)(N * D));
+  memcpy(hp + o_i, idx, 4 * (size_t)E);
+  EU_CUDA(cudaMemcpyAsync(dp + o_p, hp + o_p, (size_t)(o_o - o_p), cudaMemcpyHostToDevice, c->stream));
+  rc = eu_gather(c, (const float*)(dp + o_p), N, D, (const int32_t*)(dp + o_i), E, (float*)(dp + o_o));
+  if (rc) return rc;
+  EU_CUDA(cudaMemcpyAsync(hp + o_o, dp + o_o, 4 * (size_t)(E * D), cudaMemcpyDeviceToHost, c->stream));
+  EU_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(out, hp + o_o, 4 * (size_t)(E * D));
+  return EU_OK;
+}
+
+static int scatter_host(int op, eu_ctx* c, const float* u, int64_t D, const int32_t* idx, int64_t E, int64_t size, float* out) {
+  if (!c || D <= 0 || E < 0 || size < 0) { set_error("scatter_host: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  Stage st;
+  const int64_t o_u = st.take(4 * E * D), o_i = st.take(4 * E), o_o = st.take(4 * size * D);
+  int rc = ctx_stage(c, st.off, st.off);
+  if (rc) return rc;
+  char* hp = (char*)c->h_pin; char* dp = (char*)c->d_stage;
+  memcpy(hp + o_u, u, 4 * (size_t)(E * D));
+  memcpy(hp + o_i, idx, 4 * (size_t)E);
+  EU_CUDA(cudaMemcpyAsync(dp + o_u, hp + o_u, (size_t)(o_o - o_u), cudaMemcpyHostToDevice, c->stream));
+  const float* du = (const float*)(dp + o_u); const int32_t* di = (const int32_t*)(dp + o_i); float* dout = (float*)(dp + o_o);
+  rc = op == 0 ? eu_scatter_add(c, du, D, di, E, size, dout) : eu_scatter_max(c, du, D, di, E, size, dout);
+  if (rc) return rc;
+  EU_CUDA(cudaMemcpyAsync(hp + o_o, dp + o_o, 4 * (size_t)(size * D), cudaMemcpyDeviceToHost, c->stream));
+  EU_CUDA(cudaStreamSynchronize(c->stream));
+  memcpy(out, hp + o_o, 4 * (size_t)(size * D));
+  return EU_OK;
+}
+int eu_scatter_add_host(eu_ctx* c, const float* u, int64_t D, const int32_t* idx, int64_t E, int64_t size, float* out) { return scatter_host(0, c, u, D, idx, E, size, out); }
+int eu_scatter_max_host(eu_ctx* c, const float* u, int64_t D, const int32_t* idx, int64_t E, int64_t size, float* out) { return scatter_host(1, c, u, D, idx, E, size, out); }
+
+// ------------------------------------------------------------------------------ InitQueryProxy
+eu_graph* eu_default_graph(void) { std::lock_guard<std::mutex> l(g_default_mu); return g_default_graph; }
+eu_ctx* eu_default_ctx(void) { std::lock_guard<std::mutex> l(g_default_mu); return g_default_ctx; }
+
+int eu_set_default_graph(eu_graph* g, eu_rng_kind rng, uint64_t seed) {
+  std::lock_guard<std::mutex> l(g_default_mu);
+  if (g_default_ctx) { eu_ctx_destroy(g_default_ctx); g_default_ctx = nullptr; }
+  g_default_graph = g;
+  if (!g) return EU_OK;
+  return eu_ctx_create(g, rng, seed, nullptr, &g_default_ctx);
+}
+
+// tf_euler/utils/init_query_proxy.cc:19-36: split on ';' then '=', false only when the list is
+// empty or an item is not exactly k=v; the graph-load status is NOT propagated (:34).
+bool InitQueryProxy(const char* conf) {
+  if (!conf) return false;
+  std::map<std::string, std::string> kv;
+  std::string s(conf);
+  size_t pos = 0;
+  int items = 0;
+  while (pos <= s.size()) {
+    size_t end = s.find(';', pos);
+    if (end == std::string::npos) end = s.size();
+    std::string item = s.substr(pos, end - pos);
+    pos = end + 1;
+    if (item.empty()) continue;
+    size_t eq = item.find('=');
+    if (eq == std::string::npos || item.find('=', eq + 1) != std::string::npos) return false;
+    kv[item.substr(0, eq)] = item.substr(eq + 1);
+    ++items;
+  }
+  if (items == 0) return false;
+  std::string mode = kv.count("mode") ? kv["mode"] : "local";
+  if (mode != "local") {
+    fprintf(stderr, "[euler_b200] ERROR InitQueryProxy: mode=%s is not on this path (only mode=local; sharding is eu_* over NCCL)\n", mode.c_str());
+    return true;
+  }
+  int device = kv.count("device") ? atoi(kv["device"].c_str()) : 0;
+  uint64_t seed = kv.count("seed") ? strtoull(kv["seed"].c_str(), nullptr, 10) : 1;
+  eu_rng_kind rng = (kv.count("rng") && kv["rng"] == "philox") ? EU_RNG_PHILOX : EU_RNG_MINSTD;
+  eu_graph* g = nullptr;
+  int rc = eu_graph_load(kv["data_path"].c_str(), 0, 1, device, &g);
+  if (rc != EU_OK) {
+    fprintf(stderr, "[euler_b200] ERROR InitQueryProxy: graph load failed: %s\n", eu_last_error());
+    return true;
+  }
+  rc = eu_set_default_graph(g, rng, seed);
+  if (rc != EU_OK) fprintf(stderr, "[euler_b200] ERROR InitQueryProxy: %s\n", eu_last_error());
+  return true;
+}
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+// euler_b200 device-side building blocks (sm_100a).
+//   * DevGraph: the HBM-resident CSR a kernel sees
+//   * exact RNG: minstd_rand0 + libstdc++ generate_canonical<double,53>, with multiplicative
+//     jump-ahead so each warp/lane starts at its own position of the ONE serial stream the
+//     reference consumes (euler/common/random.cc:22-28)
+//   * Philox4x32-10 keyed on (node id, draw) for the throughput mode
+//   * inverse-CDF pick equivalent to RandomSelect (euler/common/compact_weighted_collection.h:30-52)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define EU_WARP 32
+#define EU_MAX_ETYPES 32
+#define EU_MAX_FEAT_SLOTS 16
+
+namespace eu {
+
+struct HashSlot {  // 16 B, one 128-bit load
+  unsigned long long key;
+  unsigned long long row;  // EU_EMPTY_ROW if free
+};
+static constexpr unsigned long long kEmptyRow = 0xFFFFFFFFFFFFFFFFull;
+
+struct DevGraph {
+  int64_t n;        // rows
+  int64_t E;        // edges
+  int32_t T;        // edge-type groups per row
+  int32_t n_node_types;
+  const unsigned long long* ids;  // [n]
+  const int32_t* node_type;       // [n]
+  const float* node_w;            // [n]
+  const int64_t* grp_ptr;         // [n*T+1]
+  const unsigned long long* nbr;  // [E]
+  const float* cum_w;             // [E]
+  const float* grp_cum;           // [n*T] (T>1) or nullptr
+  // id -> row
+  int32_t dense_ids;              // ids[r] == id_base + r for all r
+  unsigned long long id_base;
+  const HashSlot* htab;
+  unsigned long long hmask;       // capacity-1 (capacity is a power of two)
+  // dense f32 features: row-major [n, feat_dim]; slot s occupies columns [slot_off[s], +slot_dim[s])
+  int32_t feat_dim;
+  const float* feat;
+  int32_t n_slots;
+  int32_t slot_off[EU_MAX_FEAT_SLOTS];
+  int32_t slot_dim[EU_MAX_FEAT_SLOTS];
+};
+
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
+  return k;
+}
+
+// Graph::GetNodeByID (euler/core/graph/graph.h:87-93): row or -1.
+__device__ __forceinline__ int64_t lookup_row(const DevGraph& g, unsigned long long id) {
+  if (g.dense_ids) {
+    unsigned long long r = id - g.id_base;
+    return r < (unsigned long long)g.n ? (int64_t)r : -1;
+  }
+  unsigned long long h = mix64(id) & g.hmask;
+  while (true) {
+    const ulonglong2 s = __ldg(reinterpret_cast<const ulonglong2*>(g.htab + h));
+    if (s.y == kEmptyRow) return -1;
+    if (s.x == id) return (int64_t)s.y;
+    h = (h + 1) & g.hmask;
+  }
+}
+
+// ---------------------------------------------------------------------------------- minstd_rand0
+static constexpr uint32_t kM = 2147483647u;  // 2^31-1
+static constexpr uint32_t kA = 16807u;
+
+__host__ __device__ __forceinline__ uint32_t modmul(uint32_t a, uint32_t b) {
+  unsigned long long p = (unsigned long long)a * b;     // < 2^62
+  unsigned long long r = (p & kM) + (p >> 31);          // < 2^32
+  r = (r & kM) + (r >> 31);
+  return (uint32_t)(r >= kM ? r - kM : r);
+}
+
+__host__ __device__ __forceinline__ uint32_t modpow_a(unsigned long long e) {  // A^e mod M
+  uint32_t base = kA, acc = 1;
+  while (e) {
+    if (e & 1) acc = modmul(acc, base);
+    base = modmul(base, base);
+    e >>= 1;
+  }
+  return acc;
+}
+
+// A^(e) for small e (< 256) with compile-time squarings: used for per-lane offsets.
+__device__ __forceinline__ uint32_t modpow_a_small(uint32_t e) {
+  // A^(2^k) mod M, k = 0..7
+  constexpr uint32_t P0 = 16807u;
+  uint32_t acc = 1, base = P0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (e & (1u << k)) acc = modmul(acc, base);
+    base = modmul(base, base);
+  }
+  return acc;
+}
+
+// One uniform_real_distribution<double>(0,1) draw from engine state `x` (state BEFORE the draw);
+// advances x by two engine steps.  Arithmetic order of libstdc++ 13 generate_canonical<double,53>:
+//   sum = double(x1-1); sum += double(x2-1) * R; ret = sum / (R*R); ret >= 1 -> nextafter(1,0)
+// with R = 2147483646.0.  Explicit _rn intrinsics: no FMA contraction allowed (Appendix A-13/15).
+__device__ __forceinline__ double minstd_uniform(uint32_t& x) {
+  const double R = 2147483646.0;
+  const double RR = 4611686009837453316.0;  // fl(R*R)
+  x = modmul(x, kA);
+  double sum = (double)(x - 1u);
+  x = modmul(x, kA);
+  sum = __dadd_rn(sum, __dmul_rn((double)(x - 1u), R));
+  double ret = __ddiv_rn(sum, RR);
+  if (ret >= 1.0) ret = 0x1.fffffffffffffp-1;  // nextafter(1.0, 0.0)
+  return ret;
+}
+
+// ---------------------------------------------------------------------------------- philox4x32-10
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  uint32_t hi0 = __umulhi(M0, c[0]), lo0 = M0 * c[0];
+  uint32_t hi1 = __umulhi(M1, c[2]), lo1 = M1 * c[2];
+  uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+// 2 uniforms in [0,1) with 53 bits from counter (id, draw) and key (seed, call)
+__device__ __forceinline__ void philox_uniform2(unsigned long long id, uint32_t draw, uint32_t salt,
+                                                unsigned long long key, double& u0, double& u1) {
+  uint32_t c[4] = {(uint32_t)id, (uint32_t)(id >> 32), draw, salt};
+  uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  unsigned long long a = ((unsigned long long)c[0] << 32) | c[1];
+  unsigned long long b = ((unsigned long long)c[2] << 32) | c[3];
+  u0 = (double)(a >> 11) * (1.0 / 9007199254740992.0);
+  u1 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// ---------------------------------------------------------------------------------- CDF pick
+// r for a pick in [begin,end] of a cumulative array (compact_weighted_collection.h:33-36):
+//   limit_begin = begin==first ? 0 : cum[begin-1]; r = u * (double)(limit_end - limit_begin) + limit_begin
+// (f32 subtraction, then f64 multiply and f64 add, unfused).
+__device__ __forceinline__ double pick_r(double u, float limit_begin, float limit_end) {
+  float diff = __fsub_rn(limit_end, limit_begin);
+  return __dadd_rn(__dmul_rn(u, (double)diff), (double)limit_begin);
+}
+
+// RandomSelect == min(end, first j in [begin,end] with (double)cum[j] > r) for non-decreasing cum
+// (proof sketch in DESIGN.md; checked against the literal search in tests/test_oracle_golden.py).
+// Binary search over global memory, [lo,hi] inclusive indices into cum.
+__device__ __forceinline__ int64_t upper_bound_clamped(const float* __restrict__ cum, int64_t begin,
+                                                       int64_t end, double r) {
+  int64_t lo = begin, hi = end;  // answer in [begin, end]
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if ((double)__ldg(cum + mid) > r) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+}  // namespace eu

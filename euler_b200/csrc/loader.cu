@@ -1,0 +1,214 @@
+// Euler 2.0 on-disk format -> host CSR -> eu_graph_create.
+//
+// Format (writer euler/tools/{util,node,graph_meta}.py, reader
+// euler/core/graph/node.cc:414-526, euler/core/graph/graph_builder.cc:230-332,
+// euler/common/bytes_io.h:28-81): little-endian; list<T> = u32 n + n items; str = u32 len + bytes.
+//   <dir>/euler.meta : str name, str version, u64 nodes, u64 edges, i32 partitions,
+//                      u32 nf x {str name, i32 kind, i32 idx, i64 dim}, u32 ef x {...},
+//                      u32 nnt x {str name, u32 id}, u32 net x {str name, u32 id}
+//   <dir>/Node/<prefix>_<p>.dat : records  u32 len + { u64 id, i32 type, f32 weight,
+//        out block, in block, list<i32> u64 ends, list<u64>, list<i32> f32 ends, list<f32>,
+//        list<i32> bin ends, str bin };  block = list<i32> group ids, list<f32> group weights,
+//        list<i32> group ends, list<u64> neighbor ids, list<f32> cumulative weights
+// A shard loads <prefix>_<p>.dat iff the name splits into exactly 3 tokens on '_' '.', the last is
+// "dat" and p % shard_number == shard_index (euler/core/graph/graph.cc:90-98).
+#include <dirent.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "internal.h"
+
+namespace eu {
+
+struct Reader {
+  const unsigned char* p;
+  const unsigned char* end;
+  bool ok = true;
+  template <typename T>
+  T get() {
+    T v{};
+    if (p + sizeof(T) > end) { ok = false; return v; }
+    memcpy(&v, p, sizeof(T));
+    p += sizeof(T);
+    return v;
+  }
+  template <typename T>
+  void list(std::vector<T>* out) {
+    uint32_t n = get<uint32_t>();
+    if (!ok || p + (size_t)n * sizeof(T) > end) { ok = false; return; }
+    out->resize(n);
+    if (n) memcpy(out->data(), p, (size_t)n * sizeof(T));
+    p += (size_t)n * sizeof(T);
+  }
+  std::string str() {
+    uint32_t n = get<uint32_t>();
+    if (!ok || p + n > end) { ok = false; return std::string(); }
+    std::string s((const char*)p, n);
+    p += n;
+    return s;
+  }
+};
+
+static bool read_file(const std::string& path, std::vector<unsigned char>* buf) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  buf->resize(sz > 0 ? sz : 0);
+  size_t got = sz > 0 ? fread(buf->data(), 1, sz, f) : 0;
+  fclose(f);
+  return got == (size_t)(sz > 0 ? sz : 0);
+}
+
+static std::vector<std::string> split_any(const std::string& s, const char* seps) {
+  std::vector<std::string> out;
+  std::string cur;
+  for (char ch : s) {
+    if (strchr(seps, ch)) { if (!cur.empty()) out.push_back(cur); cur.clear(); }
+    else cur.push_back(ch);
+  }
+  if (!cur.empty()) out.push_back(cur);
+  return out;
+}
+
+}  // namespace eu
+
+using namespace eu;
+
+extern "C" int eu_graph_load(const char* data_path, int shard_index, int shard_number, int device,
+                             eu_graph** out) {
+  if (!data_path || !out || shard_number <= 0 || shard_index < 0 || shard_index >= shard_number) {
+    set_error("eu_graph_load: bad argument (shard %d of %d)", shard_index, shard_number);
+    return EU_ERR_INVALID;
+  }
+  const std::string dir(data_path);
+  // ---- meta
+  std::vector<unsigned char> buf;
+  if (!read_file(dir + "/euler.meta", &buf)) { set_error("cannot read %s/euler.meta", data_path); return EU_ERR_IO; }
+  Reader m{buf.data(), buf.data() + buf.size()};
+  m.str(); m.str();
+  m.get<uint64_t>(); m.get<uint64_t>();
+  int32_t partitions = m.get<int32_t>();
+  std::map<int32_t, std::pair<std::string, int64_t>> dense;  // idx -> (name, dim)
+  uint32_t nf = m.get<uint32_t>();
+  for (uint32_t i = 0; i < nf && m.ok; ++i) {
+    std::string name = m.str();
+    int32_t kind = m.get<int32_t>(), idx = m.get<int32_t>();
+    int64_t dim = m.get<int64_t>();
+    if (kind == 1) dense[idx] = std::make_pair(name, dim);
+  }
+  uint32_t ef = m.get<uint32_t>();
+  for (uint32_t i = 0; i < ef && m.ok; ++i) { m.str(); m.get<int32_t>(); m.get<int32_t>(); m.get<int64_t>(); }
+  std::map<uint32_t, std::string> ntypes, etypes;
+  uint32_t nnt = m.get<uint32_t>();
+  for (uint32_t i = 0; i < nnt && m.ok; ++i) { std::string s = m.str(); ntypes[m.get<uint32_t>()] = s; }
+  uint32_t net = m.get<uint32_t>();
+  for (uint32_t i = 0; i < net && m.ok; ++i) { std::string s = m.str(); etypes[m.get<uint32_t>()] = s; }
+  if (!m.ok || partitions <= 0) { set_error("malformed euler.meta in %s", data_path); return EU_ERR_IO; }
+  const int32_t T = (int32_t)net, NT = (int32_t)nnt;
+  if (T < 1 || T > EU_MAX_ETYPES) { set_error("%d edge types unsupported", T); return EU_ERR_UNSUPPORTED; }
+  const int32_t n_slots = dense.empty() ? 0 : dense.rbegin()->first + 1;
+  if (n_slots > EU_MAX_FEAT_SLOTS) { set_error("%d dense features unsupported", n_slots); return EU_ERR_UNSUPPORTED; }
+  std::vector<int32_t> slot_dims(n_slots, 0), slot_off(n_slots, 0);
+  int32_t width = 0;
+  for (int32_t s = 0; s < n_slots; ++s) {
+    slot_dims[s] = dense.count(s) ? (int32_t)dense[s].second : 0;
+    slot_off[s] = width;
+    width += slot_dims[s];
+  }
+  // ---- node files of this shard, in name order
+  std::vector<std::string> files;
+  {
+    DIR* d = opendir((dir + "/Node").c_str());
+    if (!d) { set_error("no such directory %s/Node", data_path); return EU_ERR_IO; }
+    while (dirent* e = readdir(d)) {
+      std::string fn(e->d_name);
+      auto tok = split_any(fn, "_.");
+      if (tok.size() == 3 && tok[2] == "dat" && atoi(tok[1].c_str()) % shard_number == shard_index) files.push_back(fn);
+    }
+    closedir(d);
+    std::sort(files.begin(), files.end());
+  }
+  std::vector<uint64_t> ids, nbr;
+  std::vector<int32_t> ntype;
+  std::vector<float> nw, cum, gcum, feat;
+  std::vector<int64_t> gptr(1, 0);
+  std::vector<int32_t> gi, ge, fe;
+  std::vector<float> gw, cw, fv;
+  std::vector<uint64_t> nb, u64v;
+  for (const auto& fn : files) {
+    if (!read_file(dir + "/Node/" + fn, &buf)) { set_error("cannot read %s", fn.c_str()); return EU_ERR_IO; }
+    Reader f{buf.data(), buf.data() + buf.size()};
+    while (f.p < f.end) {
+      uint32_t len = f.get<uint32_t>();
+      if (!f.ok || f.p + len > f.end) { set_error("truncated record in %s", fn.c_str()); return EU_ERR_IO; }
+      Reader r{f.p, f.p + len};
+      f.p += len;
+      ids.push_back(r.get<uint64_t>());
+      ntype.push_back(r.get<int32_t>());
+      nw.push_back(r.get<float>());
+      r.list(&gi); r.list(&gw); r.list(&ge); r.list(&nb); r.list(&cw);
+      if (!r.ok || gi.size() != gw.size() || gi.size() != ge.size() || nb.size() != cw.size() || (int32_t)gi.size() > T) {
+        set_error("malformed node record (id %llu) in %s", (unsigned long long)ids.back(), fn.c_str());
+        return EU_ERR_IO;
+      }
+      for (size_t k = 0; k < gi.size(); ++k)
+        if (gi[k] != (int32_t)k) { set_error("edge group ids are not 0..T-1 for node %llu", (unsigned long long)ids.back()); return EU_ERR_UNSUPPORTED; }
+      // edge_group_collection.Init(group ids, group weights): running f32 sum (compact_weighted_collection.h:82-97).
+      // Nodes that carry fewer than T groups are padded with empty groups.
+      const int64_t base = (int64_t)nbr.size();
+      float run = 0.f;
+      int32_t last_end = 0;
+      for (int32_t t = 0; t < T; ++t) {
+        if (t < (int32_t)gi.size()) { run += gw[t]; last_end = ge[t]; }
+        gcum.push_back(run);
+        gptr.push_back(base + last_end);
+      }
+      if (last_end != (int32_t)nb.size()) { set_error("group ends do not cover the neighbor list of node %llu", (unsigned long long)ids.back()); return EU_ERR_IO; }
+      nbr.insert(nbr.end(), nb.begin(), nb.end());
+      cum.insert(cum.end(), cw.begin(), cw.end());
+      // in-neighbor block: not on this path (sample_neighbor / walks use out edges only)
+      r.list(&gi); r.list(&gw); r.list(&ge); r.list(&nb); r.list(&cw);
+      r.list(&fe); r.list(&u64v);
+      r.list(&fe); r.list(&fv);
+      if (!r.ok) { set_error("malformed feature block (id %llu)", (unsigned long long)ids.back()); return EU_ERR_IO; }
+      // dense slots: zero-padded / clipped to the meta dim (get_dense_feature_op.cc:66-75 zero-fills)
+      const size_t fbase = feat.size();
+      feat.resize(fbase + width, 0.f);
+      for (int32_t s = 0; s < n_slots && s < (int32_t)fe.size(); ++s) {
+        int32_t b = s == 0 ? 0 : fe[s - 1], e = fe[s];
+        int32_t len = std::min(e - b, slot_dims[s]);
+        if (b < 0 || e > (int32_t)fv.size() || e < b) { set_error("bad f32 feature ends (id %llu)", (unsigned long long)ids.back()); return EU_ERR_IO; }
+        if (len > 0) memcpy(&feat[fbase + slot_off[s]], &fv[b], sizeof(float) * len);
+      }
+    }
+  }
+  eu_graph_desc d{};
+  d.n_nodes = (int64_t)ids.size();
+  d.n_edge_types = T;
+  d.n_node_types = NT > 0 ? NT : 1;
+  d.ids = ids.data(); d.node_type = ntype.data(); d.node_w = nw.data();
+  d.grp_ptr = gptr.data(); d.nbr = nbr.data(); d.cum_w = cum.data(); d.grp_cum = gcum.data();
+  d.feat_dim = width; d.feat = width > 0 ? feat.data() : nullptr;
+  d.n_feat_slots = width > 0 ? n_slots : 0; d.feat_slot_dims = slot_dims.data();
+  int rc = eu_graph_create(&d, device, out);
+  if (rc) return rc;
+  eu_graph* g = *out;
+  g->edge_type_names.assign(T, "");
+  for (auto& kv : etypes) if ((int32_t)kv.first < T) g->edge_type_names[kv.first] = kv.second;
+  g->node_type_names.assign(d.n_node_types, "");
+  for (auto& kv : ntypes) if ((int32_t)kv.first < d.n_node_types) g->node_type_names[kv.first] = kv.second;
+  g->dense_feature_names.assign(d.n_feat_slots, "");
+  for (auto& kv : dense) {
+    std::string nm = kv.second.first;
+    if (nm.rfind("dense_", 0) == 0) nm = nm.substr(6);
+    if (kv.first < d.n_feat_slots) g->dense_feature_names[kv.first] = nm;
+  }
+  return EU_OK;
+}

@@ -1,0 +1,555 @@
+// Weighted neighbor sampling / multi-hop fanout / global node sampling on the HBM-resident CSR.
+//
+// Reference semantics reproduced (file:line relative to /root/reference):
+//   Node::__SampleNeighbor            euler/core/graph/node.cc:98-161
+//   RandomSelect                      euler/common/compact_weighted_collection.h:30-52
+//   euler::SampleNeighbor             euler/core/api/api.cc:223-236
+//   engine: ID_UNIQUE -> API_SAMPLE_NB -> gather   euler/core/kernels/id_unique_op.cc:41-66,
+//       sample_neighbor_op.cc:37-147 (default fill :135-143), idx_gather_op.cc:45-55,
+//       data_gather_op.cc:34-46; rule euler/parser/compiler.cc:76-90
+//   TF packing                        tf_euler/kernels/sample_neighbor_op.cc:79-81,114-122
+//   fanout chaining                   tf_euler/kernels/sample_fanout_op.cc:36-43,116-140
+//   Graph::SampleNode / alias         euler/core/graph/graph.cc:221-275, euler/common/alias_method.cc:66-78
+//
+// B200 design: one warp per seed row, one lane per draw.  The reference's single serial engine
+// stream is reproduced by (1) a device hash that resolves each seed's first occurrence
+// (ID_UNIQUE order), (2) a multiplicative prefix "scan" that hands every first-occurrence row the
+// engine state it would have had in the serial loop, (3) lanes jumping ahead A^(2*k*lane).
+// Duplicate seeds re-derive the identical row from the first occurrence's state, so there is no
+// gather pass and the frontier (engine ids) stays in HBM between hops.
+#include "internal.h"
+
+namespace eu {
+
+struct ETypes {
+  int32_t K;
+  int32_t v[EU_MAX_ETYPES];
+};
+
+// ---------------------------------------------------------------------------- 1. seed dedup
+__global__ void k_dedup_clear(HashSlot* tab, int64_t cap) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < cap) { tab[i].key = 0; tab[i].row = kEmptyRow; }
+}
+
+// tab[h] = {id+1, min index}.  key 0 = free.
+__global__ void k_dedup_insert(HashSlot* tab, unsigned long long mask,
+                               const unsigned long long* __restrict__ seeds, int64_t rows) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  unsigned long long id = seeds[i], tag = id + 1;
+  if (tag == 0ull) {  // id == 2^64-1 (e.g. default_node -1 fed back as a seed): dedicated slot [mask+1]
+    atomicMin(&tab[mask + 1].row, (unsigned long long)i);
+    return;
+  }
+  unsigned long long h = mix64(id) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS(&tab[h].key, 0ull, tag);
+    if (prev == 0ull || prev == tag) {
+      atomicMin(&tab[h].row, (unsigned long long)i);
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+__device__ __forceinline__ int64_t dedup_first(const HashSlot* tab, unsigned long long mask,
+                                               unsigned long long id) {
+  unsigned long long tag = id + 1;
+  if (tag == 0ull) return (int64_t)tab[mask + 1].row;
+  unsigned long long h = mix64(id) & mask;
+  while (true) {
+    const ulonglong2 s = *reinterpret_cast<const ulonglong2*>(tab + h);
+    if (s.x == tag) return (int64_t)s.y;
+    h = (h + 1) & mask;
+  }
+}
+
+// edge_group_collection.sum_weights_[t]; for T == 1 it is not stored: the single group's f32 sum is
+// the row's last cumulative weight (node.cc:59-68 accumulates both with the same additions).
+__device__ __forceinline__ float grp_cum_at(const DevGraph& g, int64_t row, int32_t t) {
+  if (g.grp_cum) return __ldg(g.grp_cum + row * g.T + t);
+  const int64_t b = g.grp_ptr[row], e = g.grp_ptr[row + 1];
+  return e > b ? __ldg(g.cum_w + e - 1) : 0.f;
+}
+
+// Row eligibility = "would Node::SampleNeighbor return `count` entries" (node.cc:106-148), i.e.
+// does this row consume uniforms.  mode 0: K==1; 1: strict subset; 2: all groups.
+__device__ __forceinline__ bool row_eligible(const DevGraph& g, int64_t row, const ETypes& et, int mode) {
+  if (row < 0) return false;
+  const int32_t T = g.T;
+  if (mode == 0) {
+    int32_t t = et.v[0];
+    if (t < 0 || t >= T) return false;
+    return g.grp_ptr[row * T + t + 1] > g.grp_ptr[row * T + t];
+  }
+  if (mode == 1) {
+    float s = 0.f;
+    for (int32_t i = 0; i < et.K; ++i) {
+      int32_t t = et.v[i];
+      if (t < 0 || t >= T) return false;
+      float pre = t > 0 ? grp_cum_at(g, row, t - 1) : 0.f;
+      s = __fadd_rn(s, __fsub_rn(grp_cum_at(g, row, t), pre));
+    }
+    return s != 0.f;
+  }
+  return grp_cum_at(g, row, T - 1) != 0.f;
+}
+
+// ---------------------------------------------------------------------------- 2. prepare
+__global__ void k_prepare(DevGraph g, const HashSlot* tab, unsigned long long mask,
+                          const unsigned long long* __restrict__ seeds, int64_t rows, ETypes et,
+                          int mode, int32_t* first, int64_t* rowof, uint8_t* elig) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  unsigned long long id = seeds[i];
+  int64_t f = dedup_first(tab, mask, id);
+  first[i] = (int32_t)f;
+  uint8_t e = 0;
+  if (f == i) {
+    int64_t row = lookup_row(g, id);
+    rowof[i] = row;
+    e = row_eligible(g, row, et, mode) ? 1 : 0;
+  }
+  elig[i] = e;
+}
+
+// ---------------------------------------------------------------------------- 3. engine-state scan
+// state_before[i] = x * F^(#eligible first-occurrence rows before i), F = A^(uniforms per row * 2).
+// One block; thread t owns a contiguous chunk.  Also advances the ctx engine.
+__global__ void __launch_bounds__(1024) k_state_scan(const uint8_t* __restrict__ elig, int64_t rows,
+                                                     uint32_t F, unsigned long long draws_per_row,
+                                                     uint32_t* state, EuRngState* rng) {
+  __shared__ uint32_t s_part[1024];
+  __shared__ uint32_t s_cnt[1024];
+  const int t = threadIdx.x;
+  const int64_t chunk = (rows + 1023) / 1024;
+  const int64_t b = t * chunk, e = min(rows, b + chunk);
+  uint32_t prod = 1, cnt = 0;
+  for (int64_t i = b; i < e; ++i)
+    if (elig[i]) { prod = modmul(prod, F); ++cnt; }
+  s_part[t] = prod;
+  s_cnt[t] = cnt;
+  __syncthreads();
+  // inclusive Hillis-Steele scan of products (modmul is associative and commutative)
+  for (int off = 1; off < 1024; off <<= 1) {
+    uint32_t v = 1, c = 0;
+    if (t >= off) { v = s_part[t - off]; c = s_cnt[t - off]; }
+    __syncthreads();
+    if (t >= off) { s_part[t] = modmul(s_part[t], v); s_cnt[t] += c; }
+    __syncthreads();
+  }
+  const uint32_t x0 = rng->x;
+  uint32_t run = modmul(x0, t > 0 ? s_part[t - 1] : 1u);
+  for (int64_t i = b; i < e; ++i) {
+    state[i] = run;
+    if (elig[i]) run = modmul(run, F);
+  }
+  __syncthreads();
+  if (t == 1023) {
+    rng->x = modmul(x0, s_part[1023]);
+    rng->draws += (unsigned long long)s_cnt[1023] * draws_per_row;
+  }
+}
+
+// ---------------------------------------------------------------------------- 4. sample
+struct SampleArgs {
+  const unsigned long long* seeds;  // [rows]
+  int64_t rows;
+  int32_t count;
+  long long default_node;
+  ETypes et;
+  int mode;
+  // minstd
+  const int32_t* first;
+  const int64_t* rowof;
+  const uint8_t* elig;
+  const uint32_t* state;
+  // philox
+  unsigned long long key;
+  const EuRngState* rng;
+  // outputs
+  unsigned long long* eng_ids;  // [rows*count] engine ids (0 placeholder) = next frontier; may be null
+  long long* out_ids;           // [rows*count] TF-packed; may be null
+  float* out_w;
+  int32_t* out_t;
+};
+
+// shuffle binary search over 32 lane-resident values c (non-decreasing, +inf padded):
+// first local index in [lo,hi] with (double)c > r, else hi.
+__device__ __forceinline__ int lane_upper_bound(float c, int lo, int hi, double r) {
+#pragma unroll
+  for (int it = 0; it < 5; ++it) {
+    int mid = (lo + hi) >> 1;
+    float v = __shfl_sync(0xffffffffu, c, mid);
+    bool go = lo < hi;
+    bool gt = (double)v > r;
+    hi = (go && gt) ? mid : hi;
+    lo = (go && !gt) ? mid + 1 : lo;
+  }
+  return lo;
+}
+
+template <bool PHILOX>
+__global__ void __launch_bounds__(256) k_sample(DevGraph g, SampleArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (w >= a.rows) return;
+  const int32_t count = a.count;
+  const int32_t T = g.T;
+  const int64_t obase = w * (int64_t)count;
+
+  int64_t row;
+  bool ok;
+  uint32_t st = 0;
+  unsigned long long seed_id = 0;
+  if (PHILOX) {
+    seed_id = a.seeds[w];
+    row = lookup_row(g, seed_id);
+    ok = row_eligible(g, row, a.et, a.mode);
+  } else {
+    const int32_t f = a.first[w];
+    ok = a.elig[f] != 0;
+    row = ok ? a.rowof[f] : -1;
+    st = ok ? a.state[f] : 0;
+  }
+  if (!ok) {
+    for (int32_t j = lane; j < count; j += 32) {
+      if (a.eng_ids) a.eng_ids[obase + j] = 0ull;
+      if (a.out_ids) { a.out_ids[obase + j] = a.default_node; a.out_w[obase + j] = 0.f; a.out_t[obase + j] = -1; }
+    }
+    return;
+  }
+
+  const int64_t* gp = g.grp_ptr + row * T;
+  const int64_t base = gp[0];
+  const int64_t rlen = gp[T] - base;  // whole row
+  // stage the row's cumulative weights in lanes when it fits one warp
+  const bool small_row = rlen <= 32;
+  float c = __int_as_float(0x7f800000);  // +inf
+  if (small_row && lane < rlen) c = __ldg(g.cum_w + base + lane);
+
+  // mode 0: fixed group
+  int64_t gb = 0, ge = 0;  // group [gb, ge] inclusive, global indices
+  float lim_b = 0.f, lim_e = 0.f;
+  if (a.mode == 0) {
+    const int32_t t = a.et.v[0];
+    gb = gp[t];
+    ge = gp[t + 1] - 1;
+    lim_b = gb == base ? 0.f : __ldg(g.cum_w + gb - 1);
+    lim_e = __ldg(g.cum_w + ge);
+  }
+  // modes 1/2: type-pick table in lanes: tc[k] = prefix over listed types (1) or grp_cum (2)
+  float tc = __int_as_float(0x7f800000);
+  int ntc = 0;
+  if (a.mode == 1) {
+    ntc = a.et.K;
+    float s = 0.f, mine = 0.f;
+    for (int32_t i = 0; i < ntc; ++i) {
+      int32_t t = a.et.v[i];
+      float pre = t > 0 ? grp_cum_at(g, row, t - 1) : 0.f;
+      s = __fadd_rn(s, __fsub_rn(grp_cum_at(g, row, t), pre));
+      if (i == lane) mine = s;
+    }
+    if (lane < ntc) tc = mine;
+  } else if (a.mode == 2) {
+    ntc = T;
+    if (lane < T) tc = grp_cum_at(g, row, lane);
+  }
+  const float tc_end = __shfl_sync(0xffffffffu, tc, ntc > 0 ? ntc - 1 : 0);
+
+  const uint32_t upd = a.mode == 0 ? 1u : 2u;  // uniforms per draw
+  // engine state before this lane's first draw, and the stride for draws lane+32, lane+64, ...
+  uint32_t x = 0, stride = 0;
+  if (!PHILOX) {
+    x = modmul(st, modpow_a_small(2u * upd * (uint32_t)lane));
+    stride = modpow_a_small(2u * upd * 32u);
+  }
+  const uint32_t salt = PHILOX ? (uint32_t)a.rng->calls : 0u;
+
+  bool keep = true;
+  bool bad = false;
+  for (int32_t j0 = 0; j0 < count; j0 += 32) {
+    const int32_t j = j0 + lane;
+    const bool active = j < count;
+    double u_t = 0.0, u_n = 0.0;
+    if (PHILOX) {
+      philox_uniform2(seed_id, (uint32_t)j, salt, a.key, u_t, u_n);
+    } else {
+      uint32_t xs = x;
+      if (upd == 2u) u_t = minstd_uniform(xs);
+      u_n = minstd_uniform(xs);
+      x = modmul(x, stride);
+    }
+    int32_t etype = a.mode == 0 ? a.et.v[0] : 0;
+    int64_t b = gb, e = ge;
+    float lb = lim_b, le = lim_e;
+    if (a.mode != 0) {
+      // type pick: RandomSelect(sum_weights_, 0, n-1)
+      double rt = pick_r(u_t, 0.f, tc_end);
+      int k = lane_upper_bound(tc, 0, ntc - 1, rt);
+      etype = a.mode == 1 ? a.et.v[k] : k;
+      b = gp[etype];
+      e = gp[etype + 1] - 1;
+      if (e < b) {  // zero-weight group reached through the fall-through: UB in the reference (SURVEY A-17)
+        bad = bad || active;
+        b = base; e = base;  // keep addresses valid
+      }
+      lb = b == base ? 0.f : __ldg(g.cum_w + b - 1);
+      le = __ldg(g.cum_w + e);
+    }
+    const double r = pick_r(u_n, lb, le);
+    int64_t m;
+    float wgt;
+    if (small_row) {
+      int li = lane_upper_bound(c, (int)(b - base), (int)(e - base), r);
+      float hi_v = __shfl_sync(0xffffffffu, c, li);
+      float lo_v = __shfl_sync(0xffffffffu, c, li > 0 ? li - 1 : 0);
+      m = base + li;
+      wgt = __fsub_rn(hi_v, li > 0 ? lo_v : 0.f);
+    } else {
+      m = upper_bound_clamped(g.cum_w, b, e, r);
+      float hi_v = __ldg(g.cum_w + m);
+      float lo_v = m > base ? __ldg(g.cum_w + m - 1) : 0.f;
+      wgt = __fsub_rn(hi_v, lo_v);
+    }
+    const unsigned long long nid = active ? __ldg(g.nbr + m) : 0ull;
+    if (j0 == 0) {
+      // TF packing keeps the row iff its first engine id != DEFAULT_UINT64 (0)
+      unsigned long long first_id = __shfl_sync(0xffffffffu, nid, 0);
+      keep = first_id != 0ull;
+    }
+    if (active) {
+      if (a.eng_ids) a.eng_ids[obase + j] = nid;
+      if (a.out_ids) {
+        a.out_ids[obase + j] = keep ? (long long)nid : a.default_node;
+        a.out_w[obase + j] = keep ? wgt : 0.f;
+        a.out_t[obase + j] = keep ? etype : -1;
+      }
+    }
+  }
+  if (__any_sync(0xffffffffu, bad)) {
+    for (int32_t j = lane; j < count; j += 32) {
+      if (a.eng_ids) a.eng_ids[obase + j] = 0ull;
+      if (a.out_ids) { a.out_ids[obase + j] = a.default_node; a.out_w[obase + j] = 0.f; a.out_t[obase + j] = -1; }
+    }
+  }
+}
+
+__global__ void k_bump_calls(EuRngState* rng) { rng->calls += 1; }
+
+// ---------------------------------------------------------------------------- global node sampler
+struct NodeSamplerDev {
+  int32_t n_types;
+  const unsigned long long* ids[EU_MAX_ETYPES];
+  const float* prob[EU_MAX_ETYPES];
+  const int32_t* alias[EU_MAX_ETYPES];
+  long long n[EU_MAX_ETYPES];
+  const float* type_prob;
+  const int32_t* type_alias;
+  // mode 0: single type `type0`; 1: all types (alias over types); 2: CWC over listed types
+  int mode;
+  int32_t type0;
+  int32_t n_sub;
+  int32_t sub_ids[EU_MAX_ETYPES];
+  float sub_cum[EU_MAX_ETYPES];
+};
+
+// AliasMethod::Next (alias_method.cc:66-78): column = floor(n*U1); U2 < prob[column] ? column : alias
+__device__ __forceinline__ long long alias_next(const float* prob, const int32_t* alias, long long n,
+                                                double u1, double u2) {
+  long long col = (long long)floor(__dmul_rn((double)n, u1));
+  bool coin = u2 < (double)__ldg(prob + col);
+  return coin ? col : (long long)__ldg(alias + col);
+}
+
+template <bool PHILOX>
+__global__ void k_sample_node(NodeSamplerDev s, int32_t count, int32_t upd, unsigned long long key,
+                              EuRngState* rng, long long* out) {
+  const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < count) {
+    double u[4] = {0, 0, 0, 0};
+    if (PHILOX) {
+      philox_uniform2(0x5A4D504C45ull, (uint32_t)j, (uint32_t)rng->calls, key, u[0], u[1]);
+      philox_uniform2(0x5A4D504C46ull, (uint32_t)j, (uint32_t)rng->calls, key, u[2], u[3]);
+      if (s.mode == 0) { u[2] = u[0]; u[3] = u[1]; }  // keep "node pick" in u[2],u[3]
+    } else {
+      uint32_t x = modmul(rng->x, modpow_a(2ull * upd * (unsigned long long)j));
+      if (s.mode == 1) { u[0] = minstd_uniform(x); u[1] = minstd_uniform(x); }
+      if (s.mode == 2) { u[0] = minstd_uniform(x); }
+      u[2] = minstd_uniform(x);
+      u[3] = minstd_uniform(x);
+    }
+    int32_t t = s.type0;
+    if (s.mode == 1) {
+      t = (int32_t)alias_next(s.type_prob, s.type_alias, s.n_types, u[0], u[1]);
+    } else if (s.mode == 2) {
+      double r = pick_r(u[0], 0.f, s.sub_cum[s.n_sub - 1]);
+      int k = 0;
+      while (k < s.n_sub - 1 && !((double)s.sub_cum[k] > r)) ++k;
+      t = s.sub_ids[k];
+    }
+    long long col = alias_next(s.prob[t], s.alias[t], s.n[t], u[2], u[3]);
+    out[j] = (long long)__ldg(s.ids[t] + col);
+  }
+}
+
+__global__ void k_advance_engine(EuRngState* rng, unsigned long long uniforms) {
+  rng->x = modmul(rng->x, modpow_a(2ull * uniforms));
+  rng->draws += uniforms;
+  rng->calls += 1;
+}
+
+// ---------------------------------------------------------------------------- host side
+// engine-state scan over c->d_elig[0..rows): c->d_state[i] = state before row i's first draw
+int launch_state_scan(eu_ctx* c, int64_t rows, unsigned long long uniforms_per_row) {
+  k_state_scan<<<1, 1024, 0, c->stream>>>(c->d_elig, rows, modpow_a(2ull * uniforms_per_row), uniforms_per_row,
+                                          c->d_state, c->d_rng);
+  EU_LAUNCHED();
+  return EU_OK;
+}
+
+static int classify(const DevGraph& d, const int32_t* etypes, int32_t K, ETypes* et, int* mode) {
+  if (K < 0 || K > EU_MAX_ETYPES) { set_error("edge_types: K=%d unsupported (max %d)", K, EU_MAX_ETYPES); return EU_ERR_UNSUPPORTED; }
+  et->K = K;
+  for (int i = 0; i < K; ++i) et->v[i] = etypes[i];
+  // node.cc:106-148: K==1 -> that group; 1<K<T -> sub collection; K==0 or K>=T -> all groups
+  if (K == 1) *mode = 0;
+  else if (K > 1 && K < d.T) *mode = 1;
+  else *mode = 2;
+  return EU_OK;
+}
+
+// One sampleNB hop: seeds (device u64[rows]) -> engine ids (device u64[rows*count], may be null)
+// and TF-packed outputs (may be null).
+int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows, const int32_t* etypes,
+               int32_t K, int32_t count, int64_t default_node, unsigned long long* eng_ids,
+               int64_t* out_ids, float* out_w, int32_t* out_t) {
+  if (rows == 0 || count == 0) return EU_OK;
+  const DevGraph& d = c->g->d;
+  SampleArgs a{};
+  int rc = classify(d, etypes, K, &a.et, &a.mode);
+  if (rc) return rc;
+  if (a.mode != 0 && d.T > 32) { set_error("T > 32 unsupported"); return EU_ERR_UNSUPPORTED; }
+  cudaStream_t s = c->stream;
+  a.seeds = seeds; a.rows = rows; a.count = count; a.default_node = default_node;
+  a.eng_ids = eng_ids; a.out_ids = (long long*)out_ids; a.out_w = out_w; a.out_t = out_t;
+  a.rng = c->d_rng;
+  const unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
+  if (c->rng == EU_RNG_PHILOX) {
+    a.key = c->seed;
+    k_sample<true><<<blocks, 256, 0, s>>>(d, a);
+    EU_LAUNCHED();
+    k_bump_calls<<<1, 1, 0, s>>>(c->d_rng);
+    EU_LAUNCHED();
+    return EU_OK;
+  }
+  if (rows >= ((int64_t)1 << 31)) { set_error("rows >= 2^31"); return EU_ERR_UNSUPPORTED; }
+  rc = ctx_reserve(c, rows);
+  if (rc) return rc;
+  int64_t cap = 64;
+  while (cap < rows * 2) cap <<= 1;
+  const int tb = 256;
+  k_dedup_clear<<<(unsigned)ceil_div(cap + 1, tb), tb, 0, s>>>(c->d_dedup, cap + 1);
+  EU_LAUNCHED();
+  k_dedup_insert<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(c->d_dedup, (unsigned long long)cap - 1, seeds, rows);
+  EU_LAUNCHED();
+  k_prepare<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(d, c->d_dedup, (unsigned long long)cap - 1, seeds, rows,
+                                                         a.et, a.mode, c->d_first, c->d_rowof, c->d_elig);
+  EU_LAUNCHED();
+  const unsigned long long upr = (unsigned long long)count * (a.mode == 0 ? 1 : 2);
+  rc = launch_state_scan(c, rows, upr);
+  if (rc) return rc;
+  a.first = c->d_first; a.rowof = c->d_rowof; a.elig = c->d_elig; a.state = c->d_state;
+  k_sample<false><<<blocks, 256, 0, s>>>(d, a);
+  EU_LAUNCHED();
+  return EU_OK;
+}
+
+}  // namespace eu
+
+using namespace eu;
+
+extern "C" {
+
+int eu_sample_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
+                       int32_t count, int64_t default_node, int64_t* out_ids, float* out_w,
+                       int32_t* out_t) {
+  if (!c || B < 0 || count < 0 || (K > 0 && !etypes)) { set_error("eu_sample_neighbor: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  return hop(c, (const unsigned long long*)nodes, B, etypes, K, count, default_node, nullptr, out_ids, out_w, out_t);
+}
+
+int eu_sample_fanout(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
+                     const int32_t* counts, int32_t L, int64_t default_node, int64_t* const* out_ids,
+                     float* const* out_w, int32_t* const* out_t) {
+  if (!c || B < 0 || L < 0 || !counts || (K > 0 && !etypes)) { set_error("eu_sample_fanout: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  int64_t rows = B, widest = B;
+  for (int l = 0; l < L; ++l) { if (counts[l] < 0) { set_error("negative count"); return EU_ERR_INVALID; } rows *= counts[l]; if (rows > widest) widest = rows; }
+  int rc = ctx_reserve(c, widest);
+  if (rc) return rc;
+  const unsigned long long* seeds = (const unsigned long long*)nodes;
+  rows = B;
+  for (int l = 0; l < L; ++l) {
+    unsigned long long* eng = (l + 1 < L) ? c->d_front[l & 1] : nullptr;
+    rc = hop(c, seeds, rows, etypes + (int64_t)l * K, K, counts[l], default_node, eng,
+             out_ids ? out_ids[l] : nullptr, out_w ? out_w[l] : nullptr, out_t ? out_t[l] : nullptr);
+    if (rc) return rc;
+    seeds = eng;
+    rows *= counts[l];
+  }
+  return EU_OK;
+}
+
+int eu_sample_node(eu_ctx* c, int32_t count, const int32_t* types, int32_t n_types, int64_t* out) {
+  if (!c || count < 0 || n_types < 1 || !types) { set_error("eu_sample_node: bad argument"); return EU_ERR_INVALID; }
+  eu_graph* g = c->g;
+  EU_CUDA(cudaSetDevice(g->device));
+  int rc = graph_build_sampler(g);
+  if (rc) return rc;
+  const int32_t NT = g->d.n_node_types;
+  if (NT > EU_MAX_ETYPES) { set_error("more than %d node types", EU_MAX_ETYPES); return EU_ERR_UNSUPPORTED; }
+  NodeSamplerDev s{};
+  s.n_types = NT;
+  for (int t = 0; t < NT; ++t) {
+    s.ids[t] = g->samplers[t].ids; s.prob[t] = g->samplers[t].prob; s.alias[t] = g->samplers[t].alias;
+    s.n[t] = g->samplers[t].n;
+  }
+  s.type_prob = g->d_type_prob; s.type_alias = g->d_type_alias;
+  uint32_t upd;
+  // api.cc:32-37 dispatch; Graph::SampleNode graph.cc:221-275.  Empty result == reference returns
+  // an empty vector (the TF kernel then aborts with "SampleNode Result Size 0", sample_node_op.cc:83-86).
+  if (n_types == 1) {
+    int32_t t = types[0];
+    if (t == -1) {
+      if (g->type_fwc_sum == 0.f) { set_error("sample_node: total node weight is 0"); return EU_ERR_STATE; }
+      s.mode = 1; upd = 4;
+    } else {
+      if (t < 0 || t >= NT) { set_error("sample_node: node type %d out of range", t); return EU_ERR_INVALID; }
+      if (g->samplers[t].fwc_sum == 0.f) { set_error("sample_node: node type %d is empty", t); return EU_ERR_STATE; }
+      s.mode = 0; s.type0 = t; upd = 2;
+    }
+  } else {
+    s.mode = 2; upd = 3;
+    float sum = 0.f;
+    for (int t = 0; t < NT; ++t) {
+      bool in = false;
+      for (int k = 0; k < n_types; ++k) in |= types[k] == t;
+      if (in) { sum += g->type_sums[t]; s.sub_ids[s.n_sub] = t; s.sub_cum[s.n_sub] = sum; ++s.n_sub; }
+    }
+    if (!(sum > 0)) { set_error("sample_node: listed node types are empty"); return EU_ERR_STATE; }
+  }
+  if (count == 0) return EU_OK;
+  const unsigned blocks = (unsigned)ceil_div(count, 256);
+  if (c->rng == EU_RNG_PHILOX)
+    k_sample_node<true><<<blocks, 256, 0, c->stream>>>(s, count, upd, c->seed, c->d_rng, (long long*)out);
+  else
+    k_sample_node<false><<<blocks, 256, 0, c->stream>>>(s, count, upd, c->seed, c->d_rng, (long long*)out);
+  EU_LAUNCHED();
+  k_advance_engine<<<1, 1, 0, c->stream>>>(c->d_rng, (unsigned long long)upd * (unsigned long long)count);
+  EU_LAUNCHED();
+  return EU_OK;
+}
+
+}  // extern "C"

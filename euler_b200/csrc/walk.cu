@@ -1,0 +1,242 @@
+// random_walk: uniform (p=q=1) and node2vec-biased walks, walkers resident on the device for all L steps.
+//
+// Reference (file:line relative to /root/reference):
+//   RandomWalk::ComputeAsync          tf_euler/kernels/random_walk_op.cc:249-289
+//   TraditionalRandomWalk (p=q=1)     :207-247  = L chained sampleNB(count=1) hops, id 0 -> default_node
+//   RWCallback::operator() (node2vec) :83-138   per step: full neighbor list of the current node
+//                                               (Node::__GetFullNeighbor, euler/core/graph/node.cc:176-198),
+//   BuildWeights                      :140-168  two-pointer merge against the parent's list,
+//   CompactWeightedCollection::Init/Sample      euler/common/compact_weighted_collection.h:82-128
+//                                               sequential f32 prefix + one RandomSelect draw.
+// The reference makes one host round trip (a GQL query) per step; here a step is two small kernels
+// and the frontier never leaves HBM.  Exact-RNG order: one uniform per LIVE walker, in walker order.
+#include "internal.h"
+
+namespace eu {
+
+struct ETypes2 {
+  int32_t K;
+  int32_t v[EU_MAX_ETYPES];
+};
+
+// Sequential view of Node::GetFullNeighbor(edge_types): listed types in listed order (invalid ones
+// skipped, duplicates repeated), stored order within a group; weight = cum[j] - cum[j-1] (0 at row start).
+struct NbIter {
+  const DevGraph* g;
+  const int64_t* gp;  // grp_ptr + row*T
+  int64_t base;
+  const ETypes2* et;
+  int32_t k;          // position in et
+  int64_t j, jend;
+  __device__ void init(const DevGraph* g_, int64_t row, const ETypes2* et_) {
+    g = g_; et = et_; k = -1; j = 0; jend = 0;
+    if (row < 0) { gp = nullptr; k = et_->K; return; }
+    gp = g->grp_ptr + row * g->T;
+    base = gp[0];
+    advance_group();
+  }
+  __device__ void advance_group() {
+    while (j >= jend) {
+      ++k;
+      if (k >= et->K) return;
+      int32_t t = et->v[k];
+      if (t < 0 || t >= g->T) continue;
+      j = gp[t];
+      jend = gp[t + 1];
+    }
+  }
+  __device__ bool done() const { return k >= et->K; }
+  __device__ long long id() const { return (long long)__ldg(g->nbr + j); }
+  __device__ float w() const {
+    float hi = __ldg(g->cum_w + j);
+    float lo = j == base ? 0.f : __ldg(g->cum_w + j - 1);
+    return __fsub_rn(hi, lo);
+  }
+  __device__ void next() { ++j; if (j >= jend) advance_group(); }
+};
+
+__device__ __forceinline__ int64_t list_len(const DevGraph& g, int64_t row, const ETypes2& et) {
+  if (row < 0) return 0;
+  int64_t n = 0;
+  for (int32_t k = 0; k < et.K; ++k) {
+    int32_t t = et.v[k];
+    if (t >= 0 && t < g.T) n += g.grp_ptr[row * g.T + t + 1] - g.grp_ptr[row * g.T + t];
+  }
+  return n;
+}
+
+struct WalkState {
+  long long* cur;       // [B] current node id
+  long long* parent;    // [B] parent id
+  int64_t* cur_row;     // [B] row of cur (-1 absent)
+  int64_t* parent_row;  // [B] row whose list is the parent list (-1 = empty list)
+};
+
+__global__ void k_walk_init(const long long* __restrict__ nodes, int64_t B, int32_t L, WalkState s,
+                            long long* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  long long id = nodes[i];
+  out[i * (L + 1)] = id;
+  s.cur[i] = id;
+  s.parent[i] = id;       // step 0: parent = the start node itself, empty parent list (:272-287)
+  s.parent_row[i] = -1;
+}
+
+// liveness: the walker draws this step iff its current node has a non-empty neighbor list
+__global__ void k_walk_live(DevGraph g, int64_t B, ETypes2 et, WalkState s, uint8_t* live) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  int64_t row = lookup_row(g, (unsigned long long)s.cur[i]);
+  s.cur_row[i] = row;
+  live[i] = list_len(g, row, et) > 0 ? 1 : 0;
+}
+
+// One thread walks the merge (BuildWeights :140-168) and the running f32 prefix
+// (CompactWeightedCollection::Init :82-97).  Returns the total; if pick >= 0.0 also returns in *sel
+// the first position whose prefix exceeds `pick` (RandomSelect closed form), else the last position.
+__device__ float biased_prefix(const DevGraph& g, int64_t crow, const ETypes2& cet, int64_t prow,
+                               const ETypes2& pet, long long parent_id, float p, float q, bool select,
+                               double pick, long long* sel_id) {
+  NbIter c, pn;
+  c.init(&g, crow, &cet);
+  pn.init(&g, prow, &pet);
+  float sum = 0.f;
+  long long last_id = 0;
+  bool found = false;
+  long long pk = pn.done() ? 0 : pn.id();
+  while (!c.done()) {
+    const long long cid = c.id();
+    float w = c.w();
+    // advance the parent pointer past smaller ids ("else ++k")
+    while (!pn.done() && cid > pk) { pn.next(); if (!pn.done()) pk = pn.id(); }
+    if (!pn.done() && cid == pk) {
+      pn.next(); if (!pn.done()) pk = pn.id();          // shared neighbor: d_tx = 1, weight unchanged
+    } else {
+      w = cid != parent_id ? __fdiv_rn(w, q) : __fdiv_rn(w, p);  // d_tx = 2 / d_tx = 0
+    }
+    sum = __fadd_rn(sum, w);
+    last_id = cid;
+    if (select && !found && (double)sum > pick) { *sel_id = cid; found = true; if (select) break; }
+    c.next();
+  }
+  if (select && !found) *sel_id = last_id;
+  return sum;
+}
+
+// Note on the merge above: the reference loop is
+//   while (j < nc && k < np) { if (c[j] < p[k]) {bias; ++j} else if (c[j] == p[k]) {++k; ++j} else ++k }
+//   while (j < nc) {bias; ++j}
+// For a fixed j the inner "else ++k" steps are exactly the `while (cid > pk)` loop, then one of the
+// first two branches fires (or k ran out and the tail loop biases) -- same visit order, same state.
+
+__global__ void __launch_bounds__(128) k_walk_step(DevGraph g, int64_t B, int32_t L, int32_t step, ETypes2 cet,
+                                                   ETypes2 pet, float p, float q, long long default_node,
+                                                   WalkState s, const uint8_t* __restrict__ live,
+                                                   const uint32_t* __restrict__ state, bool philox,
+                                                   unsigned long long key, long long* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const long long cur = s.cur[i];
+  const int64_t crow = s.cur_row[i];
+  long long next = default_node;
+  if (live[i]) {
+    const int64_t prow = s.parent_row[i];
+    const long long parent_id = s.parent[i];
+    const float total = biased_prefix(g, crow, cet, prow, pet, parent_id, p, q, false, 0.0, nullptr);
+    double u, u2;
+    if (philox) {
+      philox_uniform2((unsigned long long)i, (uint32_t)step, 0x77616C6Bu, key, u, u2);
+    } else {
+      uint32_t x = state[i];
+      u = minstd_uniform(x);
+    }
+    const double r = pick_r(u, 0.f, total);
+    biased_prefix(g, crow, cet, prow, pet, parent_id, p, q, true, r, &next);
+  }
+  out[i * (L + 1) + step + 1] = next;
+  // parent_neighbors_ = this step's lists, parent_ids_ = this step's nodes (:128-131)
+  s.parent[i] = cur;
+  s.parent_row[i] = crow;
+  s.cur[i] = next;
+}
+
+__global__ void k_walk_col(const unsigned long long* __restrict__ eng, int64_t B, int32_t L, int32_t col,
+                           long long default_node, long long* __restrict__ out) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  unsigned long long v = eng[i];
+  out[i * (L + 1) + col] = v == 0ull ? default_node : (long long)v;
+}
+
+}  // namespace eu
+
+using namespace eu;
+
+extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
+                              int32_t L, float p, float q, int64_t default_node, int64_t* out) {
+  if (!c || B < 0 || L < 0 || K < 0 || K > EU_MAX_ETYPES || (L > 0 && K > 0 && !etypes) || (B > 0 && (!nodes || !out))) {
+    set_error("eu_random_walk: bad argument");
+    return EU_ERR_INVALID;
+  }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  if (B == 0) return EU_OK;
+  const DevGraph& d = c->g->d;
+  cudaStream_t s = c->stream;
+  const int tb = 256;
+  int rc = ctx_reserve(c, B);
+  if (rc) return rc;
+  const float kEps = 1.0e-6f;
+  if (fabs((double)p - 1.0) <= kEps && fabs((double)q - 1.0) <= kEps) {
+    // TraditionalRandomWalk: chained sampleNB(count=1); the frontier is the ENGINE id (0 placeholder)
+    EU_CUDA(cudaMemcpy2DAsync(out, sizeof(int64_t) * (L + 1), nodes, sizeof(int64_t), sizeof(int64_t), (size_t)B,
+                              cudaMemcpyDeviceToDevice, s));
+    const unsigned long long* seeds = (const unsigned long long*)nodes;
+    for (int l = 0; l < L; ++l) {
+      unsigned long long* eng = c->d_front[l & 1];
+      rc = hop(c, seeds, B, etypes + (int64_t)l * K, K, 1, default_node, eng, nullptr, nullptr, nullptr);
+      if (rc) return rc;
+      k_walk_col<<<(unsigned)ceil_div(B, tb), tb, 0, s>>>(eng, B, L, l + 1, default_node, (long long*)out);
+      EU_LAUNCHED();
+      seeds = eng;
+    }
+    return EU_OK;
+  }
+  // node2vec
+  rc = ctx_misc(c, 256 + B * (8 + 8 + 8 + 8));
+  if (rc) return rc;
+  char* m = (char*)c->d_misc + 256;
+  WalkState ws;
+  ws.cur = (long long*)m; m += 8 * B;
+  ws.parent = (long long*)m; m += 8 * B;
+  ws.cur_row = (int64_t*)m; m += 8 * B;
+  ws.parent_row = (int64_t*)m;
+  k_walk_init<<<(unsigned)ceil_div(B, tb), tb, 0, s>>>((const long long*)nodes, B, L, ws, (long long*)out);
+  EU_LAUNCHED();
+  ETypes2 pet{};
+  pet.K = 0;
+  for (int l = 0; l < L; ++l) {
+    ETypes2 cet{};
+    cet.K = K;
+    for (int k = 0; k < K; ++k) cet.v[k] = etypes[(int64_t)l * K + k];
+    k_walk_live<<<(unsigned)ceil_div(B, tb), tb, 0, s>>>(d, B, cet, ws, c->d_elig);
+    EU_LAUNCHED();
+    if (c->rng == EU_RNG_MINSTD) {
+      rc = launch_state_scan(c, B, 1);
+      if (rc) return rc;
+    }
+    k_walk_step<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(d, B, L, l, cet, pet, p, q, default_node, ws, c->d_elig,
+                                                           c->d_state, c->rng == EU_RNG_PHILOX, c->seed ^ 0x6E32766563ull,
+                                                           (long long*)out);
+    EU_LAUNCHED();
+    pet = cet;
+  }
+  return EU_OK;
+}
+
+extern "C" int eu_get_full_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
+                                    int64_t cap, int64_t* out_ptr, int64_t* out_ids, float* out_w, int32_t* out_t) {
+  (void)c; (void)nodes; (void)B; (void)etypes; (void)K; (void)cap; (void)out_ptr; (void)out_ids; (void)out_w; (void)out_t;
+  set_error("eu_get_full_neighbor: not implemented yet (SURVEY section 8f next-1)");
+  return EU_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,335 @@
+"""tf_euler's Python op API for the minibatch-construction path, over torch CUDA tensors.
+
+Same names, argument meaning and error behaviour as the reference wrappers
+(tf_euler/python/euler_ops/{base,neighbor_ops,walk_ops,sample_ops,feature_ops,mp_ops,type_ops}.py);
+each function cites the wrapper it mirrors.  Tensors are torch tensors on the graph's device; every
+op enqueues kernels from libeuler_b200.so on the current torch stream.  Nothing here computes on the
+CPU and nothing falls back to PyTorch ops: if the library or the GPU is missing, calls raise.
+"""
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EulerError, check
+from .graph import Context, Graph
+
+_state = threading.local()
+_default = {"graph": None, "rng": "minstd", "seed": 1}
+
+
+# ------------------------------------------------------------------------------------ init
+def initialize_graph(config):
+    """base.initialize_graph (tf_euler/python/euler_ops/base.py:37-60): str or dict of k=v;
+    TypeError otherwise.  Returns what InitQueryProxy returns."""
+    if isinstance(config, dict):
+        config = ';'.join('{}={}'.format(key, value) for key, value in config.items())
+    if not isinstance(config, str):
+        raise TypeError('Expect str or dict for graph config, got {}.'.format(type(config).__name__))
+    lib = _lib.load()
+    ok = bool(lib.InitQueryProxy(config.encode()))
+    h = lib.eu_default_graph()
+    if h:
+        kv = dict(item.split('=') for item in config.split(';') if item)
+        g = Graph(C.c_void_p(h), int(kv.get('device', 0)))
+        g.close = lambda: None  # owned by the library's default slot
+        set_graph(g, rng=kv.get('rng', 'minstd'), seed=int(kv.get('seed', 1)))
+    return ok
+
+
+def initialize_embedded_graph(data_dir, sampler_type='all', data_type='all'):
+    """base.initialize_embedded_graph (base.py:63-67)."""
+    return initialize_graph({'mode': 'local', 'data_path': data_dir, 'data_type': data_type,
+                             'sampler_type': sampler_type})
+
+
+def set_graph(graph, rng="minstd", seed=1):
+    """Install an already-built Graph (synthetic / from arrays) as the process default."""
+    _default.update(graph=graph, rng=rng, seed=seed)
+    _state.__dict__.pop("ctx", None)
+
+
+def get_graph():
+    if _default["graph"] is None:
+        raise EulerError("graph is not initialized: call initialize_graph / set_graph first")
+    return _default["graph"]
+
+
+def context():
+    """Per-thread Context of the default graph (one engine per client thread, like
+    euler/common/random.cc:22's thread_local engine)."""
+    ctx = getattr(_state, "ctx", None)
+    if ctx is None or ctx.graph is not _default["graph"]:
+        ctx = Context(get_graph(), _default["rng"], _default["seed"])
+        _state.ctx = ctx
+    return ctx
+
+
+def seed(s):
+    """Re-seed this thread's engine (the reference has no seed API; parity tests need one)."""
+    context().seed(s)
+
+
+def _dev():
+    return torch.device("cuda", get_graph().device)
+
+
+def _ctx_on_stream():
+    ctx = context()
+    ctx.set_stream(torch.cuda.current_stream(_dev()).cuda_stream)
+    return ctx
+
+
+def _t(x, dtype):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=_dev(), dtype=dtype).contiguous()
+    return torch.as_tensor(np.asarray(x), dtype=dtype, device=_dev()).contiguous()
+
+
+def _i32_host(x):
+    if isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    return np.ascontiguousarray(np.asarray(x).reshape(-1), dtype=np.int32)
+
+
+# ------------------------------------------------------------------------------------ type ops
+def get_edge_type_id(type_id_or_names):
+    """type_ops.get_edge_type_id (type_ops.py:57-68): names resolved through graph meta."""
+    return _type_ids(type_id_or_names, get_graph().edge_type_id)
+
+
+def get_node_type_id(type_id_or_names):
+    """type_ops.get_node_type_id (type_ops.py:42-54)."""
+    return _type_ids(type_id_or_names, get_graph().node_type_id)
+
+
+def _type_ids(v, lookup):
+    if isinstance(v, torch.Tensor):
+        return _i32_host(v)
+    arr = np.asarray(v).reshape(-1)
+    if arr.dtype.kind in "US":
+        return np.asarray([lookup(str(s)) for s in arr], np.int32)
+    return arr.astype(np.int32)
+
+
+# ------------------------------------------------------------------------------------ sampling
+def sample_neighbor(nodes, edge_types, count, default_node=-1, condition=''):
+    """neighbor_ops.sample_neighbor (neighbor_ops.py:39-41).  Returns (neighbors i64[B,count],
+    weights f32[B,count], types i32[B,count])."""
+    if condition:
+        raise EulerError("sample_neighbor: `condition` (index queries) is outside this path")
+    nodes = _t(nodes, torch.int64).reshape(-1)
+    et = get_edge_type_id(edge_types)
+    B = nodes.numel()
+    ids = torch.empty((B, count), dtype=torch.int64, device=nodes.device)
+    w = torch.empty((B, count), dtype=torch.float32, device=nodes.device)
+    t = torch.empty((B, count), dtype=torch.int32, device=nodes.device)
+    ctx = _ctx_on_stream()
+    check(_lib.load().eu_sample_neighbor(ctx._h, nodes.data_ptr(), B, et.ctypes.data, len(et), count,
+                                         default_node, ids.data_ptr(), w.data_ptr(), t.data_ptr()))
+    return ids, w, t
+
+
+def sample_fanout(nodes, edge_types, counts, default_node=-1):
+    """neighbor_ops.sample_fanout (neighbor_ops.py:122-158).  edge_types: list (per hop) of 1-D
+    type lists of equal length.  Returns (neighbors_list[L+1], weights_list[L], types_list[L]),
+    all flattened like the reference."""
+    nodes = _t(nodes, torch.int64).reshape(-1)
+    L = len(counts)
+    ets = [get_edge_type_id(e) for e in edge_types]
+    if len(ets) != L or any(len(e) != len(ets[0]) for e in ets):
+        raise EulerError("sample_fanout: edge_types must hold one equal-length type list per hop")
+    et = np.ascontiguousarray(np.stack(ets) if L else np.zeros((0, 0)), dtype=np.int32)
+    cs = np.ascontiguousarray(counts, dtype=np.int32)
+    B = nodes.numel()
+    ids, ws, ts, rows = [], [], [], B
+    for c in counts:
+        rows *= int(c)
+        ids.append(torch.empty(rows, dtype=torch.int64, device=nodes.device))
+        ws.append(torch.empty(rows, dtype=torch.float32, device=nodes.device))
+        ts.append(torch.empty(rows, dtype=torch.int32, device=nodes.device))
+    P = C.c_void_p * max(L, 1)
+    ctx = _ctx_on_stream()
+    check(_lib.load().eu_sample_fanout(ctx._h, nodes.data_ptr(), B, et.ctypes.data,
+                                       et.shape[1] if L else 0, cs.ctypes.data, L, default_node,
+                                       P(*[x.data_ptr() for x in ids]), P(*[x.data_ptr() for x in ws]),
+                                       P(*[x.data_ptr() for x in ts])))
+    return [nodes] + ids, ws, ts
+
+
+def sample_node(count, node_type, condition=''):
+    """sample_ops.sample_node (sample_ops.py:38-54); node_type '-1' (or -1) = all types."""
+    if condition:
+        raise EulerError("sample_node: `condition` (index queries) is outside this path")
+    if isinstance(node_type, str) and node_type == '-1':
+        types = np.asarray([-1], np.int32)
+    else:
+        types = get_node_type_id(node_type)
+    count = int(count)
+    out = torch.empty(count, dtype=torch.int64, device=_dev())
+    ctx = _ctx_on_stream()
+    check(_lib.load().eu_sample_node(ctx._h, count, types.ctypes.data, len(types), out.data_ptr()))
+    return out
+
+
+def random_walk(nodes, edge_types, p=1.0, q=1.0, default_node=-1):
+    """walk_ops.random_walk (walk_ops.py:29-43).  edge_types: list of L 1-D type lists.
+    Returns i64[B, L+1]."""
+    nodes = _t(nodes, torch.int64).reshape(-1)
+    ets = [get_edge_type_id(e) for e in edge_types]
+    L = len(ets)
+    if any(len(e) != len(ets[0]) for e in ets):
+        raise EulerError("random_walk: every step needs the same number of edge types here")
+    et = np.ascontiguousarray(np.stack(ets) if L else np.zeros((0, 0)), dtype=np.int32)
+    B = nodes.numel()
+    out = torch.empty((B, L + 1), dtype=torch.int64, device=nodes.device)
+    ctx = _ctx_on_stream()
+    check(_lib.load().eu_random_walk(ctx._h, nodes.data_ptr(), B, et.ctypes.data,
+                                     et.shape[1] if L else 0, L, float(p), float(q), default_node,
+                                     out.data_ptr()))
+    return out
+
+
+def get_dense_feature(nodes, feature_names, dimensions, thread_num=1):
+    """feature_ops.get_dense_feature (feature_ops.py:111-125): list of f32[M, dim_i]; names are
+    looked up as "dense_"+name in the graph meta (get_dense_feature_op.cc:83); ints are slot ids."""
+    del thread_num  # the reference splits the batch over TF threads; one launch here
+    nodes = _t(nodes, torch.int64).reshape(-1)
+    g = get_graph()
+    outs = []
+    ctx = _ctx_on_stream()
+    for name, dim in zip(feature_names, dimensions):
+        fid = name if isinstance(name, (int, np.integer)) else g.dense_feature_id(name)
+        out = torch.empty((nodes.numel(), int(dim)), dtype=torch.float32, device=nodes.device)
+        check(_lib.load().eu_get_dense_feature(ctx._h, nodes.data_ptr(), nodes.numel(), int(fid),
+                                               int(dim), out.data_ptr()))
+        outs.append(out)
+    return outs
+
+
+def sage_mean_aggregate(neighbor_ids, count, dim):
+    """Fused get_dense_feature + scatter_mean for fixed-fanout blocks (SAGEConv's neighbor mean,
+    tf_euler/python/convolution/sage_conv.py:33-38 over sage_dataflow.py:43-46 blocks)."""
+    ids = _t(neighbor_ids, torch.int64).reshape(-1)
+    rows = ids.numel() // int(count)
+    out = torch.empty((rows, int(dim)), dtype=torch.float32, device=ids.device)
+    ctx = _ctx_on_stream()
+    check(_lib.load().eu_sage_mean_aggregate(ctx._h, ids.data_ptr(), rows, int(count), int(dim),
+                                             out.data_ptr()))
+    return out
+
+
+# ------------------------------------------------------------------------------------ mp ops
+def _raw_gather(params, indices):
+    params = params.contiguous()
+    out = torch.empty((indices.numel(), params.shape[1]), dtype=torch.float32, device=params.device)
+    ctx = _ctx_on_stream()
+    check(_lib.load().eu_gather(ctx._h, params.data_ptr(), params.shape[0], params.shape[1],
+                                indices.data_ptr(), indices.numel(), out.data_ptr()))
+    return out
+
+
+def _raw_scatter(name, updates, indices, size):
+    updates = updates.contiguous()
+    out = torch.empty((int(size), updates.shape[1]), dtype=torch.float32, device=updates.device)
+    ctx = _ctx_on_stream()
+    check(getattr(_lib.load(), name)(ctx._h, updates.data_ptr(), updates.shape[1], indices.data_ptr(),
+                                     indices.numel(), int(size), out.data_ptr()))
+    return out
+
+
+class _Gather(torch.autograd.Function):
+    """MPGather with gradient scatter_add(grad, indices, N) (mp_ops.py:39-43)."""
+
+    @staticmethod
+    def forward(ctx, params, indices):
+        ctx.save_for_backward(indices)
+        ctx.n = params.shape[0]
+        return _raw_gather(params, indices)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (indices,) = ctx.saved_tensors
+        return _raw_scatter("eu_scatter_add", grad, indices, ctx.n), None
+
+
+class _ScatterAdd(torch.autograd.Function):
+    """MPScatterAdd with gradient gather(grad, indices) (mp_ops.py:46-49)."""
+
+    @staticmethod
+    def forward(ctx, updates, indices, size):
+        ctx.save_for_backward(indices)
+        return _raw_scatter("eu_scatter_add", updates, indices, size)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (indices,) = ctx.saved_tensors
+        return _raw_gather(grad, indices), None, None
+
+
+class _ScatterMax(torch.autograd.Function):
+    """MPScatterMax; gradient splits evenly among ties (mp_ops.py:52-62)."""
+
+    @staticmethod
+    def forward(ctx, updates, indices, size):
+        out = _raw_scatter("eu_scatter_max", updates, indices, size)
+        ctx.save_for_backward(updates, indices, out)
+        ctx.size = size
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        updates, indices, out = ctx.saved_tensors
+        indicators = (updates == _raw_gather(out, indices)).to(updates.dtype)
+        num_selected = _raw_scatter("eu_scatter_add", indicators, indices, ctx.size)
+        indicators = indicators / _raw_gather(num_selected, indices)
+        return indicators * _raw_gather(grad, indices), None, None
+
+
+def _f32(x):
+    x = _t(x, torch.float32)
+    return x if x.dim() == 2 else x.reshape(x.shape[0], -1)
+
+
+def gather(params, indices):
+    """mp_ops.gather = MPGather (mp_ops.py:27): out[i,:] = params[indices[i],:]."""
+    return _Gather.apply(_f32(params), _t(indices, torch.int32).reshape(-1))
+
+
+def scatter_add(updates, indices, size=None):
+    """mp_ops.scatter_add = MPScatterAdd (mp_ops.py:28)."""
+    return _ScatterAdd.apply(_f32(updates), _t(indices, torch.int32).reshape(-1), int(size))
+
+
+def scatter_max(updates, indices, size=None):
+    """mp_ops.scatter_max = MPScatterMax (mp_ops.py:29); output initialised to -1e9."""
+    return _ScatterMax.apply(_f32(updates), _t(indices, torch.int32).reshape(-1), int(size))
+
+
+def scatter_mean(updates, indices, size=None):
+    """mp_ops.scatter_mean (mp_ops.py:65-69): scatter_add / (scatter_add(ones) + 1e-7).
+    Without autograd the fused kernel is used (same arithmetic)."""
+    updates = _f32(updates)
+    indices = _t(indices, torch.int32).reshape(-1)
+    if not (torch.is_grad_enabled() and updates.requires_grad):
+        return _raw_scatter("eu_scatter_mean", updates, indices, int(size))
+    out = scatter_add(updates, indices, size)
+    ep = 1e-7
+    ones = torch.ones((updates.shape[0], 1), dtype=torch.float32, device=updates.device)
+    count = scatter_add(ones, indices, size) + ep
+    return out / count
+
+
+def scatter_(op, updates, indices, size):
+    """mp_ops.scatter_ (mp_ops.py:72-73)."""
+    return globals()['scatter_' + op](updates, indices, size)
+
+
+def scatter_softmax(updates, indices, size=None):
+    """mp_ops.scatter_softmax (mp_ops.py:76-79)."""
+    updates = _f32(updates)
+    updates = updates - gather(scatter_max(updates, indices, size), indices)
+    updates = torch.exp(updates)
+    return updates / gather(scatter_add(updates, indices, size), indices)

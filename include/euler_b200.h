@@ -1,0 +1,207 @@
+/* euler_b200 -- C ABI of the B200-native minibatch-construction path of alibaba/euler.
+ *
+ * This is the drop-in boundary (seam B2).  The reference exports exactly one
+ * C symbol, `bool InitQueryProxy(const char*)` (tf_euler/utils/init_query_proxy.cc:19-36); every
+ * other entry point of the hot path is a TensorFlow op registered in C++.  Since TF's registry is
+ * not part of this build, each TF op of the path is exported here as a flat function with the
+ * op's own argument meaning; the reference-side binding a maintainer would add is shown in
+ * INTEGRATION.md.  Plain pointers and sizes only -- no torch / TF types.
+ *
+ * Conventions
+ *   - every function returns 0 (EU_OK) or a nonzero eu_status; nothing throws across the ABI;
+ *   - `eu_ctx` = one execution lane: a CUDA stream + one RNG engine + scratch.  It plays the role of
+ *     one thread of the reference's client pool (euler/client/query_proxy.cc:205-210: 8 threads,
+ *     each with its own thread_local engine, euler/common/random.cc:22).  Calls on one ctx are
+ *     stream-ordered; different ctxs may run concurrently; the graph is immutable after creation;
+ *   - functions without a `_host` suffix take DEVICE pointers and only enqueue work on the ctx
+ *     stream (no host synchronisation, capturable in a CUDA graph);
+ *   - `_host` variants take HOST pointers, stage through pinned buffers owned by the ctx, and
+ *     return after the results have landed (this is what a CPU-tensor framework binds);
+ *   - edge-type / count lists are HOST arrays (they are op attributes / tiny tensors upstream).
+ */
+#ifndef EULER_B200_H_
+#define EULER_B200_H_
+
+#include <stdbool.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  EU_OK = 0,
+  EU_ERR_INVALID = 1,      /* bad argument */
+  EU_ERR_CUDA = 2,         /* a CUDA call failed; see eu_last_error() */
+  EU_ERR_NO_GPU = 3,       /* no CUDA device: this library has no CPU fallback */
+  EU_ERR_UNSUPPORTED = 4,  /* valid in the reference but outside this path (e.g. `condition`) */
+  EU_ERR_IO = 5,
+  EU_ERR_STATE = 6         /* e.g. op called before a graph was initialised */
+} eu_status;
+
+/* RNG engines.  EU_RNG_MINSTD reproduces the reference's engine and draw order bit-exactly
+ * (std::default_random_engine + uniform_real_distribution<double>, euler/common/random.cc:22-28);
+ * EU_RNG_PHILOX is a counter-based engine keyed on (node id, draw) for throughput runs: same
+ * algorithm, same distribution, different stream. */
+typedef enum { EU_RNG_MINSTD = 0, EU_RNG_PHILOX = 1 } eu_rng_kind;
+
+typedef struct eu_graph eu_graph;
+typedef struct eu_ctx eu_ctx;
+
+const char* eu_last_error(void);
+const char* eu_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t eu_launch_count(void);
+
+/* ------------------------------------------------------------------ graph -------------------- */
+/* CSR description, HOST arrays.  Mirrors what a reference Node holds (euler/core/graph/node.h:49-57,
+ * node.cc:37-96): for row r and edge type t the adjacency group is
+ *   [grp_ptr[r*T+t], grp_ptr[r*T+t+1])  -- neighbor_groups_idx, made global;
+ * cum_w is the NODE-GLOBAL cumulative f32 weight exactly as stored (node.cc:59-65); grp_cum[r*T+t] is
+ * edge_group_collection.sum_weights_[t].  If cum_w == NULL, `w` (raw weights) must be given and the
+ * prefix sums are accumulated the way Node::Init does (sequential f32, eu_graph builds them). */
+typedef struct {
+  int64_t n_nodes;
+  int32_t n_edge_types;    /* T */
+  int32_t n_node_types;
+  const uint64_t* ids;     /* [n] node id of each row; id 0 is unusable (DEFAULT_UINT64) */
+  const int32_t* node_type;/* [n] or NULL (all 0) */
+  const float* node_w;     /* [n] or NULL (all 1.0) */
+  const int64_t* grp_ptr;  /* [n*T+1] */
+  const uint64_t* nbr;     /* [E] */
+  const float* cum_w;      /* [E] or NULL */
+  const float* grp_cum;    /* [n*T] or NULL (required iff cum_w given and T > 1) */
+  const float* w;          /* [E] raw weights, used iff cum_w == NULL */
+  int32_t feat_dim;        /* dense f32 feature slot 0: row length, 0 = none */
+  const float* feat;       /* [n*feat_dim] or NULL */
+  const int64_t* sampler_order; /* [n] rows in the order the global node sampler enumerates them
+                                   (graph.cc:349-354 uses unordered_map order); NULL = row order */
+  /* optional: several dense f32 feature slots (Node::float_features_idx_, node.h); when
+   * n_feat_slots > 0, feat is [n, sum(feat_slot_dims)] and feat_dim must equal that sum */
+  int32_t n_feat_slots;
+  const int32_t* feat_slot_dims;
+} eu_graph_desc;
+
+int eu_graph_create(const eu_graph_desc* desc, int device, eu_graph** out);
+/* Synthetic R-MAT graph generated, sorted and prefix-summed on the device (SURVEY.md section 8d "G-RMAT"):
+ * ids 1..n, one node/edge type, n_edges directed edges with (a,b,c,d), adjacency sorted by dst,
+ * weight = 1 + (hash(src,dst) % 100) / 10, feat ~ U(-1,1).  feat_dim may be 0. */
+int eu_graph_create_rmat(int64_t n_nodes, int64_t n_edges, double a, double b, double c,
+                         uint64_t seed, int32_t feat_dim, uint64_t feat_seed, int device,
+                         eu_graph** out);
+/* Euler 2.0 on-disk format (euler.meta + Node/*.dat), shard `shard_index` of
+ * `shard_number` with the reference's file filter (graph.cc:90-98).  = Graph::Init, graph.h:53-56. */
+int eu_graph_load(const char* data_path, int shard_index, int shard_number, int device,
+                  eu_graph** out);
+int eu_graph_destroy(eu_graph* g);
+int64_t eu_graph_num_nodes(const eu_graph* g);
+int64_t eu_graph_num_edges(const eu_graph* g);
+int32_t eu_graph_num_edge_types(const eu_graph* g);
+int32_t eu_graph_num_node_types(const eu_graph* g);
+int32_t eu_graph_feat_dim(const eu_graph* g);
+int64_t eu_graph_hbm_bytes(const eu_graph* g);
+/* Copy the device CSR back to caller-allocated HOST arrays (any pointer may be NULL). */
+int eu_graph_export(const eu_graph* g, uint64_t* ids, int32_t* node_type, float* node_w,
+                    int64_t* grp_ptr, uint64_t* nbr, float* cum_w, float* grp_cum, float* feat);
+/* type-name lookup from euler.meta (tf_euler/python/euler_ops/type_ops.py:31-64); -1 if unknown */
+int32_t eu_graph_edge_type_id(const eu_graph* g, const char* name);
+int32_t eu_graph_node_type_id(const eu_graph* g, const char* name);
+/* dense feature slot of feature `name` (looked up as "dense_"+name like get_dense_feature_op.cc:83);
+ * -1 if unknown.  eu_graph_dense_feature_dim: stored width of a slot. */
+int32_t eu_graph_dense_feature_id(const eu_graph* g, const char* name);
+int32_t eu_graph_dense_feature_dim(const eu_graph* g, int32_t fid);
+
+/* ------------------------------------------------------------------ contexts ----------------- */
+/* stream: a cudaStream_t (NULL = legacy default stream). */
+int eu_ctx_create(eu_graph* g, eu_rng_kind rng, uint64_t seed, void* stream, eu_ctx** out);
+int eu_ctx_destroy(eu_ctx* c);
+int eu_ctx_set_stream(eu_ctx* c, void* stream);
+int eu_ctx_seed(eu_ctx* c, uint64_t seed);           /* engine.seed(seed); stream-ordered */
+int eu_ctx_reserve(eu_ctx* c, int64_t max_rows);      /* pre-size scratch (required before graph capture) */
+int eu_ctx_sync(eu_ctx* c);
+/* number of uniforms the MINSTD engine has produced since the last seed (synchronises) */
+int eu_ctx_draws(eu_ctx* c, uint64_t* draws);
+
+/* ------------------------------------------------------------------ sampling ops ------------- */
+/* tf_euler.sample_neighbor -- TF op SampleNeighbor (tf_euler/ops/neighbor_ops.cc:138-163, kernel
+ * tf_euler/kernels/sample_neighbor_op.cc:54-129).  nodes i64[B]; etypes i32[K] (host);
+ * outputs [B,count]: ids i64 (default_node fill), w f32 (0 fill), t i32 (-1 fill). */
+int eu_sample_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
+                       int32_t count, int64_t default_node, int64_t* out_ids, float* out_w,
+                       int32_t* out_t);
+int eu_sample_neighbor_host(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes,
+                            int32_t K, int32_t count, int64_t default_node, int64_t* out_ids,
+                            float* out_w, int32_t* out_t);
+/* tf_euler.sample_fanout -- TF op SampleFanout (tf_euler/ops/neighbor_ops.cc:228-280, kernel
+ * tf_euler/kernels/sample_fanout_op.cc:60-145).  etypes i32[L,K] (host), counts i32[L] (host);
+ * out_*[l] point to B*prod(counts[0..l]) elements.  The frontier never leaves the device. */
+int eu_sample_fanout(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
+                     const int32_t* counts, int32_t L, int64_t default_node, int64_t* const* out_ids,
+                     float* const* out_w, int32_t* const* out_t);
+int eu_sample_fanout_host(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes,
+                          int32_t K, const int32_t* counts, int32_t L, int64_t default_node,
+                          int64_t* const* out_ids, float* const* out_w, int32_t* const* out_t);
+/* tf_euler.sample_node -- TF op SampleNode (tf_euler/ops/sample_ops.cc:22-37, kernel
+ * tf_euler/kernels/sample_node_op.cc:39-96; euler::SampleNode api.cc:32-37).  types i32[n_types]
+ * (host); a single -1 means all types.  out i64[count]. */
+int eu_sample_node(eu_ctx* c, int32_t count, const int32_t* types, int32_t n_types, int64_t* out);
+int eu_sample_node_host(eu_ctx* c, int32_t count, const int32_t* types, int32_t n_types,
+                        int64_t* out);
+/* tf_euler.random_walk -- TF op RandomWalk (tf_euler/ops/walk_ops.cc:77-107, kernel
+ * tf_euler/kernels/random_walk_op.cc:83-289).  etypes i32[L,K] (host); out i64[B,L+1]. */
+int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
+                   int32_t L, float p, float q, int64_t default_node, int64_t* out);
+int eu_random_walk_host(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes,
+                        int32_t K, int32_t L, float p, float q, int64_t default_node, int64_t* out);
+/* tf_euler.get_dense_feature, one feature -- TF op GetDenseFeature (tf_euler/ops/feature_ops.cc:94-140,
+ * kernel tf_euler/kernels/get_dense_feature_op.cc:63-121).  out f32[M,dim], zero fill. */
+int eu_get_dense_feature(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid, int32_t dim,
+                         float* out);
+int eu_get_dense_feature_host(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid, int32_t dim,
+                              float* out);
+/* tf_euler.get_full_neighbor core (euler::GetFullNeighbor api.cc:208-221): CSR-style output.
+ * out_ptr i64[B+1] (device); if cap < total only the first cap entries are written.  *total (host)
+ * is filled by the _host variant only. */
+int eu_get_full_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
+                         int64_t cap, int64_t* out_ptr, int64_t* out_ids, float* out_w,
+                         int32_t* out_t);
+
+/* ------------------------------------------------------------------ message-passing ops ------ */
+/* MPGather / MPScatterAdd / MPScatterMax (tf_euler/ops/mp_ops.cc:22-81; kernels
+ * tf_euler/kernels/gather_op.cc:31-52, scatter_op.cc:32-92).  f32 data, i32 indices, as registered. */
+int eu_gather(eu_ctx* c, const float* params, int64_t N, int64_t D, const int32_t* idx, int64_t E,
+              float* out);
+int eu_scatter_add(eu_ctx* c, const float* updates, int64_t D, const int32_t* idx, int64_t E,
+                   int64_t size, float* out);
+int eu_scatter_max(eu_ctx* c, const float* updates, int64_t D, const int32_t* idx, int64_t E,
+                   int64_t size, float* out);
+/* scatter_mean (tf_euler/python/euler_ops/mp_ops.py:65-69): add / (add(ones) + 1e-7) */
+int eu_scatter_mean(eu_ctx* c, const float* updates, int64_t D, const int32_t* idx, int64_t E,
+                    int64_t size, float* out);
+/* Fused SAGE aggregation for fixed-fanout blocks (sage_dataflow.py:43-46 edge_src = repeat(range(B),count)):
+ * out[r,:] = mean_{j<count} feat[row(nbr_ids[r*count+j]),:] with scatter_mean's (count + 1e-7)
+ * divisor; ids not in the graph (default fill) contribute zeros, as get_dense_feature would. */
+int eu_sage_mean_aggregate(eu_ctx* c, const int64_t* nbr_ids, int64_t rows, int32_t count,
+                           int32_t dim, float* out);
+int eu_gather_host(eu_ctx* c, const float* params, int64_t N, int64_t D, const int32_t* idx,
+                   int64_t E, float* out);
+int eu_scatter_add_host(eu_ctx* c, const float* updates, int64_t D, const int32_t* idx, int64_t E,
+                        int64_t size, float* out);
+int eu_scatter_max_host(eu_ctx* c, const float* updates, int64_t D, const int32_t* idx, int64_t E,
+                        int64_t size, float* out);
+
+/* ------------------------------------------------------------------ reference entry point ---- */
+/* bool InitQueryProxy(const char* conf) -- tf_euler/utils/init_query_proxy.cc:19-36.  "k=v;k=v";
+ * keys of euler/client/query_proxy.cc:41-160 that apply here: mode (local only), data_path,
+ * sampler_type, data_type, shard_num(=1); new keys: device, seed, rng (minstd|philox).
+ * Returns false only for an empty / malformed list (as the reference does, :22-33); load errors are
+ * logged.  Creates the process-wide default graph + ctx used by the *_default accessors. */
+bool InitQueryProxy(const char* conf);
+eu_graph* eu_default_graph(void);
+eu_ctx* eu_default_ctx(void);
+int eu_set_default_graph(eu_graph* g, eu_rng_kind rng, uint64_t seed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EULER_B200_H_ */

@@ -1,0 +1,72 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/euler_b200.h declares;
+without a GPU it refuses to work instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+import graphs  # noqa: F401  (sys.path)
+from euler_b200 import _lib, build
+
+HEADER = os.path.join(graphs.ROOT, "include", "euler_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b((?:eu_[a-z0-9_]+|InitQueryProxy))\s*\(", src)
+    return sorted(set(names) - {"eu_status", "eu_rng_kind"})
+
+
+def test_library_builds_and_exports_header_symbols():
+    build.build()
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 45
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+        assert n in _lib.SIGNATURES, "python binding lacks " + n
+    assert set(_lib.SIGNATURES) <= set(names), set(_lib.SIGNATURES) - set(names)
+    assert b"sm_100a" in lib.eu_version()
+
+
+def test_sass_is_sm100a():
+    out = os.popen("cuobjdump -lelf %s 2>/dev/null" % _lib.SO_PATH).read()
+    assert "sm_100a" in out
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_gpu_means_loud_failure_not_fallback():
+    lib = _lib.load()
+    h = C.c_void_p()
+    rc = lib.eu_graph_create_rmat(100, 1000, 0.57, 0.19, 0.19, 42, 0, 7, 0, C.byref(h))
+    assert rc == 3  # EU_ERR_NO_GPU
+    assert b"no CPU fallback" in lib.eu_last_error()
+    import euler_b200
+    with pytest.raises(euler_b200.EulerError):
+        euler_b200.Graph.rmat(100, 1000)
+    with pytest.raises(euler_b200.EulerError):
+        euler_b200.sample_neighbor([1], [0], 3)  # no graph initialised
+
+
+def test_init_query_proxy_contract():
+    # tf_euler/utils/init_query_proxy.cc:19-36: false only for an empty / malformed k=v list
+    lib = _lib.load()
+    assert lib.InitQueryProxy(b"") is False
+    assert lib.InitQueryProxy(b"mode") is False
+    assert lib.InitQueryProxy(b"a=b=c") is False
+    assert lib.InitQueryProxy(b"mode=remote;zk_server=x") is True   # logged, not propagated (:34)
+    import euler_b200
+    with pytest.raises(TypeError):
+        euler_b200.initialize_graph(42)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(graphs.ROOT, "euler_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "pyoracle" not in txt and "euler_oracle" not in txt and "libeuler_ref" not in txt, f

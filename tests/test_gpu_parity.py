@@ -1,0 +1,342 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI / the Python mirror
+of tf_euler's op API, against (a) golden vectors produced by the reference itself, (b) the pinned
+CPU oracle on fresh seeded inputs, (c) size-independent properties at large sizes.
+Integer / id / index outputs and sampled weights: bit-exact.  Float aggregations: bit-exact on the
+sorted-index path, 1e-5 relative (north_star tolerance) on the unsorted atomic path."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import graphs
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5  # BASELINE.json north_star: "within 1e-5 relative for float aggregations"
+
+
+@pytest.fixture(autouse=True)
+def _sync_after():
+    yield
+    torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------ golden replays (reference outputs)
+def test_tiny_golden_from_csr():
+    g = graphs.load_tiny_csr()
+    cases.replay_tiny(cases.CudaBackend(g, g["map_order"]))
+
+
+def test_tiny_loaded_from_reference_dat_files(tiny_dir):
+    import euler_b200
+    gr = euler_b200.Graph.load(tiny_dir)
+    z = graphs.load_tiny_csr()
+    ex = gr.export()
+    for k in ("ids", "node_type", "node_w", "grp_ptr", "nbr", "cum_w", "grp_cum"):
+        assert np.array_equal(ex[k], z[k]), k
+    cases.eq(ex["feat"], z["feat"], "dense features")
+    # meta: names resolve like type_ops.py (node "1"->0, "0"->1; edge "0"->0, "1"->1)
+    assert gr.node_type_id("1") == 0 and gr.node_type_id("0") == 1
+    assert gr.edge_type_id("0") == 0 and gr.edge_type_id("1") == 1
+    assert gr.dense_feature_id("f3") == 0 and gr.dense_feature_id("f4") == 1 and gr.dense_feature_dim(1) == 3
+    euler_b200.set_graph(gr)
+    f3, f4 = euler_b200.get_dense_feature([1, 9, 4], ["f3", "f4"], [2, 3])
+    cases.eq(f4.cpu().numpy(), cases.golden()["tiny_feat_f4"], "f4")
+    assert np.allclose(f3.cpu().numpy()[0], [1.1, 1.2])
+    # config C1: SampleNeighbor fanout=[10] batch=128 on the tools/test_data graph, fixed seed
+    og = graphs.oracle_graph(z)
+    seeds = np.random.RandomState(0).randint(0, 9, size=128).astype(np.int64)
+    euler_b200.seed(2024)
+    po.seed(2024)
+    got = [x.cpu().numpy() for x in euler_b200.sample_neighbor(seeds, ["0", "1"], 10)]
+    for a, b in zip(got, og.op_sample_neighbor(seeds, [0, 1], 10)):
+        cases.eq(a, b, "C1 sample_neighbor")
+
+
+@pytest.mark.parametrize("name", sorted(cases.SYNTH))
+@pytest.mark.parametrize("raw", [False, True])
+def test_synth_golden(name, raw):
+    g = graphs.random_graph(**cases.SYNTH[name])
+    cases.replay_synth(name, cases.CudaBackend(g, cases.golden()[name + "_map_order"], raw_weights=raw))
+
+
+# ------------------------------------------------------------------ fresh inputs vs the oracle
+@pytest.mark.parametrize("seed,T,kw", [(21, 1, dict(hub=5000)), (22, 3, dict(zero_w_frac=0.15, id_stride=1009, id_base=77)),
+                                       (23, 8, dict(empty_frac=0.4, hub=900, n_node_types=4))])
+def test_random_graph_vs_oracle(seed, T, kw):
+    n = 20000
+    g = graphs.random_graph(seed=seed, n=n, T=T, avg_deg=8, **kw)
+    order = np.random.RandomState(seed).permutation(g["ids"])
+    be, ob = cases.CudaBackend(g, order), cases.OracleBackend(g, order)
+    rs = np.random.RandomState(seed + 1)
+    seeds = g["ids"][rs.randint(0, n, size=3000)].astype(np.int64)
+    seeds[::13] = 987654321012
+    seeds[5::17] = -1
+    seeds[3::19] = 0
+    for et, cnt in [([0], 25), ([T - 1], 1), (list(range(T)), 70), ([0, T - 1], 33), ([], 10), ([T + 3], 4)]:
+        be.seed(seed); ob.seed(seed)
+        for a, b in zip(be.op_sample_neighbor(seeds, et, cnt, -5), ob.op_sample_neighbor(seeds, et, cnt, -5)):
+            cases.eq(a, b, "sample_neighbor et=%s count=%d" % (et, cnt))
+        assert be.draws() == ob.draws()
+    ets = [[0, T - 1], [T - 1, 0]]
+    be.seed(seed + 2); ob.seed(seed + 2)
+    a, b = be.op_sample_fanout(seeds[:600], ets, [25, 10], -1), ob.op_sample_fanout(seeds[:600], ets, [25, 10], -1)
+    for x, y in zip(a, b):
+        for l in range(2):
+            cases.eq(x[l], y[l], "fanout hop %d" % l)
+    # engine stream continues across calls exactly like one reference thread
+    a2, b2 = be.op_sample_neighbor(seeds, [0], 3, -1), ob.op_sample_neighbor(seeds, [0], 3, -1)
+    cases.eq(a2[0], b2[0], "second call on the same stream")
+    wet = np.asarray([list(range(T))] * 12, np.int32)
+    for p, q in [(0.5, 2.0), (1.0, 1.0), (2.0, 0.5)]:
+        be.seed(seed + 3); ob.seed(seed + 3)
+        cases.eq(be.op_random_walk(seeds[:500], wet, p, q, -1), ob.op_random_walk(seeds[:500], wet, p, q, -1),
+                 "walk p=%s q=%s" % (p, q))
+    for types in ([-1], [0], list(range(g["n_node_types"]))):
+        be.seed(seed + 4); ob.seed(seed + 4)
+        cases.eq(be.sample_node(types, 4097), ob.sample_node(types, 4097), "sample_node %s" % types)
+
+
+def test_empty_and_degenerate_inputs():
+    import euler_b200
+    g = graphs.random_graph(seed=31, n=50, T=2)
+    be = cases.CudaBackend(g, g["ids"])
+    ids, w, t = euler_b200.sample_neighbor(np.zeros(0, np.int64), [0], 5)
+    assert ids.shape == (0, 5)
+    ids, w, t = euler_b200.sample_neighbor([1, 2], [0], 0)
+    assert ids.shape == (2, 0)
+    out = euler_b200.random_walk([1, 2, 3], [], 0.5, 2.0)
+    assert out.cpu().numpy().tolist() == [[1], [2], [3]]
+    # every seed absent -> all defaults, no draws
+    be.seed(1)
+    ids, w, t = be.op_sample_neighbor(np.asarray([10 ** 12, -1, 0], np.int64), [0, 1], 4, -9)
+    assert (ids == -9).all() and (w == 0).all() and (t == -1).all() and be.draws() == 0
+
+
+def test_host_buffer_entry_points_match_device_ones():
+    import euler_b200
+    from euler_b200 import _lib
+    g = graphs.random_graph(seed=41, n=5000, T=2, feat_dim=16)
+    be = cases.CudaBackend(g, g["ids"])
+    lib, ctx = _lib.load(), euler_b200.context()
+    seeds = g["ids"][np.random.RandomState(3).randint(0, 5000, size=700)].astype(np.int64)
+    et = np.asarray([[0, 1], [1, 0]], np.int32)
+    cs = np.asarray([6, 5], np.int32)
+    be.seed(77)
+    d_ids, d_w, d_t = be.op_sample_fanout(seeds, et, [6, 5], -1)
+    h_ids = [np.zeros(700 * 6, np.int64), np.zeros(700 * 30, np.int64)]
+    h_w = [np.zeros(700 * 6, np.float32), np.zeros(700 * 30, np.float32)]
+    h_t = [np.zeros(700 * 6, np.int32), np.zeros(700 * 30, np.int32)]
+    P = C.c_void_p * 2
+    be.seed(77)
+    _lib.check(lib.eu_sample_fanout_host(ctx._h, seeds.ctypes.data, 700, et.ctypes.data, 2, cs.ctypes.data, 2, -1,
+                                         P(*[x.ctypes.data for x in h_ids]), P(*[x.ctypes.data for x in h_w]),
+                                         P(*[x.ctypes.data for x in h_t])))
+    for l in range(2):
+        cases.eq(h_ids[l], d_ids[l], "host fanout ids"); cases.eq(h_w[l], d_w[l], "host fanout w"); cases.eq(h_t[l], d_t[l], "host fanout t")
+    out = np.zeros((700, 16), np.float32)
+    _lib.check(lib.eu_get_dense_feature_host(ctx._h, seeds.ctypes.data, 700, 0, 16, out.ctypes.data))
+    cases.eq(out, graphs.oracle_graph(g).op_get_dense_feature(seeds, 16), "host dense feature")
+    x = np.random.RandomState(1).randn(300, 8).astype(np.float32)
+    idx = np.sort(np.random.RandomState(2).randint(0, 40, size=300)).astype(np.int32)
+    o = np.zeros((40, 8), np.float32)
+    _lib.check(lib.eu_scatter_add_host(ctx._h, x.ctypes.data, 8, idx.ctypes.data, 300, 40, o.ctypes.data))
+    cases.eq(o, po.scatter_add(x, idx, 40), "host scatter_add")
+    _lib.check(lib.eu_scatter_max_host(ctx._h, x.ctypes.data, 8, idx.ctypes.data, 300, 40, o.ctypes.data))
+    cases.eq(o, po.scatter_max(x, idx, 40), "host scatter_max")
+    o2 = np.zeros((300, 8), np.float32)
+    _lib.check(lib.eu_gather_host(ctx._h, x.ctypes.data, 300, 8, idx.ctypes.data, 300, o2.ctypes.data))
+    cases.eq(o2, po.gather(x, idx), "host gather")
+    wk = np.zeros((700, 5), np.int64)
+    wet = np.asarray([[0, 1]] * 4, np.int32)
+    be.seed(5)
+    ref = be.op_random_walk(seeds, wet, 0.25, 4.0, -1)
+    be.seed(5)
+    _lib.check(lib.eu_random_walk_host(ctx._h, seeds.ctypes.data, 700, wet.ctypes.data, 2, 4, 0.25, 4.0, -1, wk.ctypes.data))
+    cases.eq(wk, ref, "host random_walk")
+    sn = np.zeros(100, np.int64)
+    t0 = np.asarray([0], np.int32)
+    be.seed(6)
+    ref = be.sample_node([0], 100)
+    be.seed(6)
+    _lib.check(lib.eu_sample_node_host(ctx._h, 100, t0.ctypes.data, 1, sn.ctypes.data))
+    cases.eq(sn.astype(np.uint64), ref, "host sample_node")
+
+
+# ------------------------------------------------------------------ message passing
+@pytest.mark.parametrize("D", [1, 3, 64, 128, 200, 256])
+def test_mp_ops_vs_oracle(D):
+    import euler_b200
+    g = graphs.random_graph(seed=51, n=10, T=1)
+    cases.CudaBackend(g, g["ids"])
+    rs = np.random.RandomState(D)
+    N, E, size = 5000, 40000, 3000
+    params = rs.randn(N, D).astype(np.float32)
+    idx = rs.randint(0, N, size=E).astype(np.int32)
+    cases.eq(euler_b200.gather(params, idx).cpu().numpy(), po.gather(params, idx), "gather")
+    upd = rs.randn(E, D).astype(np.float32)
+    sidx = np.sort(rs.randint(0, size, size=E)).astype(np.int32)
+    sidx[sidx == 7] = 8  # an empty output row
+    # sorted indices (what the dataflows emit): the reference's summation order -> bit-exact
+    cases.eq(euler_b200.scatter_add(upd, sidx, size).cpu().numpy(), po.scatter_add(upd, sidx, size), "scatter_add sorted")
+    cases.eq(euler_b200.scatter_max(upd, sidx, size).cpu().numpy(), po.scatter_max(upd, sidx, size), "scatter_max sorted")
+    cases.eq(euler_b200.scatter_mean(upd, sidx, size).cpu().numpy(), po.scatter_mean(upd, sidx, size), "scatter_mean sorted")
+    # unsorted indices: order-free atomics, 1e-5 relative (max is exact)
+    uidx = rs.permutation(sidx).astype(np.int32)
+    for name in ("scatter_add", "scatter_mean"):
+        got = getattr(euler_b200, name)(upd, uidx, size).cpu().numpy()
+        want = getattr(po, name)(upd, uidx, size)
+        scale = np.maximum(np.abs(want), po.scatter_add(np.abs(upd), uidx, size) if name == "scatter_add" else 1.0)
+        assert (np.abs(got - want) <= RTOL * np.maximum(scale, 1e-30)).all(), name
+    cases.eq(euler_b200.scatter_max(upd, uidx, size).cpu().numpy(), po.scatter_max(upd, uidx, size), "scatter_max unsorted")
+
+
+def test_mp_ops_reference_test_vectors_and_gradients():
+    """tf_euler/python/euler_ops/mp_ops_test.py:30-94 incl. its numeric-gradient checks."""
+    import euler_b200 as mp_ops
+    g = graphs.random_graph(seed=52, n=10, T=1)
+    cases.CudaBackend(g, g["ids"])
+    x = torch.tensor([[1., 2.], [3., 4.], [5., 6.]], device="cuda")
+    idx = torch.tensor([1, 0, 1], device="cuda")
+    assert mp_ops.scatter_add(x, idx, size=2).cpu().tolist() == [[3., 4.], [6., 8.]]
+    assert (mp_ops.scatter_mean(x, idx, size=2).cpu() - torch.tensor([[3., 4.], [3., 4.]])).abs().sum() < 1e-6
+    x2 = torch.tensor([[1., 6.], [3., 4.], [5., 2.]], device="cuda")
+    assert mp_ops.scatter_max(x2, idx, size=2).cpu().tolist() == [[3., 4.], [5., 6.]]
+    idx4 = torch.tensor([1, 0, 1, 2], device="cuda")
+    assert mp_ops.gather(x, idx4).cpu().tolist() == [[3., 4.], [1., 2.], [3., 4.], [5., 6.]]
+
+    def numeric_grad_err(fn, x0):
+        xg = x0.clone().requires_grad_(True)
+        y = fn(xg)
+        wgt = torch.arange(1, y.numel() + 1, device="cuda", dtype=torch.float32).reshape(y.shape)
+        (y * wgt).sum().backward()
+        an = xg.grad.clone()
+        num = torch.zeros_like(x0)
+        eps = 1e-2
+        for i in range(x0.numel()):
+            d = torch.zeros_like(x0).reshape(-1)
+            d[i] = eps
+            d = d.reshape(x0.shape)
+            num.reshape(-1)[i] = ((fn(x0 + d) * wgt).sum() - (fn(x0 - d) * wgt).sum()) / (2 * eps)
+        return (an - num).abs().max().item()
+
+    assert numeric_grad_err(lambda v: mp_ops.scatter_add(v, idx, size=2), x) < 1e-2
+    assert numeric_grad_err(lambda v: mp_ops.scatter_mean(v, idx, size=2), x) < 1e-2
+    assert numeric_grad_err(lambda v: mp_ops.gather(v, idx4), x) < 1e-2
+    x3 = torch.tensor([[1., 2., 7.], [3., 4., 8.], [5., 6., 7.]], device="cuda")
+    xg = x3.clone().requires_grad_(True)
+    mp_ops.scatter_max(xg, idx, size=2).sum().backward()
+    # ties split evenly (mp_ops.py:52-62): column 2 of rows 0 and 2 tie at 7
+    assert xg.grad.cpu().tolist() == [[0., 0., .5], [1., 1., 1.], [1., 1., .5]]
+    sm = mp_ops.scatter_softmax(x3, idx, size=2).cpu()
+    assert torch.allclose(sm[0] + sm[2], torch.ones(3)) and torch.allclose(sm[1], torch.ones(3))
+
+
+@pytest.mark.parametrize("D,count", [(128, 10), (256, 15), (64, 25), (128, 40)])
+def test_dense_feature_and_fused_sage_mean(D, count):
+    import euler_b200
+    n = 4000
+    g = graphs.random_graph(seed=61 + D, n=n, T=1, feat_dim=D, id_stride=3 if D == 64 else 1)
+    cases.CudaBackend(g, g["ids"])
+    og = graphs.oracle_graph(g)
+    rs = np.random.RandomState(D)
+    ids = g["ids"][rs.randint(0, n, size=700 * count)].astype(np.int64)
+    ids[::29] = -1  # default-filled slots -> zero rows
+    (f,) = euler_b200.get_dense_feature(ids, [0], [D])
+    want = og.op_get_dense_feature(ids, D)
+    cases.eq(f.cpu().numpy(), want, "get_dense_feature")
+    (fpad,) = euler_b200.get_dense_feature(ids[:100], [0], [D + 8])
+    assert np.array_equal(fpad.cpu().numpy()[:, :D], want[:100]) and not fpad.cpu().numpy()[:, D:].any()
+    (fclip,) = euler_b200.get_dense_feature(ids[:100], [0], [D // 2])
+    assert np.array_equal(fclip.cpu().numpy(), want[:100, :D // 2])
+    (funk,) = euler_b200.get_dense_feature(ids[:10], [3], [4])
+    assert not funk.cpu().numpy().any()
+    # fused gather + mean == get_dense_feature followed by scatter_mean over repeat(range(rows), count)
+    src = np.repeat(np.arange(700, dtype=np.int32), count)
+    cases.eq(euler_b200.sage_mean_aggregate(ids, count, D).cpu().numpy(), po.scatter_mean(want, src, 700), "sage_mean")
+    cases.eq(euler_b200.scatter_mean(f, src, 700).cpu().numpy(), po.scatter_mean(want, src, 700), "scatter_mean of gathered")
+
+
+# ------------------------------------------------------------------ throughput engine (philox)
+def test_philox_mode_semantics_and_distribution():
+    import euler_b200
+    g = graphs.random_graph(seed=71, n=3000, T=2, avg_deg=6, hub=400)
+    gr = graphs.cuda_graph(g)
+    euler_b200.set_graph(gr, rng="philox", seed=9)
+    seeds = np.concatenate([g["ids"][:500], g["ids"][:500], [10 ** 12]]).astype(np.int64)
+    ids, w, t = [x.cpu().numpy() for x in euler_b200.sample_neighbor(seeds, [0, 1], 16, -1)]
+    assert np.array_equal(ids[:500], ids[500:1000])          # duplicate seeds share one sample row
+    assert (ids[-1] == -1).all()
+    ids2 = euler_b200.sample_neighbor(seeds, [0, 1], 16, -1)[0].cpu().numpy()
+    assert not np.array_equal(ids, ids2)                      # next call, new stream position
+    # every sampled (neighbor, weight, type) is a real edge of its seed
+    og = graphs.oracle_graph(g)
+    for i in range(0, 500, 7):
+        lens, nb, ww, tt = og.get_full_neighbor([seeds[i]], [0, 1])
+        edges = set(zip(nb.tolist(), ww.tolist(), tt.tolist()))
+        if not edges:
+            assert (ids[i] == -1).all()
+        else:
+            assert set(zip(ids[i].tolist(), w[i].tolist(), t[i].tolist())) <= edges
+    # distribution: hub row, type 0 group, empirical frequencies ~ weights
+    hub = int(np.argmax(np.diff(g["grp_ptr"])))
+    r, tt = divmod(hub, 2)
+    b, e = g["grp_ptr"][hub], g["grp_ptr"][hub + 1]
+    wts = g["w"][b:e].astype(np.float64)
+    draws = euler_b200.sample_neighbor(np.full(4000, g["ids"][r], np.int64), [tt], 1)[0]
+    many = torch.cat([euler_b200.sample_neighbor([g["ids"][r]], [tt], 4096)[0].reshape(-1) for _ in range(40)]).cpu().numpy()
+    assert (draws.cpu().numpy() == draws.cpu().numpy()[0]).all()
+    exp = {}
+    for nid, ww in zip(g["nbr"][b:e].tolist(), wts):
+        exp[nid] = exp.get(nid, 0.0) + ww
+    tot = sum(exp.values())
+    uniq, cnt = np.unique(many, return_counts=True)
+    chi2 = sum((c - many.size * exp[int(u)] / tot) ** 2 / (many.size * exp[int(u)] / tot) for u, c in zip(uniq, cnt))
+    assert chi2 < 2.0 * len(exp) + 100, chi2
+
+
+# ------------------------------------------------------------------ large-size properties
+def test_rmat_large_properties():
+    """RMAT 2M nodes / 20M edges generated on the device: structure invariants, and at BASELINE's
+    fanout [25,10] x batch 1024 every sampled edge is a real edge with its stored weight; minstd
+    results equal the oracle run on the exported graph (bit-exact at full fanout)."""
+    import euler_b200
+    n, E = 2_000_000, 20_000_000
+    gr = euler_b200.Graph.rmat(n, E, feat_dim=32)
+    ex = gr.export(with_feat=False)
+    ptr, nbr, cum = ex["grp_ptr"], ex["nbr"], ex["cum_w"]
+    assert ptr[0] == 0 and ptr[-1] == E and (np.diff(ptr) >= 0).all()
+    assert nbr.min() >= 1 and nbr.max() <= n
+    row_of_edge = np.repeat(np.arange(n), np.diff(ptr))
+    key = row_of_edge.astype(np.int64) * (n + 1) + nbr.astype(np.int64)
+    assert (np.diff(key) >= 0).all()                      # adjacency sorted by dst within each row
+    first = ptr[:-1][np.diff(ptr) > 0]
+    w = np.diff(cum, prepend=np.float32(0))
+    w[first] = cum[first]
+    assert w.min() > 0.5 and w.max() < 11.5               # 1 + (h%100)/10, up to f32 prefix rounding on hub rows
+    deg = np.diff(ptr)
+    assert deg.max() > 50 * deg.mean()                    # heavy tail
+    euler_b200.set_graph(gr, rng="minstd", seed=12345)
+    seeds = np.random.RandomState(1000).randint(1, n + 1, size=1024).astype(np.int64)
+    ids, ws, ts = euler_b200.sample_fanout(seeds, [[0], [0]], [25, 10])
+    og = po.OracleGraph(ex["ids"], ex["node_type"], ex["node_w"], 1, ptr, nbr, cum, np.zeros(n, np.float32))
+    po.seed(12345)
+    o_ids, o_ws, o_ts = og.op_sample_fanout(seeds, [[0], [0]], [25, 10])
+    for l in range(2):
+        cases.eq(ids[l + 1].cpu().numpy(), o_ids[l], "rmat fanout ids hop %d" % l)
+        cases.eq(ws[l].cpu().numpy(), o_ws[l], "rmat fanout w hop %d" % l)
+    # membership: (src row, dst) must exist
+    src = np.repeat(ids[1].cpu().numpy(), 10)
+    dst = ids[2].cpu().numpy()
+    ok = dst != -1
+    k2 = (src[ok] - 1) * (n + 1) + dst[ok]
+    pos = np.searchsorted(key, k2)
+    assert (key[np.minimum(pos, E - 1)] == k2).all()
+    # features of the sampled frontier: exact row copies of the generator's U(-1,1) rows
+    (f,) = euler_b200.get_dense_feature(ids[1], [0], [32])
+    f = f.cpu().numpy()
+    assert np.abs(f).max() <= 1.0 and f.std() > 0.5
+    (f2,) = euler_b200.get_dense_feature(ids[1], [0], [32])
+    assert np.array_equal(f, f2.cpu().numpy())
