@@ -1,0 +1,450 @@
+#!/usr/bin/env python
+"""bench.py -- the minibatch-construction step of BASELINE.json configs[1] on N B200s.
+
+    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (host cores)
+
+A "step" = one pass of the hot path over one batch of synthetic input (BASELINE.json configs[1]):
+  RMAT 10M nodes / 100M edges resident in HBM, batch 1024 seeds,
+  sample_fanout [25,10]  ->  dense features (dim 128) of the seeds and of hop 1 (self inputs)
+  ->  GraphSAGE neighbor mean of hop 1 per seed and of hop 2 per hop-1 node (fused gather+mean).
+metric = sampled edges/s (slots delivered: B*25 + B*250 per step); extra key agg_feat_gbs =
+algorithmic bytes of the feature gather + segment mean per second.
+
+One JSON line on stdout (rank 0).  See the task's bench contract for the keys.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=400)
+    p.add_argument("--warmup", type=int, default=20)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--rng", default="minstd", choices=["minstd", "philox"])
+    p.add_argument("--nodes", type=int, default=10_000_000)
+    p.add_argument("--edges", type=int, default=100_000_000)
+    p.add_argument("--batch", type=int, default=1024)
+    p.add_argument("--fanout", default="25,10")
+    p.add_argument("--dim", type=int, default=128)
+    p.add_argument("--lanes", type=int, default=4, help="execution contexts (streams) with batches in flight")
+    p.add_argument("--no-fuse", action="store_true", help="get_dense_feature + scatter_mean instead of the fused kernel")
+    p.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph per step")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--cpu-seconds", type=float, default=15.0)
+    p.add_argument("--breakdown-iters", type=int, default=50)
+    return p.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
+        sm = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            for k, nm in enumerate(names):
+                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(rows[0][2]) if rows and rows[0][2].replace(".", "").isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(rows)}
+
+
+# ----------------------------------------------------------------------------- our arm
+def step_bytes(B, counts, D):
+    """Algorithmic bytes.  Sampling: 48 B per sampled edge + 40 B per seed (CDF mode,
+    mean degree 10).  Aggregation (fused): 8 B id + 4D B row read per edge, 4D B write per output row.
+    Self features: 8 B id + 4D read + 4D write per row."""
+    rows, edges, seeds = B, 0, 0
+    agg = 0
+    for c in counts:
+        seeds += rows
+        edges += rows * c
+        agg += rows * c * (8 + 4 * D) + rows * 4 * D
+        rows *= c
+    self_rows = B + B * counts[0] if len(counts) > 1 else B
+    feat = self_rows * (8 + 8 * D)
+    return {"sample": edges * 48 + seeds * 40, "agg": agg, "self_feat": feat, "edges": edges}
+
+
+class Lane:
+    """One execution context: own stream, RNG engine, pinned input + output buffers."""
+
+    def __init__(self, eb, graph, args, counts, seed, torch):
+        self.t = torch
+        self.stream = torch.cuda.Stream()
+        self.ctx = eb.Context(graph, args.rng, seed, self.stream.cuda_stream)
+        B, D = args.batch, args.dim
+        dev = "cuda"
+        self.B, self.D, self.counts = B, D, counts
+        rows = B
+        self.n = [B]
+        for c in counts:
+            rows *= c
+            self.n.append(rows)
+        self.ctx.reserve(max(self.n))
+        self.d_seeds = torch.empty(B, dtype=torch.int64, device=dev)
+        self.ids = [torch.empty(n, dtype=torch.int64, device=dev) for n in self.n[1:]]
+        self.w = [torch.empty(n, dtype=torch.float32, device=dev) for n in self.n[1:]]
+        self.ty = [torch.empty(n, dtype=torch.int32, device=dev) for n in self.n[1:]]
+        L = len(counts)
+        self.x = [torch.empty((self.n[l], D), dtype=torch.float32, device=dev) for l in range(L)]      # self feats
+        self.agg = [torch.empty((self.n[l], D), dtype=torch.float32, device=dev) for l in range(L)]    # neighbor means
+        self.hop_feat = None
+        if args.no_fuse:
+            self.hop_feat = [torch.empty((self.n[l + 1], D), dtype=torch.float32, device=dev) for l in range(L)]
+            self.src = [torch.arange(self.n[l], dtype=torch.int32, device=dev).repeat_interleave(counts[l]) for l in range(L)]
+        # host side of the e2e path
+        self.h_seeds = torch.empty(B, dtype=torch.int64).pin_memory()
+        self.h_ids = [torch.empty(n, dtype=torch.int64).pin_memory() for n in self.n[1:]]
+        self.h_x = [torch.empty((self.n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
+        self.h_agg = [torch.empty((self.n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
+        self.h2d = 8 * B
+        self.d2h = sum(8 * n for n in self.n[1:]) + 2 * sum(4 * self.n[l] * D for l in range(L))
+
+
+def make_step(lib, C, args, counts, et):
+    import ctypes
+    L = len(counts)
+    cs = np.ascontiguousarray(counts, dtype=np.int32)
+    P = ctypes.c_void_p * L
+
+    def step(lane, seeds_dev):
+        h = lane.ctx._h
+        rc = lib.eu_sample_fanout(h, seeds_dev.data_ptr(), lane.B, et.ctypes.data, et.shape[1], cs.ctypes.data, L, -1,
+                                  P(*[x.data_ptr() for x in lane.ids]), P(*[x.data_ptr() for x in lane.w]),
+                                  P(*[x.data_ptr() for x in lane.ty]))
+        for l in range(L):
+            src_ids = seeds_dev if l == 0 else lane.ids[l - 1]
+            rc |= lib.eu_get_dense_feature(h, src_ids.data_ptr(), lane.n[l], 0, lane.D, lane.x[l].data_ptr())
+            if args.no_fuse:
+                rc |= lib.eu_get_dense_feature(h, lane.ids[l].data_ptr(), lane.n[l + 1], 0, lane.D, lane.hop_feat[l].data_ptr())
+                rc |= lib.eu_scatter_mean(h, lane.hop_feat[l].data_ptr(), lane.D, lane.src[l].data_ptr(), lane.n[l + 1],
+                                          lane.n[l], lane.agg[l].data_ptr())
+            else:
+                rc |= lib.eu_sage_mean_aggregate(h, lane.ids[l].data_ptr(), lane.n[l], counts[l], lane.D, lane.agg[l].data_ptr())
+        if rc:
+            raise RuntimeError("euler_b200: " + lib.eu_last_error().decode())
+    return step
+
+
+def run_ours(args):
+    import torch
+    import euler_b200 as eb
+    from euler_b200 import _lib
+    import ctypes as C
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        raise SystemExit("bench.py: sharded multi-GPU path is provided by bench_sharded (see DESIGN.md)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    lib = _lib.load()
+    counts = [int(x) for x in args.fanout.split(",")]
+    et = np.zeros((len(counts), 1), np.int32)
+    t0 = time.time()
+    graph = eb.Graph.rmat(args.nodes, args.edges, feat_dim=args.dim, device=local)
+    torch.cuda.synchronize()
+    t_graph = time.time() - t0
+    lanes = [Lane(eb, graph, args, counts, 12345 + i, torch) for i in range(args.lanes)]
+    raw_step = make_step(lib, C, args, counts, et)
+    per_step_launches = None
+    use_graphs = not args.no_graphs
+    if use_graphs:
+        # the step has static shapes and device-resident RNG state: capture it once per lane and
+        # replay (one graph launch per step instead of ~14 kernel launches from Python)
+        for ln in lanes:
+            with torch.cuda.stream(ln.stream):
+                raw_step(ln, ln.d_seeds)          # warm (also sizes every scratch buffer)
+            ln.stream.synchronize()
+            l_before = lib.eu_launch_count()
+            ln.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ln.graph, stream=ln.stream):
+                raw_step(ln, ln.d_seeds)
+            per_step_launches = lib.eu_launch_count() - l_before
+
+    def step(ln, seeds_dev):
+        if use_graphs:
+            if seeds_dev is not ln.d_seeds:
+                ln.d_seeds.copy_(seeds_dev, non_blocking=True)
+            ln.graph.replay()
+        else:
+            raw_step(ln, seeds_dev)
+    nb = args.warmup + args.steps
+    host_seeds = np.stack([np.random.RandomState(1000 + i).randint(1, args.nodes + 1, size=args.batch)
+                           for i in range(max(nb, 64))]).astype(np.int64)
+    dev_seeds = torch.from_numpy(host_seeds).cuda()
+    bts = step_bytes(args.batch, counts, args.dim)
+    main = torch.cuda.current_stream()
+
+    def run(n_steps, first, e2e):
+        """n_steps steps round-robin over the lanes; returns device ms (events on the main stream,
+        lanes fork from / join into it)."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record(main)
+        for ln in lanes:
+            ln.stream.wait_event(ev0)
+        for i in range(n_steps):
+            ln = lanes[i % len(lanes)]
+            with torch.cuda.stream(ln.stream):
+                if e2e:
+                    # the lane's pinned buffers are reused every len(lanes) steps
+                    ln.stream.synchronize() if i >= len(lanes) else None
+                    ln.h_seeds.copy_(torch.from_numpy(host_seeds[(first + i) % len(host_seeds)]))
+                    ln.d_seeds.copy_(ln.h_seeds, non_blocking=True)
+                    step(ln, ln.d_seeds)
+                    for l in range(len(counts)):
+                        ln.h_ids[l].copy_(ln.ids[l], non_blocking=True)
+                        ln.h_x[l].copy_(ln.x[l], non_blocking=True)
+                        ln.h_agg[l].copy_(ln.agg[l], non_blocking=True)
+                else:
+                    step(ln, dev_seeds[(first + i) % len(host_seeds)])
+        for ln in lanes:
+            main.wait_stream(ln.stream)
+        ev1.record(main)
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1)
+
+    run(args.warmup, 0, False)
+    clocks = Clocks(local)
+    clocks.start()
+    time.sleep(0.3)
+    l0 = lib.eu_launch_count()
+    w0 = time.time()
+    ms = run(args.steps, args.warmup, False)
+    w1 = time.time()
+    launches = lib.eu_launch_count() - l0
+    if use_graphs:
+        launches = per_step_launches * args.steps  # kernels of ours inside the replayed graphs
+    clk = clocks.stop(w0, w1)
+    run(min(args.warmup, 8), 0, True)
+    ms_e2e = run(args.steps, args.warmup, True)
+    edges_step = bts["edges"]
+    value = edges_step * args.steps / (ms * 1e-3)
+    e2e_value = edges_step * args.steps / (ms_e2e * 1e-3)
+
+    # ---- per-kernel breakdown on one lane, serial, events between phases (explains `value`)
+    ln = lanes[0]
+    phases = {}
+    with torch.cuda.stream(ln.stream):
+        import ctypes
+        Lh = len(counts)
+        cs = np.ascontiguousarray(counts, dtype=np.int32)
+        P = ctypes.c_void_p * Lh
+        names = ["sample_fanout"] + ["self_feat_hop%d" % l for l in range(Lh)] + ["agg_hop%d" % (l + 1) for l in range(Lh)]
+        tot = {k: 0.0 for k in names}
+        for it in range(args.breakdown_iters):
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+            sd = dev_seeds[it % len(host_seeds)]
+            h = ln.ctx._h
+            evs[0].record(ln.stream)
+            lib.eu_sample_fanout(h, sd.data_ptr(), ln.B, et.ctypes.data, 1, cs.ctypes.data, Lh, -1,
+                                 P(*[x.data_ptr() for x in ln.ids]), P(*[x.data_ptr() for x in ln.w]), P(*[x.data_ptr() for x in ln.ty]))
+            evs[1].record(ln.stream)
+            k = 1
+            for l in range(Lh):
+                src_ids = sd if l == 0 else ln.ids[l - 1]
+                lib.eu_get_dense_feature(h, src_ids.data_ptr(), ln.n[l], 0, ln.D, ln.x[l].data_ptr())
+                k += 1
+                evs[k].record(ln.stream)
+            for l in range(Lh):
+                lib.eu_sage_mean_aggregate(h, ln.ids[l].data_ptr(), ln.n[l], counts[l], ln.D, ln.agg[l].data_ptr())
+                k += 1
+                evs[k].record(ln.stream)
+            ln.stream.synchronize()
+            for j, nm in enumerate(names):
+                tot[nm] += evs[j].elapsed_time(evs[j + 1])
+        phases = {k: v / args.breakdown_iters for k, v in tot.items()}
+    # dominant kernel = k_sage_mean over the last hop (one launch per call)
+    Lh = len(counts)
+    dom = "agg_hop%d" % Lh
+    dom_rows = lanes[0].n[Lh - 1]
+    dom_bytes = dom_rows * counts[-1] * (8 + 4 * args.dim) + dom_rows * 4 * args.dim
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = dom_bytes / (phases[dom] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "k_sage_mean<1> (hop-%d neighbor mean, %d rows x %d)" % (Lh, dom_rows, counts[-1]),
+            "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+            "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)",
+            "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": round(phases[dom], 5)}
+    agg_bytes = bts["agg"] + bts["self_feat"]
+    out = {
+        "metric": "sampled_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 ids / f32 weights+features (f64 CDF compare)", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: RMAT %dM nodes/%dM edges in HBM, 2-hop sample_fanout %s batch=%d, "
+                               "GraphSAGE-mean aggregation, feat_dim=%d" % (args.nodes // 10**6, args.edges // 10**6, counts, args.batch, args.dim),
+                   "nodes": args.nodes, "edges": args.edges, "batch": args.batch, "fanout": counts, "feat_dim": args.dim,
+                   "rng": args.rng, "lanes_in_flight": args.lanes, "cuda_graphs": use_graphs, "fused_aggregation": not args.no_fuse,
+                   "l2_policy": "inputs larger than L2 (%.1f GB graph, random seeds per step)" % (graph.hbm_bytes / 1e9),
+                   "parallelism": "1 GPU, %d streams" % args.lanes},
+        "agg_feat_gbs": agg_bytes * args.steps / (ms * 1e-3) / 1e9,
+        "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": lanes[0].h2d, "d2h_bytes_per_step": lanes[0].d2h,
+                "ms_per_step": ms_e2e / args.steps,
+                "note": "host seeds -> pinned -> H2D; D2H of hop ids + self features + neighbor means every step"},
+        "gpu_launches": int(launches),
+        "clocks": clk,
+        "roofline": roof,
+        "phases_ms_single_lane": {k: round(v, 5) for k, v in phases.items()},
+        "step_algorithmic_bytes": bts,
+        "graph_build_s": round(t_graph, 2), "hbm_graph_bytes": graph.hbm_bytes,
+    }
+    if not args.no_cpu_baseline and rank == 0:
+        out["cpu_baseline"] = cpu_baseline(graph, args, counts, host_seeds)
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def build_cpu_graph(ex, args, use_ref):
+    from oracle import pyoracle as po
+    n = len(ex["ids"])
+    if use_ref:
+        # raw weights are needed by Node::Init; de-cumulate exactly as stored differences
+        cum = ex["cum_w"]
+        ptr = ex["grp_ptr"]
+        w = np.diff(cum, prepend=np.float32(0)).astype(np.float32)
+        first = ptr[:-1][np.diff(ptr) > 0]
+        w[first] = cum[first]
+        return po.RefGraph.build(ex["ids"], ex["node_type"], ex["node_w"], 1, ptr, ex["nbr"], w, 1,
+                                 ex["feat"], sampler=False), None
+    og = po.OracleGraph(ex["ids"], ex["node_type"], ex["node_w"], 1, ex["grp_ptr"], ex["nbr"], ex["cum_w"],
+                        np.zeros(n, np.float32), ex["feat"])
+    return None, og
+
+
+def time_cpu(rg, og, args, counts, host_seeds, threads, target_s):
+    from oracle import pyoracle as po
+    et = [[0]] * len(counts)
+    seeds = host_seeds[:64]
+    fn = (lambda it: po.ref_bench_step(seeds, et, counts, args.dim, threads, it)) if rg is not None else \
+         (lambda it: po.oracle_bench_step(og, seeds, et, counts, args.dim, threads, it))
+    sec, edges = fn(1)
+    iters = max(1, min(200, int(target_s / max(sec, 1e-3))))
+    if iters > 1:
+        sec, edges = fn(iters)
+    return edges / sec, sec, iters
+
+
+def cpu_baseline(graph, args, counts, host_seeds):
+    """cpu_baseline leg: the reference's own sources (oracle/_ref, kind "reference") when the prebuilt
+    shim travelled with the repo, else the C restatement (kind "port"); all host cores, bounded sample."""
+    from oracle import pyoracle as po
+    use_ref = po.have_ref()
+    ex = graph.export(with_feat=True)
+    rg, og = build_cpu_graph(ex, args, use_ref)
+    cores = host_cores()
+    v, sec, iters = time_cpu(rg, og, args, counts, host_seeds, cores, args.cpu_seconds)
+    v1, sec1, it1 = time_cpu(rg, og, args, counts, host_seeds, 1, min(args.cpu_seconds, 5.0))
+    return {"value": v, "unit": "edges/s", "cores": cores, "kind": "reference" if use_ref else "port",
+            "sample": "%d threads x %d batches of the same step (sample_fanout + dense features of every hop + neighbor "
+                      "means) on the same exported graph, %.1f s" % (cores, iters, sec),
+            "one_thread_value": v1}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the same step on the host cores."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    import euler_b200 as eb
+    from oracle import pyoracle as po
+    counts = [int(x) for x in args.fanout.split(",")]
+    # inputs: the same synthetic graph, generated on the device and exported (not timed)
+    graph = eb.Graph.rmat(args.nodes, args.edges, feat_dim=args.dim, device=0)
+    ex = graph.export(with_feat=True)
+    graph.close()
+    torch.cuda.empty_cache()
+    use_ref = po.have_ref()
+    rg, og = build_cpu_graph(ex, args, use_ref)
+    cores = host_cores()
+    nb = max(args.warmup + args.steps, 64)
+    host_seeds = np.stack([np.random.RandomState(1000 + i).randint(1, args.nodes + 1, size=args.batch)
+                           for i in range(nb)]).astype(np.int64)
+    et = [[0]] * len(counts)
+    fn = (lambda s, it: po.ref_bench_step(s, et, counts, args.dim, cores, it)) if use_ref else \
+         (lambda s, it: po.oracle_bench_step(og, s, et, counts, args.dim, cores, it))
+    # a "step" of this arm = one bounded sample: every core runs one batch
+    fn(host_seeds[:64], 1)
+    steps = min(args.steps, 6)
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        fn(host_seeds[:64], 1)
+    t_edges, t_sec = 0, 0.0
+    for _ in range(steps):
+        sec, edges = fn(host_seeds[:64], 1)
+        t_edges += edges
+        t_sec += sec
+    v = t_edges / t_sec
+    out = {"impl": "reference", "metric": "sampled_edges_per_sec", "value": v, "unit": "edges/s",
+           "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_sec / steps,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 ids / f32", "data": "synthetic",
+           "config": {"workload": "BASELINE configs[1]: RMAT %dM nodes/%dM edges, 2-hop sample_fanout %s batch=%d, GraphSAGE-mean "
+                                  "aggregation, feat_dim=%d" % (args.nodes // 10**6, args.edges // 10**6, counts, args.batch, args.dim),
+                      "step": "one bounded sample = %d host threads x 1 batch each" % cores},
+           "cpu_baseline": {"value": v, "unit": "edges/s", "cores": cores, "kind": "reference" if use_ref else "port",
+                            "sample": "%d steps of %d threads x 1 batch" % (steps, cores)},
+           "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

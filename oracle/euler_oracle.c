@@ -715,6 +715,66 @@ static void* bench_worker(void* p) {
   return NULL;
 }
 
+/* full step (sample_fanout + dense features of every hop + neighbor means), see ref_shim.cc ref_bench_step */
+typedef struct {
+  const eo_graph* g; const int64_t* seeds; int64_t n_batches, B; const int32_t* etypes; int32_t K;
+  const int32_t* counts; int32_t L; int32_t dim; int32_t iters; int32_t tid; int64_t edges;
+} eo_step_arg;
+
+static void* step_worker(void* p) {
+  eo_step_arg* a = (eo_step_arg*)p;
+  eo_rng rng;
+  eo_seed(&rng, 12345 + a->tid);
+  const int32_t L = a->L, dim = a->dim;
+  int64_t rows[17];
+  int64_t per_batch = 0;
+  rows[0] = a->B;
+  for (int32_t l = 0; l < L; ++l) { rows[l + 1] = rows[l] * a->counts[l]; per_batch += rows[l + 1]; }
+  int64_t* o_ids[16]; float* o_w[16]; int32_t* o_t[16]; float* feat[17]; float* agg[16];
+  for (int32_t l = 0; l < L; ++l) {
+    o_ids[l] = (int64_t*)malloc(sizeof(int64_t) * rows[l + 1]);
+    o_w[l] = (float*)malloc(sizeof(float) * rows[l + 1]);
+    o_t[l] = (int32_t*)malloc(sizeof(int32_t) * rows[l + 1]);
+    agg[l] = (float*)malloc(sizeof(float) * rows[l] * dim);
+  }
+  for (int32_t l = 0; l <= L; ++l) feat[l] = (float*)malloc(sizeof(float) * rows[l] * dim);
+  int32_t* idx = (int32_t*)malloc(sizeof(int32_t) * rows[L]);
+  for (int32_t b = 0; b < a->iters; ++b) {
+    const int64_t* s = a->seeds + (((int64_t)a->tid * a->iters + b) % a->n_batches) * a->B;
+    op_sample_fanout(a->g, s, a->B, a->etypes, a->K, a->counts, L, -1, &rng, o_ids, o_w, o_t);
+    for (int32_t l = 0; l <= L; ++l) eo_op_get_dense_feature(a->g, l == 0 ? s : o_ids[l - 1], rows[l], dim, feat[l]);
+    for (int32_t l = 0; l < L; ++l) {
+      for (int64_t i = 0; i < rows[l + 1]; ++i) idx[i] = (int32_t)(i / a->counts[l]);
+      eo_scatter_mean(feat[l + 1], dim, idx, rows[l + 1], rows[l], agg[l]);
+    }
+    a->edges += per_batch;
+  }
+  for (int32_t l = 0; l < L; ++l) { free(o_ids[l]); free(o_w[l]); free(o_t[l]); free(agg[l]); }
+  for (int32_t l = 0; l <= L; ++l) free(feat[l]);
+  free(idx);
+  return NULL;
+}
+
+double eo_bench_step(const eo_graph* g, const int64_t* seeds, int64_t n_batches, int64_t B,
+                     const int32_t* etypes, int32_t K, const int32_t* counts, int32_t L, int32_t dim,
+                     int32_t n_threads, int32_t iters, int64_t* edges) {
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * n_threads);
+  eo_step_arg* args = (eo_step_arg*)calloc(n_threads, sizeof(eo_step_arg));
+  struct timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  for (int32_t t = 0; t < n_threads; ++t) {
+    eo_step_arg a = {g, seeds, n_batches, B, etypes, K, counts, L, dim, iters, t, 0};
+    args[t] = a;
+    pthread_create(&th[t], NULL, step_worker, &args[t]);
+  }
+  int64_t tot = 0;
+  for (int32_t t = 0; t < n_threads; ++t) { pthread_join(th[t], NULL); tot += args[t].edges; }
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  *edges = tot;
+  free(th); free(args);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
 double eo_bench_fanout(const eo_graph* g, const int64_t* seeds, int64_t n_batches, int64_t B,
                        const int32_t* etypes, int32_t K, const int32_t* counts, int32_t L,
                        int32_t n_threads, int32_t iters, int64_t* edges) {

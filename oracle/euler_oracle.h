@@ -120,6 +120,10 @@ double eo_bench_fanout(const eo_graph* g, const int64_t* seeds, int64_t n_batche
                        const int32_t* etypes, int32_t K, const int32_t* counts, int32_t L,
                        int32_t n_threads, int32_t iters, int64_t* edges);
 
+double eo_bench_step(const eo_graph* g, const int64_t* seeds, int64_t n_batches, int64_t B,
+                     const int32_t* etypes, int32_t K, const int32_t* counts, int32_t L, int32_t dim,
+                     int32_t n_threads, int32_t iters, int64_t* edges);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,6 +107,9 @@ def lib():
         L.eo_bench_fanout.restype = C.c_double
         L.eo_bench_fanout.argtypes = [C.c_void_p, i64p, C.c_int64, C.c_int64, i32p, C.c_int32, i32p,
                                       C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
+        L.eo_bench_step.restype = C.c_double
+        L.eo_bench_step.argtypes = [C.c_void_p, i64p, C.c_int64, C.c_int64, i32p, C.c_int32, i32p,
+                                    C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
         _lib = L
     return _lib
 
@@ -273,6 +276,28 @@ class OracleGraph:
         return sec, edges.value
 
 
+def _bench_args(seeds, etypes, counts):
+    seeds = _arr(seeds, np.int64)
+    et = _arr(etypes, np.int32).reshape(len(counts), -1)
+    return seeds, et, _arr(counts, np.int32)
+
+
+def oracle_bench_step(og, seeds, etypes, counts, dim, n_threads, iters):
+    seeds, et, cs = _bench_args(seeds, etypes, counts)
+    edges = C.c_int64(0)
+    sec = lib().eo_bench_step(og.h, seeds, seeds.shape[0], seeds.shape[1], et, et.shape[1], cs, len(cs),
+                              dim, n_threads, iters, C.byref(edges))
+    return sec, edges.value
+
+
+def ref_bench_step(seeds, etypes, counts, dim, n_threads, iters):
+    seeds, et, cs = _bench_args(seeds, etypes, counts)
+    edges = C.c_int64(0)
+    sec = ref().ref_bench_step(seeds, seeds.shape[0], seeds.shape[1], et, et.shape[1], cs, len(cs), dim,
+                               n_threads, iters, C.byref(edges))
+    return sec, edges.value
+
+
 def gather(params, idx):
     params = _arr(params, np.float32)
     idx = _arr(idx, np.int32)
@@ -353,6 +378,9 @@ def ref():
         R.ref_bench_fanout.restype = C.c_double
         R.ref_bench_fanout.argtypes = [i64p, C.c_int64, C.c_int64, i32p, C.c_int32, i32p, C.c_int32,
                                        C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
+        R.ref_bench_step.restype = C.c_double
+        R.ref_bench_step.argtypes = [i64p, C.c_int64, C.c_int64, i32p, C.c_int32, i32p, C.c_int32,
+                                     C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
         R.ref_bench_feature.restype = C.c_double
         R.ref_bench_feature.argtypes = [i64p, C.c_int64, C.c_int32, C.c_int32, C.c_int32]
         _ref = R

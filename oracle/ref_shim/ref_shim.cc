@@ -510,6 +510,72 @@ double ref_bench_fanout(const int64_t* seeds, int64_t n_batches, int64_t B,
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// One full minibatch-construction step per batch, the way the reference's ops compose it
+// (tf_euler/python/utils/encoders.py:475-491): sample_fanout, get_dense_feature for every hop, then
+// the neighbor mean of each hop (scatter_add / (scatter_add(ones) + 1e-7), mp_ops.py:65-69 over
+// scatter_op.cc:44-55).  Returns wall seconds; *edges = sampled slots delivered.
+double ref_bench_step(const int64_t* seeds, int64_t n_batches, int64_t B, const int32_t* etypes,
+                      int32_t K, const int32_t* counts, int32_t L, int32_t dim, int32_t n_threads,
+                      int32_t iters, int64_t* edges) {
+  std::atomic<int64_t> total(0);
+  auto worker = [&](int t) {
+    ref_seed(12345 + t);
+    std::vector<std::vector<int64_t>> o_ids(L);
+    std::vector<std::vector<float>> o_w(L);
+    std::vector<std::vector<int32_t>> o_t(L);
+    std::vector<int64_t*> p_ids(L);
+    std::vector<float*> p_w(L);
+    std::vector<int32_t*> p_t(L);
+    std::vector<std::vector<float>> feat(L + 1), agg(L);
+    std::vector<int64_t> rows(L + 1);
+    rows[0] = B;
+    int64_t per_batch = 0;
+    for (int l = 0; l < L; ++l) {
+      rows[l + 1] = rows[l] * counts[l];
+      per_batch += rows[l + 1];
+      o_ids[l].resize(rows[l + 1]); o_w[l].resize(rows[l + 1]); o_t[l].resize(rows[l + 1]);
+      p_ids[l] = o_ids[l].data(); p_w[l] = o_w[l].data(); p_t[l] = o_t[l].data();
+      agg[l].resize(rows[l] * (int64_t)dim);
+    }
+    for (int l = 0; l <= L; ++l) feat[l].resize(rows[l] * (int64_t)dim);
+    std::vector<int32_t> len(rows[L]);
+    std::vector<float> cnt;
+    int64_t local = 0;
+    for (int b = 0; b < iters; ++b) {
+      const int64_t* s = seeds + (((int64_t)t * iters + b) % n_batches) * B;
+      ref_op_sample_fanout(s, B, etypes, K, counts, L, -1, p_ids.data(), p_w.data(), p_t.data());
+      for (int l = 0; l <= L; ++l) {
+        const int64_t* ids = l == 0 ? s : p_ids[l - 1];
+        ref_get_dense_feature(reinterpret_cast<const uint64_t*>(ids), rows[l], 0, dim, feat[l].data(), len.data());
+      }
+      for (int l = 0; l < L; ++l) {
+        float* out = agg[l].data();
+        std::fill_n(out, rows[l] * (int64_t)dim, 0);
+        cnt.assign(rows[l], 0.f);
+        const float* upd = feat[l + 1].data();
+        for (int64_t i = 0; i < rows[l + 1]; ++i) {
+          int64_t r = i / counts[l];
+          for (int j = 0; j < dim; ++j) out[r * dim + j] += upd[i * dim + j];
+          cnt[r] += 1.0f;
+        }
+        for (int64_t r = 0; r < rows[l]; ++r) {
+          float c = cnt[r] + 1e-7f;
+          for (int j = 0; j < dim; ++j) out[r * dim + j] = out[r * dim + j] / c;
+        }
+      }
+      local += per_batch;
+    }
+    total += local;
+  };
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; ++t) th.emplace_back(worker, t);
+  for (auto& x : th) x.join();
+  auto t1 = std::chrono::steady_clock::now();
+  *edges = total.load();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
 // Dense feature fetch of `rows` ids through euler::GetNodeFloat32Feature,
 // n_threads workers each doing `iters` passes.  Returns wall seconds.
 double ref_bench_feature(const int64_t* ids, int64_t rows, int32_t dim, int32_t n_threads,

@@ -34,9 +34,18 @@ def test_tiny_loaded_from_reference_dat_files(tiny_dir):
     gr = euler_b200.Graph.load(tiny_dir)
     z = graphs.load_tiny_csr()
     ex = gr.export()
-    for k in ("ids", "node_type", "node_w", "grp_ptr", "nbr", "cum_w", "grp_cum"):
-        assert np.array_equal(ex[k], z[k]), k
-    cases.eq(ex["feat"], z["feat"], "dense features")
+    # rows come in file order (partition 0: ids 2,4,6; partition 1: 1,3,5); compare node by node
+    assert sorted(ex["ids"].tolist()) == z["ids"].tolist()
+    T = z["T"]
+    for r, i in enumerate(ex["ids"]):
+        zr = int(np.searchsorted(z["ids"], i))
+        assert ex["node_type"][r] == z["node_type"][zr] and ex["node_w"][r] == z["node_w"][zr]
+        for t in range(T):
+            b, e = ex["grp_ptr"][r * T + t], ex["grp_ptr"][r * T + t + 1]
+            zb, ze = z["grp_ptr"][zr * T + t], z["grp_ptr"][zr * T + t + 1]
+            assert np.array_equal(ex["nbr"][b:e], z["nbr"][zb:ze]) and np.array_equal(ex["cum_w"][b:e], z["cum_w"][zb:ze])
+            assert ex["grp_cum"][r * T + t] == z["grp_cum"][zr * T + t]
+        assert np.array_equal(ex["feat"][r], z["feat"][zr])
     # meta: names resolve like type_ops.py (node "1"->0, "0"->1; edge "0"->0, "1"->1)
     assert gr.node_type_id("1") == 0 and gr.node_type_id("0") == 1
     assert gr.edge_type_id("0") == 0 and gr.edge_type_id("1") == 1
