@@ -57,6 +57,8 @@ SIGNATURES = {
     "eu_ctx_reserve": (C.c_int, [_P, _I64]),
     "eu_ctx_sync": (C.c_int, [_P]),
     "eu_ctx_draws": (C.c_int, [_P, C.POINTER(_U64)]),
+    "eu_ctx_profile": (C.c_int, [_P, C.c_int]),
+    "eu_ctx_profile_read": (C.c_int, [_P, C.c_char_p, _I64]),
     "eu_sample_neighbor": (C.c_int, [_P, _P, _I64, _P, _I32, _I32, _I64, _P, _P, _P]),
     "eu_sample_neighbor_host": (C.c_int, [_P, _P, _I64, _P, _I32, _I32, _I64, _P, _P, _P]),
     "eu_sample_fanout": (C.c_int, [_P, _P, _I64, _P, _I32, _P, _I32, _I64, _P, _P, _P]),

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <string>
@@ -41,10 +42,19 @@ int ctx_reserve(eu_ctx* c, int64_t rows) {
   int rc;
   if ((rc = regrow(&c->d_dedup, cap + 1))) return rc;
   c->dedup_cap = cap;
+  // all-free table: key 0, row = kEmptyRow (see hop() invariant)
+  for (int64_t off = 0; off < cap + 1; off += (int64_t)1 << 20) {
+    int64_t n = std::min<int64_t>((int64_t)1 << 20, cap + 1 - off);
+    EU_CUDA(cudaMemset2DAsync(&c->d_dedup[off].key, sizeof(HashSlot), 0x00, 8, (size_t)n, c->stream));
+    EU_CUDA(cudaMemset2DAsync(&c->d_dedup[off].row, sizeof(HashSlot), 0xFF, 8, (size_t)n, c->stream));
+  }
   if ((rc = regrow(&c->d_first, rows))) return rc;
   if ((rc = regrow(&c->d_rowof, rows))) return rc;
   if ((rc = regrow(&c->d_elig, rows))) return rc;
   if ((rc = regrow(&c->d_state, rows))) return rc;
+  if ((rc = regrow(&c->d_emask, rows / 32 + 2))) return rc;
+  if ((rc = regrow(&c->d_woff, rows / 32 + 2))) return rc;
+  if ((rc = regrow(&c->d_blkpre, rows / 256 + 2))) return rc;
   if ((rc = regrow(&c->d_front[0], rows))) return rc;
   if ((rc = regrow(&c->d_front[1], rows))) return rc;
   c->cap_rows = rows;
@@ -117,7 +127,7 @@ int eu_ctx_destroy(eu_ctx* c) {
   cudaSetDevice(c->g->device);
   cudaStreamSynchronize(c->stream);
   cudaFree(c->d_rng); cudaFree(c->d_dedup); cudaFree(c->d_first); cudaFree(c->d_rowof);
-  cudaFree(c->d_elig); cudaFree(c->d_state); cudaFree(c->d_front[0]); cudaFree(c->d_front[1]);
+  cudaFree(c->d_elig); cudaFree(c->d_state); cudaFree(c->d_emask); cudaFree(c->d_woff); cudaFree(c->d_blkpre); cudaFree(c->d_front[0]); cudaFree(c->d_front[1]);
   cudaFree(c->d_misc); cudaFree(c->d_stage);
   if (c->h_pin) cudaFreeHost(c->h_pin);
   delete c;
@@ -161,6 +171,38 @@ int eu_ctx_draws(eu_ctx* c, uint64_t* draws) {
   EU_CUDA(cudaMemcpyAsync(&h, c->d_rng, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   EU_CUDA(cudaStreamSynchronize(c->stream));
   *draws = h.draws;
+  return EU_OK;
+}
+
+int eu_ctx_profile(eu_ctx* c, int enable) {
+  if (!c) { set_error("null ctx"); return EU_ERR_INVALID; }
+  c->prof = enable != 0;
+  return EU_OK;
+}
+
+// Synchronises, then writes "name,rows,launches,total_ms\n" lines (aggregated) into buf and clears the log.
+int eu_ctx_profile_read(eu_ctx* c, char* buf, int64_t cap) {
+  if (!c || !buf || cap <= 0) { set_error("eu_ctx_profile_read: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  EU_CUDA(cudaStreamSynchronize(c->stream));
+  std::map<std::pair<std::string, int64_t>, std::pair<int64_t, double>> agg;
+  for (auto& r : c->prof_recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    auto& a = agg[std::make_pair(std::string(r.name), r.rows)];
+    a.first += 1; a.second += ms;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  c->prof_recs.clear();
+  std::string out;
+  char line[256];
+  for (auto& kv : agg) {
+    snprintf(line, sizeof(line), "%s,%lld,%lld,%.6f\n", kv.first.first.c_str(), (long long)kv.first.second,
+             (long long)kv.second.first, kv.second.second);
+    out += line;
+  }
+  if ((int64_t)out.size() + 1 > cap) { set_error("profile buffer too small"); return EU_ERR_INVALID; }
+  memcpy(buf, out.c_str(), out.size() + 1);
   return EU_OK;
 }
 

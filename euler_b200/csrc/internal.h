@@ -84,7 +84,7 @@ struct eu_graph {
 // Device-resident engine state of one ctx.
 struct EuRngState {
   uint32_t x;                 // minstd engine state
-  uint32_t pad;
+  uint32_t x_prev;             // engine state before the hop in flight (rows derive theirs from it)
   unsigned long long draws;   // uniforms produced since seed
   unsigned long long calls;   // philox: hop counter (salt)
   unsigned int blocks_done;   // last-block-done ticket
@@ -104,7 +104,10 @@ struct eu_ctx {
   int32_t* d_first = nullptr;        // [rows] first occurrence index of each seed
   int64_t* d_rowof = nullptr;        // [rows] graph row (valid where first==i), -1 if absent
   uint8_t* d_elig = nullptr;         // [rows]
-  uint32_t* d_state = nullptr;       // [rows] engine state before the row's first draw
+  uint32_t* d_state = nullptr;       // [rows] engine state before the row's first draw (walks)
+  uint32_t* d_emask = nullptr;       // [rows/32] eligible-first-occurrence ballots
+  uint32_t* d_woff = nullptr;        // [rows/32] count in earlier warps of the block
+  uint32_t* d_blkpre = nullptr;      // [rows/256] count in earlier blocks
   unsigned long long* d_front[2] = {nullptr, nullptr};  // engine-id frontier ping-pong [rows]
   // extra scratch for walks / scatter
   void* d_misc = nullptr;
@@ -114,6 +117,24 @@ struct eu_ctx {
   int64_t pin_bytes = 0;
   void* d_stage = nullptr;
   int64_t stage_bytes = 0;
+  // optional per-kernel timing (eu_ctx_profile): CUDA events on the ctx stream around each kernel
+  bool prof = false;
+  struct ProfRec { const char* name; int64_t rows; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof_recs;
+};
+
+// RAII-free helper: EU_PROF(c, "name", rows) { launch; }  records events around the launch when profiling
+struct EuProfScope {
+  eu_ctx* c; size_t idx;
+  EuProfScope(eu_ctx* c_, const char* name, int64_t rows) : c(c_), idx((size_t)-1) {
+    if (!c->prof) return;
+    eu_ctx::ProfRec r{name, rows, nullptr, nullptr};
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, c->stream);
+    c->prof_recs.push_back(r);
+    idx = c->prof_recs.size() - 1;
+  }
+  ~EuProfScope() { if (idx != (size_t)-1) cudaEventRecord(c->prof_recs[idx].e1, c->stream); }
 };
 
 namespace eu {

@@ -311,6 +311,7 @@ int eu_get_dense_feature(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid
   const bool vec = (dim % 4 == 0) && (d.feat_dim % 4 == 0) && (soff % 4 == 0) && (sdim % 4 == 0) && aligned16(out);
   const int G = vec ? lanes_per_row(dim) : (dim >= 32 ? 32 : 1);
   const unsigned blocks = (unsigned)ceil_div(M * G, 256);
+  EuProfScope ps(c, "k_feature", M);
   if (vec) k_feature<true><<<blocks, 256, 0, c->stream>>>(d, (const unsigned long long*)nodes, M, dim, G, soff, sdim, out);
   else k_feature<false><<<blocks, 256, 0, c->stream>>>(d, (const unsigned long long*)nodes, M, dim, G, soff, sdim, out);
   EU_LAUNCHED();
@@ -348,6 +349,7 @@ int eu_sage_mean_aggregate(eu_ctx* c, const int64_t* nbr_ids, int64_t rows, int3
   const DevGraph& d = c->g->d;
   const unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
   const unsigned long long* ids = (const unsigned long long*)nbr_ids;
+  EuProfScope ps(c, "k_sage_mean", rows);
   if (d.n_slots == 1 && dim == d.feat_dim && dim == 128 && aligned16(out)) k_sage_mean<1><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
   else if (d.n_slots == 1 && dim == d.feat_dim && dim == 256 && aligned16(out)) k_sage_mean<2><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
   else k_sage_mean_generic<<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, dim, out);

@@ -38,6 +38,11 @@ __global__ void k_dedup_insert(HashSlot* tab, unsigned long long mask,
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= rows) return;
   unsigned long long id = seeds[i], tag = id + 1;
+  // Warp-aggregate: frontiers are full of runs of equal ids (a default row is `count` zeros, hubs
+  // repeat), and equal ids hammer one slot.  The lowest lane of each equal-id group carries the
+  // group's minimum index, so only it touches the table.
+  const unsigned peers = __match_any_sync(__activemask(), id);
+  if ((threadIdx.x & 31) != __ffs(peers) - 1) return;
   if (tag == 0ull) {  // id == 2^64-1 (e.g. default_node -1 fed back as a seed): dedicated slot [mask+1]
     atomicMin(&tab[mask + 1].row, (unsigned long long)i);
     return;
@@ -97,21 +102,79 @@ __device__ __forceinline__ bool row_eligible(const DevGraph& g, int64_t row, con
 }
 
 // ---------------------------------------------------------------------------- 2. prepare
-__global__ void k_prepare(DevGraph g, const HashSlot* tab, unsigned long long mask,
-                          const unsigned long long* __restrict__ seeds, int64_t rows, ETypes et,
-                          int mode, int32_t* first, int64_t* rowof, uint8_t* elig) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= rows) return;
-  unsigned long long id = seeds[i];
-  int64_t f = dedup_first(tab, mask, id);
-  first[i] = (int32_t)f;
-  uint8_t e = 0;
-  if (f == i) {
-    int64_t row = lookup_row(g, id);
-    rowof[i] = row;
-    e = row_eligible(g, row, et, mode) ? 1 : 0;
+// Per row: first occurrence (ID_UNIQUE), graph row and eligibility of first occurrences.  The number
+// of ELIGIBLE FIRST-OCCURRENCE rows before row i -- its position in the reference's serial draw
+// order -- is kept as a 3-level count: emask[i/32] (ballot), woff[i/32] (count in earlier warps of
+// the block), blkpre[i/256] (count in earlier blocks; exclusive prefix written by the last block to
+// finish, which also advances the ctx engine by total * draws_per_row uniforms).
+static constexpr int kPrepBlock = 256;
+
+__global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSlot* tab, unsigned long long mask,
+                                                        const unsigned long long* __restrict__ seeds, int64_t rows,
+                                                        ETypes et, int mode, uint32_t F, unsigned long long draws_per_row,
+                                                        int32_t* first, int64_t* rowof, uint32_t* emask, uint32_t* woff,
+                                                        uint32_t* blkpre, EuRngState* rng) {
+  __shared__ uint32_t s_w[kPrepBlock / 32];
+  __shared__ bool s_last;
+  const int64_t i = blockIdx.x * (int64_t)kPrepBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  bool e = false;
+  if (i < rows) {
+    const unsigned long long id = seeds[i];
+    const int64_t f = dedup_first(tab, mask, id);
+    first[i] = (int32_t)f;
+    if (f == i) {
+      const int64_t row = lookup_row(g, id);
+      rowof[i] = row;
+      e = row_eligible(g, row, et, mode);
+    }
   }
-  elig[i] = e;
+  const uint32_t m = __ballot_sync(0xffffffffu, e);
+  if (lane == 0) s_w[wid] = __popc(m);
+  __syncthreads();
+  if (lane == 0 && i < rows) {
+    uint32_t off = 0;
+    for (int k = 0; k < wid; ++k) off += s_w[k];
+    emask[i >> 5] = m;
+    woff[i >> 5] = off;
+  }
+  if (threadIdx.x == 0) {
+    uint32_t tot = 0;
+    for (int k = 0; k < kPrepBlock / 32; ++k) tot += s_w[k];
+    blkpre[blockIdx.x] = tot;
+    __threadfence();
+    s_last = atomicAdd(&rng->blocks_done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // last block: exclusive prefix over the per-block counts, in place
+  __threadfence();
+  __shared__ uint32_t s_scan[kPrepBlock];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < gridDim.x; base += kPrepBlock) {
+    const uint32_t b = base + threadIdx.x;
+    const uint32_t v = b < gridDim.x ? __ldcg(blkpre + b) : 0u;  // written by other blocks: read at L2
+    s_scan[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = 1; off < kPrepBlock; off <<= 1) {
+      uint32_t t = threadIdx.x >= off ? s_scan[threadIdx.x - off] : 0u;
+      __syncthreads();
+      s_scan[threadIdx.x] += t;
+      __syncthreads();
+    }
+    if (b < gridDim.x) blkpre[b] = carry + s_scan[threadIdx.x] - v;
+    carry += s_scan[kPrepBlock - 1];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    // engine after this hop = x * F^total; rows read x_prev
+    uint32_t fp = 1, base = F;
+    for (uint32_t t = carry; t; t >>= 1) { if (t & 1) fp = modmul(fp, base); base = modmul(base, base); }
+    rng->x_prev = rng->x;
+    rng->x = modmul(rng->x, fp);
+    rng->draws += (unsigned long long)carry * draws_per_row;
+    rng->blocks_done = 0;
+  }
 }
 
 // ---------------------------------------------------------------------------- 3. engine-state scan
@@ -160,11 +223,16 @@ struct SampleArgs {
   long long default_node;
   ETypes et;
   int mode;
-  // minstd
+  // minstd: serial-stream position of a first-occurrence row f =
+  //   blkpre[f/256] + woff[f/32] + popc(emask[f/32] & lanes_below(f%32));  engine state = x_prev * F^pos
   const int32_t* first;
   const int64_t* rowof;
-  const uint8_t* elig;
-  const uint32_t* state;
+  const uint32_t* emask;
+  const uint32_t* woff;
+  const uint32_t* blkpre;
+  uint32_t fpow2[32];           // F^(2^k) mod M
+  HashSlot* clear_tab;          // dedup table of THIS hop, cleared here for the next user
+  int64_t clear_n;
   // philox
   unsigned long long key;
   const EuRngState* rng;
@@ -191,9 +259,13 @@ __device__ __forceinline__ int lane_upper_bound(float c, int lo, int hi, double 
 }
 
 template <bool PHILOX>
-__global__ void __launch_bounds__(256) k_sample(DevGraph g, SampleArgs a) {
+__global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
   const int lane = threadIdx.x & 31;
-  const int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (!PHILOX) {  // k_prepare (the only reader of this hop's dedup table) has finished: wipe it
+    for (int64_t s = gtid; s < a.clear_n; s += (int64_t)gridDim.x * blockDim.x) { a.clear_tab[s].key = 0; a.clear_tab[s].row = kEmptyRow; }
+  }
+  const int64_t w = gtid >> 5;
   if (w >= a.rows) return;
   const int32_t count = a.count;
   const int32_t T = g.T;
@@ -209,9 +281,18 @@ __global__ void __launch_bounds__(256) k_sample(DevGraph g, SampleArgs a) {
     ok = row_eligible(g, row, a.et, a.mode);
   } else {
     const int32_t f = a.first[w];
-    ok = a.elig[f] != 0;
-    row = ok ? a.rowof[f] : -1;
-    st = ok ? a.state[f] : 0;
+    const uint32_t m = a.emask[f >> 5];
+    ok = (m >> (f & 31)) & 1u;
+    if (ok) {
+      row = a.rowof[f];
+      uint32_t pos = a.blkpre[f / kPrepBlock] + a.woff[f >> 5] + __popc(m & ((1u << (f & 31)) - 1u));
+      st = a.rng->x_prev;
+#pragma unroll 1
+      for (int k = 0; pos; ++k, pos >>= 1)
+        if (pos & 1u) st = modmul(st, a.fpow2[k]);
+    } else {
+      row = -1;
+    }
   }
   if (!ok) {
     for (int32_t j = lane; j < count; j += 32) {
@@ -438,7 +519,7 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows, const int32_t*
   const unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
   if (c->rng == EU_RNG_PHILOX) {
     a.key = c->seed;
-    k_sample<true><<<blocks, 256, 0, s>>>(d, a);
+    { EuProfScope ps(c, "k_sample<philox>", rows); k_sample<true><<<blocks, 256, 0, s>>>(d, a); }
     EU_LAUNCHED();
     k_bump_calls<<<1, 1, 0, s>>>(c->d_rng);
     EU_LAUNCHED();
@@ -449,19 +530,25 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows, const int32_t*
   if (rc) return rc;
   int64_t cap = 64;
   while (cap < rows * 2) cap <<= 1;
-  const int tb = 256;
-  k_dedup_clear<<<(unsigned)ceil_div(cap + 1, tb), tb, 0, s>>>(c->d_dedup, cap + 1);
-  EU_LAUNCHED();
-  k_dedup_insert<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(c->d_dedup, (unsigned long long)cap - 1, seeds, rows);
-  EU_LAUNCHED();
-  k_prepare<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(d, c->d_dedup, (unsigned long long)cap - 1, seeds, rows,
-                                                         a.et, a.mode, c->d_first, c->d_rowof, c->d_elig);
+  const int tb = kPrepBlock;
+  // invariant: the dedup table is all-free on entry (cleared at allocation, and by every k_sample
+  // after its hop's k_prepare has consumed it)
+  { EuProfScope ps(c, "k_dedup_insert", rows);
+    k_dedup_insert<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(c->d_dedup, (unsigned long long)cap - 1, seeds, rows); }
   EU_LAUNCHED();
   const unsigned long long upr = (unsigned long long)count * (a.mode == 0 ? 1 : 2);
-  rc = launch_state_scan(c, rows, upr);
-  if (rc) return rc;
-  a.first = c->d_first; a.rowof = c->d_rowof; a.elig = c->d_elig; a.state = c->d_state;
-  k_sample<false><<<blocks, 256, 0, s>>>(d, a);
+  const uint32_t F = modpow_a(2ull * upr);
+  { EuProfScope ps(c, "k_prepare", rows);
+    k_prepare<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(d, c->d_dedup, (unsigned long long)cap - 1, seeds, rows,
+                                                           a.et, a.mode, F, upr, c->d_first, c->d_rowof, c->d_emask,
+                                                           c->d_woff, c->d_blkpre, c->d_rng); }
+  EU_LAUNCHED();
+  a.first = c->d_first; a.rowof = c->d_rowof; a.emask = c->d_emask; a.woff = c->d_woff; a.blkpre = c->d_blkpre;
+  a.fpow2[0] = F;
+  for (int k = 1; k < 32; ++k) a.fpow2[k] = modmul(a.fpow2[k - 1], a.fpow2[k - 1]);
+  a.clear_tab = c->d_dedup;
+  a.clear_n = cap + 1;
+  { EuProfScope ps(c, "k_sample<minstd>", rows); k_sample<false><<<blocks, 256, 0, s>>>(d, a); }
   EU_LAUNCHED();
   return EU_OK;
 }

@@ -121,6 +121,10 @@ int eu_ctx_reserve(eu_ctx* c, int64_t max_rows);      /* pre-size scratch (requi
 int eu_ctx_sync(eu_ctx* c);
 /* number of uniforms the MINSTD engine has produced since the last seed (synchronises) */
 int eu_ctx_draws(eu_ctx* c, uint64_t* draws);
+/* Per-kernel timing: while enabled, every kernel this ctx launches is bracketed by CUDA events on the
+ * ctx stream.  eu_ctx_profile_read synchronises and returns "name,rows,launches,total_ms" lines. */
+int eu_ctx_profile(eu_ctx* c, int enable);
+int eu_ctx_profile_read(eu_ctx* c, char* buf, int64_t cap);
 
 /* ------------------------------------------------------------------ sampling ops ------------- */
 /* tf_euler.sample_neighbor -- TF op SampleNeighbor (tf_euler/ops/neighbor_ops.cc:138-163, kernel

@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include <string.h>
 #include <math.h>
+#include <malloc.h>
 
 #include <algorithm>
 #include <atomic>
@@ -47,6 +48,17 @@ std::shared_ptr<ServerRegister> GetServerRegister(const std::string&,
 }  // namespace euler
 
 namespace {
+
+// The reference is built with jemalloc by default (CMakeLists.txt:13,41-43); it is not available
+// offline.  Keep glibc malloc from returning freed pages to the OS on every batch (the feature path
+// allocates ~3 small vectors per node), which otherwise serialises worker threads on mmap_sem.
+struct MallocTune {
+  MallocTune() {
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TOP_PAD, 256 << 20);
+  }
+} g_malloc_tune;
 
 euler::Graph& G() { return euler::Graph::Instance(); }
 
