@@ -175,7 +175,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        raise SystemExit("bench.py: sharded multi-GPU path is provided by bench_sharded (see DESIGN.md)")
+        return run_sharded(args, world, rank, local)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
@@ -357,6 +357,127 @@ def run_ours(args):
     if not args.no_cpu_baseline and rank == 0:
         out["cpu_baseline"] = cpu_baseline(graph, args, counts, host_seeds)
     print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------- sharded arm (N > 1)
+def run_sharded(args, world, rank, local):
+    """Weak scaling: the graph is hash-partitioned by id over the ranks (owner = id % N, Euler's shard scheme),
+    every rank constructs its own batch per step; each hop and the feature fetch resolve remote ids with
+    NCCL all-to-all over NVLink (euler_b200/sharded.py)."""
+    import torch
+    import torch.distributed as dist
+    import euler_b200 as eb
+    from euler_b200 import _lib
+    from euler_b200.sharded import CudaShardOps, ShardedGraph, TorchExchange
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    counts = [int(x) for x in args.fanout.split(",")]
+    L, B, D = len(counts), args.batch, args.dim
+    graph = eb.Graph.rmat_shard(args.nodes, args.edges, rank, world, feat_dim=D, device=local)
+    ops = CudaShardOps(graph, args.rng, 12345 + rank)
+    sg = ShardedGraph(ops, TorchExchange())
+    n = [B]
+    for c in counts:
+        n.append(n[-1] * c)
+    ops.ctx.reserve(max(n) * 2 + sum(n))
+    nb = args.warmup + args.steps
+    host_seeds = np.stack([np.random.RandomState(1000 + rank * 100003 + i).randint(1, args.nodes + 1, size=B)
+                           for i in range(max(nb, 16))]).astype(np.int64)
+    dev_seeds = torch.from_numpy(host_seeds).cuda()
+    src = [torch.arange(n[l], dtype=torch.int32, device="cuda").repeat_interleave(counts[l]) for l in range(L)]
+    agg = [torch.empty((n[l], D), dtype=torch.float32, device="cuda") for l in range(L)]
+    h_seeds = torch.empty(B, dtype=torch.int64).pin_memory()
+    h_out = [torch.empty(x, dtype=torch.int64).pin_memory() for x in n[1:]] + \
+            [torch.empty((n[l], D), dtype=torch.float32).pin_memory() for l in range(L)] * 2
+
+    def step(seeds_dev):
+        ids, ws, ts = sg.sample_fanout(seeds_dev, [[0]] * L, counts, -1)
+        feats = sg.get_dense_feature(torch.cat(ids), 0, D)
+        off = 0
+        x = []
+        for l in range(L + 1):
+            x.append(feats[off:off + n[l]])
+            off += n[l]
+        h = ops._stream()
+        for l in range(L):
+            rc = lib.eu_scatter_mean(h, x[l + 1].data_ptr(), D, src[l].data_ptr(), n[l + 1], n[l], agg[l].data_ptr())
+            if rc:
+                raise RuntimeError(lib.eu_last_error().decode())
+        return ids, x
+
+    def run(n_steps, first, e2e):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev0.record()
+        for i in range(n_steps):
+            if e2e:
+                h_seeds.copy_(torch.from_numpy(host_seeds[(first + i) % len(host_seeds)]))
+                sd = h_seeds.cuda(non_blocking=True)
+                ids, x = step(sd)
+                k = 0
+                for l in range(L):
+                    h_out[k].copy_(ids[l + 1], non_blocking=True); k += 1
+                for l in range(L):
+                    h_out[k].copy_(x[l], non_blocking=True); k += 1
+                for l in range(L):
+                    h_out[k].copy_(agg[l], non_blocking=True); k += 1
+            else:
+                step(dev_seeds[(first + i) % len(host_seeds)])
+        ev1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    run(args.warmup, 0, False)
+    clocks = Clocks(local)
+    clocks.start()
+    time.sleep(0.3)
+    l0 = lib.eu_launch_count()
+    w0 = time.time()
+    ms = run(args.steps, args.warmup, False)
+    w1 = time.time()
+    launches = lib.eu_launch_count() - l0
+    clk = clocks.stop(w0, w1)
+    run(min(args.warmup, 4), 0, True)
+    ms_e2e = run(args.steps, args.warmup, True)
+    bts = step_bytes(B, counts, D)
+    edges_step = bts["edges"] * world
+    remote = (world - 1) / world
+    a2a_bytes = 0
+    for l in range(L):
+        a2a_bytes += remote * n[l] * (8 + 16 * counts[l])
+    a2a_bytes += remote * sum(n) * (8 + 4 * D)
+    if rank == 0:
+        out = {
+            "metric": "sampled_edges_per_sec", "value": edges_step * args.steps / (ms * 1e-3), "unit": "edges/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 ids / f32 weights+features (f64 CDF compare)", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[1] sharded: RMAT %dM nodes/%dM edges hash-partitioned by id over %d GPUs, per rank "
+                                   "2-hop sample_fanout %s batch=%d + dense features (dim %d) + GraphSAGE mean, NCCL all-to-all per hop"
+                                   % (args.nodes // 10**6, args.edges // 10**6, world, counts, B, D),
+                       "nodes": args.nodes, "edges": args.edges, "batch_per_gpu": B, "global_batch": B * world, "fanout": counts,
+                       "feat_dim": D, "rng": args.rng, "parallelism": "graph sharded id %% %d, batches data-parallel" % world,
+                       "l2_policy": "inputs larger than L2 (random seeds per step over a %.1f GB shard)" % (graph.hbm_bytes / 1e9)},
+            "e2e": {"value": edges_step * args.steps / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 8 * B * world,
+                    "d2h_bytes_per_step": world * (sum(8 * x for x in n[1:]) + 2 * sum(4 * n[l] * D for l in range(L))),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "clocks": clk,
+            "roofline": {"bound": "nvlink", "kernel": "all-to-all exchange (seeds out, sampled rows + feature rows back)",
+                         "achieved": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9, 2), "peak": 770.0, "unit": "GB/s",
+                         "frac": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9 / 770.0, 4), "traffic": None,
+                         "peak_source": "B200_PROFILING.md measured peer copy 770 GB/s per direction",
+                         "algorithmic_bytes_per_step_per_rank": int(a2a_bytes),
+                         "note": "achieved = algorithmic all-to-all bytes per rank per step / whole step time (exchange is not timed alone)"},
+            "hbm_graph_bytes_per_rank": graph.hbm_bytes,
+        }
+        print(json.dumps(out))
+    dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------- CPU arms

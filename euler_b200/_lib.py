@@ -37,6 +37,8 @@ SIGNATURES = {
     "eu_graph_create": (C.c_int, [C.POINTER(GraphDesc), C.c_int, C.POINTER(_P)]),
     "eu_graph_create_rmat": (C.c_int, [_I64, _I64, C.c_double, C.c_double, C.c_double, _U64, _I32, _U64,
                                        C.c_int, C.POINTER(_P)]),
+    "eu_graph_create_rmat_shard": (C.c_int, [_I64, _I64, C.c_double, C.c_double, C.c_double, _U64, _I32, _U64,
+                                             C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "eu_graph_load": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "eu_graph_destroy": (C.c_int, [_P]),
     "eu_graph_num_nodes": (_I64, [_P]),
@@ -78,6 +80,9 @@ SIGNATURES = {
     "eu_gather_host": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P]),
     "eu_scatter_add_host": (C.c_int, [_P, _P, _I64, _P, _I64, _I64, _P]),
     "eu_scatter_max_host": (C.c_int, [_P, _P, _I64, _P, _I64, _I64, _P]),
+    "eu_shard_bucket": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P]),
+    "eu_shard_merge_sample": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I64, _P, _P, _P, _P]),
+    "eu_shard_merge_rows": (C.c_int, [_P, _P, _P, _I64, _I64, _P]),
     "InitQueryProxy": (C.c_bool, [C.c_char_p]),
     "eu_default_graph": (_P, []),
     "eu_default_ctx": (_P, []),

@@ -40,11 +40,11 @@ int ctx_reserve(eu_ctx* c, int64_t rows) {
   int64_t cap = 64;
   while (cap < rows * 2) cap <<= 1;
   int rc;
-  if ((rc = regrow(&c->d_dedup, cap + 1))) return rc;
+  if ((rc = regrow(&c->d_dedup, 2 * (cap + 1)))) return rc;  // two tables: hop l uses table l & 1
   c->dedup_cap = cap;
   // all-free table: key 0, row = kEmptyRow (see hop() invariant)
-  for (int64_t off = 0; off < cap + 1; off += (int64_t)1 << 20) {
-    int64_t n = std::min<int64_t>((int64_t)1 << 20, cap + 1 - off);
+  for (int64_t off = 0; off < 2 * (cap + 1); off += (int64_t)1 << 20) {
+    int64_t n = std::min<int64_t>((int64_t)1 << 20, 2 * (cap + 1) - off);
     EU_CUDA(cudaMemset2DAsync(&c->d_dedup[off].key, sizeof(HashSlot), 0x00, 8, (size_t)n, c->stream));
     EU_CUDA(cudaMemset2DAsync(&c->d_dedup[off].row, sizeof(HashSlot), 0xFF, 8, (size_t)n, c->stream));
   }

@@ -34,8 +34,9 @@ struct DevGraph {
   const float* cum_w;             // [E]
   const float* grp_cum;           // [n*T] (T>1) or nullptr
   // id -> row
-  int32_t dense_ids;              // ids[r] == id_base + r for all r
+  int32_t dense_ids;              // ids[r] == id_base + r * id_stride for all r
   unsigned long long id_base;
+  unsigned long long id_stride;   // 1, or the shard count for a shard's rows (ids congruent mod shards)
   const HashSlot* htab;
   unsigned long long hmask;       // capacity-1 (capacity is a power of two)
   // dense f32 features: row-major [n, feat_dim]; slot s occupies columns [slot_off[s], +slot_dim[s])
@@ -55,6 +56,10 @@ __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long 
 __device__ __forceinline__ int64_t lookup_row(const DevGraph& g, unsigned long long id) {
   if (g.dense_ids) {
     unsigned long long r = id - g.id_base;
+    if (g.id_stride != 1) {
+      if (id < g.id_base || r % g.id_stride) return -1;
+      r /= g.id_stride;
+    }
     return r < (unsigned long long)g.n ? (int64_t)r : -1;
   }
   unsigned long long h = mix64(id) & g.hmask;

@@ -90,8 +90,10 @@ __device__ __forceinline__ unsigned long long splitmix(unsigned long long& s) {
   return z ^ (z >> 31);
 }
 
-__global__ void k_rmat_edges(unsigned long long* keys, int64_t n_edges, int64_t n_nodes, int scale,
-                             double a, double b, double c, unsigned long long seed) {
+// keys == nullptr: only count the edges this shard owns.  Otherwise append key = local_row * n + dst
+// (cursor order is irrelevant: the keys are radix-sorted afterwards and equal keys are indistinguishable).
+__global__ void k_rmat_edges(unsigned long long* keys, unsigned long long* cursor, int64_t n_edges, int64_t n_nodes,
+                             int scale, double a, double b, double c, unsigned long long seed, int N, int shard) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
   unsigned long long s = mix64(seed ^ (unsigned long long)e * 0xD6E8FEB86659FD93ull);
@@ -105,7 +107,13 @@ __global__ void k_rmat_edges(unsigned long long* keys, int64_t n_edges, int64_t 
   // scramble so the heavy corner is not the low ids, then fold into [0, n)
   src = mix64(src + 0x51ED27) % (unsigned long long)n_nodes;
   dst = mix64(dst + 0x51ED27) % (unsigned long long)n_nodes;
-  keys[e] = src * (unsigned long long)n_nodes + dst;
+  const unsigned long long src_id = src + 1;
+  if (N > 1 && (int)(src_id % (unsigned long long)N) != shard) return;
+  if (!keys) { atomicAdd(cursor, 1ull); return; }
+  const unsigned long long base_id = shard == 0 ? (unsigned long long)N : (unsigned long long)shard;
+  const unsigned long long row = N > 1 ? (src_id - base_id) / (unsigned long long)N : src;
+  const unsigned long long pos = N > 1 ? atomicAdd(cursor, 1ull) : (unsigned long long)e;
+  keys[pos] = row * (unsigned long long)n_nodes + dst;
 }
 
 __global__ void k_count_src(const unsigned long long* keys, int64_t n_edges, int64_t n_nodes,
@@ -116,29 +124,36 @@ __global__ void k_count_src(const unsigned long long* keys, int64_t n_edges, int
 }
 
 __global__ void k_rmat_fill(const unsigned long long* keys, int64_t n_edges, int64_t n_nodes,
-                            unsigned long long* nbr, float* w) {
+                            unsigned long long* nbr, float* w, unsigned long long base_id, unsigned long long stride) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
   unsigned long long k = keys[e];
-  unsigned long long src = k / (unsigned long long)n_nodes, dst = k % (unsigned long long)n_nodes;
+  unsigned long long row = k / (unsigned long long)n_nodes, dst = k % (unsigned long long)n_nodes;
+  unsigned long long src = base_id + row * stride - 1;  // global 0-based source index
   nbr[e] = dst + 1;  // ids are 1..n
   unsigned long long h = mix64(src * 0x9E3779B97F4A7C15ull ^ dst);
   w[e] = 1.0f + (float)(h % 100ull) / 10.0f;
 }
 
-__global__ void k_iota_ids(unsigned long long* ids, int32_t* ntype, float* nw, int64_t n) {
+__global__ void k_iota_ids(unsigned long long* ids, int32_t* ntype, float* nw, int64_t n, unsigned long long base_id,
+                           unsigned long long stride) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= n) return;
-  ids[r] = (unsigned long long)r + 1;
+  ids[r] = base_id + (unsigned long long)r * stride;
   ntype[r] = 0;
   nw[r] = 1.0f;
 }
 
-__global__ void k_fill_feat(float* feat, int64_t total, unsigned long long seed) {
+// feat[row, d] = U(-1,1) from a hash of (global node index, d): identical on every shard layout
+__global__ void k_fill_feat(float* feat, int64_t n_local, int32_t dim, unsigned long long seed, unsigned long long base_id,
+                            unsigned long long stride) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (; i < total; i += stride) {
-    unsigned long long h = mix64(seed ^ ((unsigned long long)i * 0x9E3779B97F4A7C15ull));
+  const int64_t total = n_local * (int64_t)dim;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (; i < total; i += step) {
+    const unsigned long long row = (unsigned long long)(i / dim), col = (unsigned long long)(i % dim);
+    const unsigned long long gi = (base_id + row * stride - 1) * (unsigned long long)dim + col;
+    unsigned long long h = mix64(seed ^ (gi * 0x9E3779B97F4A7C15ull));
     feat[i] = (float)((double)(h >> 11) * (2.0 / 9007199254740992.0) - 1.0);
   }
 }
@@ -356,6 +371,7 @@ int eu_graph_create(const eu_graph_desc* desc, int device, eu_graph** out) {
   for (int64_t r = 0; r < n && dense; ++r) dense = desc->ids[r] == desc->ids[0] + (uint64_t)r;
   d.dense_ids = dense ? 1 : 0;
   d.id_base = n > 0 ? desc->ids[0] : 0;
+  d.id_stride = 1;
   TRY(build_hash(g));
   if (desc->sampler_order) g->sampler_order.assign(desc->sampler_order, desc->sampler_order + n);
   for (int t = 0; t < T; ++t) g->edge_type_names.push_back(std::to_string(t));
@@ -365,76 +381,102 @@ int eu_graph_create(const eu_graph_desc* desc, int device, eu_graph** out) {
   return EU_OK;
 }
 
-int eu_graph_create_rmat(int64_t n_nodes, int64_t n_edges, double a, double b, double c,
-                         uint64_t seed, int32_t feat_dim, uint64_t feat_seed, int device,
-                         eu_graph** out) {
-  if (!out || n_nodes <= 0 || n_edges < 0) { set_error("eu_graph_create_rmat: bad sizes"); return EU_ERR_INVALID; }
+// R-MAT generation, optionally restricted to the rows one shard owns (owner(id) = id % shard_number,
+// the reference's (id % partitions) % shards with partitions a multiple of shards, id_split_op.cc:46-49).
+// Every shard derives edges, weights and features from the same per-edge / per-node hashes, so the union
+// of the shards is exactly the unsharded graph.
+static int rmat_create(int64_t n_nodes, int64_t n_edges, double a, double b, double c, uint64_t seed,
+                       int32_t feat_dim, uint64_t feat_seed, int device, int shard_index, int shard_number,
+                       eu_graph** out) {
+  if (!out || n_nodes <= 0 || n_edges < 0 || shard_number < 1 || shard_index < 0 || shard_index >= shard_number) {
+    set_error("eu_graph_create_rmat: bad sizes"); return EU_ERR_INVALID;
+  }
   if ((double)n_nodes * (double)n_nodes >= 9.2e18) { set_error("n_nodes too large for 64-bit sort keys"); return EU_ERR_INVALID; }
   int rc = check_device(device);
   if (rc) return rc;
+  const int64_t N = shard_number;
+  const int64_t base_id = shard_index == 0 ? N : shard_index;           // first owned id (ids are 1..n; 0 is unusable)
+  const int64_t n_local = n_nodes >= base_id ? (n_nodes - base_id) / N + 1 : 0;
   eu_graph* g = new eu_graph();
   g->device = device;
   DevGraph& d = g->d;
-  d.n = n_nodes; d.T = 1; d.n_node_types = 1; d.E = n_edges;
+  d.n = n_local; d.T = 1; d.n_node_types = 1;
   const int tb = 256;
 #define TRY(x) do { rc = (x); if (rc) { eu_graph_destroy(g); return rc; } } while (0)
 #define TRYC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_error("%s -> %s", #x, cudaGetErrorString(_e)); eu_graph_destroy(g); return EU_ERR_CUDA; } } while (0)
+  int scale = 1;
+  while (((int64_t)1 << scale) < n_nodes) ++scale;
+  // pass 1: how many edges does this shard own
+  unsigned long long* d_cnt = nullptr;
+  TRYC(cudaMalloc(&d_cnt, sizeof(unsigned long long)));
+  TRYC(cudaMemset(d_cnt, 0, sizeof(unsigned long long)));
+  int64_t E = n_edges;
+  if (N > 1 && n_edges > 0) {
+    k_rmat_edges<<<(unsigned)ceil_div(n_edges, tb), tb>>>(nullptr, d_cnt, n_edges, n_nodes, scale, a, b, c, seed, (int)N, shard_index);
+    g_launches++;
+    unsigned long long h = 0;
+    TRYC(cudaMemcpy(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
+    E = (int64_t)h;
+    TRYC(cudaMemset(d_cnt, 0, sizeof(unsigned long long)));
+  }
+  d.E = E;
   unsigned long long *ids = nullptr, *nbr = nullptr;
   int32_t* ntype = nullptr;
   float *nw = nullptr, *cum = nullptr;
   int64_t* ptr = nullptr;
-  TRY(g->alloc(&ids, n_nodes));
-  TRY(g->alloc(&ntype, n_nodes));
-  TRY(g->alloc(&nw, n_nodes));
-  TRY(g->alloc(&ptr, n_nodes + 1));
-  TRY(g->alloc(&nbr, n_edges));
-  TRY(g->alloc(&cum, n_edges));
-  k_iota_ids<<<(unsigned)ceil_div(n_nodes, tb), tb>>>(ids, ntype, nw, n_nodes);
-  g_launches++;
-  // temporaries (freed before returning)
+  TRY(g->alloc(&ids, n_local));
+  TRY(g->alloc(&ntype, n_local));
+  TRY(g->alloc(&nw, n_local));
+  TRY(g->alloc(&ptr, n_local + 1));
+  TRY(g->alloc(&nbr, E));
+  TRY(g->alloc(&cum, E));
+  if (n_local > 0) {
+    k_iota_ids<<<(unsigned)ceil_div(n_local, tb), tb>>>(ids, ntype, nw, n_local, (unsigned long long)base_id, (unsigned long long)N);
+    g_launches++;
+  }
   unsigned long long *k0 = nullptr, *k1 = nullptr;
   float* w = nullptr;
   void* tmp = nullptr;
   size_t tmp_bytes = 0, tmp2 = 0;
-  int scale = 1;
-  while (((int64_t)1 << scale) < n_nodes) ++scale;
-  TRYC(cudaMalloc(&k0, sizeof(unsigned long long) * (size_t)(n_edges > 0 ? n_edges : 1)));
-  TRYC(cudaMalloc(&k1, sizeof(unsigned long long) * (size_t)(n_edges > 0 ? n_edges : 1)));
+  TRYC(cudaMalloc(&k0, sizeof(unsigned long long) * (size_t)(E > 0 ? E : 1)));
+  TRYC(cudaMalloc(&k1, sizeof(unsigned long long) * (size_t)(E > 0 ? E : 1)));
   if (n_edges > 0) {
-    k_rmat_edges<<<(unsigned)ceil_div(n_edges, tb), tb>>>(k0, n_edges, n_nodes, scale, a, b, c, seed);
+    k_rmat_edges<<<(unsigned)ceil_div(n_edges, tb), tb>>>(k0, d_cnt, n_edges, n_nodes, scale, a, b, c, seed, (int)N, shard_index);
     g_launches++;
   }
   int end_bit = 1;
-  while (end_bit < 64 && ((double)n_nodes * (double)n_nodes) >= ldexp(1.0, end_bit)) ++end_bit;
-  cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, k0, k1, (int64_t)n_edges, 0, end_bit);
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp2, ptr, ptr, (int64_t)(n_nodes + 1));
+  while (end_bit < 64 && ((double)(n_local > 0 ? n_local : 1) * (double)n_nodes) >= ldexp(1.0, end_bit)) ++end_bit;
+  cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, k0, k1, (int64_t)E, 0, end_bit);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp2, ptr, ptr, (int64_t)(n_local + 1));
   if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
   TRYC(cudaMalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1));
-  TRYC(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, k0, k1, (int64_t)n_edges, 0, end_bit));
-  TRYC(cudaMemset(ptr, 0, sizeof(int64_t) * (size_t)(n_nodes + 1)));
-  if (n_edges > 0) {
-    k_count_src<<<(unsigned)ceil_div(n_edges, tb), tb>>>(k1, n_edges, n_nodes, ptr);
+  TRYC(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, k0, k1, (int64_t)E, 0, end_bit));
+  TRYC(cudaMemset(ptr, 0, sizeof(int64_t) * (size_t)(n_local + 1)));
+  if (E > 0) {
+    k_count_src<<<(unsigned)ceil_div(E, tb), tb>>>(k1, E, n_nodes, ptr);
     g_launches++;
   }
-  TRYC(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, ptr, ptr, (int64_t)(n_nodes + 1)));
+  TRYC(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, ptr, ptr, (int64_t)(n_local + 1)));
   TRYC(cudaFree(k0)); k0 = nullptr;
-  TRYC(cudaMalloc(&w, sizeof(float) * (size_t)(n_edges > 0 ? n_edges : 1)));
-  if (n_edges > 0) {
-    k_rmat_fill<<<(unsigned)ceil_div(n_edges, tb), tb>>>(k1, n_edges, n_nodes, nbr, w);
+  TRYC(cudaMalloc(&w, sizeof(float) * (size_t)(E > 0 ? E : 1)));
+  if (E > 0) {
+    k_rmat_fill<<<(unsigned)ceil_div(E, tb), tb>>>(k1, E, n_nodes, nbr, w, (unsigned long long)base_id, (unsigned long long)N);
     g_launches++;
   }
-  k_build_cum<<<(unsigned)ceil_div(n_nodes, 128), 128>>>(n_nodes, 1, ptr, w, cum, nullptr);
-  g_launches++;
+  if (n_local > 0) {
+    k_build_cum<<<(unsigned)ceil_div(n_local, 128), 128>>>(n_local, 1, ptr, w, cum, nullptr);
+    g_launches++;
+  }
   TRYC(cudaDeviceSynchronize());
-  cudaFree(k1); cudaFree(w); cudaFree(tmp);
+  cudaFree(k1); cudaFree(w); cudaFree(tmp); cudaFree(d_cnt);
   d.ids = ids; d.node_type = ntype; d.node_w = nw; d.grp_ptr = ptr; d.nbr = nbr; d.cum_w = cum;
   d.grp_cum = nullptr;
-  d.dense_ids = 1; d.id_base = 1;
+  d.dense_ids = 1; d.id_base = (unsigned long long)base_id; d.id_stride = (unsigned long long)N;
   d.feat_dim = feat_dim;
   if (feat_dim > 0) {
     float* feat = nullptr;
-    TRY(g->alloc(&feat, n_nodes * (int64_t)feat_dim));
-    k_fill_feat<<<148 * 8, 256>>>(feat, n_nodes * (int64_t)feat_dim, feat_seed);
+    TRY(g->alloc(&feat, n_local * (int64_t)feat_dim));
+    k_fill_feat<<<148 * 8, 256>>>(feat, n_local, feat_dim, feat_seed, (unsigned long long)base_id, (unsigned long long)N);
     g_launches++;
     d.feat = feat;
     d.n_slots = 1; d.slot_off[0] = 0; d.slot_dim[0] = feat_dim;
@@ -447,6 +489,18 @@ int eu_graph_create_rmat(int64_t n_nodes, int64_t n_edges, double a, double b, d
 #undef TRYC
   *out = g;
   return EU_OK;
+}
+
+int eu_graph_create_rmat(int64_t n_nodes, int64_t n_edges, double a, double b, double c,
+                         uint64_t seed, int32_t feat_dim, uint64_t feat_seed, int device,
+                         eu_graph** out) {
+  return rmat_create(n_nodes, n_edges, a, b, c, seed, feat_dim, feat_seed, device, 0, 1, out);
+}
+
+int eu_graph_create_rmat_shard(int64_t n_nodes, int64_t n_edges, double a, double b, double c,
+                               uint64_t seed, int32_t feat_dim, uint64_t feat_seed, int device,
+                               int shard_index, int shard_number, eu_graph** out) {
+  return rmat_create(n_nodes, n_edges, a, b, c, seed, feat_dim, feat_seed, device, shard_index, shard_number, out);
 }
 
 int eu_graph_destroy(eu_graph* g) {

@@ -33,16 +33,9 @@ __global__ void k_dedup_clear(HashSlot* tab, int64_t cap) {
 }
 
 // tab[h] = {id+1, min index}.  key 0 = free.
-__global__ void k_dedup_insert(HashSlot* tab, unsigned long long mask,
-                               const unsigned long long* __restrict__ seeds, int64_t rows) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= rows) return;
-  unsigned long long id = seeds[i], tag = id + 1;
-  // Warp-aggregate: frontiers are full of runs of equal ids (a default row is `count` zeros, hubs
-  // repeat), and equal ids hammer one slot.  The lowest lane of each equal-id group carries the
-  // group's minimum index, so only it touches the table.
-  const unsigned peers = __match_any_sync(__activemask(), id);
-  if ((threadIdx.x & 31) != __ffs(peers) - 1) return;
+__device__ __forceinline__ void dedup_insert_one(HashSlot* tab, unsigned long long mask, unsigned long long id,
+                                                 int64_t i) {
+  const unsigned long long tag = id + 1;
   if (tag == 0ull) {  // id == 2^64-1 (e.g. default_node -1 fed back as a seed): dedicated slot [mask+1]
     atomicMin(&tab[mask + 1].row, (unsigned long long)i);
     return;
@@ -56,6 +49,19 @@ __global__ void k_dedup_insert(HashSlot* tab, unsigned long long mask,
     }
     h = (h + 1) & mask;
   }
+}
+
+__global__ void k_dedup_insert(HashSlot* tab, unsigned long long mask,
+                               const unsigned long long* __restrict__ seeds, int64_t rows) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= rows) return;
+  unsigned long long id = seeds[i];
+  // Warp-aggregate: frontiers are full of runs of equal ids (a default row is `count` zeros, hubs
+  // repeat), and equal ids hammer one slot.  The lowest lane of each equal-id group carries the
+  // group's minimum index, so only it touches the table.
+  const unsigned peers = __match_any_sync(__activemask(), id);
+  if ((threadIdx.x & 31) != __ffs(peers) - 1) return;
+  dedup_insert_one(tab, mask, id, i);
 }
 
 __device__ __forceinline__ int64_t dedup_first(const HashSlot* tab, unsigned long long mask,
@@ -233,6 +239,8 @@ struct SampleArgs {
   uint32_t fpow2[32];           // F^(2^k) mod M
   HashSlot* clear_tab;          // dedup table of THIS hop, cleared here for the next user
   int64_t clear_n;
+  HashSlot* next_tab;           // dedup table of the NEXT hop: this hop's engine ids are its seeds (or null)
+  unsigned long long next_mask;
   // philox
   unsigned long long key;
   const EuRngState* rng;
@@ -299,6 +307,7 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
       if (a.eng_ids) a.eng_ids[obase + j] = 0ull;
       if (a.out_ids) { a.out_ids[obase + j] = a.default_node; a.out_w[obase + j] = 0.f; a.out_t[obase + j] = -1; }
     }
+    if (!PHILOX && a.next_tab && lane == 0) dedup_insert_one(a.next_tab, a.next_mask, 0ull, obase);  // `count` zeros
     return;
   }
 
@@ -415,6 +424,20 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
       if (a.out_ids) { a.out_ids[obase + j] = a.default_node; a.out_w[obase + j] = 0.f; a.out_t[obase + j] = -1; }
     }
   }
+  if (!PHILOX && a.next_tab) {
+    // the engine ids just written are the next hop's seeds: enter them into its dedup table now
+    // (each lane re-reads its own stores), so the next hop needs no insert kernel
+    for (int32_t j0 = 0; j0 < count; j0 += 32) {
+      const int32_t j = j0 + lane;
+      const bool active = j < count;
+      const unsigned long long nid = active ? a.eng_ids[obase + j] : 0ull;
+      const unsigned act = __ballot_sync(0xffffffffu, active);
+      if (active) {
+        const unsigned peers = __match_any_sync(act, nid);
+        if (lane == __ffs(peers) - 1) dedup_insert_one(a.next_tab, a.next_mask, nid, obase + j);
+      }
+    }
+  }
 }
 
 __global__ void k_bump_calls(EuRngState* rng) { rng->calls += 1; }
@@ -504,8 +527,8 @@ static int classify(const DevGraph& d, const int32_t* etypes, int32_t K, ETypes*
 // One sampleNB hop: seeds (device u64[rows]) -> engine ids (device u64[rows*count], may be null)
 // and TF-packed outputs (may be null).
 int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows, const int32_t* etypes,
-               int32_t K, int32_t count, int64_t default_node, unsigned long long* eng_ids,
-               int64_t* out_ids, float* out_w, int32_t* out_t) {
+        int32_t K, int32_t count, int64_t default_node, unsigned long long* eng_ids,
+        int64_t* out_ids, float* out_w, int32_t* out_t, int hop_index, bool pre_inserted, bool insert_next) {
   if (rows == 0 || count == 0) return EU_OK;
   const DevGraph& d = c->g->d;
   SampleArgs a{};
@@ -531,23 +554,35 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows, const int32_t*
   int64_t cap = 64;
   while (cap < rows * 2) cap <<= 1;
   const int tb = kPrepBlock;
-  // invariant: the dedup table is all-free on entry (cleared at allocation, and by every k_sample
-  // after its hop's k_prepare has consumed it)
-  { EuProfScope ps(c, "k_dedup_insert", rows);
-    k_dedup_insert<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(c->d_dedup, (unsigned long long)cap - 1, seeds, rows); }
+  // Two tables, hop l uses table l & 1.  Invariant: both are all-free when an op starts (cleared at
+  // allocation; every k_sample wipes its own hop's table once k_prepare has consumed it).  The seeds of
+  // hop l+1 are entered into the other table by hop l's k_sample (pre_inserted), so only the first hop
+  // of a chain needs the insert kernel.
+  HashSlot* tab = c->d_dedup + (hop_index & 1) * (c->dedup_cap + 1);
+  HashSlot* ntab = c->d_dedup + ((hop_index + 1) & 1) * (c->dedup_cap + 1);
+  if (!pre_inserted) {
+    EuProfScope ps(c, "k_dedup_insert", rows);
+    k_dedup_insert<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(tab, (unsigned long long)cap - 1, seeds, rows);
+  }
   EU_LAUNCHED();
   const unsigned long long upr = (unsigned long long)count * (a.mode == 0 ? 1 : 2);
   const uint32_t F = modpow_a(2ull * upr);
   { EuProfScope ps(c, "k_prepare", rows);
-    k_prepare<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(d, c->d_dedup, (unsigned long long)cap - 1, seeds, rows,
+    k_prepare<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(d, tab, (unsigned long long)cap - 1, seeds, rows,
                                                            a.et, a.mode, F, upr, c->d_first, c->d_rowof, c->d_emask,
                                                            c->d_woff, c->d_blkpre, c->d_rng); }
   EU_LAUNCHED();
   a.first = c->d_first; a.rowof = c->d_rowof; a.emask = c->d_emask; a.woff = c->d_woff; a.blkpre = c->d_blkpre;
   a.fpow2[0] = F;
   for (int k = 1; k < 32; ++k) a.fpow2[k] = modmul(a.fpow2[k - 1], a.fpow2[k - 1]);
-  a.clear_tab = c->d_dedup;
+  a.clear_tab = tab;
   a.clear_n = cap + 1;
+  if (insert_next && eng_ids) {
+    int64_t ncap = 64;
+    while (ncap < rows * count * 2) ncap <<= 1;
+    a.next_tab = ntab;
+    a.next_mask = (unsigned long long)ncap - 1;
+  }
   { EuProfScope ps(c, "k_sample<minstd>", rows); k_sample<false><<<blocks, 256, 0, s>>>(d, a); }
   EU_LAUNCHED();
   return EU_OK;
@@ -564,7 +599,7 @@ int eu_sample_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t
                        int32_t* out_t) {
   if (!c || B < 0 || count < 0 || (K > 0 && !etypes)) { set_error("eu_sample_neighbor: bad argument"); return EU_ERR_INVALID; }
   EU_CUDA(cudaSetDevice(c->g->device));
-  return hop(c, (const unsigned long long*)nodes, B, etypes, K, count, default_node, nullptr, out_ids, out_w, out_t);
+  return hop(c, (const unsigned long long*)nodes, B, etypes, K, count, default_node, nullptr, out_ids, out_w, out_t, 0, false, false);
 }
 
 int eu_sample_fanout(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
@@ -581,7 +616,8 @@ int eu_sample_fanout(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* 
   for (int l = 0; l < L; ++l) {
     unsigned long long* eng = (l + 1 < L) ? c->d_front[l & 1] : nullptr;
     rc = hop(c, seeds, rows, etypes + (int64_t)l * K, K, counts[l], default_node, eng,
-             out_ids ? out_ids[l] : nullptr, out_w ? out_w[l] : nullptr, out_t ? out_t[l] : nullptr);
+             out_ids ? out_ids[l] : nullptr, out_w ? out_w[l] : nullptr, out_t ? out_t[l] : nullptr,
+             l, /*pre_inserted=*/l > 0 && c->rng == EU_RNG_MINSTD, /*insert_next=*/l + 1 < L);
     if (rc) return rc;
     seeds = eng;
     rows *= counts[l];

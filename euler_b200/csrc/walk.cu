@@ -194,7 +194,8 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
     const unsigned long long* seeds = (const unsigned long long*)nodes;
     for (int l = 0; l < L; ++l) {
       unsigned long long* eng = c->d_front[l & 1];
-      rc = hop(c, seeds, B, etypes + (int64_t)l * K, K, 1, default_node, eng, nullptr, nullptr, nullptr);
+      rc = hop(c, seeds, B, etypes + (int64_t)l * K, K, 1, default_node, eng, nullptr, nullptr, nullptr,
+               l, l > 0 && c->rng == EU_RNG_MINSTD, l + 1 < L);
       if (rc) return rc;
       k_walk_col<<<(unsigned)ceil_div(B, tb), tb, 0, s>>>(eng, B, L, l + 1, default_node, (long long*)out);
       EU_LAUNCHED();

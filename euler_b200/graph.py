@@ -61,6 +61,15 @@ class Graph:
         return cls(h, device)
 
     @classmethod
+    def rmat_shard(cls, n_nodes, n_edges, shard_index, shard_number, a=0.57, b=0.19, c=0.19, seed=42, feat_dim=0,
+                   feat_seed=7, device=0):
+        """The rows of Graph.rmat(...) owned by shard `shard_index` (owner(id) = id % shard_number)."""
+        h = C.c_void_p()
+        check(_lib.load().eu_graph_create_rmat_shard(n_nodes, n_edges, a, b, c, seed, feat_dim, feat_seed, device,
+                                                     shard_index, shard_number, C.byref(h)))
+        return cls(h, device)
+
+    @classmethod
     def load(cls, data_path, shard_index=0, shard_number=1, device=0):
         h = C.c_void_p()
         check(_lib.load().eu_graph_load(str(data_path).encode(), shard_index, shard_number, device,

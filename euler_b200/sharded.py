@@ -1,0 +1,183 @@
+"""Multi-GPU path: the graph is hash-partitioned by node id over the ranks of one box (Euler's own
+shard scheme) and every hop / feature fetch resolves remote ids with an all-to-all over NVLink.
+
+Reference being replaced (mode=remote): ID_SPLIT -> REMOTE (gRPC Execute of a sub-DAG on each shard
+server) -> IDX_MERGE / DATA_MERGE, euler/core/kernels/id_split_op.cc:46-99, remote_op.cc:60-146,
+idx_merge_op.cc:32-78, discovery through ZooKeeper.  Here: one process per GPU, torch.distributed
+(NCCL) for the exchange, CUDA kernels (csrc/shard.cu) for routing and merging.
+
+Per hop on every rank
+    bucket seeds by owner (stable)            eu_shard_bucket
+    exchange per-owner counts                 all_to_all (N ints; the only host sync of the hop)
+    exchange seeds                            all_to_all_v  (8 B / seed)
+    sample the received seeds on this shard   eu_sample_neighbor  (this shard's own engine)
+    exchange the rows back                    all_to_all_v  (16 B x count / seed)
+    merge into request order + TF packing     eu_shard_merge_sample
+
+Determinism / parity: a shard processes the concatenation of the requests of rank 0, 1, ... (each in
+batch order) as ONE sampleNB call on its own engine, so duplicate seeds -- also across requesters --
+share one sample row and the draw order is fixed.  The reference runs every request on whichever
+server thread picks it up (thread_local engines, random.cc:22), i.e. it has no defined order here;
+tests/test_sharded_*.py pin this definition against the oracle.
+
+The exchange and the per-shard ops are injected (`ops`, `xchg`) so the same orchestration runs over
+gloo on CPU in the tests.
+"""
+import ctypes as C
+
+import numpy as np
+
+
+def owner_of(ids, num_partitions, shard_num):
+    """euler/core/kernels/id_split_op.cc:46-49 (ids as uint64)."""
+    return (np.asarray(ids).astype(np.uint64) % np.uint64(num_partitions)) % np.uint64(shard_num)
+
+
+class TorchExchange:
+    """all-to-all over a torch.distributed process group (NCCL for CUDA tensors, gloo for CPU)."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def counts(self, send_counts_t):
+        """send_counts_t: int64[world] tensor (device of the backend).  Returns (send, recv) lists."""
+        import torch
+        recv = torch.empty_like(send_counts_t)
+        self.dist.all_to_all_single(recv, send_counts_t, group=self.group)
+        both = torch.stack([send_counts_t, recv]).cpu()   # the hop's single host sync
+        return both[0].tolist(), both[1].tolist()
+
+    def a2a(self, t, send, recv, width=1):
+        """t: [sum(send) * width] flat tensor; returns [sum(recv) * width]."""
+        import torch
+        out = torch.empty(int(sum(recv)) * width, dtype=t.dtype, device=t.device)
+        self.dist.all_to_all_single(out, t, [int(r) * width for r in recv], [int(s) * width for s in send],
+                                    group=self.group)
+        return out
+
+
+class CudaShardOps:
+    """Per-shard work on this rank's GPU through the C ABI."""
+
+    def __init__(self, graph, rng="minstd", seed=1):
+        import torch
+        from . import _lib
+        from .graph import Context
+        self.torch, self.lib, self.check = torch, _lib.load(), _lib.check
+        self.graph = graph
+        self.dev = torch.device("cuda", graph.device)
+        self.ctx = Context(graph, rng, seed)
+
+    def _stream(self):
+        self.ctx.set_stream(self.torch.cuda.current_stream(self.dev).cuda_stream)
+        return self.ctx._h
+
+    def to_dev(self, a, dtype):
+        t = self.torch
+        if isinstance(a, t.Tensor):
+            return a.to(device=self.dev, dtype=dtype).contiguous()
+        return t.as_tensor(np.asarray(a), dtype=dtype, device=self.dev).contiguous()
+
+    def bucket(self, ids, P, N):
+        t = self.torch
+        rows = ids.numel()
+        sorted_ids = t.empty(rows, dtype=t.int64, device=self.dev)
+        src = t.empty(rows, dtype=t.int32, device=self.dev)
+        counts = t.empty(N, dtype=t.int64, device=self.dev)
+        offs = t.empty(N + 1, dtype=t.int64, device=self.dev)
+        self.check(self.lib.eu_shard_bucket(self._stream(), ids.data_ptr(), rows, P, N, sorted_ids.data_ptr(),
+                                            src.data_ptr(), counts.data_ptr(), offs.data_ptr()))
+        return sorted_ids, src, counts
+
+    def sample_local(self, seeds, etypes, count):
+        """Engine-form rows for the received seeds: ids with 0 placeholders, w 0, t -1 on empty rows."""
+        t = self.torch
+        n = seeds.numel()
+        et = np.ascontiguousarray(etypes, dtype=np.int32)
+        ids = t.empty(n * count, dtype=t.int64, device=self.dev)
+        w = t.empty(n * count, dtype=t.float32, device=self.dev)
+        ty = t.empty(n * count, dtype=t.int32, device=self.dev)
+        self.check(self.lib.eu_sample_neighbor(self._stream(), seeds.data_ptr(), n, et.ctypes.data, len(et), count, 0,
+                                               ids.data_ptr(), w.data_ptr(), ty.data_ptr()))
+        return ids, w, ty
+
+    def merge_sample(self, r_ids, r_w, r_t, src, rows, count, default_node):
+        t = self.torch
+        eng = t.empty(rows * count, dtype=t.int64, device=self.dev)
+        o_ids = t.empty(rows * count, dtype=t.int64, device=self.dev)
+        o_w = t.empty(rows * count, dtype=t.float32, device=self.dev)
+        o_t = t.empty(rows * count, dtype=t.int32, device=self.dev)
+        self.check(self.lib.eu_shard_merge_sample(self._stream(), r_ids.data_ptr(), r_w.data_ptr(), r_t.data_ptr(),
+                                                  src.data_ptr(), rows, count, default_node, eng.data_ptr(),
+                                                  o_ids.data_ptr(), o_w.data_ptr(), o_t.data_ptr()))
+        return eng, o_ids, o_w, o_t
+
+    def feature_local(self, ids, fid, dim):
+        t = self.torch
+        out = t.empty(ids.numel() * dim, dtype=t.float32, device=self.dev)
+        self.check(self.lib.eu_get_dense_feature(self._stream(), ids.data_ptr(), ids.numel(), fid, dim, out.data_ptr()))
+        return out
+
+    def merge_rows(self, rows_in, src, rows, dim):
+        t = self.torch
+        out = t.empty((rows, dim), dtype=t.float32, device=self.dev)
+        self.check(self.lib.eu_shard_merge_rows(self._stream(), rows_in.data_ptr(), src.data_ptr(), rows, dim,
+                                                out.data_ptr()))
+        return out
+
+    def seed(self, s):
+        self.ctx.seed(s)
+
+
+class ShardedGraph:
+    """tf_euler's sampling / feature ops over a graph partitioned across the ranks of `xchg`."""
+
+    def __init__(self, ops, xchg, num_partitions=None):
+        self.ops, self.xchg = ops, xchg
+        self.N = xchg.world
+        self.P = num_partitions or self.N   # partitions a multiple of shards -> owner = id % N
+
+    def sample_neighbor(self, nodes, edge_types, count, default_node=-1):
+        eng, ids, w, t = self._hop(self.ops.to_dev(nodes, _i64(self.ops)), edge_types, count, default_node)
+        shape = (-1, count)
+        return ids.reshape(shape), w.reshape(shape), t.reshape(shape)
+
+    def sample_fanout(self, nodes, edge_types, counts, default_node=-1):
+        """neighbor_ops.sample_fanout (tf_euler/python/euler_ops/neighbor_ops.py:122-158): the next hop's
+        seeds are the ENGINE ids of this hop (0 placeholders), tf_euler/kernels/sample_fanout_op.cc:36-43."""
+        frontier = self.ops.to_dev(nodes, _i64(self.ops)).reshape(-1)
+        ids, ws, ts = [frontier], [], []
+        for et, c in zip(edge_types, counts):
+            frontier, o_ids, o_w, o_t = self._hop(frontier, et, int(c), default_node)
+            ids.append(o_ids); ws.append(o_w); ts.append(o_t)
+        return ids, ws, ts
+
+    def _hop(self, frontier, etypes, count, default_node):
+        ops, x = self.ops, self.xchg
+        rows = frontier.numel()
+        sorted_ids, src, counts = ops.bucket(frontier, self.P, self.N)
+        send, recv = x.counts(counts)
+        inbox = x.a2a(sorted_ids, send, recv)
+        r_ids, r_w, r_t = ops.sample_local(inbox, etypes, count)
+        b_ids = x.a2a(r_ids, recv, send, count)
+        b_w = x.a2a(r_w, recv, send, count)
+        b_t = x.a2a(r_t, recv, send, count)
+        return ops.merge_sample(b_ids, b_w, b_t, src, rows, count, default_node)
+
+    def get_dense_feature(self, nodes, fid, dim):
+        ops, x = self.ops, self.xchg
+        ids = ops.to_dev(nodes, _i64(ops)).reshape(-1)
+        rows = ids.numel()
+        sorted_ids, src, counts = ops.bucket(ids, self.P, self.N)
+        send, recv = x.counts(counts)
+        inbox = x.a2a(sorted_ids, send, recv)
+        feats = ops.feature_local(inbox, fid, dim)
+        back = x.a2a(feats, recv, send, dim)
+        return ops.merge_rows(back, src, rows, dim)
+
+
+def _i64(ops):
+    return ops.torch.int64 if hasattr(ops, "torch") else np.int64

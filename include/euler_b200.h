@@ -89,6 +89,12 @@ int eu_graph_create(const eu_graph_desc* desc, int device, eu_graph** out);
 int eu_graph_create_rmat(int64_t n_nodes, int64_t n_edges, double a, double b, double c,
                          uint64_t seed, int32_t feat_dim, uint64_t feat_seed, int device,
                          eu_graph** out);
+/* The rows of that same graph that shard `shard_index` of `shard_number` owns: owner(id) = id % shard_number
+ * (the reference's routing (id % partitions) % shards with partitions a multiple of shards,
+ * euler/core/kernels/id_split_op.cc:46-49).  The union of the shards is exactly eu_graph_create_rmat's graph. */
+int eu_graph_create_rmat_shard(int64_t n_nodes, int64_t n_edges, double a, double b, double c,
+                               uint64_t seed, int32_t feat_dim, uint64_t feat_seed, int device,
+                               int shard_index, int shard_number, eu_graph** out);
 /* Euler 2.0 on-disk format (euler.meta + Node/*.dat), shard `shard_index` of
  * `shard_number` with the reference's file filter (graph.cc:90-98).  = Graph::Init, graph.h:53-56. */
 int eu_graph_load(const char* data_path, int shard_index, int shard_number, int device,
@@ -193,6 +199,21 @@ int eu_scatter_add_host(eu_ctx* c, const float* updates, int64_t D, const int32_
                         int64_t size, float* out);
 int eu_scatter_max_host(eu_ctx* c, const float* updates, int64_t D, const int32_t* idx, int64_t E,
                         int64_t size, float* out);
+
+/* ------------------------------------------------------------------ sharding (multi-GPU) ----- */
+/* Replace ID_SPLIT / IDX_MERGE / DATA_MERGE (euler/core/kernels/id_split_op.cc:46-99, idx_merge_op.cc:32-78)
+ * either side of an all-to-all.  eu_shard_bucket: stable counting sort of ids by owner
+ * (id % num_partitions) % shard_num; sorted_ids[k] came from ids[src_index[k]]; counts[o] / offsets[o]
+ * (device, i64[shard_num] / [shard_num+1]) delimit owner o's segment.  eu_shard_merge_sample: replies in
+ * sorted order -> original row order + TF packing + engine-id frontier.  eu_shard_merge_rows: the same for
+ * fixed-width f32 rows (features). */
+int eu_shard_bucket(eu_ctx* c, const int64_t* ids, int64_t rows, int32_t num_partitions, int32_t shard_num,
+                    int64_t* sorted_ids, int32_t* src_index, int64_t* counts, int64_t* offsets);
+int eu_shard_merge_sample(eu_ctx* c, const int64_t* reply_ids, const float* reply_w, const int32_t* reply_t,
+                          const int32_t* src_index, int64_t rows, int32_t count, int64_t default_node,
+                          int64_t* eng_ids, int64_t* out_ids, float* out_w, int32_t* out_t);
+int eu_shard_merge_rows(eu_ctx* c, const float* rows_in, const int32_t* src_index, int64_t rows, int64_t D,
+                        float* out);
 
 /* ------------------------------------------------------------------ reference entry point ---- */
 /* bool InitQueryProxy(const char* conf) -- tf_euler/utils/init_query_proxy.cc:19-36.  "k=v;k=v";

@@ -46,6 +46,9 @@ static eo_rng g_rng = {1, 0};
 void eo_global_seed(uint64_t seed) { eo_seed(&g_rng, seed); }
 uint64_t eo_global_draws(void) { return g_rng.draws; }
 double eo_global_uniform(void) { return eo_uniform(&g_rng); }
+/* save / restore the global engine (lets one process simulate several shard engines) */
+uint64_t eo_global_state(void) { return g_rng.x; }
+void eo_global_set_state(uint64_t x, uint64_t draws) { g_rng.x = x; g_rng.draws = draws; }
 
 /* ------------------------------------------------------------------ graph */
 struct eo_graph {

@@ -29,6 +29,8 @@ double eo_uniform(eo_rng* r);
 void eo_global_seed(uint64_t seed);
 uint64_t eo_global_draws(void);
 double eo_global_uniform(void);
+uint64_t eo_global_state(void);
+void eo_global_set_state(uint64_t x, uint64_t draws);
 
 /* ---- graph in CSR form (what Node/NeighborInfo hold, euler/core/graph/node.h:49-57) */
 typedef struct eo_graph eo_graph;

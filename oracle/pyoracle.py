@@ -60,6 +60,8 @@ def lib():
         L.eo_global_seed.argtypes = [C.c_uint64]
         L.eo_global_draws.restype = C.c_uint64
         L.eo_global_uniform.restype = C.c_double
+        L.eo_global_state.restype = C.c_uint64
+        L.eo_global_set_state.argtypes = [C.c_uint64, C.c_uint64]
         L.eo_graph_create.restype = C.c_void_p
         L.eo_graph_create.argtypes = [C.c_int64, C.c_int32, u64p, i32p, f32p, i64p, u64p, f32p, f32p,
                                       C.c_int32, C.c_void_p]
@@ -135,6 +137,14 @@ def seed(s):
 
 def draws():
     return lib().eo_global_draws()
+
+
+def get_state():
+    return lib().eo_global_state(), lib().eo_global_draws()
+
+
+def set_state(st):
+    lib().eo_global_set_state(st[0], st[1])
 
 
 def build_cum(grp_ptr, w, n, T):
