@@ -80,8 +80,9 @@ SIGNATURES = {
     "eu_gather_host": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P]),
     "eu_scatter_add_host": (C.c_int, [_P, _P, _I64, _P, _I64, _I64, _P]),
     "eu_scatter_max_host": (C.c_int, [_P, _P, _I64, _P, _I64, _I64, _P]),
-    "eu_shard_bucket": (C.c_int, [_P, _P, _I64, _I32, _I32, _P, _P, _P, _P]),
-    "eu_shard_merge_sample": (C.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I64, _P, _P, _P, _P]),
+    "eu_shard_bucket": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "eu_shard_pack_sample": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
+    "eu_shard_merge_sample": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P, _P, _P, _P]),
     "eu_shard_merge_rows": (C.c_int, [_P, _P, _P, _I64, _I64, _P]),
     "InitQueryProxy": (C.c_bool, [C.c_char_p]),
     "eu_default_graph": (_P, []),

@@ -12,10 +12,16 @@ namespace eu {
 static constexpr int kMaxShards = 64;
 static constexpr int kBktBlock = 256;
 
-__device__ __forceinline__ int owner_of(unsigned long long id, int P, int N) { return (int)((id % (unsigned long long)P) % (unsigned long long)N); }
+// ids 0 (the engine's "no neighbor" placeholder, DEFAULT_UINT64) and 2^64-1 (default_node = -1 fed back as a
+// seed) exist on no shard: they resolve to empty rows wherever they are looked up, so they stay on the
+// requesting rank instead of all piling onto shard 0 / shard (2^64-1) % N.
+__device__ __forceinline__ int owner_of(unsigned long long id, int P, int N, int self) {
+  if (id == 0ull || id == ~0ull) return self;
+  return (int)((id % (unsigned long long)P) % (unsigned long long)N);
+}
 
 // pass 1: per-block histogram; the last block turns blkcnt[b][o] into exclusive bases in (owner, block) order
-__global__ void __launch_bounds__(kBktBlock) k_bucket_count(const unsigned long long* __restrict__ ids, int64_t rows, int P, int N,
+__global__ void __launch_bounds__(kBktBlock) k_bucket_count(const unsigned long long* __restrict__ ids, int64_t rows, int P, int N, int self,
                                                             uint32_t* blkcnt /*[nblk][N]*/, long long* counts /*[N]*/,
                                                             long long* offsets /*[N+1]*/, unsigned int* done) {
   __shared__ uint32_t s_cnt[kMaxShards];
@@ -23,7 +29,7 @@ __global__ void __launch_bounds__(kBktBlock) k_bucket_count(const unsigned long 
   if (threadIdx.x < N) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const int64_t i = blockIdx.x * (int64_t)kBktBlock + threadIdx.x;
-  if (i < rows) atomicAdd(&s_cnt[owner_of(ids[i], P, N)], 1u);
+  if (i < rows) atomicAdd(&s_cnt[owner_of(ids[i], P, N, self)], 1u);
   __syncthreads();
   if (threadIdx.x < N) blkcnt[(int64_t)blockIdx.x * N + threadIdx.x] = s_cnt[threadIdx.x];
   __threadfence();
@@ -58,7 +64,7 @@ __global__ void __launch_bounds__(kBktBlock) k_bucket_count(const unsigned long 
 }
 
 // pass 2: stable placement.  rank inside the block = number of earlier lanes / warps with the same owner.
-__global__ void __launch_bounds__(kBktBlock) k_bucket_place(const unsigned long long* __restrict__ ids, int64_t rows, int P, int N,
+__global__ void __launch_bounds__(kBktBlock) k_bucket_place(const unsigned long long* __restrict__ ids, int64_t rows, int P, int N, int self,
                                                             const uint32_t* __restrict__ base /*[nblk][N]*/,
                                                             unsigned long long* __restrict__ sorted_ids, int32_t* __restrict__ src_index) {
   __shared__ uint32_t s_w[kBktBlock / 32][kMaxShards];
@@ -66,7 +72,7 @@ __global__ void __launch_bounds__(kBktBlock) k_bucket_place(const unsigned long 
   const int64_t i = blockIdx.x * (int64_t)kBktBlock + threadIdx.x;
   const bool valid = i < rows;
   const unsigned long long id = valid ? ids[i] : 0ull;
-  const int o = valid ? owner_of(id, P, N) : -1;
+  const int o = valid ? owner_of(id, P, N, self) : -1;
   const unsigned peers = __match_any_sync(0xffffffffu, o);
   const int before = __popc(peers & ((1u << lane) - 1u));
   for (int k = lane; k < N; k += 32) s_w[wid][k] = 0;
@@ -84,7 +90,18 @@ __global__ void __launch_bounds__(kBktBlock) k_bucket_place(const unsigned long 
 // reply merge + TF packing for sampled rows: reply row k (sorted order) belongs to original row src_index[k].
 // eng ids (0 = placeholder) go to the next frontier; packed outputs get default_node / 0 / -1 when the row's
 // first id is 0 (tf_euler/kernels/sample_neighbor_op.cc:79-81,114-122).
-__global__ void k_merge_sample(const long long* __restrict__ r_ids, const float* __restrict__ r_w, const int32_t* __restrict__ r_t,
+// SoA (ids, w, t) -> one 16-byte record per slot {id, w bits | t << 32}: a single all-to-all carries the reply
+__global__ void k_pack_rows(const long long* __restrict__ ids, const float* __restrict__ w, const int32_t* __restrict__ t,
+                            int64_t n, longlong2* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  longlong2 v;
+  v.x = ids[i];
+  v.y = (long long)(((unsigned long long)(uint32_t)t[i] << 32) | (unsigned long long)__float_as_uint(w[i]));
+  out[i] = v;
+}
+
+__global__ void k_merge_sample(const longlong2* __restrict__ rec,
                                const int32_t* __restrict__ src_index, int64_t rows, int32_t count, long long default_node,
                                unsigned long long* __restrict__ eng_ids, long long* __restrict__ out_ids,
                                float* __restrict__ out_w, int32_t* __restrict__ out_t) {
@@ -93,10 +110,15 @@ __global__ void k_merge_sample(const long long* __restrict__ r_ids, const float*
   const int64_t k = tid / count;
   const int32_t j = (int32_t)(tid % count);
   const int64_t dst = (int64_t)src_index[k] * count + j;
-  const long long id = r_ids[tid];
-  const bool keep = r_ids[k * count] != 0;
+  const longlong2 v = rec[tid];
+  const long long id = v.x;
+  const bool keep = rec[k * count].x != 0;
   if (eng_ids) eng_ids[dst] = (unsigned long long)id;
-  if (out_ids) { out_ids[dst] = keep ? id : default_node; out_w[dst] = keep ? r_w[tid] : 0.f; out_t[dst] = keep ? r_t[tid] : -1; }
+  if (out_ids) {
+    out_ids[dst] = keep ? id : default_node;
+    out_w[dst] = keep ? __uint_as_float((uint32_t)((unsigned long long)v.y & 0xffffffffull)) : 0.f;
+    out_t[dst] = keep ? (int32_t)((unsigned long long)v.y >> 32) : -1;
+  }
 }
 
 // reply merge for fixed-width f32 rows (features): out[src_index[k], :] = rows[k, :]
@@ -121,9 +143,9 @@ using namespace eu;
 
 extern "C" {
 
-int eu_shard_bucket(eu_ctx* c, const int64_t* ids, int64_t rows, int32_t num_partitions, int32_t shard_num,
+int eu_shard_bucket(eu_ctx* c, const int64_t* ids, int64_t rows, int32_t num_partitions, int32_t shard_num, int32_t self_shard,
                     int64_t* sorted_ids, int32_t* src_index, int64_t* counts, int64_t* offsets) {
-  if (!c || rows < 0 || num_partitions <= 0 || shard_num <= 0 || shard_num > kMaxShards || !counts || !offsets ||
+  if (!c || rows < 0 || num_partitions <= 0 || shard_num <= 0 || shard_num > kMaxShards || self_shard < 0 || self_shard >= shard_num || !counts || !offsets ||
       (rows > 0 && (!ids || !sorted_ids || !src_index))) {
     set_error("eu_shard_bucket: bad argument");
     return EU_ERR_INVALID;
@@ -137,24 +159,33 @@ int eu_shard_bucket(eu_ctx* c, const int64_t* ids, int64_t rows, int32_t num_par
   uint32_t* blkcnt = (uint32_t*)((char*)c->d_misc + 256);
   cudaStream_t s = c->stream;
   EU_CUDA(cudaMemsetAsync(done, 0, sizeof(unsigned int), s));
-  k_bucket_count<<<(unsigned)nblk, kBktBlock, 0, s>>>((const unsigned long long*)ids, rows, num_partitions, shard_num, blkcnt,
+  k_bucket_count<<<(unsigned)nblk, kBktBlock, 0, s>>>((const unsigned long long*)ids, rows, num_partitions, shard_num, self_shard, blkcnt,
                                                       (long long*)counts, (long long*)offsets, done);
   EU_LAUNCHED();
   if (rows > 0) {
-    k_bucket_place<<<(unsigned)nblk, kBktBlock, 0, s>>>((const unsigned long long*)ids, rows, num_partitions, shard_num, blkcnt,
+    k_bucket_place<<<(unsigned)nblk, kBktBlock, 0, s>>>((const unsigned long long*)ids, rows, num_partitions, shard_num, self_shard, blkcnt,
                                                         (unsigned long long*)sorted_ids, src_index);
     EU_LAUNCHED();
   }
   return EU_OK;
 }
 
-int eu_shard_merge_sample(eu_ctx* c, const int64_t* reply_ids, const float* reply_w, const int32_t* reply_t,
+int eu_shard_pack_sample(eu_ctx* c, const int64_t* ids, const float* w, const int32_t* t, int64_t n, int64_t* packed) {
+  if (!c || n < 0 || (n > 0 && (!ids || !w || !t || !packed))) { set_error("eu_shard_pack_sample: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  if (n == 0) return EU_OK;
+  k_pack_rows<<<(unsigned)ceil_div(n, 256), 256, 0, c->stream>>>((const long long*)ids, w, t, n, (longlong2*)packed);
+  EU_LAUNCHED();
+  return EU_OK;
+}
+
+int eu_shard_merge_sample(eu_ctx* c, const int64_t* packed,
                           const int32_t* src_index, int64_t rows, int32_t count, int64_t default_node, int64_t* eng_ids,
                           int64_t* out_ids, float* out_w, int32_t* out_t) {
-  if (!c || rows < 0 || count < 0 || (rows * count > 0 && (!reply_ids || !src_index))) { set_error("eu_shard_merge_sample: bad argument"); return EU_ERR_INVALID; }
+  if (!c || rows < 0 || count < 0 || (rows * count > 0 && (!packed || !src_index))) { set_error("eu_shard_merge_sample: bad argument"); return EU_ERR_INVALID; }
   EU_CUDA(cudaSetDevice(c->g->device));
   if (rows * count == 0) return EU_OK;
-  k_merge_sample<<<(unsigned)ceil_div(rows * count, 256), 256, 0, c->stream>>>((const long long*)reply_ids, reply_w, reply_t, src_index, rows, count,
+  k_merge_sample<<<(unsigned)ceil_div(rows * count, 256), 256, 0, c->stream>>>((const longlong2*)packed, src_index, rows, count,
                                                                                default_node, (unsigned long long*)eng_ids, (long long*)out_ids, out_w, out_t);
   EU_LAUNCHED();
   return EU_OK;

@@ -11,7 +11,7 @@ Per hop on every rank
     exchange per-owner counts                 all_to_all (N ints; the only host sync of the hop)
     exchange seeds                            all_to_all_v  (8 B / seed)
     sample the received seeds on this shard   eu_sample_neighbor  (this shard's own engine)
-    exchange the rows back                    all_to_all_v  (16 B x count / seed)
+    exchange the rows back                    all_to_all_v  (one 16 B record {id, w | t<<32} per slot)
     merge into request order + TF packing     eu_shard_merge_sample
 
 Determinism / parity: a shard processes the concatenation of the requests of rank 0, 1, ... (each in
@@ -28,9 +28,14 @@ import ctypes as C
 import numpy as np
 
 
-def owner_of(ids, num_partitions, shard_num):
-    """euler/core/kernels/id_split_op.cc:46-49 (ids as uint64)."""
-    return (np.asarray(ids).astype(np.uint64) % np.uint64(num_partitions)) % np.uint64(shard_num)
+def owner_of(ids, num_partitions, shard_num, self_shard=None):
+    """euler/core/kernels/id_split_op.cc:46-49 (ids as uint64).  With self_shard given, ids 0 and 2^64-1
+    (engine placeholder / default fill: they exist on no shard) stay on the requesting rank."""
+    a = np.asarray(ids).astype(np.uint64)
+    own = (a % np.uint64(num_partitions)) % np.uint64(shard_num)
+    if self_shard is not None:
+        own = np.where((a == 0) | (a == np.uint64(0xFFFFFFFFFFFFFFFF)), np.uint64(self_shard), own)
+    return own
 
 
 class TorchExchange:
@@ -81,14 +86,14 @@ class CudaShardOps:
             return a.to(device=self.dev, dtype=dtype).contiguous()
         return t.as_tensor(np.asarray(a), dtype=dtype, device=self.dev).contiguous()
 
-    def bucket(self, ids, P, N):
+    def bucket(self, ids, P, N, me):
         t = self.torch
         rows = ids.numel()
         sorted_ids = t.empty(rows, dtype=t.int64, device=self.dev)
         src = t.empty(rows, dtype=t.int32, device=self.dev)
         counts = t.empty(N, dtype=t.int64, device=self.dev)
         offs = t.empty(N + 1, dtype=t.int64, device=self.dev)
-        self.check(self.lib.eu_shard_bucket(self._stream(), ids.data_ptr(), rows, P, N, sorted_ids.data_ptr(),
+        self.check(self.lib.eu_shard_bucket(self._stream(), ids.data_ptr(), rows, P, N, me, sorted_ids.data_ptr(),
                                             src.data_ptr(), counts.data_ptr(), offs.data_ptr()))
         return sorted_ids, src, counts
 
@@ -102,15 +107,18 @@ class CudaShardOps:
         ty = t.empty(n * count, dtype=t.int32, device=self.dev)
         self.check(self.lib.eu_sample_neighbor(self._stream(), seeds.data_ptr(), n, et.ctypes.data, len(et), count, 0,
                                                ids.data_ptr(), w.data_ptr(), ty.data_ptr()))
-        return ids, w, ty
+        packed = t.empty(n * count * 2, dtype=t.int64, device=self.dev)
+        self.check(self.lib.eu_shard_pack_sample(self._stream(), ids.data_ptr(), w.data_ptr(), ty.data_ptr(), n * count,
+                                                 packed.data_ptr()))
+        return packed
 
-    def merge_sample(self, r_ids, r_w, r_t, src, rows, count, default_node):
+    def merge_sample(self, packed, src, rows, count, default_node):
         t = self.torch
         eng = t.empty(rows * count, dtype=t.int64, device=self.dev)
         o_ids = t.empty(rows * count, dtype=t.int64, device=self.dev)
         o_w = t.empty(rows * count, dtype=t.float32, device=self.dev)
         o_t = t.empty(rows * count, dtype=t.int32, device=self.dev)
-        self.check(self.lib.eu_shard_merge_sample(self._stream(), r_ids.data_ptr(), r_w.data_ptr(), r_t.data_ptr(),
+        self.check(self.lib.eu_shard_merge_sample(self._stream(), packed.data_ptr(),
                                                   src.data_ptr(), rows, count, default_node, eng.data_ptr(),
                                                   o_ids.data_ptr(), o_w.data_ptr(), o_t.data_ptr()))
         return eng, o_ids, o_w, o_t
@@ -158,20 +166,18 @@ class ShardedGraph:
     def _hop(self, frontier, etypes, count, default_node):
         ops, x = self.ops, self.xchg
         rows = frontier.numel()
-        sorted_ids, src, counts = ops.bucket(frontier, self.P, self.N)
+        sorted_ids, src, counts = ops.bucket(frontier, self.P, self.N, x.rank)
         send, recv = x.counts(counts)
         inbox = x.a2a(sorted_ids, send, recv)
-        r_ids, r_w, r_t = ops.sample_local(inbox, etypes, count)
-        b_ids = x.a2a(r_ids, recv, send, count)
-        b_w = x.a2a(r_w, recv, send, count)
-        b_t = x.a2a(r_t, recv, send, count)
-        return ops.merge_sample(b_ids, b_w, b_t, src, rows, count, default_node)
+        packed = ops.sample_local(inbox, etypes, count)            # 16-byte records {id, w | t << 32}
+        back = x.a2a(packed, recv, send, count * 2)
+        return ops.merge_sample(back, src, rows, count, default_node)
 
     def get_dense_feature(self, nodes, fid, dim):
         ops, x = self.ops, self.xchg
         ids = ops.to_dev(nodes, _i64(ops)).reshape(-1)
         rows = ids.numel()
-        sorted_ids, src, counts = ops.bucket(ids, self.P, self.N)
+        sorted_ids, src, counts = ops.bucket(ids, self.P, self.N, x.rank)
         send, recv = x.counts(counts)
         inbox = x.a2a(sorted_ids, send, recv)
         feats = ops.feature_local(inbox, fid, dim)

@@ -208,10 +208,13 @@ int eu_scatter_max_host(eu_ctx* c, const float* updates, int64_t D, const int32_
  * sorted order -> original row order + TF packing + engine-id frontier.  eu_shard_merge_rows: the same for
  * fixed-width f32 rows (features). */
 int eu_shard_bucket(eu_ctx* c, const int64_t* ids, int64_t rows, int32_t num_partitions, int32_t shard_num,
-                    int64_t* sorted_ids, int32_t* src_index, int64_t* counts, int64_t* offsets);
-int eu_shard_merge_sample(eu_ctx* c, const int64_t* reply_ids, const float* reply_w, const int32_t* reply_t,
-                          const int32_t* src_index, int64_t rows, int32_t count, int64_t default_node,
-                          int64_t* eng_ids, int64_t* out_ids, float* out_w, int32_t* out_t);
+                    int32_t self_shard, int64_t* sorted_ids, int32_t* src_index, int64_t* counts, int64_t* offsets);
+/* ids 0 and 2^64-1 (placeholder / default fill) exist nowhere and are routed to self_shard.
+ * eu_shard_pack_sample: (ids, w, t)[n] -> n 16-byte records {id, w | t << 32} so one all-to-all carries a reply;
+ * eu_shard_merge_sample consumes records in sorted order. */
+int eu_shard_pack_sample(eu_ctx* c, const int64_t* ids, const float* w, const int32_t* t, int64_t n, int64_t* packed);
+int eu_shard_merge_sample(eu_ctx* c, const int64_t* packed, const int32_t* src_index, int64_t rows, int32_t count,
+                          int64_t default_node, int64_t* eng_ids, int64_t* out_ids, float* out_w, int32_t* out_t);
 int eu_shard_merge_rows(eu_ctx* c, const float* rows_in, const int32_t* src_index, int64_t rows, int64_t D,
                         float* out);
 

@@ -12,6 +12,13 @@ import graphs
 from oracle import pyoracle as po
 
 
+def route(ids_u64, P, N, me):
+    """owner of each id; 0 and 2^64-1 stay on the requesting rank (they exist nowhere)."""
+    own = ((ids_u64 % np.uint64(P)) % np.uint64(N)).astype(np.int64)
+    own[(ids_u64 == 0) | (ids_u64 == np.uint64(0xFFFFFFFFFFFFFFFF))] = me
+    return own
+
+
 def partition(g, N, P=None):
     """Split a tests/graphs.py graph dict into N shard graph dicts (rows keep their relative order)."""
     P = P or N
@@ -51,10 +58,10 @@ class OracleShardOps:
         t = self.torch
         return (a if isinstance(a, t.Tensor) else t.as_tensor(np.asarray(a))).to(dtype).contiguous()
 
-    def bucket(self, ids, P, N):
+    def bucket(self, ids, P, N, me):
         t = self.torch
         a = ids.numpy().astype(np.uint64)
-        own = ((a % np.uint64(P)) % np.uint64(N)).astype(np.int64)
+        own = route(a, P, N, me)
         order = np.argsort(own, kind="stable")
         counts = np.bincount(own, minlength=N).astype(np.int64)
         return t.from_numpy(a[order].astype(np.int64)), t.from_numpy(order.astype(np.int32)), t.from_numpy(counts)
@@ -62,11 +69,17 @@ class OracleShardOps:
     def sample_local(self, seeds, etypes, count):
         t = self.torch
         ids, w, ty = self.og.op_sample_neighbor(seeds.numpy(), etypes, count, 0)
-        return t.from_numpy(ids.reshape(-1)), t.from_numpy(w.reshape(-1)), t.from_numpy(ty.reshape(-1))
+        lo = w.reshape(-1).view(np.uint32).astype(np.uint64) | (ty.reshape(-1).astype(np.uint32).astype(np.uint64) << np.uint64(32))
+        packed = np.stack([ids.reshape(-1), lo.view(np.int64)], axis=1).reshape(-1)
+        return t.from_numpy(np.ascontiguousarray(packed))
 
-    def merge_sample(self, r_ids, r_w, r_t, src, rows, count, default_node):
+    def merge_sample(self, packed, src, rows, count, default_node):
         t = self.torch
-        r_ids, r_w, r_t = r_ids.numpy().reshape(rows, count), r_w.numpy().reshape(rows, count), r_t.numpy().reshape(rows, count)
+        rec = packed.numpy().reshape(rows, count, 2)
+        r_ids = rec[:, :, 0]
+        lo = rec[:, :, 1].view(np.uint64)
+        r_w = (lo & np.uint64(0xFFFFFFFF)).astype(np.uint32).view(np.float32)
+        r_t = (lo >> np.uint64(32)).astype(np.uint32).view(np.int32)
         src = src.numpy()
         eng = np.zeros((rows, count), np.int64)
         eng[src] = r_ids
@@ -99,7 +112,7 @@ def simulate(shards, seeds_per_rank, ets, counts, shard_seeds, default_node=-1, 
     frontier = [np.asarray(x, np.int64) for x in seeds_per_rank]
     res = [([f.copy()], [], []) for f in frontier]
     for et, c in zip(ets, counts):
-        own = [((f.astype(np.uint64) % np.uint64(P)) % np.uint64(N)).astype(np.int64) for f in frontier]
+        own = [route(f.astype(np.uint64), P, N, r) for r, f in enumerate(frontier)]
         order = [np.argsort(o, kind="stable") for o in own]
         new_frontier = [np.zeros((len(f), c), np.int64) for f in frontier]
         packed = [[np.zeros((len(f), c), np.int64), np.zeros((len(f), c), np.float32), np.zeros((len(f), c), np.int32)] for f in frontier]

@@ -23,8 +23,9 @@ def test_bucket_and_merge_kernels_vs_numpy():
         ids[::5] = 0
         if rows > 3:
             ids[3] = -1
-        s_ids, src, counts = ops.bucket(ops.to_dev(ids, torch.int64), P, N)
-        own = owner_of(ids.astype(np.uint64), P, N).astype(np.int64)
+        me = N - 1
+        s_ids, src, counts = ops.bucket(ops.to_dev(ids, torch.int64), P, N, me)
+        own = owner_of(ids.astype(np.uint64), P, N, me).astype(np.int64)
         order = np.argsort(own, kind="stable")
         cases.eq(s_ids.cpu().numpy(), ids[order], "sorted ids rows=%d" % rows)
         cases.eq(src.cpu().numpy(), order.astype(np.int32), "src index")
@@ -36,8 +37,10 @@ def test_bucket_and_merge_kernels_vs_numpy():
         r_ids[::3, 0] = 0
         r_w = rs.rand(rows, c).astype(np.float32)
         r_t = rs.randint(0, 4, size=(rows, c)).astype(np.int32)
-        eng, o_ids, o_w, o_t = ops.merge_sample(ops.to_dev(r_ids.reshape(-1), torch.int64), ops.to_dev(r_w.reshape(-1), torch.float32),
-                                                 ops.to_dev(r_t.reshape(-1), torch.int32), src, rows, c, -9)
+        packed = torch.empty(rows * c * 2, dtype=torch.int64, device="cuda")
+        d_ids, d_w, d_t = ops.to_dev(r_ids.reshape(-1), torch.int64), ops.to_dev(r_w.reshape(-1), torch.float32), ops.to_dev(r_t.reshape(-1), torch.int32)
+        ops.check(ops.lib.eu_shard_pack_sample(ops._stream(), d_ids.data_ptr(), d_w.data_ptr(), d_t.data_ptr(), rows * c, packed.data_ptr()))
+        eng, o_ids, o_w, o_t = ops.merge_sample(packed, src, rows, c, -9)
         keep = r_ids[:, :1] != 0
         want = np.zeros((rows, c), np.int64); want[order] = r_ids
         cases.eq(eng.cpu().numpy().reshape(rows, c), want, "engine frontier")
