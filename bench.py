@@ -39,7 +39,9 @@ def parse():
     p.add_argument("--batch", type=int, default=1024)
     p.add_argument("--fanout", default="25,10")
     p.add_argument("--dim", type=int, default=128)
-    p.add_argument("--lanes", type=int, default=4, help="execution contexts (streams) with batches in flight")
+    p.add_argument("--lanes", type=int, default=2, help="execution contexts (streams) with launch groups in flight")
+    p.add_argument("--group", type=int, default=8, help="steps (batches) per launch group: each batch keeps its own engine and "
+                                                          "dedup scope (eu_sample_fanout_batched), only the kernel launches are shared")
     p.add_argument("--no-fuse", action="store_true", help="get_dense_feature + scatter_mean instead of the fused kernel")
     p.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph per step")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -112,16 +114,17 @@ class Lane:
         self.t = torch
         self.stream = torch.cuda.Stream()
         self.ctx = eb.Context(graph, args.rng, seed, self.stream.cuda_stream)
-        B, D = args.batch, args.dim
+        B, D, G = args.batch, args.dim, args.group
         dev = "cuda"
-        self.B, self.D, self.counts = B, D, counts
-        rows = B
-        self.n = [B]
+        self.B, self.D, self.G, self.counts = B, D, G, counts
+        self.ctx.set_engines(G, [seed * 1000 + b for b in range(G)])
+        rows = G * B                      # rows of one launch group = G batches
+        self.n = [rows]
         for c in counts:
             rows *= c
             self.n.append(rows)
         self.ctx.reserve(max(self.n))
-        self.d_seeds = torch.empty(B, dtype=torch.int64, device=dev)
+        self.d_seeds = torch.empty(G * B, dtype=torch.int64, device=dev)
         self.ids = [torch.empty(n, dtype=torch.int64, device=dev) for n in self.n[1:]]
         self.w = [torch.empty(n, dtype=torch.float32, device=dev) for n in self.n[1:]]
         self.ty = [torch.empty(n, dtype=torch.int32, device=dev) for n in self.n[1:]]
@@ -133,12 +136,12 @@ class Lane:
             self.hop_feat = [torch.empty((self.n[l + 1], D), dtype=torch.float32, device=dev) for l in range(L)]
             self.src = [torch.arange(self.n[l], dtype=torch.int32, device=dev).repeat_interleave(counts[l]) for l in range(L)]
         # host side of the e2e path
-        self.h_seeds = torch.empty(B, dtype=torch.int64).pin_memory()
+        self.h_seeds = torch.empty(G * B, dtype=torch.int64).pin_memory()
         self.h_ids = [torch.empty(n, dtype=torch.int64).pin_memory() for n in self.n[1:]]
         self.h_x = [torch.empty((self.n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
         self.h_agg = [torch.empty((self.n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
-        self.h2d = 8 * B
-        self.d2h = sum(8 * n for n in self.n[1:]) + 2 * sum(4 * self.n[l] * D for l in range(L))
+        self.h2d = 8 * B                  # per step
+        self.d2h = (sum(8 * n for n in self.n[1:]) + 2 * sum(4 * self.n[l] * D for l in range(L))) // G
 
 
 def make_step(lib, C, args, counts, et):
@@ -149,9 +152,9 @@ def make_step(lib, C, args, counts, et):
 
     def step(lane, seeds_dev):
         h = lane.ctx._h
-        rc = lib.eu_sample_fanout(h, seeds_dev.data_ptr(), lane.B, et.ctypes.data, et.shape[1], cs.ctypes.data, L, -1,
-                                  P(*[x.data_ptr() for x in lane.ids]), P(*[x.data_ptr() for x in lane.w]),
-                                  P(*[x.data_ptr() for x in lane.ty]))
+        rc = lib.eu_sample_fanout_batched(h, seeds_dev.data_ptr(), lane.G, lane.B, et.ctypes.data, et.shape[1], cs.ctypes.data, L, -1,
+                                          P(*[x.data_ptr() for x in lane.ids]), P(*[x.data_ptr() for x in lane.w]),
+                                          P(*[x.data_ptr() for x in lane.ty]))
         for l in range(L):
             src_ids = seeds_dev if l == 0 else lane.ids[l - 1]
             rc |= lib.eu_get_dense_feature(h, src_ids.data_ptr(), lane.n[l], 0, lane.D, lane.x[l].data_ptr())
@@ -182,6 +185,9 @@ def run_ours(args):
     lib = _lib.load()
     counts = [int(x) for x in args.fanout.split(",")]
     et = np.zeros((len(counts), 1), np.int32)
+    import math
+    args.group = max(1, math.gcd(args.group, args.steps))   # exactly K steps are timed: groups must tile K
+    G = args.group
     t0 = time.time()
     graph = eb.Graph.rmat(args.nodes, args.edges, feat_dim=args.dim, device=local)
     torch.cuda.synchronize()
@@ -201,7 +207,7 @@ def run_ours(args):
             ln.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(ln.graph, stream=ln.stream):
                 raw_step(ln, ln.d_seeds)
-            per_step_launches = lib.eu_launch_count() - l_before
+            per_step_launches = (lib.eu_launch_count() - l_before) / G
 
     def step(ln, seeds_dev):
         if use_graphs:
@@ -211,9 +217,15 @@ def run_ours(args):
         else:
             raw_step(ln, seeds_dev)
     nb = args.warmup + args.steps
+    n_seed_batches = -(-max(nb, 64) // G) * G
     host_seeds = np.stack([np.random.RandomState(1000 + i).randint(1, args.nodes + 1, size=args.batch)
-                           for i in range(max(nb, 64))]).astype(np.int64)
+                           for i in range(n_seed_batches)]).astype(np.int64)
     dev_seeds = torch.from_numpy(host_seeds).cuda()
+    n_groups_avail = n_seed_batches // G
+
+    def group_seeds(first, i):
+        g0 = ((first // G + i) % n_groups_avail) * G
+        return g0, dev_seeds[g0:g0 + G].reshape(-1)
     bts = step_bytes(args.batch, counts, args.dim)
     main = torch.cuda.current_stream()
 
@@ -225,13 +237,14 @@ def run_ours(args):
         ev0.record(main)
         for ln in lanes:
             ln.stream.wait_event(ev0)
-        for i in range(n_steps):
+        for i in range(-(-n_steps // G)):     # launch groups of G steps
             ln = lanes[i % len(lanes)]
+            g0, sd = group_seeds(first, i)
             with torch.cuda.stream(ln.stream):
                 if e2e:
-                    # the lane's pinned buffers are reused every len(lanes) steps
+                    # the lane's pinned buffers are reused every len(lanes) groups
                     ln.stream.synchronize() if i >= len(lanes) else None
-                    ln.h_seeds.copy_(torch.from_numpy(host_seeds[(first + i) % len(host_seeds)]))
+                    ln.h_seeds.copy_(torch.from_numpy(host_seeds[g0:g0 + G].reshape(-1)))
                     ln.d_seeds.copy_(ln.h_seeds, non_blocking=True)
                     step(ln, ln.d_seeds)
                     for l in range(len(counts)):
@@ -239,14 +252,14 @@ def run_ours(args):
                         ln.h_x[l].copy_(ln.x[l], non_blocking=True)
                         ln.h_agg[l].copy_(ln.agg[l], non_blocking=True)
                 else:
-                    step(ln, dev_seeds[(first + i) % len(host_seeds)])
+                    step(ln, sd)
         for ln in lanes:
             main.wait_stream(ln.stream)
         ev1.record(main)
         torch.cuda.synchronize()
         return ev0.elapsed_time(ev1)
 
-    run(args.warmup, 0, False)
+    run(-(-args.warmup // G) * G, 0, False)
     clocks = Clocks(local)
     clocks.start()
     time.sleep(0.3)
@@ -256,7 +269,7 @@ def run_ours(args):
     w1 = time.time()
     launches = lib.eu_launch_count() - l0
     if use_graphs:
-        launches = per_step_launches * args.steps  # kernels of ours inside the replayed graphs
+        launches = int(per_step_launches * args.steps)  # kernels of ours inside the replayed graphs
     clk = clocks.stop(w0, w1)
     run(min(args.warmup, 8), 0, True)
     ms_e2e = run(args.steps, args.warmup, True)
@@ -273,7 +286,7 @@ def run_ours(args):
     lib.eu_ctx_profile(ln.ctx._h, 1)
     with torch.cuda.stream(ln.stream):
         for it in range(args.breakdown_iters):
-            raw_step(ln, dev_seeds[it % len(host_seeds)])
+            raw_step(ln, group_seeds(0, it)[1])
             for l in range(Lh):
                 valid_edges[l] += int((ln.ids[l] != -1).sum().item())
     buf = ctypes.create_string_buffer(1 << 16)
@@ -282,8 +295,8 @@ def run_ours(args):
     kernels = []
     for line in buf.value.decode().strip().splitlines():
         nm, rows, n, ms_tot = line.split(",")
-        kernels.append({"kernel": nm, "rows": int(rows), "launches_per_step": int(n) / args.breakdown_iters,
-                        "ms_per_launch": float(ms_tot) / int(n), "ms_per_step": float(ms_tot) / args.breakdown_iters})
+        kernels.append({"kernel": nm, "rows": int(rows), "launches_per_step": int(n) / (args.breakdown_iters * G),
+                        "ms_per_launch": float(ms_tot) / int(n), "ms_per_step": float(ms_tot) / (args.breakdown_iters * G)})
     kernels.sort(key=lambda k: -k["ms_per_step"])
     phases = {"%s[rows=%d]" % (k["kernel"], k["rows"]): round(k["ms_per_step"], 5) for k in kernels}
     valid_frac = [valid_edges[l] / (args.breakdown_iters * ln.n[l + 1]) for l in range(Lh)]
@@ -333,6 +346,7 @@ def run_ours(args):
         agg_bytes += ln.n[l] * counts[l] * 8 + valid_frac[l] * ln.n[l] * counts[l] * 4 * D + ln.n[l] * 4 * D
         vf = 1.0 if l == 0 else valid_frac[l - 1]
         agg_bytes += ln.n[l] * 8 + vf * ln.n[l] * 4 * D + ln.n[l] * 4 * D
+    agg_bytes /= G   # ln.n counts the rows of a whole launch group
     out = {
         "metric": "sampled_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -340,9 +354,9 @@ def run_ours(args):
         "config": {"workload": "BASELINE configs[1]: RMAT %dM nodes/%dM edges in HBM, 2-hop sample_fanout %s batch=%d, "
                                "GraphSAGE-mean aggregation, feat_dim=%d" % (args.nodes // 10**6, args.edges // 10**6, counts, args.batch, args.dim),
                    "nodes": args.nodes, "edges": args.edges, "batch": args.batch, "fanout": counts, "feat_dim": args.dim,
-                   "rng": args.rng, "lanes_in_flight": args.lanes, "cuda_graphs": use_graphs, "fused_aggregation": not args.no_fuse,
+                   "rng": args.rng, "lanes_in_flight": args.lanes, "steps_per_launch_group": G, "cuda_graphs": use_graphs, "fused_aggregation": not args.no_fuse,
                    "l2_policy": "inputs larger than L2 (%.1f GB graph, random seeds per step)" % (graph.hbm_bytes / 1e9),
-                   "parallelism": "1 GPU, %d streams" % args.lanes},
+                   "parallelism": "1 GPU, %d streams x groups of %d independent batches per launch" % (args.lanes, G)},
         "agg_feat_gbs": agg_bytes * args.steps / (ms * 1e-3) / 1e9,
         "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": lanes[0].h2d, "d2h_bytes_per_step": lanes[0].d2h,
                 "ms_per_step": ms_e2e / args.steps,
@@ -433,7 +447,7 @@ def run_sharded(args, world, rank, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    run(args.warmup, 0, False)
+    run(-(-args.warmup // G) * G, 0, False)
     clocks = Clocks(local)
     clocks.start()
     time.sleep(0.3)

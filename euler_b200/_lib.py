@@ -56,6 +56,7 @@ SIGNATURES = {
     "eu_ctx_destroy": (C.c_int, [_P]),
     "eu_ctx_set_stream": (C.c_int, [_P, _P]),
     "eu_ctx_seed": (C.c_int, [_P, _U64]),
+    "eu_ctx_set_engines": (C.c_int, [_P, _I32, _P]),
     "eu_ctx_reserve": (C.c_int, [_P, _I64]),
     "eu_ctx_sync": (C.c_int, [_P]),
     "eu_ctx_draws": (C.c_int, [_P, C.POINTER(_U64)]),
@@ -64,6 +65,7 @@ SIGNATURES = {
     "eu_sample_neighbor": (C.c_int, [_P, _P, _I64, _P, _I32, _I32, _I64, _P, _P, _P]),
     "eu_sample_neighbor_host": (C.c_int, [_P, _P, _I64, _P, _I32, _I32, _I64, _P, _P, _P]),
     "eu_sample_fanout": (C.c_int, [_P, _P, _I64, _P, _I32, _P, _I32, _I64, _P, _P, _P]),
+    "eu_sample_fanout_batched": (C.c_int, [_P, _P, _I32, _I64, _P, _I32, _P, _I32, _I64, _P, _P, _P]),
     "eu_sample_fanout_host": (C.c_int, [_P, _P, _I64, _P, _I32, _P, _I32, _I64, _P, _P, _P]),
     "eu_sample_node": (C.c_int, [_P, _I32, _P, _I32, _P]),
     "eu_sample_node_host": (C.c_int, [_P, _I32, _P, _I32, _P]),

@@ -12,13 +12,20 @@
 
 namespace eu {
 
-__global__ void k_seed(EuRngState* r, unsigned long long seed) {
+// engine e is seeded with seeds[e] (or seed0 + e when seeds == nullptr)
+__global__ void k_seed(EuRngState* rs, int n, unsigned long long seed0, const unsigned long long* seeds) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const unsigned long long seed = seeds ? seeds[e] : seed0 + (unsigned long long)e;
+  EuRngState* r = rs + e;
   // std::minstd_rand0::seed(s): x = s mod m, 1 if that is 0
   unsigned long long x = seed % 2147483647ull;
   r->x = x == 0 ? 1u : (uint32_t)x;
+  r->x_prev = r->x;
   r->draws = 0;
   r->calls = 0;
   r->blocks_done = 0;
+  r->key = seed * 0x9E3779B97F4A7C15ull;
 }
 
 template <typename T>
@@ -33,28 +40,29 @@ static int regrow(T** p, int64_t count) {
   return EU_OK;
 }
 
-int ctx_reserve(eu_ctx* c, int64_t rows) {
-  if (rows <= c->cap_rows) return EU_OK;
-  // growing while the stream still uses the old buffers would be a race
-  EU_CUDA(cudaStreamSynchronize(c->stream));
-  int64_t cap = 64;
-  while (cap < rows * 2) cap <<= 1;
+int ctx_reserve(eu_ctx* c, int64_t rows, int64_t table_slots) {
   int rc;
-  if ((rc = regrow(&c->d_dedup, 2 * (cap + 1)))) return rc;  // two tables: hop l uses table l & 1
-  c->dedup_cap = cap;
-  // all-free table: key 0, row = kEmptyRow (see hop() invariant)
-  for (int64_t off = 0; off < 2 * (cap + 1); off += (int64_t)1 << 20) {
-    int64_t n = std::min<int64_t>((int64_t)1 << 20, 2 * (cap + 1) - off);
-    EU_CUDA(cudaMemset2DAsync(&c->d_dedup[off].key, sizeof(HashSlot), 0x00, 8, (size_t)n, c->stream));
-    EU_CUDA(cudaMemset2DAsync(&c->d_dedup[off].row, sizeof(HashSlot), 0xFF, 8, (size_t)n, c->stream));
+  if (table_slots > c->tab_set_slots) {
+    EU_CUDA(cudaStreamSynchronize(c->stream));  // growing while the stream still uses the old buffers would be a race
+    const int64_t slots = table_slots + 64;
+    if ((rc = regrow(&c->d_dedup, 2 * slots))) return rc;  // two table sets: hop l uses set l & 1
+    c->tab_set_slots = slots;
+    // all-free tables: key 0, row = kEmptyRow (see hop() invariant)
+    for (int64_t off = 0; off < 2 * slots; off += (int64_t)1 << 20) {
+      int64_t n = std::min<int64_t>((int64_t)1 << 20, 2 * slots - off);
+      EU_CUDA(cudaMemset2DAsync(&c->d_dedup[off].key, sizeof(HashSlot), 0x00, 8, (size_t)n, c->stream));
+      EU_CUDA(cudaMemset2DAsync(&c->d_dedup[off].row, sizeof(HashSlot), 0xFF, 8, (size_t)n, c->stream));
+    }
   }
+  if (rows <= c->cap_rows) return EU_OK;
+  EU_CUDA(cudaStreamSynchronize(c->stream));
   if ((rc = regrow(&c->d_first, rows))) return rc;
   if ((rc = regrow(&c->d_rowof, rows))) return rc;
   if ((rc = regrow(&c->d_elig, rows))) return rc;
   if ((rc = regrow(&c->d_state, rows))) return rc;
   if ((rc = regrow(&c->d_emask, rows / 32 + 2))) return rc;
   if ((rc = regrow(&c->d_woff, rows / 32 + 2))) return rc;
-  if ((rc = regrow(&c->d_blkpre, rows / 256 + 2))) return rc;
+  if ((rc = regrow(&c->d_blkpre, rows / 256 + 66))) return rc;
   if ((rc = regrow(&c->d_front[0], rows))) return rc;
   if ((rc = regrow(&c->d_front[1], rows))) return rc;
   c->cap_rows = rows;
@@ -116,7 +124,7 @@ int eu_ctx_create(eu_graph* g, eu_rng_kind rng, uint64_t seed, void* stream, eu_
   c->g = g; c->rng = rng; c->seed = seed; c->stream = (cudaStream_t)stream;
   cudaError_t e = cudaMalloc(&c->d_rng, sizeof(EuRngState));
   if (e != cudaSuccess) { set_error("cudaMalloc rng -> %s", cudaGetErrorString(e)); delete c; return EU_ERR_CUDA; }
-  k_seed<<<1, 1, 0, c->stream>>>(c->d_rng, seed);
+  k_seed<<<1, 64, 0, c->stream>>>(c->d_rng, 1, seed, nullptr);
   g_launches++;
   *out = c;
   return EU_OK;
@@ -144,15 +152,39 @@ int eu_ctx_seed(eu_ctx* c, uint64_t seed) {
   if (!c) { set_error("null ctx"); return EU_ERR_INVALID; }
   EU_CUDA(cudaSetDevice(c->g->device));
   c->seed = seed;
-  k_seed<<<1, 1, 0, c->stream>>>(c->d_rng, seed);
+  k_seed<<<1, 64, 0, c->stream>>>(c->d_rng, c->n_eng, seed, nullptr);
   EU_LAUNCHED();
+  return EU_OK;
+}
+
+// n engines, engine e seeded with seeds[e] (seeds == NULL: seed + e).  Batch b of a *_batched call uses engine b.
+int eu_ctx_set_engines(eu_ctx* c, int32_t n, const uint64_t* seeds) {
+  if (!c || n < 1 || n > 64) { set_error("eu_ctx_set_engines: 1..64 engines"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  EU_CUDA(cudaStreamSynchronize(c->stream));
+  EuRngState* r = nullptr;
+  EU_CUDA(cudaMalloc(&r, sizeof(EuRngState) * n));
+  unsigned long long* d_seeds = nullptr;
+  if (seeds) {
+    EU_CUDA(cudaMalloc(&d_seeds, sizeof(unsigned long long) * n));
+    EU_CUDA(cudaMemcpy(d_seeds, seeds, sizeof(unsigned long long) * n, cudaMemcpyHostToDevice));
+    c->seed = seeds[0];
+  }
+  cudaFree(c->d_rng);
+  c->d_rng = r;
+  c->n_eng = n;
+  k_seed<<<1, 64, 0, c->stream>>>(c->d_rng, n, c->seed, d_seeds);
+  EU_LAUNCHED();
+  EU_CUDA(cudaStreamSynchronize(c->stream));
+  if (d_seeds) cudaFree(d_seeds);
   return EU_OK;
 }
 
 int eu_ctx_reserve(eu_ctx* c, int64_t max_rows) {
   if (!c || max_rows < 0) { set_error("eu_ctx_reserve: bad argument"); return EU_ERR_INVALID; }
   EU_CUDA(cudaSetDevice(c->g->device));
-  int rc = ctx_reserve(c, max_rows);
+  const int nb = c->n_eng;
+  int rc = ctx_reserve(c, max_rows + 256 * nb, 4 * max_rows + 65 * nb);
   if (rc) return rc;
   return ctx_misc(c, 256 + 4 * max_rows);
 }

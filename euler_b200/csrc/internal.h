@@ -89,6 +89,7 @@ struct EuRngState {
   unsigned long long calls;   // philox: hop counter (salt)
   unsigned int blocks_done;   // last-block-done ticket
   unsigned int pad2;
+  unsigned long long key;     // philox: per-engine key
 };
 
 struct eu_ctx {
@@ -96,11 +97,12 @@ struct eu_ctx {
   eu_rng_kind rng = EU_RNG_MINSTD;
   uint64_t seed = 0;
   cudaStream_t stream = nullptr;
-  EuRngState* d_rng = nullptr;
-  // scratch (device), sized for `cap_rows` rows of the widest hop
+  EuRngState* d_rng = nullptr;       // [n_eng] engines; batch b of a batched call uses engine b, plain ops engine 0
+  int n_eng = 1;
+  // scratch (device), sized for `cap_rows` (padded) rows of the widest hop
   int64_t cap_rows = 0;
-  eu::HashSlot* d_dedup = nullptr;   // capacity = dedup_cap slots
-  int64_t dedup_cap = 0;
+  eu::HashSlot* d_dedup = nullptr;   // two table sets of tab_set_slots slots each
+  int64_t tab_set_slots = 0;
   int32_t* d_first = nullptr;        // [rows] first occurrence index of each seed
   int64_t* d_rowof = nullptr;        // [rows] graph row (valid where first==i), -1 if absent
   uint8_t* d_elig = nullptr;         // [rows]
@@ -138,7 +140,9 @@ struct EuProfScope {
 };
 
 namespace eu {
-int ctx_reserve(eu_ctx* c, int64_t rows);
+int ctx_reserve(eu_ctx* c, int64_t rows, int64_t table_slots);
+int64_t hop_scratch_rows(int nb, int64_t rows_b);
+int64_t hop_table_slots(int nb, int64_t rows_b);
 int ctx_misc(eu_ctx* c, int64_t bytes);
 int ctx_stage(eu_ctx* c, int64_t host_bytes, int64_t dev_bytes);
 int graph_build_sampler(eu_graph* g);
@@ -147,5 +151,5 @@ int launch_state_scan(eu_ctx* c, int64_t rows, unsigned long long uniforms_per_r
 // null) and TF-packed outputs (may be null)
 int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows, const int32_t* etypes, int32_t K,
         int32_t count, int64_t default_node, unsigned long long* eng_ids, int64_t* out_ids,
-        float* out_w, int32_t* out_t, int hop_index, bool pre_inserted, bool insert_next);
+        float* out_w, int32_t* out_t, int hop_index, bool pre_inserted, bool insert_next, int nb);
 }  // namespace eu

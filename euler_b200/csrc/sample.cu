@@ -17,6 +17,8 @@
 // engine state it would have had in the serial loop, (3) lanes jumping ahead A^(2*k*lane).
 // Duplicate seeds re-derive the identical row from the first occurrence's state, so there is no
 // gather pass and the frontier (engine ids) stays in HBM between hops.
+#include <algorithm>
+
 #include "internal.h"
 
 namespace eu {
@@ -26,12 +28,18 @@ struct ETypes {
   int32_t v[EU_MAX_ETYPES];
 };
 
-// ---------------------------------------------------------------------------- 1. seed dedup
-__global__ void k_dedup_clear(HashSlot* tab, int64_t cap) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i < cap) { tab[i].key = 0; tab[i].row = kEmptyRow; }
-}
+// A launch covers `nb` independent batches of `rows_b` seeds each (nb = 1 for the plain ops).  Batch b has
+// its own engine (EuRngState[b]), its own dedup scope (table region b) and its own serial draw order, i.e.
+// it is exactly one reference op call on one client thread; batching only shares the kernel launches.
+struct Geom {
+  int32_t nb;        // batches
+  int32_t nblk_b;    // 256-row blocks per batch
+  int64_t rows_b;    // seeds per batch (dense in the seed / output arrays)
+  int64_t rows_pad;  // nblk_b * 256: stride of the per-row scratch arrays
+  int64_t cap_b;     // dedup slots per batch (power of two) ; region stride = cap_b + 1
+};
 
+// ---------------------------------------------------------------------------- 1. seed dedup
 // tab[h] = {id+1, min index}.  key 0 = free.
 __device__ __forceinline__ void dedup_insert_one(HashSlot* tab, unsigned long long mask, unsigned long long id,
                                                  int64_t i) {
@@ -51,17 +59,19 @@ __device__ __forceinline__ void dedup_insert_one(HashSlot* tab, unsigned long lo
   }
 }
 
-__global__ void k_dedup_insert(HashSlot* tab, unsigned long long mask,
-                               const unsigned long long* __restrict__ seeds, int64_t rows) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= rows) return;
-  unsigned long long id = seeds[i];
-  // Warp-aggregate: frontiers are full of runs of equal ids (a default row is `count` zeros, hubs
-  // repeat), and equal ids hammer one slot.  The lowest lane of each equal-id group carries the
-  // group's minimum index, so only it touches the table.
-  const unsigned peers = __match_any_sync(__activemask(), id);
+__global__ void k_dedup_insert(HashSlot* tabs, Geom gm, const unsigned long long* __restrict__ seeds) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= gm.nb * gm.rows_b) return;
+  const int b = (int)(i / gm.rows_b);
+  const int64_t li = i - b * gm.rows_b;
+  const unsigned long long id = seeds[i];
+  // Warp-aggregate: frontiers are full of runs of equal ids (a default row is `count` zeros, hubs repeat)
+  // and equal ids hammer one slot.  The lowest lane of each (batch, id) group carries the group's minimum
+  // index, so only it touches the table.
+  const unsigned act = __activemask();
+  const unsigned peers = __match_any_sync(act, id) & __match_any_sync(act, b);
   if ((threadIdx.x & 31) != __ffs(peers) - 1) return;
-  dedup_insert_one(tab, mask, id, i);
+  dedup_insert_one(tabs + (int64_t)b * (gm.cap_b + 1), (unsigned long long)gm.cap_b - 1, id, li);
 }
 
 __device__ __forceinline__ int64_t dedup_first(const HashSlot* tab, unsigned long long mask,
@@ -109,57 +119,62 @@ __device__ __forceinline__ bool row_eligible(const DevGraph& g, int64_t row, con
 
 // ---------------------------------------------------------------------------- 2. prepare
 // Per row: first occurrence (ID_UNIQUE), graph row and eligibility of first occurrences.  The number
-// of ELIGIBLE FIRST-OCCURRENCE rows before row i -- its position in the reference's serial draw
-// order -- is kept as a 3-level count: emask[i/32] (ballot), woff[i/32] (count in earlier warps of
-// the block), blkpre[i/256] (count in earlier blocks; exclusive prefix written by the last block to
-// finish, which also advances the ctx engine by total * draws_per_row uniforms).
+// of ELIGIBLE FIRST-OCCURRENCE rows before row i of its batch -- its position in the reference's serial
+// draw order -- is kept as a 3-level count: emask[ii/32] (ballot), woff[ii/32] (count in earlier warps of
+// the block), blkpre[b][ii/256] (count in earlier blocks of the batch; exclusive prefix written by the last
+// block of the batch to finish, which also advances that batch's engine by total * draws_per_row uniforms).
+// grid = (nblk_b, nb); ii = b * rows_pad + li indexes the scratch arrays.
 static constexpr int kPrepBlock = 256;
 
-__global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSlot* tab, unsigned long long mask,
-                                                        const unsigned long long* __restrict__ seeds, int64_t rows,
+__global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSlot* tabs, Geom gm,
+                                                        const unsigned long long* __restrict__ seeds,
                                                         ETypes et, int mode, uint32_t F, unsigned long long draws_per_row,
                                                         int32_t* first, int64_t* rowof, uint32_t* emask, uint32_t* woff,
-                                                        uint32_t* blkpre, EuRngState* rng) {
+                                                        uint32_t* blkpre, EuRngState* rngs) {
   __shared__ uint32_t s_w[kPrepBlock / 32];
   __shared__ bool s_last;
-  const int64_t i = blockIdx.x * (int64_t)kPrepBlock + threadIdx.x;
+  const int b = blockIdx.y;
+  const int64_t li = blockIdx.x * (int64_t)kPrepBlock + threadIdx.x;
+  const int64_t ii = b * gm.rows_pad + li;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  EuRngState* rng = rngs + b;
   bool e = false;
-  if (i < rows) {
-    const unsigned long long id = seeds[i];
-    const int64_t f = dedup_first(tab, mask, id);
-    first[i] = (int32_t)f;
-    if (f == i) {
+  if (li < gm.rows_b) {
+    const unsigned long long id = seeds[b * gm.rows_b + li];
+    const int64_t f = dedup_first(tabs + (int64_t)b * (gm.cap_b + 1), (unsigned long long)gm.cap_b - 1, id);
+    first[ii] = (int32_t)f;
+    if (f == li) {
       const int64_t row = lookup_row(g, id);
-      rowof[i] = row;
+      rowof[ii] = row;
       e = row_eligible(g, row, et, mode);
     }
   }
   const uint32_t m = __ballot_sync(0xffffffffu, e);
   if (lane == 0) s_w[wid] = __popc(m);
   __syncthreads();
-  if (lane == 0 && i < rows) {
+  if (lane == 0) {  // rows_pad is a multiple of 256: every group of the block exists in the scratch arrays
     uint32_t off = 0;
     for (int k = 0; k < wid; ++k) off += s_w[k];
-    emask[i >> 5] = m;
-    woff[i >> 5] = off;
+    emask[ii >> 5] = m;
+    woff[ii >> 5] = off;
   }
+  uint32_t* bp = blkpre + (int64_t)b * gm.nblk_b;
   if (threadIdx.x == 0) {
     uint32_t tot = 0;
     for (int k = 0; k < kPrepBlock / 32; ++k) tot += s_w[k];
-    blkpre[blockIdx.x] = tot;
+    bp[blockIdx.x] = tot;
     __threadfence();
     s_last = atomicAdd(&rng->blocks_done, 1u) == gridDim.x - 1;
   }
   __syncthreads();
   if (!s_last) return;
-  // last block: exclusive prefix over the per-block counts, in place
+  // last block of this batch: exclusive prefix over the batch's per-block counts, in place
   __threadfence();
   __shared__ uint32_t s_scan[kPrepBlock];
   uint32_t carry = 0;
   for (uint32_t base = 0; base < gridDim.x; base += kPrepBlock) {
-    const uint32_t b = base + threadIdx.x;
-    const uint32_t v = b < gridDim.x ? __ldcg(blkpre + b) : 0u;  // written by other blocks: read at L2
+    const uint32_t k = base + threadIdx.x;
+    const uint32_t v = k < gridDim.x ? __ldcg(bp + k) : 0u;  // written by other blocks: read at L2
     s_scan[threadIdx.x] = v;
     __syncthreads();
     for (int off = 1; off < kPrepBlock; off <<= 1) {
@@ -168,7 +183,7 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSl
       s_scan[threadIdx.x] += t;
       __syncthreads();
     }
-    if (b < gridDim.x) blkpre[b] = carry + s_scan[threadIdx.x] - v;
+    if (k < gridDim.x) bp[k] = carry + s_scan[threadIdx.x] - v;
     carry += s_scan[kPrepBlock - 1];
     __syncthreads();
   }
@@ -183,8 +198,8 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSl
   }
 }
 
-// ---------------------------------------------------------------------------- 3. engine-state scan
-// state_before[i] = x * F^(#eligible first-occurrence rows before i), F = A^(uniforms per row * 2).
+// ---------------------------------------------------------------------------- 3. engine-state scan (walks)
+// state_before[i] = x * F^(#eligible rows before i), F = A^(uniforms per row * 2).
 // One block; thread t owns a contiguous chunk.  Also advances the ctx engine.
 __global__ void __launch_bounds__(1024) k_state_scan(const uint8_t* __restrict__ elig, int64_t rows,
                                                      uint32_t F, unsigned long long draws_per_row,
@@ -223,30 +238,31 @@ __global__ void __launch_bounds__(1024) k_state_scan(const uint8_t* __restrict__
 
 // ---------------------------------------------------------------------------- 4. sample
 struct SampleArgs {
-  const unsigned long long* seeds;  // [rows]
-  int64_t rows;
+  const unsigned long long* seeds;  // [nb*rows_b]
+  Geom gm;
   int32_t count;
   long long default_node;
   ETypes et;
   int mode;
-  // minstd: serial-stream position of a first-occurrence row f =
-  //   blkpre[f/256] + woff[f/32] + popc(emask[f/32] & lanes_below(f%32));  engine state = x_prev * F^pos
+  // minstd: serial-stream position of a first-occurrence row f of batch b =
+  //   blkpre[b][f/256] + woff[ff/32] + popc(emask[ff/32] & lanes_below(f%32)), ff = b*rows_pad + f;
+  //   engine state = rng[b].x_prev * F^pos
   const int32_t* first;
   const int64_t* rowof;
   const uint32_t* emask;
   const uint32_t* woff;
   const uint32_t* blkpre;
   uint32_t fpow2[32];           // F^(2^k) mod M
-  HashSlot* clear_tab;          // dedup table of THIS hop, cleared here for the next user
+  HashSlot* clear_tab;          // dedup tables of THIS hop (all batches), cleared here for the next user
   int64_t clear_n;
-  HashSlot* next_tab;           // dedup table of the NEXT hop: this hop's engine ids are its seeds (or null)
-  unsigned long long next_mask;
+  HashSlot* next_tabs;          // dedup tables of the NEXT hop: this hop's engine ids are its seeds (or null)
+  int64_t next_cap_b;
   // philox
   unsigned long long key;
-  const EuRngState* rng;
+  const EuRngState* rngs;
   // outputs
-  unsigned long long* eng_ids;  // [rows*count] engine ids (0 placeholder) = next frontier; may be null
-  long long* out_ids;           // [rows*count] TF-packed; may be null
+  unsigned long long* eng_ids;  // [nb*rows_b*count] engine ids (0 placeholder) = next frontier; may be null
+  long long* out_ids;           // [nb*rows_b*count] TF-packed; may be null
   float* out_w;
   int32_t* out_t;
 };
@@ -270,14 +286,20 @@ template <bool PHILOX>
 __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (!PHILOX) {  // k_prepare (the only reader of this hop's dedup table) has finished: wipe it
+  if (!PHILOX) {  // k_prepare (the only reader of this hop's dedup tables) has finished: wipe them
     for (int64_t s = gtid; s < a.clear_n; s += (int64_t)gridDim.x * blockDim.x) { a.clear_tab[s].key = 0; a.clear_tab[s].row = kEmptyRow; }
   }
   const int64_t w = gtid >> 5;
-  if (w >= a.rows) return;
+  if (w >= a.gm.nb * a.gm.rows_b) return;
+  const int bidx = (int)(w / a.gm.rows_b);
+  const int64_t li = w - bidx * a.gm.rows_b;
   const int32_t count = a.count;
   const int32_t T = g.T;
   const int64_t obase = w * (int64_t)count;
+  const EuRngState* rng = a.rngs + bidx;
+  HashSlot* ntab = a.next_tabs ? a.next_tabs + (int64_t)bidx * (a.next_cap_b + 1) : nullptr;
+  const unsigned long long nmask = (unsigned long long)a.next_cap_b - 1;
+  const int64_t nbase = li * (int64_t)count;  // index of this row's first id inside the next hop's batch
 
   int64_t row;
   bool ok;
@@ -288,13 +310,15 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
     row = lookup_row(g, seed_id);
     ok = row_eligible(g, row, a.et, a.mode);
   } else {
-    const int32_t f = a.first[w];
-    const uint32_t m = a.emask[f >> 5];
+    const int64_t ib = bidx * a.gm.rows_pad;
+    const int32_t f = a.first[ib + li];
+    const uint32_t m = a.emask[(ib + f) >> 5];
     ok = (m >> (f & 31)) & 1u;
     if (ok) {
-      row = a.rowof[f];
-      uint32_t pos = a.blkpre[f / kPrepBlock] + a.woff[f >> 5] + __popc(m & ((1u << (f & 31)) - 1u));
-      st = a.rng->x_prev;
+      row = a.rowof[ib + f];
+      uint32_t pos = a.blkpre[(int64_t)bidx * a.gm.nblk_b + f / kPrepBlock] + a.woff[(ib + f) >> 5] +
+                     __popc(m & ((1u << (f & 31)) - 1u));
+      st = rng->x_prev;
 #pragma unroll 1
       for (int k = 0; pos; ++k, pos >>= 1)
         if (pos & 1u) st = modmul(st, a.fpow2[k]);
@@ -307,7 +331,7 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
       if (a.eng_ids) a.eng_ids[obase + j] = 0ull;
       if (a.out_ids) { a.out_ids[obase + j] = a.default_node; a.out_w[obase + j] = 0.f; a.out_t[obase + j] = -1; }
     }
-    if (!PHILOX && a.next_tab && lane == 0) dedup_insert_one(a.next_tab, a.next_mask, 0ull, obase);  // `count` zeros
+    if (!PHILOX && ntab && lane == 0) dedup_insert_one(ntab, nmask, 0ull, nbase);  // `count` zeros
     return;
   }
 
@@ -355,7 +379,8 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
     x = modmul(st, modpow_a_small(2u * upd * (uint32_t)lane));
     stride = modpow_a_small(2u * upd * 32u);
   }
-  const uint32_t salt = PHILOX ? (uint32_t)a.rng->calls : 0u;
+  const uint32_t salt = PHILOX ? (uint32_t)rng->calls : 0u;
+  const unsigned long long pkey = PHILOX ? a.key ^ rng->key : 0ull;
 
   bool keep = true;
   bool bad = false;
@@ -364,7 +389,7 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
     const bool active = j < count;
     double u_t = 0.0, u_n = 0.0;
     if (PHILOX) {
-      philox_uniform2(seed_id, (uint32_t)j, salt, a.key, u_t, u_n);
+      philox_uniform2(seed_id, (uint32_t)j, salt, pkey, u_t, u_n);
     } else {
       uint32_t xs = x;
       if (upd == 2u) u_t = minstd_uniform(xs);
@@ -392,11 +417,11 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
     int64_t m;
     float wgt;
     if (small_row) {
-      int li = lane_upper_bound(c, (int)(b - base), (int)(e - base), r);
-      float hi_v = __shfl_sync(0xffffffffu, c, li);
-      float lo_v = __shfl_sync(0xffffffffu, c, li > 0 ? li - 1 : 0);
-      m = base + li;
-      wgt = __fsub_rn(hi_v, li > 0 ? lo_v : 0.f);
+      int li2 = lane_upper_bound(c, (int)(b - base), (int)(e - base), r);
+      float hi_v = __shfl_sync(0xffffffffu, c, li2);
+      float lo_v = __shfl_sync(0xffffffffu, c, li2 > 0 ? li2 - 1 : 0);
+      m = base + li2;
+      wgt = __fsub_rn(hi_v, li2 > 0 ? lo_v : 0.f);
     } else {
       m = upper_bound_clamped(g.cum_w, b, e, r);
       float hi_v = __ldg(g.cum_w + m);
@@ -424,7 +449,7 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
       if (a.out_ids) { a.out_ids[obase + j] = a.default_node; a.out_w[obase + j] = 0.f; a.out_t[obase + j] = -1; }
     }
   }
-  if (!PHILOX && a.next_tab) {
+  if (!PHILOX && ntab) {
     // the engine ids just written are the next hop's seeds: enter them into its dedup table now
     // (each lane re-reads its own stores), so the next hop needs no insert kernel
     for (int32_t j0 = 0; j0 < count; j0 += 32) {
@@ -434,13 +459,15 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
       const unsigned act = __ballot_sync(0xffffffffu, active);
       if (active) {
         const unsigned peers = __match_any_sync(act, nid);
-        if (lane == __ffs(peers) - 1) dedup_insert_one(a.next_tab, a.next_mask, nid, obase + j);
+        if (lane == __ffs(peers) - 1) dedup_insert_one(ntab, nmask, nid, nbase + j);
       }
     }
   }
 }
 
-__global__ void k_bump_calls(EuRngState* rng) { rng->calls += 1; }
+__global__ void k_bump_calls(EuRngState* rngs, int nb) {
+  if (threadIdx.x < nb) rngs[threadIdx.x].calls += 1;
+}
 
 // ---------------------------------------------------------------------------- global node sampler
 struct NodeSamplerDev {
@@ -524,64 +551,79 @@ static int classify(const DevGraph& d, const int32_t* etypes, int32_t K, ETypes*
   return EU_OK;
 }
 
-// One sampleNB hop: seeds (device u64[rows]) -> engine ids (device u64[rows*count], may be null)
-// and TF-packed outputs (may be null).
-int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows, const int32_t* etypes,
+static Geom make_geom(int nb, int64_t rows_b) {
+  Geom gm{};
+  gm.nb = nb;
+  gm.rows_b = rows_b;
+  gm.nblk_b = (int32_t)ceil_div(rows_b > 0 ? rows_b : 1, kPrepBlock);
+  gm.rows_pad = (int64_t)gm.nblk_b * kPrepBlock;
+  gm.cap_b = 64;
+  while (gm.cap_b < rows_b * 2) gm.cap_b <<= 1;
+  return gm;
+}
+
+// scratch needed by a hop over nb batches of rows_b seeds (see ctx_reserve)
+int64_t hop_scratch_rows(int nb, int64_t rows_b) { return make_geom(nb, rows_b).rows_pad * nb; }
+int64_t hop_table_slots(int nb, int64_t rows_b) { return (make_geom(nb, rows_b).cap_b + 1) * nb; }
+
+// One sampleNB hop over nb batches: seeds (device u64[nb*rows_b]) -> engine ids (device u64[nb*rows_b*count], may
+// be null) and TF-packed outputs (may be null).  Batch b uses engine b of the ctx.
+int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_t* etypes,
         int32_t K, int32_t count, int64_t default_node, unsigned long long* eng_ids,
-        int64_t* out_ids, float* out_w, int32_t* out_t, int hop_index, bool pre_inserted, bool insert_next) {
+        int64_t* out_ids, float* out_w, int32_t* out_t, int hop_index, bool pre_inserted, bool insert_next, int nb) {
+  const int64_t rows = rows_b * nb;
   if (rows == 0 || count == 0) return EU_OK;
+  if (nb < 1 || nb > c->n_eng) { set_error("hop: %d batches but the ctx has %d engines", nb, c->n_eng); return EU_ERR_INVALID; }
   const DevGraph& d = c->g->d;
   SampleArgs a{};
   int rc = classify(d, etypes, K, &a.et, &a.mode);
   if (rc) return rc;
   if (a.mode != 0 && d.T > 32) { set_error("T > 32 unsupported"); return EU_ERR_UNSUPPORTED; }
   cudaStream_t s = c->stream;
-  a.seeds = seeds; a.rows = rows; a.count = count; a.default_node = default_node;
+  const Geom gm = make_geom(nb, rows_b);
+  a.seeds = seeds; a.gm = gm; a.count = count; a.default_node = default_node;
   a.eng_ids = eng_ids; a.out_ids = (long long*)out_ids; a.out_w = out_w; a.out_t = out_t;
-  a.rng = c->d_rng;
+  a.rngs = c->d_rng;
   const unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
   if (c->rng == EU_RNG_PHILOX) {
     a.key = c->seed;
     { EuProfScope ps(c, "k_sample<philox>", rows); k_sample<true><<<blocks, 256, 0, s>>>(d, a); }
     EU_LAUNCHED();
-    k_bump_calls<<<1, 1, 0, s>>>(c->d_rng);
+    k_bump_calls<<<1, 64, 0, s>>>(c->d_rng, nb);
     EU_LAUNCHED();
     return EU_OK;
   }
-  if (rows >= ((int64_t)1 << 31)) { set_error("rows >= 2^31"); return EU_ERR_UNSUPPORTED; }
-  rc = ctx_reserve(c, rows);
+  if (rows >= ((int64_t)1 << 31) || nb > 64) { set_error("rows >= 2^31 or more than 64 batches"); return EU_ERR_UNSUPPORTED; }
+  const Geom ng = make_geom(nb, rows_b * count);  // next hop's geometry (its seeds = this hop's engine ids)
+  const bool chain = insert_next && eng_ids;
+  rc = ctx_reserve(c, std::max(gm.rows_pad, chain ? ng.rows_pad : 0) * nb, (std::max(gm.cap_b, chain ? ng.cap_b : 0) + 1) * nb);
   if (rc) return rc;
-  int64_t cap = 64;
-  while (cap < rows * 2) cap <<= 1;
   const int tb = kPrepBlock;
-  // Two tables, hop l uses table l & 1.  Invariant: both are all-free when an op starts (cleared at
-  // allocation; every k_sample wipes its own hop's table once k_prepare has consumed it).  The seeds of
-  // hop l+1 are entered into the other table by hop l's k_sample (pre_inserted), so only the first hop
-  // of a chain needs the insert kernel.
-  HashSlot* tab = c->d_dedup + (hop_index & 1) * (c->dedup_cap + 1);
-  HashSlot* ntab = c->d_dedup + ((hop_index + 1) & 1) * (c->dedup_cap + 1);
+  // Two table sets, hop l uses set l & 1; batch b owns region b (stride cap_b + 1) of a set.  Invariant: both
+  // sets are all-free when an op starts (cleared at allocation; every k_sample wipes its own hop's regions once
+  // k_prepare has consumed them).  The seeds of hop l+1 are entered into the other set by hop l's k_sample
+  // (pre_inserted), so only the first hop of a chain needs the insert kernel.
+  HashSlot* tabs = c->d_dedup + (hop_index & 1) * c->tab_set_slots;
+  HashSlot* ntabs = c->d_dedup + ((hop_index + 1) & 1) * c->tab_set_slots;
   if (!pre_inserted) {
     EuProfScope ps(c, "k_dedup_insert", rows);
-    k_dedup_insert<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(tab, (unsigned long long)cap - 1, seeds, rows);
+    k_dedup_insert<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(tabs, gm, seeds);
   }
   EU_LAUNCHED();
   const unsigned long long upr = (unsigned long long)count * (a.mode == 0 ? 1 : 2);
   const uint32_t F = modpow_a(2ull * upr);
   { EuProfScope ps(c, "k_prepare", rows);
-    k_prepare<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(d, tab, (unsigned long long)cap - 1, seeds, rows,
-                                                           a.et, a.mode, F, upr, c->d_first, c->d_rowof, c->d_emask,
-                                                           c->d_woff, c->d_blkpre, c->d_rng); }
+    k_prepare<<<dim3((unsigned)gm.nblk_b, (unsigned)nb), tb, 0, s>>>(d, tabs, gm, seeds, a.et, a.mode, F, upr, c->d_first,
+                                                                     c->d_rowof, c->d_emask, c->d_woff, c->d_blkpre, c->d_rng); }
   EU_LAUNCHED();
   a.first = c->d_first; a.rowof = c->d_rowof; a.emask = c->d_emask; a.woff = c->d_woff; a.blkpre = c->d_blkpre;
   a.fpow2[0] = F;
   for (int k = 1; k < 32; ++k) a.fpow2[k] = modmul(a.fpow2[k - 1], a.fpow2[k - 1]);
-  a.clear_tab = tab;
-  a.clear_n = cap + 1;
-  if (insert_next && eng_ids) {
-    int64_t ncap = 64;
-    while (ncap < rows * count * 2) ncap <<= 1;
-    a.next_tab = ntab;
-    a.next_mask = (unsigned long long)ncap - 1;
+  a.clear_tab = tabs;
+  a.clear_n = (gm.cap_b + 1) * nb;
+  if (chain) {
+    a.next_tabs = ntabs;
+    a.next_cap_b = ng.cap_b;
   }
   { EuProfScope ps(c, "k_sample<minstd>", rows); k_sample<false><<<blocks, 256, 0, s>>>(d, a); }
   EU_LAUNCHED();
@@ -599,30 +641,42 @@ int eu_sample_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t
                        int32_t* out_t) {
   if (!c || B < 0 || count < 0 || (K > 0 && !etypes)) { set_error("eu_sample_neighbor: bad argument"); return EU_ERR_INVALID; }
   EU_CUDA(cudaSetDevice(c->g->device));
-  return hop(c, (const unsigned long long*)nodes, B, etypes, K, count, default_node, nullptr, out_ids, out_w, out_t, 0, false, false);
+  return hop(c, (const unsigned long long*)nodes, B, etypes, K, count, default_node, nullptr, out_ids, out_w, out_t, 0, false, false, 1);
+}
+
+int eu_sample_fanout_batched(eu_ctx* c, const int64_t* nodes, int32_t nb, int64_t B, const int32_t* etypes, int32_t K,
+                             const int32_t* counts, int32_t L, int64_t default_node, int64_t* const* out_ids,
+                             float* const* out_w, int32_t* const* out_t) {
+  if (!c || nb < 1 || B < 0 || L < 0 || !counts || (K > 0 && !etypes)) { set_error("eu_sample_fanout: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  if (nb > c->n_eng) { set_error("eu_sample_fanout_batched: %d batches but the ctx has %d engines (eu_ctx_set_engines)", nb, c->n_eng); return EU_ERR_INVALID; }
+  int64_t rows_b = B, max_rows = hop_scratch_rows(nb, B), max_slots = hop_table_slots(nb, B), widest = B * nb;
+  for (int l = 0; l < L; ++l) {
+    if (counts[l] < 0) { set_error("negative count"); return EU_ERR_INVALID; }
+    rows_b *= counts[l];
+    if (l + 1 < L) { max_rows = std::max(max_rows, hop_scratch_rows(nb, rows_b)); max_slots = std::max(max_slots, hop_table_slots(nb, rows_b)); }
+    widest = std::max(widest, rows_b * nb);
+  }
+  int rc = ctx_reserve(c, std::max(max_rows, widest), max_slots);
+  if (rc) return rc;
+  const unsigned long long* seeds = (const unsigned long long*)nodes;
+  rows_b = B;
+  for (int l = 0; l < L; ++l) {
+    unsigned long long* eng = (l + 1 < L) ? c->d_front[l & 1] : nullptr;
+    rc = hop(c, seeds, rows_b, etypes + (int64_t)l * K, K, counts[l], default_node, eng,
+             out_ids ? out_ids[l] : nullptr, out_w ? out_w[l] : nullptr, out_t ? out_t[l] : nullptr,
+             l, /*pre_inserted=*/l > 0 && c->rng == EU_RNG_MINSTD, /*insert_next=*/l + 1 < L, nb);
+    if (rc) return rc;
+    seeds = eng;
+    rows_b *= counts[l];
+  }
+  return EU_OK;
 }
 
 int eu_sample_fanout(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
                      const int32_t* counts, int32_t L, int64_t default_node, int64_t* const* out_ids,
                      float* const* out_w, int32_t* const* out_t) {
-  if (!c || B < 0 || L < 0 || !counts || (K > 0 && !etypes)) { set_error("eu_sample_fanout: bad argument"); return EU_ERR_INVALID; }
-  EU_CUDA(cudaSetDevice(c->g->device));
-  int64_t rows = B, widest = B;
-  for (int l = 0; l < L; ++l) { if (counts[l] < 0) { set_error("negative count"); return EU_ERR_INVALID; } rows *= counts[l]; if (rows > widest) widest = rows; }
-  int rc = ctx_reserve(c, widest);
-  if (rc) return rc;
-  const unsigned long long* seeds = (const unsigned long long*)nodes;
-  rows = B;
-  for (int l = 0; l < L; ++l) {
-    unsigned long long* eng = (l + 1 < L) ? c->d_front[l & 1] : nullptr;
-    rc = hop(c, seeds, rows, etypes + (int64_t)l * K, K, counts[l], default_node, eng,
-             out_ids ? out_ids[l] : nullptr, out_w ? out_w[l] : nullptr, out_t ? out_t[l] : nullptr,
-             l, /*pre_inserted=*/l > 0 && c->rng == EU_RNG_MINSTD, /*insert_next=*/l + 1 < L);
-    if (rc) return rc;
-    seeds = eng;
-    rows *= counts[l];
-  }
-  return EU_OK;
+  return eu_sample_fanout_batched(c, nodes, 1, B, etypes, K, counts, L, default_node, out_ids, out_w, out_t);
 }
 
 int eu_sample_node(eu_ctx* c, int32_t count, const int32_t* types, int32_t n_types, int64_t* out) {

@@ -184,7 +184,7 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
   const DevGraph& d = c->g->d;
   cudaStream_t s = c->stream;
   const int tb = 256;
-  int rc = ctx_reserve(c, B);
+  int rc = ctx_reserve(c, hop_scratch_rows(1, B), hop_table_slots(1, B));
   if (rc) return rc;
   const float kEps = 1.0e-6f;
   if (fabs((double)p - 1.0) <= kEps && fabs((double)q - 1.0) <= kEps) {
@@ -195,7 +195,7 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
     for (int l = 0; l < L; ++l) {
       unsigned long long* eng = c->d_front[l & 1];
       rc = hop(c, seeds, B, etypes + (int64_t)l * K, K, 1, default_node, eng, nullptr, nullptr, nullptr,
-               l, l > 0 && c->rng == EU_RNG_MINSTD, l + 1 < L);
+               l, l > 0 && c->rng == EU_RNG_MINSTD, l + 1 < L, 1);
       if (rc) return rc;
       k_walk_col<<<(unsigned)ceil_div(B, tb), tb, 0, s>>>(eng, B, L, l + 1, default_node, (long long*)out);
       EU_LAUNCHED();

@@ -151,6 +151,11 @@ class Context:
     def seed(self, s):
         check(_lib.load().eu_ctx_seed(self._h, s))
 
+    def set_engines(self, n, seeds=None):
+        """n engines; batch b of a batched call runs on engine b (seeds[b], default seed + b)."""
+        arr = None if seeds is None else np.ascontiguousarray(seeds, dtype=np.uint64)
+        check(_lib.load().eu_ctx_set_engines(self._h, n, None if arr is None else arr.ctypes.data))
+
     def set_stream(self, stream_ptr):
         check(_lib.load().eu_ctx_set_stream(self._h, stream_ptr))
 

@@ -159,6 +159,31 @@ def sample_fanout(nodes, edge_types, counts, default_node=-1):
     return [nodes] + ids, ws, ts
 
 
+def sample_fanout_batched(nodes, edge_types, counts, default_node=-1, ctx=None):
+    """nb independent sample_fanout calls in one set of kernel launches.  nodes: [nb, B]; batch b runs on engine b
+    of `ctx` (Context.set_engines), i.e. it returns exactly what sample_fanout(nodes[b]) returns on a context
+    seeded like engine b.  Returns (neighbors_list[L+1], weights_list[L], types_list[L]) with a leading nb dim."""
+    nodes = _t(nodes, torch.int64)
+    nb, B = nodes.shape
+    L = len(counts)
+    ets = [get_edge_type_id(e) for e in edge_types]
+    et = np.ascontiguousarray(np.stack(ets) if L else np.zeros((0, 0)), dtype=np.int32)
+    cs = np.ascontiguousarray(counts, dtype=np.int32)
+    ids, ws, ts, rows = [], [], [], B
+    for c in counts:
+        rows *= int(c)
+        ids.append(torch.empty((nb, rows), dtype=torch.int64, device=nodes.device))
+        ws.append(torch.empty((nb, rows), dtype=torch.float32, device=nodes.device))
+        ts.append(torch.empty((nb, rows), dtype=torch.int32, device=nodes.device))
+    P = C.c_void_p * max(L, 1)
+    ctx = ctx or _ctx_on_stream()
+    check(_lib.load().eu_sample_fanout_batched(ctx._h, nodes.data_ptr(), nb, B, et.ctypes.data,
+                                               et.shape[1] if L else 0, cs.ctypes.data, L, default_node,
+                                               P(*[x.data_ptr() for x in ids]), P(*[x.data_ptr() for x in ws]),
+                                               P(*[x.data_ptr() for x in ts])))
+    return [nodes] + ids, ws, ts
+
+
 def sample_node(count, node_type, condition=''):
     """sample_ops.sample_node (sample_ops.py:38-54); node_type '-1' (or -1) = all types."""
     if condition:

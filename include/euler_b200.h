@@ -122,7 +122,11 @@ int32_t eu_graph_dense_feature_dim(const eu_graph* g, int32_t fid);
 int eu_ctx_create(eu_graph* g, eu_rng_kind rng, uint64_t seed, void* stream, eu_ctx** out);
 int eu_ctx_destroy(eu_ctx* c);
 int eu_ctx_set_stream(eu_ctx* c, void* stream);
-int eu_ctx_seed(eu_ctx* c, uint64_t seed);           /* engine.seed(seed); stream-ordered */
+int eu_ctx_seed(eu_ctx* c, uint64_t seed);           /* engine e <- seed + e; stream-ordered */
+/* A ctx may carry several engines: batch b of a *_batched call runs on engine b (its own draw stream and
+ * its own dedup scope), i.e. each batch is exactly one reference op call on one client thread; batching only
+ * shares kernel launches.  seeds == NULL: engine e <- seed + e.  Plain ops use engine 0. */
+int eu_ctx_set_engines(eu_ctx* c, int32_t n, const uint64_t* seeds);
 int eu_ctx_reserve(eu_ctx* c, int64_t max_rows);      /* pre-size scratch (required before graph capture) */
 int eu_ctx_sync(eu_ctx* c);
 /* number of uniforms the MINSTD engine has produced since the last seed (synchronises) */
@@ -148,6 +152,10 @@ int eu_sample_neighbor_host(eu_ctx* c, const int64_t* nodes, int64_t B, const in
 int eu_sample_fanout(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
                      const int32_t* counts, int32_t L, int64_t default_node, int64_t* const* out_ids,
                      float* const* out_w, int32_t* const* out_t);
+/* nb independent batches of B seeds in one set of launches (nodes / outputs batch-major). */
+int eu_sample_fanout_batched(eu_ctx* c, const int64_t* nodes, int32_t nb, int64_t B, const int32_t* etypes, int32_t K,
+                             const int32_t* counts, int32_t L, int64_t default_node, int64_t* const* out_ids,
+                             float* const* out_w, int32_t* const* out_t);
 int eu_sample_fanout_host(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes,
                           int32_t K, const int32_t* counts, int32_t L, int64_t default_node,
                           int64_t* const* out_ids, float* const* out_w, int32_t* const* out_t);

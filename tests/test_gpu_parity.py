@@ -108,6 +108,52 @@ def test_random_graph_vs_oracle(seed, T, kw):
         cases.eq(be.sample_node(types, 4097), ob.sample_node(types, 4097), "sample_node %s" % types)
 
 
+@pytest.mark.parametrize("nb,B,T", [(1, 300, 2), (5, 257, 3), (8, 1024, 1), (16, 33, 4)])
+def test_batched_fanout_equals_independent_calls(nb, B, T):
+    """eu_sample_fanout_batched: batch b == one sample_fanout call on an engine seeded like engine b."""
+    import euler_b200
+    g = graphs.random_graph(seed=90 + nb, n=8000, T=T, avg_deg=7, hub=700, id_stride=3, zero_w_frac=0.05)
+    gr = graphs.cuda_graph(g)
+    og = graphs.oracle_graph(g)
+    euler_b200.set_graph(gr)
+    ctx = euler_b200.Context(gr, "minstd", 1)
+    seeds_e = [1000 + 17 * b for b in range(nb)]
+    ctx.set_engines(nb, seeds_e)
+    rs = np.random.RandomState(nb)
+    nodes = g["ids"][rs.randint(0, 8000, size=(nb, B))].astype(np.int64)
+    nodes[:, ::9] = 77777777
+    nodes[0, :20] = nodes[0, 0]
+    ets = [[0, T - 1], [T - 1, 0]] if T > 1 else [[0], [0]]
+    states = {}
+    for rep in range(2):  # second call: every engine continues its own stream
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ids, ws, ts = euler_b200.sample_fanout_batched(nodes, ets, [6, 40], -1, ctx=ctx)
+        for b in range(nb):
+            if rep == 0:
+                po.seed(seeds_e[b])
+            else:
+                po.set_state(states[b])
+            o_ids, o_ws, o_ts = _oracle_fanout(og, nodes[b], ets, [6, 40])
+            states[b] = po.get_state()
+            for l in range(2):
+                cases.eq(ids[l + 1][b].cpu().numpy(), o_ids[l], "batch %d rep %d ids hop %d" % (b, rep, l))
+                cases.eq(ws[l][b].cpu().numpy(), o_ws[l], "batch %d w hop %d" % (b, l))
+                cases.eq(ts[l][b].cpu().numpy(), o_ts[l], "batch %d t hop %d" % (b, l))
+
+
+def _oracle_fanout(og, nodes, ets, counts):
+    """sample_fanout with a different edge-type list length per hop = chained op_sample_neighbor on ENGINE ids."""
+    frontier = np.asarray(nodes, np.int64)
+    ids, ws, ts = [], [], []
+    for et, c in zip(ets, counts):
+        e_ids, e_w, e_t = og.op_sample_neighbor(frontier, et, c, 0)      # default_node 0 == engine form
+        keep = e_ids[:, :1] != 0
+        ids.append(np.where(keep, e_ids, -1).reshape(-1)); ws.append(np.where(keep, e_w, 0).astype(np.float32).reshape(-1))
+        ts.append(np.where(keep, e_t, -1).astype(np.int32).reshape(-1))
+        frontier = e_ids.reshape(-1)
+    return ids, ws, ts
+
+
 def test_empty_and_degenerate_inputs():
     import euler_b200
     g = graphs.random_graph(seed=31, n=50, T=2)
