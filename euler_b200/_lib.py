@@ -39,6 +39,8 @@ SIGNATURES = {
                                        C.c_int, C.POINTER(_P)]),
     "eu_graph_create_rmat_shard": (C.c_int, [_I64, _I64, C.c_double, C.c_double, C.c_double, _U64, _I32, _U64,
                                              C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "eu_graph_create_rmat_hetero": (C.c_int, [_I64, _I64, _I32, _I32, C.c_double, C.c_double, C.c_double, _U64, _I32, _U64,
+                                              C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "eu_graph_load": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "eu_graph_destroy": (C.c_int, [_P]),
     "eu_graph_num_nodes": (_I64, [_P]),

@@ -93,7 +93,7 @@ __device__ __forceinline__ unsigned long long splitmix(unsigned long long& s) {
 // keys == nullptr: only count the edges this shard owns.  Otherwise append key = local_row * n + dst
 // (cursor order is irrelevant: the keys are radix-sorted afterwards and equal keys are indistinguishable).
 __global__ void k_rmat_edges(unsigned long long* keys, unsigned long long* cursor, int64_t n_edges, int64_t n_nodes,
-                             int scale, double a, double b, double c, unsigned long long seed, int N, int shard) {
+                             int scale, double a, double b, double c, unsigned long long seed, int N, int shard, int T) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
   unsigned long long s = mix64(seed ^ (unsigned long long)e * 0xD6E8FEB86659FD93ull);
@@ -113,7 +113,9 @@ __global__ void k_rmat_edges(unsigned long long* keys, unsigned long long* curso
   const unsigned long long base_id = shard == 0 ? (unsigned long long)N : (unsigned long long)shard;
   const unsigned long long row = N > 1 ? (src_id - base_id) / (unsigned long long)N : src;
   const unsigned long long pos = N > 1 ? atomicAdd(cursor, 1ull) : (unsigned long long)e;
-  keys[pos] = row * (unsigned long long)n_nodes + dst;
+  // heterogeneous graphs: edge type = hash(edge index) % T; adjacency groups are (row, type)
+  const unsigned long long et = T > 1 ? mix64(seed * 0x2545F4914F6CDD1Dull + (unsigned long long)e) % (unsigned long long)T : 0ull;
+  keys[pos] = (row * (unsigned long long)T + et) * (unsigned long long)n_nodes + dst;
 }
 
 __global__ void k_count_src(const unsigned long long* keys, int64_t n_edges, int64_t n_nodes,
@@ -124,11 +126,11 @@ __global__ void k_count_src(const unsigned long long* keys, int64_t n_edges, int
 }
 
 __global__ void k_rmat_fill(const unsigned long long* keys, int64_t n_edges, int64_t n_nodes,
-                            unsigned long long* nbr, float* w, unsigned long long base_id, unsigned long long stride) {
+                            unsigned long long* nbr, float* w, unsigned long long base_id, unsigned long long stride, int T) {
   int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
   unsigned long long k = keys[e];
-  unsigned long long row = k / (unsigned long long)n_nodes, dst = k % (unsigned long long)n_nodes;
+  unsigned long long row = k / (unsigned long long)n_nodes / (unsigned long long)T, dst = k % (unsigned long long)n_nodes;
   unsigned long long src = base_id + row * stride - 1;  // global 0-based source index
   nbr[e] = dst + 1;  // ids are 1..n
   unsigned long long h = mix64(src * 0x9E3779B97F4A7C15ull ^ dst);
@@ -136,11 +138,11 @@ __global__ void k_rmat_fill(const unsigned long long* keys, int64_t n_edges, int
 }
 
 __global__ void k_iota_ids(unsigned long long* ids, int32_t* ntype, float* nw, int64_t n, unsigned long long base_id,
-                           unsigned long long stride) {
+                           unsigned long long stride, int NT) {
   int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (r >= n) return;
   ids[r] = base_id + (unsigned long long)r * stride;
-  ntype[r] = 0;
+  ntype[r] = (int32_t)(ids[r] % (unsigned long long)NT);  // node type = id % NT
   nw[r] = 1.0f;
 }
 
@@ -387,8 +389,9 @@ int eu_graph_create(const eu_graph_desc* desc, int device, eu_graph** out) {
 // of the shards is exactly the unsharded graph.
 static int rmat_create(int64_t n_nodes, int64_t n_edges, double a, double b, double c, uint64_t seed,
                        int32_t feat_dim, uint64_t feat_seed, int device, int shard_index, int shard_number,
-                       eu_graph** out) {
-  if (!out || n_nodes <= 0 || n_edges < 0 || shard_number < 1 || shard_index < 0 || shard_index >= shard_number) {
+                       int T, int NT, eu_graph** out) {
+  if (!out || n_nodes <= 0 || n_edges < 0 || shard_number < 1 || shard_index < 0 || shard_index >= shard_number ||
+      T < 1 || T > EU_MAX_ETYPES || NT < 1 || NT > EU_MAX_ETYPES || (double)n_nodes * (double)n_nodes * T >= 9.2e18) {
     set_error("eu_graph_create_rmat: bad sizes"); return EU_ERR_INVALID;
   }
   if ((double)n_nodes * (double)n_nodes >= 9.2e18) { set_error("n_nodes too large for 64-bit sort keys"); return EU_ERR_INVALID; }
@@ -400,7 +403,7 @@ static int rmat_create(int64_t n_nodes, int64_t n_edges, double a, double b, dou
   eu_graph* g = new eu_graph();
   g->device = device;
   DevGraph& d = g->d;
-  d.n = n_local; d.T = 1; d.n_node_types = 1;
+  d.n = n_local; d.T = T; d.n_node_types = NT;
   const int tb = 256;
 #define TRY(x) do { rc = (x); if (rc) { eu_graph_destroy(g); return rc; } } while (0)
 #define TRYC(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) { set_error("%s -> %s", #x, cudaGetErrorString(_e)); eu_graph_destroy(g); return EU_ERR_CUDA; } } while (0)
@@ -412,7 +415,7 @@ static int rmat_create(int64_t n_nodes, int64_t n_edges, double a, double b, dou
   TRYC(cudaMemset(d_cnt, 0, sizeof(unsigned long long)));
   int64_t E = n_edges;
   if (N > 1 && n_edges > 0) {
-    k_rmat_edges<<<(unsigned)ceil_div(n_edges, tb), tb>>>(nullptr, d_cnt, n_edges, n_nodes, scale, a, b, c, seed, (int)N, shard_index);
+    k_rmat_edges<<<(unsigned)ceil_div(n_edges, tb), tb>>>(nullptr, d_cnt, n_edges, n_nodes, scale, a, b, c, seed, (int)N, shard_index, T);
     g_launches++;
     unsigned long long h = 0;
     TRYC(cudaMemcpy(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost));
@@ -427,11 +430,14 @@ static int rmat_create(int64_t n_nodes, int64_t n_edges, double a, double b, dou
   TRY(g->alloc(&ids, n_local));
   TRY(g->alloc(&ntype, n_local));
   TRY(g->alloc(&nw, n_local));
-  TRY(g->alloc(&ptr, n_local + 1));
+  const int64_t n_grp = n_local * T;   // adjacency groups
+  float* gcum = nullptr;
+  TRY(g->alloc(&ptr, n_grp + 1));
+  if (T > 1) TRY(g->alloc(&gcum, n_grp));
   TRY(g->alloc(&nbr, E));
   TRY(g->alloc(&cum, E));
   if (n_local > 0) {
-    k_iota_ids<<<(unsigned)ceil_div(n_local, tb), tb>>>(ids, ntype, nw, n_local, (unsigned long long)base_id, (unsigned long long)N);
+    k_iota_ids<<<(unsigned)ceil_div(n_local, tb), tb>>>(ids, ntype, nw, n_local, (unsigned long long)base_id, (unsigned long long)N, NT);
     g_launches++;
   }
   unsigned long long *k0 = nullptr, *k1 = nullptr;
@@ -441,36 +447,36 @@ static int rmat_create(int64_t n_nodes, int64_t n_edges, double a, double b, dou
   TRYC(cudaMalloc(&k0, sizeof(unsigned long long) * (size_t)(E > 0 ? E : 1)));
   TRYC(cudaMalloc(&k1, sizeof(unsigned long long) * (size_t)(E > 0 ? E : 1)));
   if (n_edges > 0) {
-    k_rmat_edges<<<(unsigned)ceil_div(n_edges, tb), tb>>>(k0, d_cnt, n_edges, n_nodes, scale, a, b, c, seed, (int)N, shard_index);
+    k_rmat_edges<<<(unsigned)ceil_div(n_edges, tb), tb>>>(k0, d_cnt, n_edges, n_nodes, scale, a, b, c, seed, (int)N, shard_index, T);
     g_launches++;
   }
   int end_bit = 1;
-  while (end_bit < 64 && ((double)(n_local > 0 ? n_local : 1) * (double)n_nodes) >= ldexp(1.0, end_bit)) ++end_bit;
+  while (end_bit < 64 && ((double)(n_grp > 0 ? n_grp : 1) * (double)n_nodes) >= ldexp(1.0, end_bit)) ++end_bit;
   cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, k0, k1, (int64_t)E, 0, end_bit);
-  cub::DeviceScan::ExclusiveSum(nullptr, tmp2, ptr, ptr, (int64_t)(n_local + 1));
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp2, ptr, ptr, (int64_t)(n_grp + 1));
   if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
   TRYC(cudaMalloc(&tmp, tmp_bytes > 0 ? tmp_bytes : 1));
   TRYC(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, k0, k1, (int64_t)E, 0, end_bit));
-  TRYC(cudaMemset(ptr, 0, sizeof(int64_t) * (size_t)(n_local + 1)));
+  TRYC(cudaMemset(ptr, 0, sizeof(int64_t) * (size_t)(n_grp + 1)));
   if (E > 0) {
     k_count_src<<<(unsigned)ceil_div(E, tb), tb>>>(k1, E, n_nodes, ptr);
     g_launches++;
   }
-  TRYC(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, ptr, ptr, (int64_t)(n_local + 1)));
+  TRYC(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, ptr, ptr, (int64_t)(n_grp + 1)));
   TRYC(cudaFree(k0)); k0 = nullptr;
   TRYC(cudaMalloc(&w, sizeof(float) * (size_t)(E > 0 ? E : 1)));
   if (E > 0) {
-    k_rmat_fill<<<(unsigned)ceil_div(E, tb), tb>>>(k1, E, n_nodes, nbr, w, (unsigned long long)base_id, (unsigned long long)N);
+    k_rmat_fill<<<(unsigned)ceil_div(E, tb), tb>>>(k1, E, n_nodes, nbr, w, (unsigned long long)base_id, (unsigned long long)N, T);
     g_launches++;
   }
   if (n_local > 0) {
-    k_build_cum<<<(unsigned)ceil_div(n_local, 128), 128>>>(n_local, 1, ptr, w, cum, nullptr);
+    k_build_cum<<<(unsigned)ceil_div(n_local, 128), 128>>>(n_local, T, ptr, w, cum, gcum);
     g_launches++;
   }
   TRYC(cudaDeviceSynchronize());
   cudaFree(k1); cudaFree(w); cudaFree(tmp); cudaFree(d_cnt);
   d.ids = ids; d.node_type = ntype; d.node_w = nw; d.grp_ptr = ptr; d.nbr = nbr; d.cum_w = cum;
-  d.grp_cum = nullptr;
+  d.grp_cum = gcum;
   d.dense_ids = 1; d.id_base = (unsigned long long)base_id; d.id_stride = (unsigned long long)N;
   d.feat_dim = feat_dim;
   if (feat_dim > 0) {
@@ -483,8 +489,8 @@ static int rmat_create(int64_t n_nodes, int64_t n_edges, double a, double b, dou
     g->dense_feature_names.push_back("feat0");
   }
   TRY(build_hash(g));
-  g->edge_type_names.push_back("0");
-  g->node_type_names.push_back("0");
+  for (int t = 0; t < T; ++t) g->edge_type_names.push_back(std::to_string(t));
+  for (int t = 0; t < NT; ++t) g->node_type_names.push_back(std::to_string(t));
 #undef TRY
 #undef TRYC
   *out = g;
@@ -494,13 +500,20 @@ static int rmat_create(int64_t n_nodes, int64_t n_edges, double a, double b, dou
 int eu_graph_create_rmat(int64_t n_nodes, int64_t n_edges, double a, double b, double c,
                          uint64_t seed, int32_t feat_dim, uint64_t feat_seed, int device,
                          eu_graph** out) {
-  return rmat_create(n_nodes, n_edges, a, b, c, seed, feat_dim, feat_seed, device, 0, 1, out);
+  return rmat_create(n_nodes, n_edges, a, b, c, seed, feat_dim, feat_seed, device, 0, 1, 1, 1, out);
+}
+
+int eu_graph_create_rmat_hetero(int64_t n_nodes, int64_t n_edges, int32_t n_edge_types, int32_t n_node_types, double a,
+                                double b, double c, uint64_t seed, int32_t feat_dim, uint64_t feat_seed, int device,
+                                int shard_index, int shard_number, eu_graph** out) {
+  return rmat_create(n_nodes, n_edges, a, b, c, seed, feat_dim, feat_seed, device, shard_index, shard_number, n_edge_types,
+                     n_node_types, out);
 }
 
 int eu_graph_create_rmat_shard(int64_t n_nodes, int64_t n_edges, double a, double b, double c,
                                uint64_t seed, int32_t feat_dim, uint64_t feat_seed, int device,
                                int shard_index, int shard_number, eu_graph** out) {
-  return rmat_create(n_nodes, n_edges, a, b, c, seed, feat_dim, feat_seed, device, shard_index, shard_number, out);
+  return rmat_create(n_nodes, n_edges, a, b, c, seed, feat_dim, feat_seed, device, shard_index, shard_number, 1, 1, out);
 }
 
 int eu_graph_destroy(eu_graph* g) {

@@ -70,6 +70,15 @@ class Graph:
         return cls(h, device)
 
     @classmethod
+    def rmat_hetero(cls, n_nodes, n_edges, n_edge_types, n_node_types, shard_index=0, shard_number=1, a=0.57, b=0.19,
+                    c=0.19, seed=44, feat_dim=0, feat_seed=7, device=0):
+        """Heterogeneous R-MAT graph (edge type = hash(edge) % T, node type = id % NT), optionally one shard of it."""
+        h = C.c_void_p()
+        check(_lib.load().eu_graph_create_rmat_hetero(n_nodes, n_edges, n_edge_types, n_node_types, a, b, c, seed,
+                                                      feat_dim, feat_seed, device, shard_index, shard_number, C.byref(h)))
+        return cls(h, device)
+
+    @classmethod
     def load(cls, data_path, shard_index=0, shard_number=1, device=0):
         h = C.c_void_p()
         check(_lib.load().eu_graph_load(str(data_path).encode(), shard_index, shard_number, device,

@@ -95,6 +95,11 @@ int eu_graph_create_rmat(int64_t n_nodes, int64_t n_edges, double a, double b, d
 int eu_graph_create_rmat_shard(int64_t n_nodes, int64_t n_edges, double a, double b, double c,
                                uint64_t seed, int32_t feat_dim, uint64_t feat_seed, int device,
                                int shard_index, int shard_number, eu_graph** out);
+/* Heterogeneous variant (BASELINE configs[4]): edge type = hash(edge) % n_edge_types (adjacency grouped by
+ * (row, type), one node-global cumulative weight array as node.cc:59-65), node type = id % n_node_types. */
+int eu_graph_create_rmat_hetero(int64_t n_nodes, int64_t n_edges, int32_t n_edge_types, int32_t n_node_types, double a,
+                                double b, double c, uint64_t seed, int32_t feat_dim, uint64_t feat_seed, int device,
+                                int shard_index, int shard_number, eu_graph** out);
 /* Euler 2.0 on-disk format (euler.meta + Node/*.dat), shard `shard_index` of
  * `shard_number` with the reference's file filter (graph.cc:90-98).  = Graph::Init, graph.h:53-56. */
 int eu_graph_load(const char* data_path, int shard_index, int shard_number, int device,

@@ -154,6 +154,32 @@ def _oracle_fanout(og, nodes, ets, counts):
     return ids, ws, ts
 
 
+def test_hetero_rmat_graph_vs_oracle():
+    """Device-generated heterogeneous graph (configs[4] shape): export -> oracle -> all edge-type modes."""
+    import euler_b200
+    n, E, T, NT = 30000, 240000, 5, 3
+    gr = euler_b200.Graph.rmat_hetero(n, E, T, NT, feat_dim=8)
+    ex = gr.export()
+    assert (ex["node_type"] == ex["ids"] % NT).all() and ex["grp_ptr"][-1] == E
+    og = po.OracleGraph(ex["ids"], ex["node_type"], ex["node_w"], T, ex["grp_ptr"], ex["nbr"], ex["cum_w"], ex["grp_cum"], ex["feat"])
+    # the generator's prefix sums equal Node::Init's accumulation of the de-cumulated weights group by group
+    euler_b200.set_graph(gr)
+    seeds = np.random.RandomState(4).randint(1, n + 1, size=2000).astype(np.int64)
+    for et, cnt in [([2], 10), (list(range(T)), 10), ([4, 0, 1], 7), ([], 3)]:
+        euler_b200.seed(5); po.seed(5)
+        got = [x.cpu().numpy() for x in euler_b200.sample_neighbor(seeds, et, cnt)]
+        for a, b in zip(got, og.op_sample_neighbor(seeds, et, cnt)):
+            cases.eq(a, b, "hetero sample_neighbor %s" % et)
+    og.build_node_sampler(np.arange(n), NT)
+    for types in ('-1', [1], [0, 2]):
+        euler_b200.seed(6)
+        r = po.Rng(6)
+        want = og.sample_node([-1] if types == '-1' else types, 3000, r)
+        cases.eq(euler_b200.sample_node(3000, types).cpu().numpy().astype(np.uint64), want, "hetero sample_node %s" % (types,))
+    x = euler_b200.get_dense_feature(seeds[:50], [0], [8])[0].cpu().numpy()
+    cases.eq(x, og.op_get_dense_feature(seeds[:50], 8), "hetero features")
+
+
 def test_empty_and_degenerate_inputs():
     import euler_b200
     g = graphs.random_graph(seed=31, n=50, T=2)
