@@ -155,36 +155,24 @@ __device__ __forceinline__ double pick_r(double u, float limit_begin, float limi
   return __dadd_rn(__dmul_rn(u, (double)diff), (double)limit_begin);
 }
 
+// Smallest f32 whose value exceeds r (r >= 0: cumulative weights are non-negative).  For an f32 c,
+// (double)c > r  <=>  c >= gt_threshold(r), which turns every probe of the search into one FSETP instead of
+// F2F.F64 + DSETP.
+__device__ __forceinline__ float gt_threshold(double r) {
+  float f = __double2float_ru(r);                       // (double)f >= r
+  if ((double)f == r) f = __int_as_float(__float_as_int(f) + 1);  // next f32 up (valid for f >= +0)
+  return f;
+}
+
 // RandomSelect == min(end, first j in [begin,end] with (double)cum[j] > r) for non-decreasing cum
 // (proof sketch in DESIGN.md; checked against the literal search in tests/test_oracle_golden.py).
-// Binary search over global memory, [lo,hi] inclusive indices into cum.
-__device__ __forceinline__ int64_t upper_bound_clamped(const float* __restrict__ cum, int64_t begin,
-                                                       int64_t end, double r) {
-  // Invariant: the answer lies in [lo, hi]; hi is `end` (the clamp) or an index with cum[hi] > r.
-  // 8-ary descent: 7 independent probes per round trip instead of 1 -- the rows that matter here are hubs
-  // (a hop-2 frontier is degree-biased), where a binary search is ~15 dependent L2 round trips.
-  int64_t lo = begin, hi = end;
-  while (hi - lo >= 8) {
-    const int64_t n = hi - lo;
-    float v[7];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) v[i] = __ldg(cum + lo + (((i + 1) * n) >> 3));  // lo < p_0 < ... < p_6 < hi
-    int c = 0;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) c += ((double)v[i] > r) ? 0 : 1;                 // monotone: a prefix is <= r
-    const int64_t nlo = c > 0 ? lo + ((c * n) >> 3) + 1 : lo;
-    const int64_t nhi = c < 7 ? lo + (((c + 1) * n) >> 3) : hi;
-    lo = nlo; hi = nhi;
-  }
-  if (lo < hi) {  // fewer than 8 candidates left below hi: one more round of independent probes
-    const int64_t n = hi - lo;
-    int c = 0;
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      const float v = i < n ? __ldg(cum + lo + i) : __int_as_float(0x7f800000);
-      c += ((double)v > r) ? 0 : 1;
-    }
-    lo += c;
+// Binary search over a row slice in global memory; `base` points at the slice, offsets are 32-bit
+// (a row has < 2^31 edges), thr = gt_threshold(r).  Returns the offset in [lo, hi].
+__device__ __forceinline__ int32_t upper_bound_clamped(const float* __restrict__ base, int32_t lo, int32_t hi,
+                                                       float thr) {
+  while (lo < hi) {
+    const int32_t mid = (int32_t)(((uint32_t)lo + (uint32_t)hi) >> 1);
+    if (__ldg(base + mid) >= thr) hi = mid; else lo = mid + 1;
   }
   return lo;
 }

@@ -108,8 +108,9 @@ struct eu_ctx {
   uint8_t* d_elig = nullptr;         // [rows]
   uint32_t* d_state = nullptr;       // [rows] engine state before the row's first draw (walks)
   uint32_t* d_emask = nullptr;       // [rows/32] eligible-first-occurrence ballots
-  uint32_t* d_woff = nullptr;        // [rows/32] count in earlier warps of the block
+  uint32_t* d_woff = nullptr;        // [rows/32] F^(count in earlier warps of the block)
   uint32_t* d_blkpre = nullptr;      // [rows/256] count in earlier blocks
+  uint32_t* d_blkmul = nullptr;      // [rows/256] F^that count
   unsigned long long* d_front[2] = {nullptr, nullptr};  // engine-id frontier ping-pong [rows]
   // extra scratch for walks / scatter
   void* d_misc = nullptr;

@@ -35,8 +35,8 @@ __global__ void __launch_bounds__(256) k_feature(DevGraph g, const unsigned long
                                                  int64_t M, int32_t dim, int G, int32_t soff, int32_t sdim,
                                                  float* __restrict__ out) {
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t i = tid / G;
-  const int sub = (int)(tid % G);
+  const int64_t i = tid >> (31 - __clz(G));   // G is a power of two
+  const int sub = (int)(tid & (G - 1));
   if (i >= M) return;
   const int64_t row = sdim > 0 ? lookup_row(g, ids[i]) : -1;
   const int32_t fd = sdim;  // stored width of this slot
@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(256) k_gather(const float* __restrict__ params
                                                 const int32_t* __restrict__ idx, int64_t E, int G,
                                                 float* __restrict__ out) {
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t i = tid / G;
-  const int sub = (int)(tid % G);
+  const int64_t i = tid >> (31 - __clz(G));   // G is a power of two
+  const int sub = (int)(tid & (G - 1));
   if (i >= E) return;
   const float* src = params + (int64_t)__ldg(idx + i) * D;  // no bounds check, as gather_op.cc:47-51
   float* o = out + i * D;
@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(256) k_scatter_sorted(const float* __restrict_
                                                         float* __restrict__ out) {
   if (*unsorted) return;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t r = tid / G;
-  const int sub = (int)(tid % G);
+  const int64_t r = tid >> (31 - __clz(G));   // G is a power of two
+  const int sub = (int)(tid & (G - 1));
   if (r >= size) return;
   const int64_t b = lower_bound_i32(idx, E, r), e = lower_bound_i32(idx, E, r + 1);
   const float init = OP == OP_MAX ? -1e9f : 0.f;
@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(256) k_scatter_atomic(const float* __restrict_
                                                         float* __restrict__ cnt) {
   if (!*unsorted) return;
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t i = tid / G;
-  const int sub = (int)(tid % G);
+  const int64_t i = tid >> (31 - __clz(G));   // G is a power of two
+  const int sub = (int)(tid & (G - 1));
   if (i >= E) return;
   const int64_t r = __ldg(idx + i);
   float* o = out + r * D;
@@ -193,27 +193,36 @@ __global__ void __launch_bounds__(256) k_sage_mean(DevGraph g, const unsigned lo
   const int lane = threadIdx.x & 31;
   const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (r >= rows) return;
-  const int32_t fd = g.feat_dim;  // == NV*128
+  constexpr int32_t fd = NV * 128;  // == g.feat_dim (checked by the launcher)
+  const float* __restrict__ feat = g.feat + lane * 4;
   float4 acc[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int32_t j0 = 0; j0 < count; j0 += 32) {
-    const int32_t nj = min(32, count - j0);
-    int64_t my = -1;
-    if (lane < nj) my = lookup_row(g, __ldg(ids + r * count + j0 + lane));
-    for (int32_t j = 0; j < nj; j += 4) {
+    // the id -> row lookups of up to 32 neighbors run in parallel across the lanes (rows < 2^31: launcher)
+    int32_t my = -1;
+    if (j0 + lane < count) my = (int32_t)lookup_row(g, __ldg(ids + r * count + j0 + lane));
+    // Only neighbors that exist are visited, in ascending j.  Skipping an absent one is exact: it would add a
+    // row of +0.0 and the accumulator can never be -0.0 (it starts at +0.0 and x + (-0.0) keeps +0.0's sign).
+    unsigned valid = __ballot_sync(0xffffffffu, my >= 0);
+    while (valid) {  // warp-uniform
       float4 v[4][NV];
+      int n = 0;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int64_t row = __shfl_sync(0xffffffffu, my, min(j + q, 31));
-        const bool ok = (j + q < nj) && row >= 0;
+      for (int q = 0; q < 4; ++q) {  // 4 independent row reads in flight
+        if (valid) {
+          const int j = __ffs(valid) - 1;
+          valid &= valid - 1;
+          const int32_t row = __shfl_sync(0xffffffffu, my, j);
+          const float* p = feat + (int64_t)row * fd;
 #pragma unroll
-        for (int t = 0; t < NV; ++t)
-          v[q][t] = ok ? ldg4(g.feat + row * (int64_t)fd + t * 128 + lane * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int t = 0; t < NV; ++t) v[q][t] = ldg4(p + t * 128);
+          n = q + 1;
+        }
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        if (j + q < nj) {
+        if (q < n) {
 #pragma unroll
           for (int t = 0; t < NV; ++t) {
             acc[t].x = __fadd_rn(acc[t].x, v[q][t].x); acc[t].y = __fadd_rn(acc[t].y, v[q][t].y);
@@ -224,11 +233,12 @@ __global__ void __launch_bounds__(256) k_sage_mean(DevGraph g, const unsigned lo
     }
   }
   const float denom = __fadd_rn((float)count, 1e-7f);
+  float* o = out + r * (int64_t)fd + lane * 4;
 #pragma unroll
   for (int t = 0; t < NV; ++t) {
     float4 a = acc[t];
     a.x = __fdiv_rn(a.x, denom); a.y = __fdiv_rn(a.y, denom); a.z = __fdiv_rn(a.z, denom); a.w = __fdiv_rn(a.w, denom);
-    st4(out + r * (int64_t)fd + t * 128 + lane * 4, a);
+    st4(o + t * 128, a);
   }
 }
 
@@ -350,8 +360,8 @@ int eu_sage_mean_aggregate(eu_ctx* c, const int64_t* nbr_ids, int64_t rows, int3
   const unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
   const unsigned long long* ids = (const unsigned long long*)nbr_ids;
   EuProfScope ps(c, "k_sage_mean", rows);
-  if (d.n_slots == 1 && dim == d.feat_dim && dim == 128 && aligned16(out)) k_sage_mean<1><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
-  else if (d.n_slots == 1 && dim == d.feat_dim && dim == 256 && aligned16(out)) k_sage_mean<2><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
+  if (d.n < ((int64_t)1 << 31) && d.n_slots == 1 && dim == d.feat_dim && dim == 128 && aligned16(out)) k_sage_mean<1><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
+  else if (d.n < ((int64_t)1 << 31) && d.n_slots == 1 && dim == d.feat_dim && dim == 256 && aligned16(out)) k_sage_mean<2><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
   else k_sage_mean_generic<<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, dim, out);
   EU_LAUNCHED();
   return EU_OK;

@@ -129,8 +129,8 @@ static constexpr int kPrepBlock = 256;
 __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSlot* tabs, Geom gm,
                                                         const unsigned long long* __restrict__ seeds,
                                                         ETypes et, int mode, uint32_t F, unsigned long long draws_per_row,
-                                                        int32_t* first, int64_t* rowof, uint32_t* emask, uint32_t* woff,
-                                                        uint32_t* blkpre, EuRngState* rngs) {
+                                                        int32_t* first, int64_t* rowof, uint32_t* emask, uint32_t* wmul,
+                                                        uint32_t* blkpre, uint32_t* blkmul, EuRngState* rngs) {
   __shared__ uint32_t s_w[kPrepBlock / 32];
   __shared__ bool s_last;
   const int b = blockIdx.y;
@@ -156,7 +156,10 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSl
     uint32_t off = 0;
     for (int k = 0; k < wid; ++k) off += s_w[k];
     emask[ii >> 5] = m;
-    woff[ii >> 5] = off;
+    // F^(eligible rows in earlier warps of this block), off < 256: the rows multiply instead of exponentiating
+    uint32_t fp = 1, fb = F;
+    for (; off; off >>= 1) { if (off & 1) fp = modmul(fp, fb); fb = modmul(fb, fb); }
+    wmul[ii >> 5] = fp;
   }
   uint32_t* bp = blkpre + (int64_t)b * gm.nblk_b;
   if (threadIdx.x == 0) {
@@ -183,7 +186,13 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSl
       s_scan[threadIdx.x] += t;
       __syncthreads();
     }
-    if (k < gridDim.x) bp[k] = carry + s_scan[threadIdx.x] - v;
+    if (k < gridDim.x) {
+      uint32_t pre = carry + s_scan[threadIdx.x] - v;   // eligible rows in earlier blocks of the batch
+      bp[k] = pre;
+      uint32_t fp = 1, fb = F;
+      for (; pre; pre >>= 1) { if (pre & 1) fp = modmul(fp, fb); fb = modmul(fb, fb); }
+      blkmul[(int64_t)b * gm.nblk_b + k] = fp;          // F^pre
+    }
     carry += s_scan[kPrepBlock - 1];
     __syncthreads();
   }
@@ -246,13 +255,15 @@ struct SampleArgs {
   int mode;
   // minstd: serial-stream position of a first-occurrence row f of batch b =
   //   blkpre[b][f/256] + woff[ff/32] + popc(emask[ff/32] & lanes_below(f%32)), ff = b*rows_pad + f;
-  //   engine state = rng[b].x_prev * F^pos
+  //   engine state = rng[b].x_prev * F^pos = x_prev * blkmul[b][f/256] * wmul[ff/32] * F^popc
   const int32_t* first;
   const int64_t* rowof;
   const uint32_t* emask;
-  const uint32_t* woff;
-  const uint32_t* blkpre;
-  uint32_t fpow2[32];           // F^(2^k) mod M
+  const uint32_t* wmul;         // F^(eligible rows in earlier warps of the block)
+  const uint32_t* blkmul;       // F^(eligible rows in earlier blocks of the batch)
+  uint32_t F;                   // A^(2 * uniforms per row) mod M
+  uint32_t lanepow[32];         // A^(2 * uniforms per draw * lane): a lane's jump from the row state
+  uint32_t stride;              // A^(2 * uniforms per draw * 32)
   HashSlot* clear_tab;          // dedup tables of THIS hop (all batches), cleared here for the next user
   int64_t clear_n;
   HashSlot* next_tabs;          // dedup tables of the NEXT hop: this hop's engine ids are its seeds (or null)
@@ -269,13 +280,13 @@ struct SampleArgs {
 
 // shuffle binary search over 32 lane-resident values c (non-decreasing, +inf padded):
 // first local index in [lo,hi] with (double)c > r, else hi.
-__device__ __forceinline__ int lane_upper_bound(float c, int lo, int hi, double r) {
+__device__ __forceinline__ int lane_upper_bound(float c, int lo, int hi, float thr) {
 #pragma unroll
   for (int it = 0; it < 5; ++it) {
     int mid = (lo + hi) >> 1;
     float v = __shfl_sync(0xffffffffu, c, mid);
     bool go = lo < hi;
-    bool gt = (double)v > r;
+    bool gt = v >= thr;   // (double)v > r, see gt_threshold
     hi = (go && gt) ? mid : hi;
     lo = (go && !gt) ? mid + 1 : lo;
   }
@@ -286,6 +297,17 @@ template <bool PHILOX>
 __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  __shared__ uint32_t s_lanepow[32];  // A^(2k*lane)
+  __shared__ uint32_t s_fpow[32];     // F^k, k < 32
+  if (!PHILOX) {
+    if (threadIdx.x < 32) {
+      s_lanepow[threadIdx.x] = a.lanepow[threadIdx.x];
+      uint32_t fp = 1, fb = a.F;
+      for (uint32_t e = threadIdx.x; e; e >>= 1) { if (e & 1) fp = modmul(fp, fb); fb = modmul(fb, fb); }
+      s_fpow[threadIdx.x] = fp;
+    }
+    __syncthreads();
+  }
   if (!PHILOX) {  // k_prepare (the only reader of this hop's dedup tables) has finished: wipe them
     for (int64_t s = gtid; s < a.clear_n; s += (int64_t)gridDim.x * blockDim.x) { a.clear_tab[s].key = 0; a.clear_tab[s].row = kEmptyRow; }
   }
@@ -316,12 +338,8 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
     ok = (m >> (f & 31)) & 1u;
     if (ok) {
       row = a.rowof[ib + f];
-      uint32_t pos = a.blkpre[(int64_t)bidx * a.gm.nblk_b + f / kPrepBlock] + a.woff[(ib + f) >> 5] +
-                     __popc(m & ((1u << (f & 31)) - 1u));
-      st = rng->x_prev;
-#pragma unroll 1
-      for (int k = 0; pos; ++k, pos >>= 1)
-        if (pos & 1u) st = modmul(st, a.fpow2[k]);
+      st = modmul(modmul(rng->x_prev, a.blkmul[(int64_t)bidx * a.gm.nblk_b + f / kPrepBlock]),
+                  modmul(a.wmul[(ib + f) >> 5], s_fpow[__popc(m & ((1u << (f & 31)) - 1u))]));
     } else {
       row = -1;
     }
@@ -374,11 +392,9 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
 
   const uint32_t upd = a.mode == 0 ? 1u : 2u;  // uniforms per draw
   // engine state before this lane's first draw, and the stride for draws lane+32, lane+64, ...
-  uint32_t x = 0, stride = 0;
-  if (!PHILOX) {
-    x = modmul(st, modpow_a_small(2u * upd * (uint32_t)lane));
-    stride = modpow_a_small(2u * upd * 32u);
-  }
+  uint32_t x = 0;
+  const uint32_t stride = a.stride;
+  if (!PHILOX) x = modmul(st, s_lanepow[lane]);
   const uint32_t salt = PHILOX ? (uint32_t)rng->calls : 0u;
   const unsigned long long pkey = PHILOX ? a.key ^ rng->key : 0ull;
 
@@ -401,8 +417,8 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
     float lb = lim_b, le = lim_e;
     if (a.mode != 0) {
       // type pick: RandomSelect(sum_weights_, 0, n-1)
-      double rt = pick_r(u_t, 0.f, tc_end);
-      int k = lane_upper_bound(tc, 0, ntc - 1, rt);
+      const float tt = gt_threshold(pick_r(u_t, 0.f, tc_end));
+      int k = lane_upper_bound(tc, 0, ntc - 1, tt);
       etype = a.mode == 1 ? a.et.v[k] : k;
       b = gp[etype];
       e = gp[etype + 1] - 1;
@@ -413,17 +429,17 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
       lb = b == base ? 0.f : __ldg(g.cum_w + b - 1);
       le = __ldg(g.cum_w + e);
     }
-    const double r = pick_r(u_n, lb, le);
+    const float thr = gt_threshold(pick_r(u_n, lb, le));
     int64_t m;
     float wgt;
     if (small_row) {
-      int li2 = lane_upper_bound(c, (int)(b - base), (int)(e - base), r);
+      int li2 = lane_upper_bound(c, (int)(b - base), (int)(e - base), thr);
       float hi_v = __shfl_sync(0xffffffffu, c, li2);
       float lo_v = __shfl_sync(0xffffffffu, c, li2 > 0 ? li2 - 1 : 0);
       m = base + li2;
       wgt = __fsub_rn(hi_v, li2 > 0 ? lo_v : 0.f);
     } else {
-      m = upper_bound_clamped(g.cum_w, b, e, r);
+      m = b + upper_bound_clamped(g.cum_w + b, 0, (int32_t)(e - b), thr);
       float hi_v = __ldg(g.cum_w + m);
       float lo_v = m > base ? __ldg(g.cum_w + m - 1) : 0.f;
       wgt = __fsub_rn(hi_v, lo_v);
@@ -442,6 +458,14 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
         a.out_t[obase + j] = keep ? etype : -1;
       }
     }
+    if (!PHILOX && ntab && a.mode == 0) {
+      // mode 0 cannot hit the `bad` path: the ids are final, enter them into the next hop's dedup table now
+      const unsigned act = __ballot_sync(0xffffffffu, active);
+      if (active) {
+        const unsigned peers = __match_any_sync(act, nid);
+        if (lane == __ffs(peers) - 1) dedup_insert_one(ntab, nmask, nid, nbase + j);
+      }
+    }
   }
   if (__any_sync(0xffffffffu, bad)) {
     for (int32_t j = lane; j < count; j += 32) {
@@ -449,7 +473,7 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
       if (a.out_ids) { a.out_ids[obase + j] = a.default_node; a.out_w[obase + j] = 0.f; a.out_t[obase + j] = -1; }
     }
   }
-  if (!PHILOX && ntab) {
+  if (!PHILOX && ntab && a.mode != 0) {
     // the engine ids just written are the next hop's seeds: enter them into its dedup table now
     // (each lane re-reads its own stores), so the next hop needs no insert kernel
     for (int32_t j0 = 0; j0 < count; j0 += 32) {
@@ -614,11 +638,14 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
   const uint32_t F = modpow_a(2ull * upr);
   { EuProfScope ps(c, "k_prepare", rows);
     k_prepare<<<dim3((unsigned)gm.nblk_b, (unsigned)nb), tb, 0, s>>>(d, tabs, gm, seeds, a.et, a.mode, F, upr, c->d_first,
-                                                                     c->d_rowof, c->d_emask, c->d_woff, c->d_blkpre, c->d_rng); }
+                                                                     c->d_rowof, c->d_emask, c->d_woff, c->d_blkpre, c->d_blkmul,
+                                                                     c->d_rng); }
   EU_LAUNCHED();
-  a.first = c->d_first; a.rowof = c->d_rowof; a.emask = c->d_emask; a.woff = c->d_woff; a.blkpre = c->d_blkpre;
-  a.fpow2[0] = F;
-  for (int k = 1; k < 32; ++k) a.fpow2[k] = modmul(a.fpow2[k - 1], a.fpow2[k - 1]);
+  a.first = c->d_first; a.rowof = c->d_rowof; a.emask = c->d_emask; a.wmul = c->d_woff; a.blkmul = c->d_blkmul;
+  a.F = F;
+  const uint32_t upd = a.mode == 0 ? 1u : 2u;
+  for (uint32_t k = 0; k < 32; ++k) a.lanepow[k] = modpow_a(2ull * upd * k);
+  a.stride = modpow_a(2ull * upd * 32ull);
   a.clear_tab = tabs;
   a.clear_n = (gm.cap_b + 1) * nb;
   if (chain) {

@@ -125,8 +125,8 @@ __global__ void k_merge_sample(const longlong2* __restrict__ rec,
 __global__ void k_merge_rows(const float* __restrict__ in, const int32_t* __restrict__ src_index, int64_t rows, int64_t D,
                              int G, float* __restrict__ out) {
   const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t k = tid / G;
-  const int sub = (int)(tid % G);
+  const int64_t k = tid >> (31 - __clz(G));   // G is a power of two
+  const int sub = (int)(tid & (G - 1));
   if (k >= rows) return;
   const float* s = in + k * D;
   float* o = out + (int64_t)src_index[k] * D;
