@@ -64,6 +64,8 @@ int ctx_reserve(eu_ctx* c, int64_t rows, int64_t table_slots) {
   if ((rc = regrow(&c->d_woff, rows / 32 + 2))) return rc;
   if ((rc = regrow(&c->d_blkpre, rows / 256 + 66))) return rc;
   if ((rc = regrow(&c->d_blkmul, rows / 256 + 66))) return rc;
+  if ((rc = regrow(&c->d_live, rows))) return rc;
+  if (!c->d_nlive && (rc = regrow(&c->d_nlive, 4))) return rc;
   if ((rc = regrow(&c->d_front[0], rows))) return rc;
   if ((rc = regrow(&c->d_front[1], rows))) return rc;
   c->cap_rows = rows;
@@ -136,7 +138,7 @@ int eu_ctx_destroy(eu_ctx* c) {
   cudaSetDevice(c->g->device);
   cudaStreamSynchronize(c->stream);
   cudaFree(c->d_rng); cudaFree(c->d_dedup); cudaFree(c->d_first); cudaFree(c->d_rowof);
-  cudaFree(c->d_elig); cudaFree(c->d_state); cudaFree(c->d_emask); cudaFree(c->d_woff); cudaFree(c->d_blkpre); cudaFree(c->d_blkmul); cudaFree(c->d_front[0]); cudaFree(c->d_front[1]);
+  cudaFree(c->d_elig); cudaFree(c->d_state); cudaFree(c->d_emask); cudaFree(c->d_woff); cudaFree(c->d_blkpre); cudaFree(c->d_blkmul); cudaFree(c->d_live); cudaFree(c->d_nlive); cudaFree(c->d_front[0]); cudaFree(c->d_front[1]);
   cudaFree(c->d_misc); cudaFree(c->d_stage);
   if (c->h_pin) cudaFreeHost(c->h_pin);
   delete c;

@@ -166,13 +166,35 @@ __device__ __forceinline__ float gt_threshold(double r) {
 
 // RandomSelect == min(end, first j in [begin,end] with (double)cum[j] > r) for non-decreasing cum
 // (proof sketch in DESIGN.md; checked against the literal search in tests/test_oracle_golden.py).
-// Binary search over a row slice in global memory; `base` points at the slice, offsets are 32-bit
-// (a row has < 2^31 edges), thr = gt_threshold(r).  Returns the offset in [lo, hi].
+// Search over a row slice in global memory; `base` points at the slice, offsets are 32-bit (a row has
+// < 2^31 edges), thr = gt_threshold(r).  Returns the offset in [lo, hi].
+// Invariant: the answer lies in [lo, hi]; hi is the clamp or an offset with base[hi] >= thr.
+// 8-ary descent: 7 independent probes per round trip.  The rows that land here are hubs (a hop-2 frontier is
+// degree-biased) whose slices live in L2; the profile (profiles/r01_*) shows the kernel stalled on exactly this
+// load-compare chain, with issue slots to spare for the extra probes.
 __device__ __forceinline__ int32_t upper_bound_clamped(const float* __restrict__ base, int32_t lo, int32_t hi,
                                                        float thr) {
-  while (lo < hi) {
-    const int32_t mid = (int32_t)(((uint32_t)lo + (uint32_t)hi) >> 1);
-    if (__ldg(base + mid) >= thr) hi = mid; else lo = mid + 1;
+  while (hi - lo >= 8) {
+    const uint32_t n = (uint32_t)(hi - lo);
+    float v[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) v[i] = __ldg(base + lo + (int32_t)(((uint64_t)(i + 1) * n) >> 3));  // lo < p_0 < .. < p_6 < hi
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) c += (v[i] >= thr) ? 0 : 1;                                          // monotone: a prefix is below thr
+    const int32_t nlo = c > 0 ? lo + (int32_t)(((uint64_t)c * n) >> 3) + 1 : lo;
+    const int32_t nhi = c < 7 ? lo + (int32_t)(((uint64_t)(c + 1) * n) >> 3) : hi;
+    lo = nlo; hi = nhi;
+  }
+  if (lo < hi) {  // fewer than 8 candidates below hi: one round of independent probes
+    const int32_t n = hi - lo;
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      const float v = i < n ? __ldg(base + lo + i) : __int_as_float(0x7f800000);
+      c += (v >= thr) ? 0 : 1;
+    }
+    lo += c;
   }
   return lo;
 }

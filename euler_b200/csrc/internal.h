@@ -111,6 +111,8 @@ struct eu_ctx {
   uint32_t* d_woff = nullptr;        // [rows/32] F^(count in earlier warps of the block)
   uint32_t* d_blkpre = nullptr;      // [rows/256] count in earlier blocks
   uint32_t* d_blkmul = nullptr;      // [rows/256] F^that count
+  int32_t* d_live = nullptr;         // [rows] rows that sample, compacted by k_prepare
+  unsigned int* d_nlive = nullptr;   // their number
   unsigned long long* d_front[2] = {nullptr, nullptr};  // engine-id frontier ping-pong [rows]
   // extra scratch for walks / scatter
   void* d_misc = nullptr;

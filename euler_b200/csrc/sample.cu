@@ -117,6 +117,20 @@ __device__ __forceinline__ bool row_eligible(const DevGraph& g, int64_t row, con
   return grp_cum_at(g, row, T - 1) != 0.f;
 }
 
+// outputs k_prepare needs to finish rows that cannot sample, and the list of rows that can
+struct PrepOut {
+  unsigned long long* eng_ids;
+  long long* out_ids;
+  float* out_w;
+  int32_t* out_t;
+  int32_t count;
+  long long default_node;
+  HashSlot* next_tabs;
+  int64_t next_cap_b;
+  int32_t* live;           // [nb*rows_b] global indices of rows that sample
+  unsigned int* n_live;    // their number (zeroed before the launch)
+};
+
 // ---------------------------------------------------------------------------- 2. prepare
 // Per row: first occurrence (ID_UNIQUE), graph row and eligibility of first occurrences.  The number
 // of ELIGIBLE FIRST-OCCURRENCE rows before row i of its batch -- its position in the reference's serial
@@ -130,7 +144,7 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSl
                                                         const unsigned long long* __restrict__ seeds,
                                                         ETypes et, int mode, uint32_t F, unsigned long long draws_per_row,
                                                         int32_t* first, int64_t* rowof, uint32_t* emask, uint32_t* wmul,
-                                                        uint32_t* blkpre, uint32_t* blkmul, EuRngState* rngs) {
+                                                        uint32_t* blkpre, uint32_t* blkmul, EuRngState* rngs, PrepOut po) {
   __shared__ uint32_t s_w[kPrepBlock / 32];
   __shared__ bool s_last;
   const int b = blockIdx.y;
@@ -138,16 +152,38 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSl
   const int64_t ii = b * gm.rows_pad + li;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   EuRngState* rng = rngs + b;
-  bool e = false;
+  bool e = false;      // eligible FIRST occurrence: takes a slot of the serial draw order
+  bool own = false;    // this row samples (its id is eligible, whether or not it is the first occurrence)
   if (li < gm.rows_b) {
-    const unsigned long long id = seeds[b * gm.rows_b + li];
+    const int64_t w = b * gm.rows_b + li;
+    const unsigned long long id = seeds[w];
     const int64_t f = dedup_first(tabs + (int64_t)b * (gm.cap_b + 1), (unsigned long long)gm.cap_b - 1, id);
     first[ii] = (int32_t)f;
-    if (f == li) {
-      const int64_t row = lookup_row(g, id);
+    // A duplicate has the same id, hence the same graph row and eligibility as its first occurrence: every row
+    // resolves its own, so rows that cannot sample are finished right here and never reach k_sample.
+    const int64_t row = lookup_row(g, id);
+    own = row_eligible(g, row, et, mode);
+    e = own && f == li;
+    if (own) {
       rowof[ii] = row;
-      e = row_eligible(g, row, et, mode);
+    } else {
+      const int64_t ob = w * (int64_t)po.count;
+      for (int32_t j = 0; j < po.count; ++j) {
+        if (po.eng_ids) po.eng_ids[ob + j] = 0ull;
+        if (po.out_ids) { po.out_ids[ob + j] = po.default_node; po.out_w[ob + j] = 0.f; po.out_t[ob + j] = -1; }
+      }
+      if (po.next_tabs)  // its `count` zeros enter the next hop's dedup table with their minimum index
+        dedup_insert_one(po.next_tabs + (int64_t)b * (po.next_cap_b + 1), (unsigned long long)po.next_cap_b - 1, 0ull,
+                         li * (int64_t)po.count);
     }
+  }
+  // compact the rows that do sample (order is irrelevant: a row's engine state depends only on its position)
+  {
+    const uint32_t om = __ballot_sync(0xffffffffu, own);
+    uint32_t basepos = 0;
+    if (lane == 0 && om) basepos = atomicAdd(po.n_live, (unsigned int)__popc(om));
+    basepos = __shfl_sync(0xffffffffu, basepos, 0);
+    if (own) po.live[basepos + __popc(om & ((1u << lane) - 1u))] = (int32_t)(b * gm.rows_b + li);
   }
   const uint32_t m = __ballot_sync(0xffffffffu, e);
   if (lane == 0) s_w[wid] = __popc(m);
@@ -256,6 +292,8 @@ struct SampleArgs {
   // minstd: serial-stream position of a first-occurrence row f of batch b =
   //   blkpre[b][f/256] + woff[ff/32] + popc(emask[ff/32] & lanes_below(f%32)), ff = b*rows_pad + f;
   //   engine state = rng[b].x_prev * F^pos = x_prev * blkmul[b][f/256] * wmul[ff/32] * F^popc
+  const int32_t* live;          // rows that sample (compacted by k_prepare); null => every row (philox)
+  const unsigned int* n_live;
   const int32_t* first;
   const int64_t* rowof;
   const uint32_t* emask;
@@ -294,7 +332,7 @@ __device__ __forceinline__ int lane_upper_bound(float c, int lo, int hi, float t
 }
 
 template <bool PHILOX>
-__global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
+__global__ void __launch_bounds__(256, 8) k_sample(DevGraph g, SampleArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   __shared__ uint32_t s_lanepow[32];  // A^(2k*lane)
@@ -311,7 +349,11 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
   if (!PHILOX) {  // k_prepare (the only reader of this hop's dedup tables) has finished: wipe them
     for (int64_t s = gtid; s < a.clear_n; s += (int64_t)gridDim.x * blockDim.x) { a.clear_tab[s].key = 0; a.clear_tab[s].row = kEmptyRow; }
   }
-  const int64_t w = gtid >> 5;
+  int64_t w = gtid >> 5;
+  if (!PHILOX) {
+    if (w >= (int64_t)__ldg(a.n_live)) return;   // empty rows were finished by k_prepare
+    w = a.live[w];
+  }
   if (w >= a.gm.nb * a.gm.rows_b) return;
   const int bidx = (int)(w / a.gm.rows_b);
   const int64_t li = w - bidx * a.gm.rows_b;
@@ -337,7 +379,7 @@ __global__ void __launch_bounds__(256, 6) k_sample(DevGraph g, SampleArgs a) {
     const uint32_t m = a.emask[(ib + f) >> 5];
     ok = (m >> (f & 31)) & 1u;
     if (ok) {
-      row = a.rowof[ib + f];
+      row = a.rowof[ib + li];
       st = modmul(modmul(rng->x_prev, a.blkmul[(int64_t)bidx * a.gm.nblk_b + f / kPrepBlock]),
                   modmul(a.wmul[(ib + f) >> 5], s_fpow[__popc(m & ((1u << (f & 31)) - 1u))]));
     } else {
@@ -637,11 +679,18 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
   const unsigned long long upr = (unsigned long long)count * (a.mode == 0 ? 1 : 2);
   const uint32_t F = modpow_a(2ull * upr);
   { EuProfScope ps(c, "k_prepare", rows);
+    PrepOut po{};
+    po.eng_ids = eng_ids; po.out_ids = (long long*)out_ids; po.out_w = out_w; po.out_t = out_t;
+    po.count = count; po.default_node = default_node;
+    if (chain) { po.next_tabs = ntabs; po.next_cap_b = ng.cap_b; }
+    po.live = c->d_live; po.n_live = c->d_nlive;
+    EU_CUDA(cudaMemsetAsync(c->d_nlive, 0, sizeof(unsigned int), s));
     k_prepare<<<dim3((unsigned)gm.nblk_b, (unsigned)nb), tb, 0, s>>>(d, tabs, gm, seeds, a.et, a.mode, F, upr, c->d_first,
                                                                      c->d_rowof, c->d_emask, c->d_woff, c->d_blkpre, c->d_blkmul,
-                                                                     c->d_rng); }
+                                                                     c->d_rng, po); }
   EU_LAUNCHED();
   a.first = c->d_first; a.rowof = c->d_rowof; a.emask = c->d_emask; a.wmul = c->d_woff; a.blkmul = c->d_blkmul;
+  a.live = c->d_live; a.n_live = c->d_nlive;
   a.F = F;
   const uint32_t upd = a.mode == 0 ? 1u : 2u;
   for (uint32_t k = 0; k < 32; ++k) a.lanepow[k] = modpow_a(2ull * upd * k);
