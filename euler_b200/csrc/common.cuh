@@ -34,6 +34,7 @@ struct DevGraph {
   const float* cum_w;             // [E]
   const float* grp_cum;           // [n*T] (T>1) or nullptr
   // id -> row
+  int32_t adj_sorted;             // every adjacency group is non-decreasing in (signed) neighbor id
   int32_t dense_ids;              // ids[r] == id_base + r * id_stride for all r
   unsigned long long id_base;
   unsigned long long id_stride;   // 1, or the shard count for a shard's rows (ids congruent mod shards)

@@ -160,6 +160,15 @@ __global__ void k_fill_feat(float* feat, int64_t n_local, int32_t dim, unsigned 
   }
 }
 
+// adj_sorted: lets the node2vec step classify neighbors by merging sorted lists in parallel
+// (the reference's two-pointer merge, tf_euler/kernels/random_walk_op.cc:140-168, assumes sorted lists too).
+__global__ void k_check_adj_sorted(int64_t n_groups, const int64_t* grp_ptr, const unsigned long long* nbr, int* unsorted) {
+  int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= n_groups) return;
+  for (int64_t j = grp_ptr[k] + 1; j < grp_ptr[k + 1]; ++j)
+    if ((long long)nbr[j - 1] > (long long)nbr[j]) { *unsorted = 1; return; }
+}
+
 static int build_hash(eu_graph* g) {
   DevGraph& d = g->d;
   unsigned long long cap = 64;
@@ -178,6 +187,19 @@ static int build_hash(eu_graph* g) {
   EU_LAUNCHED();
   EU_CUDA(cudaDeviceSynchronize());
   d.htab = tab;
+  {
+    int* flag = nullptr;
+    EU_CUDA(cudaMalloc(&flag, sizeof(int)));
+    EU_CUDA(cudaMemset(flag, 0, sizeof(int)));
+    if (d.n * d.T > 0) {
+      k_check_adj_sorted<<<(unsigned)ceil_div(d.n * d.T, tb), tb>>>(d.n * d.T, d.grp_ptr, d.nbr, flag);
+      EU_LAUNCHED();
+    }
+    int h = 0;
+    EU_CUDA(cudaMemcpy(&h, flag, sizeof(int), cudaMemcpyDeviceToHost));
+    cudaFree(flag);
+    d.adj_sorted = h ? 0 : 1;
+  }
   d.hmask = cap - 1;
   return EU_OK;
 }

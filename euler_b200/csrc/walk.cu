@@ -161,6 +161,118 @@ __global__ void __launch_bounds__(128) k_walk_step(DevGraph g, int64_t B, int32_
   s.cur[i] = next;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-cooperative exact step for the common case: ONE edge type per step and adjacency groups sorted by
+// neighbor id (DevGraph::adj_sorted; the reference's merge assumes sorted lists as well).  For sorted
+// multisets C (children) and P (parent's list) the two-pointer merge of BuildWeights (:140-168) marks the
+// m-th copy (m = 0,1,..) of value v in C as "shared" iff P holds more than m copies of v; everything else is
+// biased (/p if it is the parent id, /q otherwise).  That is a per-element predicate, so 32 lanes classify 32
+// children at once by streaming P in 32-wide chunks next to C; only the f32 prefix sum (CompactWeightedCollection
+// ::Init, compact_weighted_collection.h:82-97) stays serial -- it is evaluated left to right through shuffles,
+// ~5 cycles per neighbor, which is the floor for a bit-exact sum.  Pass 1 = total, pass 2 = select.
+struct WarpWalk {
+  const DevGraph* g;
+  int64_t cb, ce, cbase;   // child group [cb, ce), first edge of the child's row
+  int64_t pb, pe;          // parent group [pb, pe) (empty at step 0 / for dead parents)
+  long long parent_id;
+  float p, q;
+  int lane;
+
+  __device__ float pass(bool select, double pick, long long* sel) const {
+    const unsigned FULL = 0xffffffffu;
+    const long long BIG = 0x7fffffffffffffffLL;
+    float run = 0.f;                // running prefix, replicated in every lane
+    int64_t pk = pb;                // first parent chunk that can still hold values >= the current child minimum
+    long long prev_val = 0;
+    int prev_run = 0;               // copies of prev_val seen so far at the end of the previous child chunk
+    long long last_id = 0;
+    for (int64_t cj = cb; cj < ce; cj += 32) {
+      const int nvalid = (int)min((int64_t)32, ce - cj);
+      const int64_t j = cj + lane;
+      const bool valid = lane < nvalid;
+      const long long cv = valid ? (long long)__ldg(g->nbr + j) : BIG;
+      float w = 0.f;
+      if (valid) {
+        const float hi = __ldg(g->cum_w + j);
+        const float lo = j == cbase ? 0.f : __ldg(g->cum_w + j - 1);
+        w = __fsub_rn(hi, lo);
+      }
+      // m = copies of cv that precede this one in C
+      const unsigned peers = __match_any_sync(FULL, cv);
+      int m = __popc(peers & ((1u << lane) - 1u));
+      if (prev_run && cv == prev_val) m += prev_run;
+      // cnt = copies of cv in P: walk the parent chunks whose value range meets [vmin, vmax]
+      const long long vmin = __shfl_sync(FULL, cv, 0), vmax = __shfl_sync(FULL, cv, nvalid - 1);
+      int cnt = 0;
+      for (int64_t tk = pk; tk < pe; tk += 32) {
+        const long long pv = tk + lane < pe ? (long long)__ldg(g->nbr + tk + lane) : BIG;
+        const long long pmin = __shfl_sync(FULL, pv, 0);
+        const long long pmax = __shfl_sync(FULL, pv, (int)min((int64_t)31, pe - tk - 1));
+        if (pmax < vmin) { pk = tk + 32; continue; }   // below every remaining child value: never needed again
+        if (pmin > vmax) break;                         // above this child chunk: the next chunk restarts at pk
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) cnt += (__shfl_sync(FULL, pv, k) == cv) ? 1 : 0;
+        if (pmax > vmax) break;
+      }
+      const bool shared = m < cnt;
+      if (valid && !shared) w = cv != parent_id ? __fdiv_rn(w, q) : __fdiv_rn(w, p);   // d_tx = 2 / d_tx = 0
+      // serial f32 prefix over the chunk, left to right
+      float mine = 0.f;
+      for (int k = 0; k < nvalid; ++k) {
+        run = __fadd_rn(run, __shfl_sync(FULL, w, k));
+        if (lane == k) mine = run;
+      }
+      if (select) {
+        const unsigned hit = __ballot_sync(FULL, valid && (double)mine > pick);
+        if (hit) { *sel = __shfl_sync(FULL, cv, __ffs(hit) - 1); return run; }
+      }
+      last_id = __shfl_sync(FULL, cv, nvalid - 1);
+      prev_val = last_id;
+      prev_run = __shfl_sync(FULL, m, nvalid - 1) + 1;
+    }
+    if (select) *sel = last_id;   // RandomSelect's fall-through: the last entry
+    return run;
+  }
+};
+
+__global__ void __launch_bounds__(256) k_walk_step_warp(DevGraph g, int64_t B, int32_t L, int32_t step, int32_t ctype,
+                                                        int32_t ptype, float p, float q, long long default_node,
+                                                        WalkState s, const uint8_t* __restrict__ live,
+                                                        const uint32_t* __restrict__ state, bool philox,
+                                                        unsigned long long key, long long* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (i >= B) return;
+  const long long cur = s.cur[i];
+  const int64_t crow = s.cur_row[i];
+  long long next = default_node;
+  if (live[i]) {
+    const int64_t prow = s.parent_row[i];
+    WarpWalk ww;
+    ww.g = &g; ww.lane = lane; ww.p = p; ww.q = q; ww.parent_id = s.parent[i];
+    ww.cbase = g.grp_ptr[crow * g.T];
+    ww.cb = g.grp_ptr[crow * g.T + ctype];
+    ww.ce = g.grp_ptr[crow * g.T + ctype + 1];
+    ww.pb = ww.pe = 0;
+    if (prow >= 0 && ptype >= 0 && ptype < g.T) { ww.pb = g.grp_ptr[prow * g.T + ptype]; ww.pe = g.grp_ptr[prow * g.T + ptype + 1]; }
+    const float total = ww.pass(false, 0.0, nullptr);
+    double u, u2;
+    if (philox) {
+      philox_uniform2((unsigned long long)i, (uint32_t)step, 0x77616C6Bu, key, u, u2);
+    } else {
+      uint32_t x = state[i];
+      u = minstd_uniform(x);
+    }
+    ww.pass(true, pick_r(u, 0.f, total), &next);
+  }
+  if (lane == 0) {
+    out[i * (L + 1) + step + 1] = next;
+    s.parent[i] = cur;
+    s.parent_row[i] = crow;
+    s.cur[i] = next;
+  }
+}
+
 __global__ void k_walk_col(const unsigned long long* __restrict__ eng, int64_t B, int32_t L, int32_t col,
                            long long default_node, long long* __restrict__ out) {
   int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -226,9 +338,17 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
       rc = launch_state_scan(c, B, 1);
       if (rc) return rc;
     }
-    k_walk_step<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(d, B, L, l, cet, pet, p, q, default_node, ws, c->d_elig,
-                                                           c->d_state, c->rng == EU_RNG_PHILOX, c->seed ^ 0x6E32766563ull,
-                                                           (long long*)out);
+    const bool one_sorted_type = d.adj_sorted && cet.K == 1 && pet.K <= 1 && cet.v[0] >= 0 && cet.v[0] < d.T;
+    if (one_sorted_type) {
+      k_walk_step_warp<<<(unsigned)ceil_div(B * 32, 256), 256, 0, s>>>(d, B, L, l, cet.v[0], pet.K == 1 ? pet.v[0] : -1, p, q,
+                                                                       default_node, ws, c->d_elig, c->d_state,
+                                                                       c->rng == EU_RNG_PHILOX, c->seed ^ 0x6E32766563ull,
+                                                                       (long long*)out);
+    } else {
+      k_walk_step<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(d, B, L, l, cet, pet, p, q, default_node, ws, c->d_elig,
+                                                             c->d_state, c->rng == EU_RNG_PHILOX, c->seed ^ 0x6E32766563ull,
+                                                             (long long*)out);
+    }
     EU_LAUNCHED();
     pet = cet;
   }

@@ -154,6 +154,23 @@ def _oracle_fanout(og, nodes, ets, counts):
     return ids, ws, ts
 
 
+@pytest.mark.parametrize("T,sorted_adj,hub", [(1, True, 3000), (3, True, 500), (2, False, 300), (1, True, 0)])
+def test_node2vec_paths_vs_oracle(T, sorted_adj, hub):
+    """Both node2vec step kernels: the warp-cooperative one (one edge type per step, sorted adjacency, incl.
+    multi-edges and hubs spanning many 32-wide chunks) and the sequential fallback (unsorted / several types)."""
+    g = graphs.random_graph(seed=200 + T + hub, n=4000, T=T, avg_deg=9, hub=hub, sorted_adj=sorted_adj, dup_edges=True,
+                            empty_frac=0.05)
+    be, ob = cases.CudaBackend(g, g["ids"]), cases.OracleBackend(g, g["ids"])
+    seeds = g["ids"][np.random.RandomState(7).randint(0, 4000, size=700)].astype(np.int64)
+    seeds[::31] = 123456789
+    for wet in ([[T - 1]] * 15, [[0], [T - 1]] * 6, [list(range(T))] * 5):
+        for p, q in [(0.5, 2.0), (3.0, 0.25)]:
+            be.seed(9); ob.seed(9)
+            cases.eq(be.op_random_walk(seeds, np.asarray(wet, np.int32), p, q, -1),
+                     ob.op_random_walk(seeds, np.asarray(wet, np.int32), p, q, -1), "walk %s p=%s q=%s" % (wet[0], p, q))
+            assert be.draws() == ob.draws()
+
+
 def test_hetero_rmat_graph_vs_oracle():
     """Device-generated heterogeneous graph (configs[4] shape): export -> oracle -> all edge-type modes."""
     import euler_b200
