@@ -88,6 +88,13 @@ SIGNATURES = {
     "eu_shard_pack_sample": (C.c_int, [_P, _P, _P, _P, _I64, _P]),
     "eu_shard_merge_sample": (C.c_int, [_P, _P, _P, _I64, _I32, _I64, _P, _P, _P, _P]),
     "eu_shard_merge_rows": (C.c_int, [_P, _P, _P, _I64, _I64, _P]),
+    "eu_sym_create": (C.c_int, [_P, _I32, _I32, _I64, _I32, _I64, _I32, C.POINTER(_P), _P]),
+    "eu_sym_connect": (C.c_int, [_P, _P]),
+    "eu_sym_destroy": (C.c_int, [_P]),
+    "eu_sym_outputs": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P)]),
+    "eu_sym_error": (C.c_int, [_P, C.POINTER(C.c_int)]),
+    "eu_sym_sample_hop": (C.c_int, [_P, _P, _I64, _P, _I32, _I32, _I64, _I32, _I32]),
+    "eu_sym_get_dense_feature": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32]),
     "InitQueryProxy": (C.c_bool, [C.c_char_p]),
     "eu_default_graph": (_P, []),
     "eu_default_ctx": (_P, []),

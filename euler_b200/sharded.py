@@ -185,5 +185,93 @@ class ShardedGraph:
         return ops.merge_rows(back, src, rows, dim)
 
 
+class PeerShardedGraph:
+    """The same ops as ShardedGraph with the exchange done by the kernels themselves over NVLink peer memory
+    (csrc/p2p.cu): no NCCL call and no host sync per hop, so a whole step can be captured in a CUDA graph.
+    torch.distributed is used once, at construction, to all_gather the cudaIpc handles."""
+
+    def __init__(self, graph, rank, world, max_rows, max_count, max_feat_rows, max_dim, rng="minstd", seed=1,
+                 num_partitions=None, group=None):
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        from .graph import Context
+        self.torch, self.lib, self.check = torch, _lib.load(), _lib.check
+        self.graph, self.rank, self.N = graph, rank, world
+        self.P = num_partitions or world
+        self.dev = torch.device("cuda", graph.device)
+        self.ctx = Context(graph, rng, seed)
+        self.ctx.reserve(world * max_rows + 1024)
+        self._h = C.c_void_p()
+        handle = (C.c_char * 64)()
+        self.check(self.lib.eu_sym_create(self.ctx._h, rank, world, max_rows, max_count, max_feat_rows, max_dim,
+                                          C.byref(self._h), handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle.raw), group=group)
+        blob = b"".join(handles)
+        self.check(self.lib.eu_sym_connect(self._h, blob))
+        dist.barrier(group=group)
+        ptrs = [C.c_void_p() for _ in range(5)]
+        self.check(self.lib.eu_sym_outputs(self._h, *[C.byref(p) for p in ptrs]))
+        mk = self._view
+        n_out = max_rows * max_count
+        self.o_eng = mk(ptrs[0].value, n_out, torch.int64)
+        self.o_ids = mk(ptrs[1].value, n_out, torch.int64)
+        self.o_w = mk(ptrs[2].value, n_out, torch.float32)
+        self.o_t = mk(ptrs[3].value, n_out, torch.int32)
+        self.o_rows = mk(ptrs[4].value, max_feat_rows * max_dim, torch.float32)
+
+    def _view(self, ptr, n, dtype):
+        """zero-copy tensor over library-owned device memory"""
+        t = self.torch
+        nbytes = max(n, 1) * t.empty(0, dtype=dtype).element_size()
+        st = t._C._construct_storage_from_data_pointer(ptr, self.dev, nbytes)
+        return t.empty(0, dtype=dtype, device=self.dev).set_(st, 0, (max(n, 1),))
+
+    def _stream(self):
+        self.ctx.set_stream(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def error(self):
+        e = C.c_int(0)
+        self.check(self.lib.eu_sym_error(self._h, C.byref(e)))
+        return e.value
+
+    def hop(self, frontier, etypes, count, default_node=-1, packed=True):
+        """frontier: device i64 tensor.  Returns (eng, ids, w, t) VIEWS into the symmetric outputs (overwritten by the
+        next hop; eng is what the next hop consumes)."""
+        self._stream()
+        et = np.ascontiguousarray(etypes, dtype=np.int32)
+        rows = frontier.numel()
+        self.check(self.lib.eu_sym_sample_hop(self._h, frontier.data_ptr(), rows, et.ctypes.data, len(et), int(count),
+                                              default_node, self.P, int(packed)))
+        n = rows * int(count)
+        return self.o_eng[:n], self.o_ids[:n], self.o_w[:n], self.o_t[:n]
+
+    def sample_fanout(self, nodes, edge_types, counts, default_node=-1):
+        t = self.torch
+        frontier = nodes if isinstance(nodes, t.Tensor) else t.as_tensor(np.asarray(nodes), dtype=t.int64, device=self.dev)
+        frontier = frontier.to(device=self.dev, dtype=t.int64).reshape(-1).contiguous()
+        ids, ws, ts = [frontier], [], []
+        for et, c in zip(edge_types, counts):
+            eng, o_ids, o_w, o_t = self.hop(frontier, et, c, default_node)
+            ids.append(o_ids.clone()); ws.append(o_w.clone()); ts.append(o_t.clone())
+            frontier = eng.clone()
+        return ids, ws, ts
+
+    def get_dense_feature(self, nodes, fid, dim, clone=True):
+        t = self.torch
+        ids = nodes.to(device=self.dev, dtype=t.int64).reshape(-1).contiguous()
+        self._stream()
+        self.check(self.lib.eu_sym_get_dense_feature(self._h, ids.data_ptr(), ids.numel(), int(fid), int(dim), self.P))
+        out = self.o_rows[:ids.numel() * dim].reshape(ids.numel(), dim)
+        return out.clone() if clone else out
+
+    def close(self):
+        if self._h:
+            self.torch.cuda.synchronize()
+            self.lib.eu_sym_destroy(self._h)
+            self._h = None
+
+
 def _i64(ops):
     return ops.torch.int64 if hasattr(ops, "torch") else np.int64

@@ -231,6 +231,21 @@ int eu_shard_merge_sample(eu_ctx* c, const int64_t* packed, const int32_t* src_i
 int eu_shard_merge_rows(eu_ctx* c, const float* rows_in, const int32_t* src_index, int64_t rows, int64_t D,
                         float* out);
 
+/* Peer-memory exchange (csrc/p2p.cu): the all-to-all of a hop / feature fetch done by the kernels themselves over
+ * NVLink peer mappings -- no NCCL call, no host sync, CUDA-graph capturable.  One eu_sym per (ctx, rank): a symmetric
+ * region exported with cudaIpc; all_gather the 64-byte handles (any out-of-band channel) and eu_sym_connect.
+ * Results land in the rank's own symmetric output arrays (eu_sym_outputs), already in request order. */
+typedef struct eu_sym eu_sym;
+int eu_sym_create(eu_ctx* c, int32_t rank, int32_t world, int64_t max_rows, int32_t max_count, int64_t max_feat_rows,
+                  int32_t max_dim, eu_sym** out, void* handle_out /* 64 bytes */);
+int eu_sym_connect(eu_sym* s, const void* handles /* world x 64 bytes, rank order */);
+int eu_sym_destroy(eu_sym* s);
+int eu_sym_outputs(eu_sym* s, int64_t** eng, int64_t** ids, float** w, int32_t** t, float** rows);
+int eu_sym_error(eu_sym* s, int* err);   /* 1 if a bounded wait timed out (synchronises) */
+int eu_sym_sample_hop(eu_sym* s, const int64_t* seeds, int64_t rows, const int32_t* etypes, int32_t K, int32_t count,
+                      int64_t default_node, int32_t num_partitions, int32_t want_packed);
+int eu_sym_get_dense_feature(eu_sym* s, const int64_t* ids, int64_t rows, int32_t fid, int32_t dim, int32_t num_partitions);
+
 /* ------------------------------------------------------------------ reference entry point ---- */
 /* bool InitQueryProxy(const char* conf) -- tf_euler/utils/init_query_proxy.cc:19-36.  "k=v;k=v";
  * keys of euler/client/query_proxy.cc:41-160 that apply here: mode (local only), data_path,

@@ -48,8 +48,27 @@ def main():
     expect2 = None
     ids2, _, _ = sg.sample_fanout(seeds[rank], ets, counts, -1)
     assert not np.array_equal(ids2[1].cpu().numpy(), ids[1].cpu().numpy())
+    # ---- the same semantics with the exchange done by the kernels over NVLink peer memory (csrc/p2p.cu)
+    from euler_b200.sharded import PeerShardedGraph
+    n1, n2 = 2048 * 25, 2048 * 250
+    pg = PeerShardedGraph(gr, rank, world, max_rows=n1, max_count=25, max_feat_rows=n2, max_dim=64, rng="minstd", seed=700 + rank)
+    p_ids, p_ws, p_ts = pg.sample_fanout(seeds[rank], ets, counts, -1)
+    assert pg.error() == 0, "peer exchange timed out"
+    for l in range(3):
+        cases.eq(p_ids[l].cpu().numpy(), expect[rank][0][l], "peer: rank %d ids hop %d" % (rank, l))
+    for l in range(2):
+        cases.eq(p_ws[l].cpu().numpy(), expect[rank][1][l], "peer: rank %d w hop %d" % (rank, l))
+        cases.eq(p_ts[l].cpu().numpy(), expect[rank][2][l], "peer: rank %d t hop %d" % (rank, l))
+    pf = pg.get_dense_feature(p_ids[2], 0, 64)
+    cases.eq(pf.cpu().numpy(), full.op_get_dense_feature(p_ids[2].cpu().numpy(), 64), "peer: rank %d features" % rank)
+    for _ in range(3):   # repeated exchanges reuse the inboxes / epochs
+        q_ids, _, _ = pg.sample_fanout(seeds[rank], ets, counts, -1)
+        qf = pg.get_dense_feature(q_ids[1], 0, 64)
+    assert pg.error() == 0
+    cases.eq(qf.cpu().numpy(), full.op_get_dense_feature(q_ids[1].cpu().numpy(), 64), "peer: features after reuse")
     torch.cuda.synchronize()
     dist.barrier()
+    pg.close()
     if rank == 0:
         print("SHARDED_GPU_OK world=%d" % world)
     dist.destroy_process_group()
