@@ -44,6 +44,7 @@ def parse():
                                                           "dedup scope (eu_sample_fanout_batched), only the kernel launches are shared")
     p.add_argument("--no-fuse", action="store_true", help="get_dense_feature + scatter_mean instead of the fused kernel")
     p.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph per step")
+    p.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N>1: in-kernel peer-memory exchange or NCCL")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=15.0)
     p.add_argument("--breakdown-iters", type=int, default=50)
@@ -375,79 +376,140 @@ def run_ours(args):
 
 # ----------------------------------------------------------------------------- sharded arm (N > 1)
 def run_sharded(args, world, rank, local):
-    """Weak scaling: the graph is hash-partitioned by id over the ranks (owner = id % N, Euler's shard scheme),
-    every rank constructs its own batch per step; each hop and the feature fetch resolve remote ids with
-    NCCL all-to-all over NVLink (euler_b200/sharded.py)."""
+    """Weak scaling: the graph is hash-partitioned by id over the ranks (owner = id % N, Euler's shard scheme), every
+    rank constructs its own batch per step; each hop and the feature fetch resolve remote ids through an all-to-all over
+    NVLink -- by default done by the kernels themselves on peer memory (csrc/p2p.cu: no NCCL call, no host sync; the
+    whole step is one CUDA graph per lane), or with NCCL (--exchange nccl, euler_b200/sharded.py::ShardedGraph)."""
+    import ctypes
     import torch
     import torch.distributed as dist
     import euler_b200 as eb
     from euler_b200 import _lib
-    from euler_b200.sharded import CudaShardOps, ShardedGraph, TorchExchange
+    from euler_b200.sharded import CudaShardOps, PeerShardedGraph, ShardedGraph, TorchExchange
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     counts = [int(x) for x in args.fanout.split(",")]
     L, B, D = len(counts), args.batch, args.dim
     graph = eb.Graph.rmat_shard(args.nodes, args.edges, rank, world, feat_dim=D, device=local)
-    ops = CudaShardOps(graph, args.rng, 12345 + rank)
-    sg = ShardedGraph(ops, TorchExchange())
     n = [B]
     for c in counts:
         n.append(n[-1] * c)
-    ops.ctx.reserve(max(n) * 2 + sum(n))
+    peer = args.exchange == "peer"
+    n_lanes = args.lanes if peer else 1
+    src = [torch.arange(n[l], dtype=torch.int32, device="cuda").repeat_interleave(counts[l]) for l in range(L)]
+
+    class SLane:
+        pass
+    lanes = []
+    for i in range(n_lanes):
+        ln = SLane()
+        ln.stream = torch.cuda.Stream()
+        seed = 12345 + rank * 1000 + i
+        if peer:
+            ln.sg = PeerShardedGraph(graph, rank, world, max_rows=max(n[:-1]), max_count=max(counts), max_feat_rows=sum(n),
+                                     max_dim=D, rng=args.rng, seed=seed)
+            ln.ctx = ln.sg.ctx
+        else:
+            ln.ops = CudaShardOps(graph, args.rng, seed)
+            ln.sg = ShardedGraph(ln.ops, TorchExchange())
+            ln.ctx = ln.ops.ctx
+            ln.ctx.reserve(max(n) * 2 + sum(n))
+        ln.d_seeds = torch.empty(B, dtype=torch.int64, device="cuda")
+        ln.agg = [torch.empty((n[l], D), dtype=torch.float32, device="cuda") for l in range(L)]
+        ln.ids = [torch.empty(x, dtype=torch.int64, device="cuda") for x in n[1:]]
+        ln.x = [torch.empty((n[l], D), dtype=torch.float32, device="cuda") for l in range(L)]
+        ln.h_seeds = torch.empty(B, dtype=torch.int64).pin_memory()
+        ln.h_ids = [torch.empty(x, dtype=torch.int64).pin_memory() for x in n[1:]]
+        ln.h_x = [torch.empty((n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
+        ln.h_agg = [torch.empty((n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
+        lanes.append(ln)
+
+    def raw_step(ln, seeds_dev):
+        sg = ln.sg
+        if peer:
+            frontier = seeds_dev
+            for l in range(L):
+                eng, o_ids, o_w, o_t = sg.hop(frontier, [0], counts[l], -1)
+                ln.ids[l].copy_(o_ids)
+                frontier = eng if l + 1 == L else eng.clone()
+            feats = sg.get_dense_feature(torch.cat([seeds_dev] + ln.ids), 0, D, clone=False)
+        else:
+            ids, ws, ts = sg.sample_fanout(seeds_dev, [[0]] * L, counts, -1)
+            for l in range(L):
+                ln.ids[l].copy_(ids[l + 1])
+            feats = sg.get_dense_feature(torch.cat(ids), 0, D)
+        ln.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        off = 0
+        xs = []
+        for l in range(L + 1):
+            xs.append(feats[off:off + n[l]])
+            off += n[l]
+        for l in range(L):
+            ln.x[l].copy_(xs[l])
+            rc = lib.eu_scatter_mean(ln.ctx._h, xs[l + 1].data_ptr(), D, src[l].data_ptr(), n[l + 1], n[l], ln.agg[l].data_ptr())
+            if rc:
+                raise RuntimeError(lib.eu_last_error().decode())
+
+    use_graphs = peer and not args.no_graphs
+    if use_graphs:
+        for ln in lanes:
+            with torch.cuda.stream(ln.stream):
+                raw_step(ln, ln.d_seeds)
+            ln.stream.synchronize()
+        dist.barrier()
+        for ln in lanes:
+            ln.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ln.graph, stream=ln.stream):
+                raw_step(ln, ln.d_seeds)
+        dist.barrier()
+
+    def step(ln, seeds_dev):
+        if use_graphs:
+            if seeds_dev is not ln.d_seeds:
+                ln.d_seeds.copy_(seeds_dev, non_blocking=True)
+            ln.graph.replay()
+        else:
+            raw_step(ln, seeds_dev)
+
     nb = args.warmup + args.steps
     host_seeds = np.stack([np.random.RandomState(1000 + rank * 100003 + i).randint(1, args.nodes + 1, size=B)
                            for i in range(max(nb, 16))]).astype(np.int64)
     dev_seeds = torch.from_numpy(host_seeds).cuda()
-    src = [torch.arange(n[l], dtype=torch.int32, device="cuda").repeat_interleave(counts[l]) for l in range(L)]
-    agg = [torch.empty((n[l], D), dtype=torch.float32, device="cuda") for l in range(L)]
-    h_seeds = torch.empty(B, dtype=torch.int64).pin_memory()
-    h_out = [torch.empty(x, dtype=torch.int64).pin_memory() for x in n[1:]] + \
-            [torch.empty((n[l], D), dtype=torch.float32).pin_memory() for l in range(L)] * 2
-
-    def step(seeds_dev):
-        ids, ws, ts = sg.sample_fanout(seeds_dev, [[0]] * L, counts, -1)
-        feats = sg.get_dense_feature(torch.cat(ids), 0, D)
-        off = 0
-        x = []
-        for l in range(L + 1):
-            x.append(feats[off:off + n[l]])
-            off += n[l]
-        h = ops._stream()
-        for l in range(L):
-            rc = lib.eu_scatter_mean(h, x[l + 1].data_ptr(), D, src[l].data_ptr(), n[l + 1], n[l], agg[l].data_ptr())
-            if rc:
-                raise RuntimeError(lib.eu_last_error().decode())
-        return ids, x
+    main = torch.cuda.current_stream()
 
     def run(n_steps, first, e2e):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
-        ev0.record()
+        ev0.record(main)
+        for ln in lanes:
+            ln.stream.wait_event(ev0)
         for i in range(n_steps):
-            if e2e:
-                h_seeds.copy_(torch.from_numpy(host_seeds[(first + i) % len(host_seeds)]))
-                sd = h_seeds.cuda(non_blocking=True)
-                ids, x = step(sd)
-                k = 0
-                for l in range(L):
-                    h_out[k].copy_(ids[l + 1], non_blocking=True); k += 1
-                for l in range(L):
-                    h_out[k].copy_(x[l], non_blocking=True); k += 1
-                for l in range(L):
-                    h_out[k].copy_(agg[l], non_blocking=True); k += 1
-            else:
-                step(dev_seeds[(first + i) % len(host_seeds)])
-        ev1.record()
+            ln = lanes[i % len(lanes)]
+            with torch.cuda.stream(ln.stream):
+                if e2e:
+                    ln.stream.synchronize() if i >= len(lanes) else None
+                    ln.h_seeds.copy_(torch.from_numpy(host_seeds[(first + i) % len(host_seeds)]))
+                    ln.d_seeds.copy_(ln.h_seeds, non_blocking=True)
+                    step(ln, ln.d_seeds)
+                    for l in range(L):
+                        ln.h_ids[l].copy_(ln.ids[l], non_blocking=True)
+                        ln.h_x[l].copy_(ln.x[l], non_blocking=True)
+                        ln.h_agg[l].copy_(ln.agg[l], non_blocking=True)
+                else:
+                    step(ln, dev_seeds[(first + i) % len(host_seeds)])
+        for ln in lanes:
+            main.wait_stream(ln.stream)
+        ev1.record(main)
         torch.cuda.synchronize()
         dist.barrier()
         t = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    run(-(-args.warmup // G) * G, 0, False)
+    run(args.warmup, 0, False)
     clocks = Clocks(local)
     clocks.start()
     time.sleep(0.3)
@@ -459,13 +521,14 @@ def run_sharded(args, world, rank, local):
     clk = clocks.stop(w0, w1)
     run(min(args.warmup, 4), 0, True)
     ms_e2e = run(args.steps, args.warmup, True)
+    err = max(ln.sg.error() for ln in lanes) if peer else 0
     bts = step_bytes(B, counts, D)
     edges_step = bts["edges"] * world
     remote = (world - 1) / world
     a2a_bytes = 0
     for l in range(L):
-        a2a_bytes += remote * n[l] * (8 + 16 * counts[l])
-    a2a_bytes += remote * sum(n) * (8 + 4 * D)
+        a2a_bytes += remote * n[l] * (12 + 24 * counts[l])
+    a2a_bytes += remote * sum(n) * (12 + 4 * D)
     if rank == 0:
         out = {
             "metric": "sampled_edges_per_sec", "value": edges_step * args.steps / (ms * 1e-3), "unit": "edges/s",
@@ -473,24 +536,31 @@ def run_sharded(args, world, rank, local):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 ids / f32 weights+features (f64 CDF compare)", "data": "synthetic",
             "config": {"workload": "BASELINE configs[1] sharded: RMAT %dM nodes/%dM edges hash-partitioned by id over %d GPUs, per rank "
-                                   "2-hop sample_fanout %s batch=%d + dense features (dim %d) + GraphSAGE mean, NCCL all-to-all per hop"
+                                   "2-hop sample_fanout %s batch=%d + dense features (dim %d) + GraphSAGE mean, all-to-all per hop"
                                    % (args.nodes // 10**6, args.edges // 10**6, world, counts, B, D),
                        "nodes": args.nodes, "edges": args.edges, "batch_per_gpu": B, "global_batch": B * world, "fanout": counts,
-                       "feat_dim": D, "rng": args.rng, "parallelism": "graph sharded id %% %d, batches data-parallel" % world,
+                       "feat_dim": D, "rng": args.rng, "exchange": "peer-memory kernels (NVLink loads/stores, no NCCL)" if peer else "NCCL all_to_all",
+                       "lanes_in_flight": n_lanes, "cuda_graphs": use_graphs, "peer_wait_timeouts": err,
+                       "parallelism": "graph sharded id %% %d, batches data-parallel" % world,
                        "l2_policy": "inputs larger than L2 (random seeds per step over a %.1f GB shard)" % (graph.hbm_bytes / 1e9)},
             "e2e": {"value": edges_step * args.steps / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 8 * B * world,
                     "d2h_bytes_per_step": world * (sum(8 * x for x in n[1:]) + 2 * sum(4 * n[l] * D for l in range(L))),
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clk,
-            "roofline": {"bound": "nvlink", "kernel": "all-to-all exchange (seeds out, sampled rows + feature rows back)",
+            "gpu_launches": int(launches) if not use_graphs else None, "clocks": clk,
+            "roofline": {"bound": "nvlink", "kernel": "exchange kernels (k_sym_push / k_sym_reply_sample / k_sym_reply_feature)" if peer else "NCCL all-to-all",
                          "achieved": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9, 2), "peak": 770.0, "unit": "GB/s",
                          "frac": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9 / 770.0, 4), "traffic": None,
                          "peak_source": "B200_PROFILING.md measured peer copy 770 GB/s per direction",
                          "algorithmic_bytes_per_step_per_rank": int(a2a_bytes),
-                         "note": "achieved = algorithmic all-to-all bytes per rank per step / whole step time (exchange is not timed alone)"},
+                         "note": "achieved = algorithmic exchange bytes per rank per step / whole step time (the exchange is not timed alone)"},
             "hbm_graph_bytes_per_rank": graph.hbm_bytes,
         }
+        if use_graphs:
+            out["gpu_launches"] = "one CUDA graph replay per step (kernels of this library only)"
         print(json.dumps(out))
+    if peer:
+        for ln in lanes:
+            ln.sg.close()
     dist.destroy_process_group()
 
 

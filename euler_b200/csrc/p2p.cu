@@ -107,14 +107,17 @@ __global__ void __launch_bounds__(256) k_sym_push(SymPeers peers, SymLayout lay,
   }
 }
 
-// ---- owner: wait for every source, zero-pad the segments
+// ---- owner: wait for every source (one small block spins; nothing else of the GPU is held)
+__global__ void k_sym_wait_in(char* base, int N) {
+  SymHeader* h = hdr_of(base);
+  if (threadIdx.x < N) spin_until(&h->flagA[threadIdx.x], h->epoch, &h->error);
+}
+
+// ---- owner: zero-pad the segments (the counts were published before the flags)
 __global__ void __launch_bounds__(256) k_sym_wait_pad(char* base, SymLayout lay, int N) {
   SymHeader* h = hdr_of(base);
   __shared__ int s_cnt[kSymMaxRanks];
-  if (threadIdx.x < N) {
-    spin_until(&h->flagA[threadIdx.x], h->epoch, &h->error);
-    s_cnt[threadIdx.x] = *reinterpret_cast<volatile int*>(&h->in_cnt[threadIdx.x]);
-  }
+  if (threadIdx.x < N) s_cnt[threadIdx.x] = *reinterpret_cast<volatile int*>(&h->in_cnt[threadIdx.x]);
   __syncthreads();
   unsigned long long* ids = reinterpret_cast<unsigned long long*>(base + lay.off_inbox_ids);
   const int64_t total = (int64_t)N * lay.cap;
@@ -351,6 +354,8 @@ int eu_sym_sample_hop(eu_sym* s, const int64_t* seeds, int64_t rows, const int32
   k_sym_push<<<(unsigned)ceil_div(std::max<int64_t>(rows, 1), 256), 256, 0, st>>>(s->peers, L, s->rank, N, (const unsigned long long*)s->d_sorted,
                                                                                   s->d_src, (const long long*)s->d_offs, rows);
   EU_LAUNCHED();
+  k_sym_wait_in<<<1, 32, 0, st>>>(s->base, N);
+  EU_LAUNCHED();
   k_sym_wait_pad<<<148, 256, 0, st>>>(s->base, L, N);
   EU_LAUNCHED();
   if (count > 0) {
@@ -388,7 +393,7 @@ int eu_sym_get_dense_feature(eu_sym* s, const int64_t* ids, int64_t rows, int32_
   k_sym_push<<<(unsigned)ceil_div(std::max<int64_t>(rows, 1), 256), 256, 0, st>>>(s->peers, L, s->rank, N, (const unsigned long long*)s->d_sorted,
                                                                                   s->d_src, (const long long*)s->d_offs, rows);
   EU_LAUNCHED();
-  k_sym_wait_pad<<<148, 256, 0, st>>>(s->base, L, N);
+  k_sym_wait_in<<<1, 32, 0, st>>>(s->base, N);
   EU_LAUNCHED();
   int G = 1;
   while (G < 32 && G < dim / 4) G <<= 1;
