@@ -371,7 +371,7 @@ def run_ours(args):
     }
     if not args.no_cpu_baseline and rank == 0:
         out["cpu_baseline"] = cpu_baseline(graph, args, counts, host_seeds)
-    print(json.dumps(out))
+    emit(out)
 
 
 # ----------------------------------------------------------------------------- sharded arm (N > 1)
@@ -433,7 +433,16 @@ def run_sharded(args, world, rank, local):
                 eng, o_ids, o_w, o_t = sg.hop(frontier, [0], counts[l], -1)
                 ln.ids[l].copy_(o_ids)
                 frontier = eng if l + 1 == L else eng.clone()
-            feats = sg.get_dense_feature(torch.cat([seeds_dev] + ln.ids), 0, D, clone=False)
+            # self features of the hop-0/1 nodes are materialised; the hop-(l+1) features are summed by their owners
+            # (eu_sym_sage_mean) and never cross NVLink row by row
+            feats = sg.get_dense_feature(torch.cat([seeds_dev] + ln.ids[:L - 1]), 0, D, clone=False)
+            off = 0
+            for l in range(L):
+                ln.x[l].copy_(feats[off:off + n[l]])
+                off += n[l]
+            for l in range(L):
+                sg.sage_mean(ln.ids[l], n[l], counts[l], D, out=ln.agg[l])
+            return
         else:
             ids, ws, ts = sg.sample_fanout(seeds_dev, [[0]] * L, counts, -1)
             for l in range(L):
@@ -522,6 +531,26 @@ def run_sharded(args, world, rank, local):
     run(min(args.warmup, 4), 0, True)
     ms_e2e = run(args.steps, args.warmup, True)
     err = max(ln.sg.error() for ln in lanes) if peer else 0
+    # per-kernel breakdown on one lane (library-side CUDA events), serial, no graphs
+    prof = {}
+    ln = lanes[0]
+    lib.eu_ctx_profile(ln.ctx._h, 1)
+    with torch.cuda.stream(ln.stream):
+        for it in range(10):
+            raw_step(ln, dev_seeds[it % len(host_seeds)])
+    ln.stream.synchronize()
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.eu_ctx_profile_read(ln.ctx._h, buf, len(buf))
+    lib.eu_ctx_profile(ln.ctx._h, 0)
+    for line in buf.value.decode().strip().splitlines():
+        nm, rows_, cnt_, ms_tot = line.split(",")
+        prof["%s[rows=%s]" % (nm, rows_)] = round(float(ms_tot) / 10, 4)
+    all_prof = [None] * world
+    dist.all_gather_object(all_prof, prof)
+    if os.environ.get("EU_BENCH_DEBUG") and rank == 0:
+        for r_, p_ in enumerate(all_prof):
+            print("rank %d profile: %s" % (r_, json.dumps(dict(sorted(p_.items(), key=lambda kv: -kv[1])))), file=sys.stderr)
+    prof = {k: max(p_.get(k, 0.0) for p_ in all_prof) for k in prof}
     bts = step_bytes(B, counts, D)
     edges_step = bts["edges"] * world
     remote = (world - 1) / world
@@ -554,10 +583,11 @@ def run_sharded(args, world, rank, local):
                          "algorithmic_bytes_per_step_per_rank": int(a2a_bytes),
                          "note": "achieved = algorithmic exchange bytes per rank per step / whole step time (the exchange is not timed alone)"},
             "hbm_graph_bytes_per_rank": graph.hbm_bytes,
+            "kernel_ms_per_step_single_lane": dict(sorted(prof.items(), key=lambda kv: -kv[1])),
         }
         if use_graphs:
             out["gpu_launches"] = "one CUDA graph replay per step (kernels of this library only)"
-        print(json.dumps(out))
+        emit(out)
     if peer:
         for ln in lanes:
             ln.sg.close()
@@ -672,10 +702,22 @@ def run_reference(args):
                             "sample": "%d steps of %d threads x 1 batch" % (steps, cores)},
            "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(out):
+    """the ONE JSON line goes to the process's real stdout; everything else any library printed went to stderr"""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(out) + "\n").encode())
 
 
 if __name__ == "__main__":
+    # libraries (NCCL's version banner, torchrun notices) print to fd 1: keep stdout for the JSON line alone
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)

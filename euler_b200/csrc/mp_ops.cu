@@ -287,6 +287,7 @@ static int scatter(eu_ctx* c, const float* upd, int64_t D, const int32_t* idx, i
     EU_LAUNCHED();
   }
   const unsigned gs = (unsigned)ceil_div(size * G, tb), ge = (unsigned)ceil_div((E > 0 ? E : 1) * G, tb);
+  EuProfScope ps(c, "scatter(sorted+fallback)", E);
   if (vec) k_scatter_sorted<OP, true><<<gs, tb, 0, s>>>(upd, D, idx, E, size, G, unsorted, out);
   else k_scatter_sorted<OP, false><<<gs, tb, 0, s>>>(upd, D, idx, E, size, G, unsorted, out);
   EU_LAUNCHED();

@@ -77,8 +77,8 @@ __global__ void __launch_bounds__(256) k_sym_push(SymPeers peers, SymLayout lay,
   __shared__ bool s_last;
   if (threadIdx.x <= N) s_off[threadIdx.x] = offsets[threadIdx.x];
   __syncthreads();
-  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (k < rows) {
+  // persistent grid: one system fence per block, not per 256 rows (a fence waits for the NVLink acks of the block's stores)
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < rows; k += (int64_t)gridDim.x * blockDim.x) {
     int o = 0;
     while (o + 1 < N && k >= s_off[o + 1]) ++o;
     const int64_t pos = k - s_off[o];
@@ -136,9 +136,8 @@ __global__ void __launch_bounds__(256) k_sym_reply_sample(SymPeers peers, SymLay
   SymHeader* mine = hdr_of(base);
   const int32_t* src = reinterpret_cast<const int32_t*>(base + lay.off_inbox_src);
   __shared__ bool s_last;
-  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const int64_t slots = (int64_t)N * lay.cap * count;
-  if (tid < slots) {
+  for (int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; tid < slots; tid += (int64_t)gridDim.x * blockDim.x) {
     const int64_t row = tid / count;            // padded inbox row
     const int32_t j = (int32_t)(tid - row * count);
     const int s = (int)(row / lay.cap);
@@ -174,10 +173,10 @@ __global__ void __launch_bounds__(256) k_sym_reply_feature(DevGraph g, SymPeers 
   const unsigned long long* ids = reinterpret_cast<const unsigned long long*>(base + lay.off_inbox_ids);
   const int32_t* src = reinterpret_cast<const int32_t*>(base + lay.off_inbox_src);
   __shared__ bool s_last;
-  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t row = tid >> (31 - __clz(G));
-  const int sub = (int)(tid & (G - 1));
-  if (row < (int64_t)N * lay.cap) {
+  const int sh = 31 - __clz(G);
+  const int sub = (int)(threadIdx.x & (G - 1));
+  for (int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> sh; row < (int64_t)N * lay.cap;
+       row += ((int64_t)gridDim.x * blockDim.x) >> sh) {
     const int s = (int)(row / lay.cap);
     if (row - (int64_t)s * lay.cap < mine->in_cnt[s]) {
       const int64_t gr = sdim > 0 ? lookup_row(g, ids[row]) : -1;
@@ -204,6 +203,154 @@ __global__ void __launch_bounds__(256) k_sym_reply_feature(DevGraph g, SymPeers 
 __global__ void k_sym_wait(char* base, int N) {
   SymHeader* h = hdr_of(base);
   if (threadIdx.x < N) spin_until(&h->flagB[threadIdx.x], h->epoch, &h->error);
+}
+
+// ---- fused sharded SAGE mean.  The requester pushes the neighbor ids of its fixed-fanout block (flat [rows*count],
+// src index = flat position, stable bucket => ascending inside every segment); the owner sums the features of ITS ids
+// per destination row, j ascending, and stores ONE partial row per (owner, destination) into the requester's `part`
+// region; the requester adds the N partials in rank order and divides.  NVLink carries rows*dim floats per owner instead
+// of rows*count*dim: the hop-2 features never cross the link (sage_dataflow.py:43-46 + mp_ops.py:65-69 fused with the
+// REMOTE get_dense_feature they follow).
+__device__ __forceinline__ int32_t warp_lower_bound(const int32_t* __restrict__ a, int32_t n, int32_t key, int lane) {
+  int32_t lo = 0, hi = n;
+  while (hi - lo > 32) {
+    const int32_t len = hi - lo;
+    const int32_t p = lo + (int32_t)(((int64_t)(lane + 1) * len) / 33);   // lo < p_0 <= .. <= p_31 < hi
+    const int c = __popc(__ballot_sync(0xffffffffu, a[p] < key));          // sorted: a prefix of the probes is below
+    const int32_t below = __shfl_sync(0xffffffffu, p, c > 0 ? c - 1 : 0);
+    const int32_t above = __shfl_sync(0xffffffffu, p, c < 32 ? c : 31);
+    lo = c > 0 ? below + 1 : lo;
+    hi = c < 32 ? above : hi;
+  }
+  const bool b = lo + lane < hi && a[lo + lane] < key;
+  return lo + __popc(__ballot_sync(0xffffffffu, b));
+}
+
+template <int NV>   // feat_dim == dim == NV*128
+__global__ void __launch_bounds__(256) k_sym_reply_sage(DevGraph g, SymPeers peers, SymLayout lay, int me, int N, int64_t rows,
+                                                        int32_t count) {
+  char* base = peers.base[me];
+  SymHeader* mine = hdr_of(base);
+  const unsigned long long* ids = reinterpret_cast<const unsigned long long*>(base + lay.off_inbox_ids);
+  const int32_t* src = reinterpret_cast<const int32_t*>(base + lay.off_inbox_src);
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31;
+  constexpr int32_t fd = NV * 128;
+  const float* __restrict__ feat = g.feat + lane * 4;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; w < (int64_t)N * rows; w += nwarps) {
+    const int s = (int)(w / rows);
+    const int64_t d = w - (int64_t)s * rows;
+    const int32_t n_s = mine->in_cnt[s];
+    const int32_t* seg = src + (int64_t)s * lay.cap;
+    const unsigned long long* sid = ids + (int64_t)s * lay.cap;
+    const int32_t key_hi = (int32_t)((d + 1) * count);
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int32_t e0 = warp_lower_bound(seg, n_s, (int32_t)(d * count), lane);; e0 += 32) {
+      const int32_t e = e0 + lane;
+      const bool in = e < n_s && seg[e] < key_hi;
+      int32_t my = -1;
+      if (in) my = (int32_t)lookup_row(g, sid[e]);
+      const int nin = __popc(__ballot_sync(0xffffffffu, in));
+      unsigned valid = __ballot_sync(0xffffffffu, my >= 0);
+      while (valid) {
+        float4 v[4][NV];
+        int n = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (valid) {
+            const int j = __ffs(valid) - 1;
+            valid &= valid - 1;
+            const int32_t row = __shfl_sync(0xffffffffu, my, j);
+            const float* p = feat + (int64_t)row * fd;
+#pragma unroll
+            for (int t = 0; t < NV; ++t) v[q][t] = __ldg(reinterpret_cast<const float4*>(p + t * 128));
+            n = q + 1;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q < n) {
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+              acc[t].x = __fadd_rn(acc[t].x, v[q][t].x); acc[t].y = __fadd_rn(acc[t].y, v[q][t].y);
+              acc[t].z = __fadd_rn(acc[t].z, v[q][t].z); acc[t].w = __fadd_rn(acc[t].w, v[q][t].w);
+            }
+          }
+        }
+      }
+      if (nin < 32) break;
+    }
+    float* o = reinterpret_cast<float*>(peers.base[s] + lay.off_rows) + ((int64_t)me * rows + d) * fd + lane * 4;
+#pragma unroll
+    for (int t = 0; t < NV; ++t) *reinterpret_cast<float4*>(o + t * 128) = acc[t];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (threadIdx.x == 0) mine->done = 0;
+  if (threadIdx.x < N) st_release_sys(&hdr_of(peers.base[threadIdx.x])->flagB[me], mine->epoch);
+}
+
+// any width: lanes over columns, entries serial (slow path, same sums)
+__global__ void __launch_bounds__(256) k_sym_reply_sage_generic(DevGraph g, SymPeers peers, SymLayout lay, int me, int N, int64_t rows,
+                                                                int32_t count, int32_t dim) {
+  char* base = peers.base[me];
+  SymHeader* mine = hdr_of(base);
+  const unsigned long long* ids = reinterpret_cast<const unsigned long long*>(base + lay.off_inbox_ids);
+  const int32_t* src = reinterpret_cast<const int32_t*>(base + lay.off_inbox_src);
+  __shared__ bool s_last;
+  const int lane = threadIdx.x & 31;
+  const int32_t fd = g.feat_dim;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; w < (int64_t)N * rows; w += nwarps) {
+    const int s = (int)(w / rows);
+    const int64_t d = w - (int64_t)s * rows;
+    const int32_t n_s = mine->in_cnt[s];
+    const int32_t* seg = src + (int64_t)s * lay.cap;
+    const unsigned long long* sid = ids + (int64_t)s * lay.cap;
+    const int32_t key_hi = (int32_t)((d + 1) * count);
+    const int32_t e_lo = warp_lower_bound(seg, n_s, (int32_t)(d * count), lane);
+    float* o = reinterpret_cast<float*>(peers.base[s] + lay.off_rows) + ((int64_t)me * rows + d) * dim;
+    for (int32_t c0 = 0; c0 < dim; c0 += 32) {
+      const int32_t col = c0 + lane;
+      float acc = 0.f;
+      for (int32_t e = e_lo; e < n_s && seg[e] < key_hi; ++e) {   // warp-uniform
+        const int64_t row = lookup_row(g, sid[e]);
+        if (row >= 0 && col < fd && col < dim) acc = __fadd_rn(acc, __ldg(g.feat + row * (int64_t)fd + col));
+      }
+      if (col < dim) o[col] = acc;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (threadIdx.x == 0) mine->done = 0;
+  if (threadIdx.x < N) st_release_sys(&hdr_of(peers.base[threadIdx.x])->flagB[me], mine->epoch);
+}
+
+// requester: out[d,:] = (part[0][d,:] + part[1][d,:] + ...) / (count + 1e-7), rank order
+__global__ void __launch_bounds__(256) k_sym_sage_reduce(const float* __restrict__ part, int N, int64_t rows, int32_t dim, int32_t count,
+                                                         float* __restrict__ out) {
+  const float denom = __fadd_rn((float)count, 1e-7f);
+  const int64_t total = rows * dim;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = part[i];
+    for (int o = 1; o < N; ++o) acc = __fadd_rn(acc, part[(int64_t)o * total + i]);
+    out[i] = __fdiv_rn(acc, denom);
+  }
+}
+
+static inline unsigned sym_grid(int64_t threads) {   // persistent: at most 8 CTAs of 256 per SM
+  return (unsigned)std::min<int64_t>(std::max<int64_t>(ceil_div(threads, 256), 1), 148 * 8);
 }
 
 static inline int64_t a256(int64_t x) { return (x + 255) & ~(int64_t)255; }
@@ -351,23 +498,25 @@ int eu_sym_sample_hop(eu_sym* s, const int64_t* seeds, int64_t rows, const int32
   cudaStream_t st = c->stream;
   rc = eu_shard_bucket(c, seeds, rows, num_partitions, N, s->rank, s->d_sorted, s->d_src, s->d_counts, s->d_offs);
   if (rc) return rc;
-  k_sym_push<<<(unsigned)ceil_div(std::max<int64_t>(rows, 1), 256), 256, 0, st>>>(s->peers, L, s->rank, N, (const unsigned long long*)s->d_sorted,
-                                                                                  s->d_src, (const long long*)s->d_offs, rows);
+  { EuProfScope ps(c, "k_sym_push", rows);
+    k_sym_push<<<sym_grid(rows), 256, 0, st>>>(s->peers, L, s->rank, N, (const unsigned long long*)s->d_sorted,
+                                                                                    s->d_src, (const long long*)s->d_offs, rows); }
   EU_LAUNCHED();
-  k_sym_wait_in<<<1, 32, 0, st>>>(s->base, N);
+  { EuProfScope ps(c, "k_sym_wait_in", rows); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, N); }
   EU_LAUNCHED();
-  k_sym_wait_pad<<<148, 256, 0, st>>>(s->base, L, N);
+  { EuProfScope ps(c, "k_sym_wait_pad", prow); k_sym_wait_pad<<<148, 256, 0, st>>>(s->base, L, N); }
   EU_LAUNCHED();
   if (count > 0) {
     rc = hop(c, (const unsigned long long*)(s->base + L.off_inbox_ids), prow, etypes, K, count, /*default_node=*/0, nullptr,
              s->d_rids, s->d_rw, s->d_rt, 0, false, false, 1);
     if (rc) return rc;
   }
-  k_sym_reply_sample<<<(unsigned)ceil_div(std::max<int64_t>(prow * count, 1), 256), 256, 0, st>>>(s->peers, L, s->rank, N, count, default_node,
-                                                                                                 (const long long*)s->d_rids, s->d_rw, s->d_rt,
-                                                                                                 want_packed != 0);
+  { EuProfScope ps(c, "k_sym_reply_sample", prow);
+    k_sym_reply_sample<<<sym_grid(prow * count), 256, 0, st>>>(s->peers, L, s->rank, N, count, default_node,
+                                                                                                   (const long long*)s->d_rids, s->d_rw, s->d_rt,
+                                                                                                   want_packed != 0); }
   EU_LAUNCHED();
-  k_sym_wait<<<1, 32, 0, st>>>(s->base, N);
+  { EuProfScope ps(c, "k_sym_wait", rows); k_sym_wait<<<1, 32, 0, st>>>(s->base, N); }
   EU_LAUNCHED();
   return EU_OK;
 }
@@ -390,18 +539,64 @@ int eu_sym_get_dense_feature(eu_sym* s, const int64_t* ids, int64_t rows, int32_
   cudaStream_t st = c->stream;
   rc = eu_shard_bucket(c, ids, rows, num_partitions, N, s->rank, s->d_sorted, s->d_src, s->d_counts, s->d_offs);
   if (rc) return rc;
-  k_sym_push<<<(unsigned)ceil_div(std::max<int64_t>(rows, 1), 256), 256, 0, st>>>(s->peers, L, s->rank, N, (const unsigned long long*)s->d_sorted,
-                                                                                  s->d_src, (const long long*)s->d_offs, rows);
+  { EuProfScope ps(c, "k_sym_push(feat)", rows);
+    k_sym_push<<<sym_grid(rows), 256, 0, st>>>(s->peers, L, s->rank, N, (const unsigned long long*)s->d_sorted,
+                                                                                    s->d_src, (const long long*)s->d_offs, rows); }
   EU_LAUNCHED();
-  k_sym_wait_in<<<1, 32, 0, st>>>(s->base, N);
+  { EuProfScope ps(c, "k_sym_wait_in(feat)", rows); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, N); }
   EU_LAUNCHED();
   int G = 1;
   while (G < 32 && G < dim / 4) G <<= 1;
   const int64_t prow = (int64_t)N * L.cap;
-  k_sym_reply_feature<<<(unsigned)ceil_div(prow * G, 256), 256, 0, st>>>(d, s->peers, L, s->rank, N, dim, soff, sdim, G);
+  { EuProfScope ps(c, "k_sym_reply_feature", prow);
+    k_sym_reply_feature<<<sym_grid(prow * G), 256, 0, st>>>(d, s->peers, L, s->rank, N, dim, soff, sdim, G); }
   EU_LAUNCHED();
-  k_sym_wait<<<1, 32, 0, st>>>(s->base, N);
+  { EuProfScope ps(c, "k_sym_wait(feat)", rows); k_sym_wait<<<1, 32, 0, st>>>(s->base, N); }
   EU_LAUNCHED();
+  return EU_OK;
+}
+
+// Sharded fused SAGE mean over a fixed-fanout block: out[r,:] = mean_j feat(nbr_ids[r*count+j]) with features fetched
+// from the owning shards and summed THERE (see k_sym_reply_sage).  Every rank calls it with the same rows/count/dim.
+// Uses the symmetric `rows` region as N partial blocks (clobbers eu_sym_get_dense_feature's output).
+int eu_sym_sage_mean(eu_sym* s, const int64_t* nbr_ids, int64_t rows, int32_t count, int32_t dim, int32_t num_partitions, float* out) {
+  if (!s || !s->connected || rows < 0 || count < 1 || dim <= 0 || (rows > 0 && (!nbr_ids || !out))) { set_error("eu_sym_sage_mean: bad argument / not connected"); return EU_ERR_INVALID; }
+  eu_ctx* c = s->c;
+  EU_CUDA(cudaSetDevice(c->g->device));
+  SymLayout L = s->lay;
+  const DevGraph& d = c->g->d;
+  const int N = s->world;
+  const int64_t nid = rows * count;
+  if (nid > L.cap || nid >= ((int64_t)1 << 31) || (int64_t)N * rows * dim > L.max_rows_f * (int64_t)L.max_dim) {
+    set_error("eu_sym_sage_mean: %lld x %d ids / %d partial blocks exceed the symmetric region", (long long)rows, count, N);
+    return EU_ERR_INVALID;
+  }
+  L.cap = std::max<int64_t>(nid, 1);
+  int rc = sym_scratch(s, std::max<int64_t>(nid, 1), 1);
+  if (rc) return rc;
+  cudaStream_t st = c->stream;
+  rc = eu_shard_bucket(c, nbr_ids, nid, num_partitions, N, s->rank, s->d_sorted, s->d_src, s->d_counts, s->d_offs);
+  if (rc) return rc;
+  { EuProfScope ps(c, "k_sym_push(sage)", nid);
+    k_sym_push<<<sym_grid(nid), 256, 0, st>>>(s->peers, L, s->rank, N, (const unsigned long long*)s->d_sorted, s->d_src,
+                                               (const long long*)s->d_offs, nid); }
+  EU_LAUNCHED();
+  { EuProfScope ps(c, "k_sym_wait_in(sage)", nid); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, N); }
+  EU_LAUNCHED();
+  { EuProfScope ps(c, "k_sym_reply_sage", (int64_t)N * rows);
+    const unsigned grid = sym_grid((int64_t)N * rows * 32);
+    const bool fast = d.n < ((int64_t)1 << 31) && d.n_slots == 1 && dim == d.feat_dim;
+    if (fast && dim == 128) k_sym_reply_sage<1><<<grid, 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count);
+    else if (fast && dim == 256) k_sym_reply_sage<2><<<grid, 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count);
+    else k_sym_reply_sage_generic<<<grid, 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count, dim); }
+  EU_LAUNCHED();
+  { EuProfScope ps(c, "k_sym_wait(sage)", rows); k_sym_wait<<<1, 32, 0, st>>>(s->base, N); }
+  EU_LAUNCHED();
+  if (rows > 0) {
+    EuProfScope ps(c, "k_sym_sage_reduce", rows);
+    k_sym_sage_reduce<<<sym_grid(rows * dim), 256, 0, st>>>((const float*)(s->base + L.off_rows), N, rows, dim, count, out);
+    EU_LAUNCHED();
+  }
   return EU_OK;
 }
 

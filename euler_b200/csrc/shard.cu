@@ -159,6 +159,7 @@ int eu_shard_bucket(eu_ctx* c, const int64_t* ids, int64_t rows, int32_t num_par
   uint32_t* blkcnt = (uint32_t*)((char*)c->d_misc + 256);
   cudaStream_t s = c->stream;
   EU_CUDA(cudaMemsetAsync(done, 0, sizeof(unsigned int), s));
+  EuProfScope ps(c, "k_bucket(count+place)", rows);
   k_bucket_count<<<(unsigned)nblk, kBktBlock, 0, s>>>((const unsigned long long*)ids, rows, num_partitions, shard_num, self_shard, blkcnt,
                                                       (long long*)counts, (long long*)offsets, done);
   EU_LAUNCHED();

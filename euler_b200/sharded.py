@@ -266,6 +266,17 @@ class PeerShardedGraph:
         out = self.o_rows[:ids.numel() * dim].reshape(ids.numel(), dim)
         return out.clone() if clone else out
 
+    def sage_mean(self, nbr_ids, rows, count, dim, out=None):
+        """fused sharded mean aggregation of a fixed-fanout block (owners sum their rows; eu_sym_sage_mean)"""
+        t = self.torch
+        ids = nbr_ids.to(device=self.dev, dtype=t.int64).reshape(-1).contiguous()
+        assert ids.numel() == rows * count
+        if out is None:
+            out = t.empty(rows, dim, dtype=t.float32, device=self.dev)
+        self._stream()
+        self.check(self.lib.eu_sym_sage_mean(self._h, ids.data_ptr(), int(rows), int(count), int(dim), self.P, out.data_ptr()))
+        return out
+
     def close(self):
         if self._h:
             self.torch.cuda.synchronize()

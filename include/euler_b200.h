@@ -245,6 +245,13 @@ int eu_sym_error(eu_sym* s, int* err);   /* 1 if a bounded wait timed out (synch
 int eu_sym_sample_hop(eu_sym* s, const int64_t* seeds, int64_t rows, const int32_t* etypes, int32_t K, int32_t count,
                       int64_t default_node, int32_t num_partitions, int32_t want_packed);
 int eu_sym_get_dense_feature(eu_sym* s, const int64_t* ids, int64_t rows, int32_t fid, int32_t dim, int32_t num_partitions);
+/* Sharded eu_sage_mean_aggregate: REMOTE get_dense_feature (euler/core/kernels/remote_op.cc:60-146) fused with the
+ * scatter_mean that follows it (tf_euler/python/euler_ops/mp_ops.py:65-69 over sage_dataflow.py:43-46's edge_src).
+ * Each owner sums the rows of ITS ids per destination (j ascending) and stores one partial row per destination in the
+ * requester's region; the requester adds the partials in rank order and divides by (count + 1e-7).  rows*count ids must
+ * fit the inbox (max(max_rows, max_feat_rows)) and world*rows*dim floats the feature region.  out: device f32[rows*dim]. */
+int eu_sym_sage_mean(eu_sym* s, const int64_t* nbr_ids, int64_t rows, int32_t count, int32_t dim, int32_t num_partitions,
+                     float* out);
 
 /* ------------------------------------------------------------------ reference entry point ---- */
 /* bool InitQueryProxy(const char* conf) -- tf_euler/utils/init_query_proxy.cc:19-36.  "k=v;k=v";

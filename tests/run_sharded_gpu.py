@@ -66,9 +66,34 @@ def main():
         qf = pg.get_dense_feature(q_ids[1], 0, 64)
     assert pg.error() == 0
     cases.eq(qf.cpu().numpy(), full.op_get_dense_feature(q_ids[1].cpu().numpy(), 64), "peer: features after reuse")
+    # ---- fused sharded SAGE mean: owners sum their rows, requester adds the partials in rank order (bit-exact association)
+    agg = pg.sage_mean(q_ids[1], 2048, 25, 64)              # generic-width kernel (dim 64)
+    cases.eq(agg.cpu().numpy(), sc.sage_mean_sharded(full, q_ids[1].cpu().numpy(), 2048, 25, 64, world, rank), "peer: sage mean dim 64")
+    agg2 = pg.sage_mean(q_ids[2][:4096 * 10], 4096, 10, 64)
+    cases.eq(agg2.cpu().numpy(), sc.sage_mean_sharded(full, q_ids[2][:4096 * 10].cpu().numpy(), 4096, 10, 64, world, rank), "peer: sage mean hop 2")
+    assert pg.error() == 0
     torch.cuda.synchronize()
     dist.barrier()
     pg.close()
+    # dim 128: the float4 warp kernel, fanout 40 > 32 (two lookup rounds per destination)
+    g2 = graphs.random_graph(seed=92, n=8000, T=1, avg_deg=9, feat_dim=128, id_stride=3, id_base=1)
+    sh2 = sc.partition(g2, world)
+    gr2 = graphs.cuda_graph(sh2[rank], device=local)
+    full2 = graphs.oracle_graph(g2)
+    pg2 = PeerShardedGraph(gr2, rank, world, max_rows=1024, max_count=40, max_feat_rows=1024 * 40, max_dim=128, rng="minstd", seed=5 + rank)
+    sd = g2["ids"][np.random.RandomState(40 + rank).randint(0, 8000, size=1024)].astype(np.int64)
+    sd[::7] = 12345678901
+    r_ids, _, _ = pg2.sample_fanout(sd, [[0]], [40], -1)
+    for _ in range(2):
+        agg3 = pg2.sage_mean(r_ids[1], 1024, 40, 128)
+    want = sc.sage_mean_sharded(full2, r_ids[1].cpu().numpy(), 1024, 40, 128, world, rank)
+    cases.eq(agg3.cpu().numpy(), want, "peer: sage mean dim 128")
+    plain = full2.op_get_dense_feature(r_ids[1].cpu().numpy(), 128).reshape(1024, 40, 128).astype(np.float64).sum(1) / (40 + 1e-7)
+    assert np.allclose(agg3.cpu().numpy(), plain, rtol=1e-5, atol=1e-6), "peer: sage mean vs f64 mean"
+    assert pg2.error() == 0
+    torch.cuda.synchronize()
+    dist.barrier()
+    pg2.close()
     if rank == 0:
         print("SHARDED_GPU_OK world=%d" % world)
     dist.destroy_process_group()

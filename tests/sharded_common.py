@@ -136,3 +136,21 @@ def simulate(shards, seeds_per_rank, ets, counts, shard_seeds, default_node=-1, 
             frontier[r] = new_frontier[r].reshape(-1)
             res[r][0].append(packed[r][0].reshape(-1)); res[r][1].append(packed[r][1].reshape(-1)); res[r][2].append(packed[r][2].reshape(-1))
     return res
+
+
+def sage_mean_sharded(full_oracle, nbr_ids, rows, count, dim, N, me, P=None):
+    """Association pinned for the fused sharded SAGE mean (eu_sym_sage_mean): owner o sums the feature rows of ITS ids per
+    destination, j ascending, in f32; the requester adds the N partial rows in rank order and divides by
+    f32(count) + 1e-7 (tf_euler/python/euler_ops/mp_ops.py:65-69).  full_oracle: OracleGraph of the WHOLE graph."""
+    from euler_b200.sharded import owner_of
+    ids = np.asarray(nbr_ids, dtype=np.int64).reshape(rows, count)
+    feats = full_oracle.op_get_dense_feature(ids.reshape(-1), dim).reshape(rows, count, dim).astype(np.float32)
+    own = owner_of(ids.reshape(-1), P or N, N, me).reshape(rows, count)
+    total = np.zeros((rows, dim), np.float32)
+    for o in range(N):
+        part = np.zeros((rows, dim), np.float32)
+        for j in range(count):
+            part = (part + np.where((own[:, j] == o)[:, None], feats[:, j, :], np.float32(0))).astype(np.float32)
+        total = (total + part).astype(np.float32)
+    denom = np.float32(np.float32(count) + np.float32(1e-7))
+    return (total / denom).astype(np.float32)
