@@ -395,9 +395,14 @@ def run_sharded(args, world, rank, local):
     n = [B]
     for c in counts:
         n.append(n[-1] * c)
+    import math
     peer = args.exchange == "peer"
     n_lanes = args.lanes if peer else 1
+    # launch group: G batches share every exchange (peer path) -- the kernels and NVLink round trips of an exchange are paid
+    # once per G steps; each batch keeps its own engine and dedup scope on every shard (eu_sym_sample_hop_batched)
+    G = max(1, math.gcd(args.group, args.steps)) if peer else 1
     src = [torch.arange(n[l], dtype=torch.int32, device="cuda").repeat_interleave(counts[l]) for l in range(L)]
+    n_self = sum(n[:L])                   # rows whose own features are materialised (hop 0 .. L-1)
 
     class SLane:
         pass
@@ -405,86 +410,88 @@ def run_sharded(args, world, rank, local):
     for i in range(n_lanes):
         ln = SLane()
         ln.stream = torch.cuda.Stream()
-        seed = 12345 + rank * 1000 + i
+        seed = 12345 + rank * 1000 + i * 64
         if peer:
-            ln.sg = PeerShardedGraph(graph, rank, world, max_rows=max(n[:-1]), max_count=max(counts), max_feat_rows=sum(n),
-                                     max_dim=D, rng=args.rng, seed=seed)
+            ln.sg = PeerShardedGraph(graph, rank, world, max_rows=G * max(n[:-1]), max_count=max(counts),
+                                     max_feat_rows=G * max(max(n), world * max(n[:-1])), max_dim=D, rng=args.rng, seed=seed, engines=G)
             ln.ctx = ln.sg.ctx
         else:
             ln.ops = CudaShardOps(graph, args.rng, seed)
             ln.sg = ShardedGraph(ln.ops, TorchExchange())
             ln.ctx = ln.ops.ctx
             ln.ctx.reserve(max(n) * 2 + sum(n))
-        ln.d_seeds = torch.empty(B, dtype=torch.int64, device="cuda")
-        ln.agg = [torch.empty((n[l], D), dtype=torch.float32, device="cuda") for l in range(L)]
-        ln.ids = [torch.empty(x, dtype=torch.int64, device="cuda") for x in n[1:]]
-        ln.x = [torch.empty((n[l], D), dtype=torch.float32, device="cuda") for l in range(L)]
-        ln.h_seeds = torch.empty(B, dtype=torch.int64).pin_memory()
-        ln.h_ids = [torch.empty(x, dtype=torch.int64).pin_memory() for x in n[1:]]
-        ln.h_x = [torch.empty((n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
-        ln.h_agg = [torch.empty((n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
+        # one id buffer: [G*n0 seeds | G*n1 hop-1 ids | ...]; slices of it are the hop outputs and the feature request
+        ln.idbuf = torch.empty(G * sum(n), dtype=torch.int64, device="cuda")
+        offs = [0]
+        for x in n:
+            offs.append(offs[-1] + G * x)
+        ln.d_seeds = ln.idbuf[:G * B].view(G, B)
+        ln.ids = [ln.idbuf[offs[l + 1]:offs[l + 2]] for l in range(L)]
+        ln.agg = [torch.empty((G * n[l], D), dtype=torch.float32, device="cuda") for l in range(L)]
+        ln.x = torch.empty((G * n_self, D), dtype=torch.float32, device="cuda")
+        ln.h_seeds = torch.empty((G, B), dtype=torch.int64).pin_memory()
+        ln.h_ids = [torch.empty(G * x, dtype=torch.int64).pin_memory() for x in n[1:]]
+        ln.h_x = torch.empty((G * n_self, D), dtype=torch.float32).pin_memory()
+        ln.h_agg = [torch.empty((G * n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
         lanes.append(ln)
 
-    def raw_step(ln, seeds_dev):
+    def raw_step(ln):
+        """one launch group = G steps; seeds are in ln.d_seeds"""
         sg = ln.sg
         if peer:
-            frontier = seeds_dev
+            frontier = ln.d_seeds.view(-1)
             for l in range(L):
-                eng, o_ids, o_w, o_t = sg.hop(frontier, [0], counts[l], -1)
+                # the frontier of hop l+1 is read straight from the symmetric output of hop l (consumed by the bucket
+                # kernels before this rank's push lets any owner overwrite it)
+                eng, o_ids, o_w, o_t = sg.hop(frontier, [0], counts[l], -1, nb=G)
                 ln.ids[l].copy_(o_ids)
-                frontier = eng if l + 1 == L else eng.clone()
-            # self features of the hop-0/1 nodes are materialised; the hop-(l+1) features are summed by their owners
-            # (eu_sym_sage_mean) and never cross NVLink row by row
-            feats = sg.get_dense_feature(torch.cat([seeds_dev] + ln.ids[:L - 1]), 0, D, clone=False)
-            off = 0
+                frontier = eng
+            # the hop-(l+1) features are summed by their owners and never cross NVLink row by row
             for l in range(L):
-                ln.x[l].copy_(feats[off:off + n[l]])
-                off += n[l]
-            for l in range(L):
-                sg.sage_mean(ln.ids[l], n[l], counts[l], D, out=ln.agg[l])
+                sg.sage_mean(ln.ids[l], G * n[l], counts[l], D, out=ln.agg[l])
+            # own features of the hop-0..L-1 nodes: rows stay in the symmetric region until the next group (a consumer
+            # reads them there); the e2e path copies them to the host from there
+            ln.x_view = sg.get_dense_feature(ln.idbuf[:G * n_self], 0, D, clone=False)
             return
-        else:
-            ids, ws, ts = sg.sample_fanout(seeds_dev, [[0]] * L, counts, -1)
-            for l in range(L):
-                ln.ids[l].copy_(ids[l + 1])
-            feats = sg.get_dense_feature(torch.cat(ids), 0, D)
-        ln.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-        off = 0
-        xs = []
-        for l in range(L + 1):
-            xs.append(feats[off:off + n[l]])
-            off += n[l]
+        seeds_dev = ln.d_seeds.view(-1)
+        ids, ws, ts = sg.sample_fanout(seeds_dev, [[0]] * L, counts, -1)
         for l in range(L):
-            ln.x[l].copy_(xs[l])
-            rc = lib.eu_scatter_mean(ln.ctx._h, xs[l + 1].data_ptr(), D, src[l].data_ptr(), n[l + 1], n[l], ln.agg[l].data_ptr())
+            ln.ids[l].copy_(ids[l + 1])
+        feats = sg.get_dense_feature(torch.cat(ids), 0, D)
+        ln.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        ln.x_view = feats[:n_self]
+        off = 0
+        for l in range(L):
+            off += n[l]
+            rc = lib.eu_scatter_mean(ln.ctx._h, feats[off:off + n[l + 1]].data_ptr(), D, src[l].data_ptr(), n[l + 1], n[l], ln.agg[l].data_ptr())
             if rc:
                 raise RuntimeError(lib.eu_last_error().decode())
+
+    n_seed_groups = max(-(-(args.warmup + args.steps) // G), 16)
+    host_seeds = np.stack([np.random.RandomState(1000 + rank * 100003 + i).randint(1, args.nodes + 1, size=(G, B))
+                           for i in range(n_seed_groups)]).astype(np.int64)
+    dev_seeds = torch.from_numpy(host_seeds).cuda()
 
     use_graphs = peer and not args.no_graphs
     if use_graphs:
         for ln in lanes:
             with torch.cuda.stream(ln.stream):
-                raw_step(ln, ln.d_seeds)
+                ln.d_seeds.copy_(dev_seeds[0])
+                raw_step(ln)
             ln.stream.synchronize()
         dist.barrier()
         for ln in lanes:
             ln.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(ln.graph, stream=ln.stream):
-                raw_step(ln, ln.d_seeds)
+                raw_step(ln)
         dist.barrier()
 
-    def step(ln, seeds_dev):
+    def step(ln):
         if use_graphs:
-            if seeds_dev is not ln.d_seeds:
-                ln.d_seeds.copy_(seeds_dev, non_blocking=True)
             ln.graph.replay()
         else:
-            raw_step(ln, seeds_dev)
+            raw_step(ln)
 
-    nb = args.warmup + args.steps
-    host_seeds = np.stack([np.random.RandomState(1000 + rank * 100003 + i).randint(1, args.nodes + 1, size=B)
-                           for i in range(max(nb, 16))]).astype(np.int64)
-    dev_seeds = torch.from_numpy(host_seeds).cuda()
     main = torch.cuda.current_stream()
 
     def run(n_steps, first, e2e):
@@ -495,20 +502,22 @@ def run_sharded(args, world, rank, local):
         ev0.record(main)
         for ln in lanes:
             ln.stream.wait_event(ev0)
-        for i in range(n_steps):
+        for i in range(-(-n_steps // G)):
             ln = lanes[i % len(lanes)]
+            sd = (first // G + i) % n_seed_groups
             with torch.cuda.stream(ln.stream):
                 if e2e:
                     ln.stream.synchronize() if i >= len(lanes) else None
-                    ln.h_seeds.copy_(torch.from_numpy(host_seeds[(first + i) % len(host_seeds)]))
+                    ln.h_seeds.copy_(torch.from_numpy(host_seeds[sd]))
                     ln.d_seeds.copy_(ln.h_seeds, non_blocking=True)
-                    step(ln, ln.d_seeds)
+                    step(ln)
+                    ln.h_x.copy_(ln.x_view, non_blocking=True)
                     for l in range(L):
                         ln.h_ids[l].copy_(ln.ids[l], non_blocking=True)
-                        ln.h_x[l].copy_(ln.x[l], non_blocking=True)
                         ln.h_agg[l].copy_(ln.agg[l], non_blocking=True)
                 else:
-                    step(ln, dev_seeds[(first + i) % len(host_seeds)])
+                    ln.d_seeds.copy_(dev_seeds[sd], non_blocking=True)
+                    step(ln)
         for ln in lanes:
             main.wait_stream(ln.stream)
         ev1.record(main)
@@ -518,33 +527,35 @@ def run_sharded(args, world, rank, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    run(args.warmup, 0, False)
+    run(max(args.warmup, G * len(lanes)), 0, False)
     clocks = Clocks(local)
     clocks.start()
     time.sleep(0.3)
-    l0 = lib.eu_launch_count()
     w0 = time.time()
     ms = run(args.steps, args.warmup, False)
     w1 = time.time()
-    launches = lib.eu_launch_count() - l0
     clk = clocks.stop(w0, w1)
-    run(min(args.warmup, 4), 0, True)
+    run(min(max(args.warmup, G), 4 * G), 0, True)
     ms_e2e = run(args.steps, args.warmup, True)
     err = max(ln.sg.error() for ln in lanes) if peer else 0
-    # per-kernel breakdown on one lane (library-side CUDA events), serial, no graphs
+    # per-kernel breakdown + launch count on one lane (library-side CUDA events), serial, no graphs
     prof = {}
     ln = lanes[0]
+    reps = 4
     lib.eu_ctx_profile(ln.ctx._h, 1)
+    l0 = lib.eu_launch_count()
     with torch.cuda.stream(ln.stream):
-        for it in range(10):
-            raw_step(ln, dev_seeds[it % len(host_seeds)])
+        for it in range(reps):
+            ln.d_seeds.copy_(dev_seeds[it % n_seed_groups])
+            raw_step(ln)
     ln.stream.synchronize()
+    launches_per_group = (lib.eu_launch_count() - l0) / reps
     buf = ctypes.create_string_buffer(1 << 16)
     lib.eu_ctx_profile_read(ln.ctx._h, buf, len(buf))
     lib.eu_ctx_profile(ln.ctx._h, 0)
     for line in buf.value.decode().strip().splitlines():
         nm, rows_, cnt_, ms_tot = line.split(",")
-        prof["%s[rows=%s]" % (nm, rows_)] = round(float(ms_tot) / 10, 4)
+        prof["%s[rows=%s]" % (nm, rows_)] = round(float(ms_tot) / reps / G, 4)
     all_prof = [None] * world
     dist.all_gather_object(all_prof, prof)
     if os.environ.get("EU_BENCH_DEBUG") and rank == 0:
@@ -554,10 +565,18 @@ def run_sharded(args, world, rank, local):
     bts = step_bytes(B, counts, D)
     edges_step = bts["edges"] * world
     remote = (world - 1) / world
+    # algorithmic NVLink bytes per rank per step: hop requests (id + src index) and replies (eng id, packed id, w, t);
+    # feature requests + rows for the hop-0..L-1 nodes; fused aggregation = neighbor ids out, one partial row per
+    # (remote owner, destination) back
     a2a_bytes = 0
     for l in range(L):
         a2a_bytes += remote * n[l] * (12 + 24 * counts[l])
-    a2a_bytes += remote * sum(n) * (12 + 4 * D)
+    if peer:
+        a2a_bytes += remote * n_self * (12 + 4 * D)
+        for l in range(L):
+            a2a_bytes += remote * n[l + 1] * 12 + (world - 1) * n[l] * 4 * D
+    else:
+        a2a_bytes += remote * sum(n) * (12 + 4 * D)
     if rank == 0:
         out = {
             "metric": "sampled_edges_per_sec", "value": edges_step * args.steps / (ms * 1e-3), "unit": "edges/s",
@@ -569,14 +588,15 @@ def run_sharded(args, world, rank, local):
                                    % (args.nodes // 10**6, args.edges // 10**6, world, counts, B, D),
                        "nodes": args.nodes, "edges": args.edges, "batch_per_gpu": B, "global_batch": B * world, "fanout": counts,
                        "feat_dim": D, "rng": args.rng, "exchange": "peer-memory kernels (NVLink loads/stores, no NCCL)" if peer else "NCCL all_to_all",
-                       "lanes_in_flight": n_lanes, "cuda_graphs": use_graphs, "peer_wait_timeouts": err,
+                       "lanes_in_flight": n_lanes, "steps_per_launch_group": G, "cuda_graphs": use_graphs, "peer_wait_timeouts": err,
+                       "aggregation": "fused at the owners (eu_sym_sage_mean: one partial row per owner and destination)" if peer else "materialised rows + scatter_mean",
                        "parallelism": "graph sharded id %% %d, batches data-parallel" % world,
                        "l2_policy": "inputs larger than L2 (random seeds per step over a %.1f GB shard)" % (graph.hbm_bytes / 1e9)},
             "e2e": {"value": edges_step * args.steps / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 8 * B * world,
                     "d2h_bytes_per_step": world * (sum(8 * x for x in n[1:]) + 2 * sum(4 * n[l] * D for l in range(L))),
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches) if not use_graphs else None, "clocks": clk,
-            "roofline": {"bound": "nvlink", "kernel": "exchange kernels (k_sym_push / k_sym_reply_sample / k_sym_reply_feature)" if peer else "NCCL all-to-all",
+            "gpu_launches": int(round(launches_per_group * (args.steps // G))), "clocks": clk,
+            "roofline": {"bound": "nvlink", "kernel": "exchange kernels (k_sym_push / k_sym_reply_sample / k_sym_reply_sage / k_sym_reply_feature)" if peer else "NCCL all-to-all",
                          "achieved": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9, 2), "peak": 770.0, "unit": "GB/s",
                          "frac": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9 / 770.0, 4), "traffic": None,
                          "peak_source": "B200_PROFILING.md measured peer copy 770 GB/s per direction",
@@ -586,7 +606,7 @@ def run_sharded(args, world, rank, local):
             "kernel_ms_per_step_single_lane": dict(sorted(prof.items(), key=lambda kv: -kv[1])),
         }
         if use_graphs:
-            out["gpu_launches"] = "one CUDA graph replay per step (kernels of this library only)"
+            out["config"]["launch"] = "one CUDA graph replay per launch group; gpu_launches counts this library's kernels inside the replays"
         emit(out)
     if peer:
         for ln in lanes:

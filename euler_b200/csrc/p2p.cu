@@ -40,7 +40,7 @@ struct SymLayout {
   int64_t max_out;      // rows * count slots of the sample outputs
   int64_t max_rows_f;   // rows of the feature output
   int32_t max_dim;
-  int64_t off_inbox_ids, off_inbox_src, off_eng, off_ids, off_w, off_t, off_rows, bytes;
+  int64_t off_inbox_ids, off_inbox_src, off_eng, off_ids, off_w, off_t, off_rows, off_flags, bytes;
 };
 
 struct SymPeers {
@@ -107,28 +107,48 @@ __global__ void __launch_bounds__(256) k_sym_push(SymPeers peers, SymLayout lay,
   }
 }
 
-// ---- owner: wait for every source (one small block spins; nothing else of the GPU is held)
-__global__ void k_sym_wait_in(char* base, int N) {
+// ---- owner: wait for every source (one small block spins; nothing else of the GPU is held).  A batched hop also
+// needs the batch boundaries inside every source's segment: the bucket is stable and src = g*rows_b + position, so
+// batch g of source s is the slice [seg_lo[s][g], seg_lo[s][g+1]) -- N*(nb+1) binary searches, done here.
+__global__ void __launch_bounds__(256) k_sym_wait_in(char* base, SymLayout lay, int N, int nb, int64_t rows_b,
+                                                     int32_t* __restrict__ seg_lo /* [N][nb+1] or null */) {
   SymHeader* h = hdr_of(base);
   if (threadIdx.x < N) spin_until(&h->flagA[threadIdx.x], h->epoch, &h->error);
+  if (!seg_lo) return;
+  __syncthreads();
+  const int32_t* src = reinterpret_cast<const int32_t*>(base + lay.off_inbox_src);
+  for (int i = threadIdx.x; i < N * (nb + 1); i += blockDim.x) {
+    const int s = i / (nb + 1), g = i - s * (nb + 1);
+    const int32_t n_s = *reinterpret_cast<volatile int*>(&h->in_cnt[s]);
+    const int32_t* seg = src + (int64_t)s * lay.cap;
+    const int32_t key = (int32_t)(g * rows_b);
+    int32_t lo = 0, hi = n_s;
+    while (lo < hi) {
+      const int32_t mid = lo + ((hi - lo) >> 1);
+      if (__ldcg(seg + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    seg_lo[i] = lo;
+  }
 }
 
-// ---- owner: zero-pad the segments (the counts were published before the flags)
-__global__ void __launch_bounds__(256) k_sym_wait_pad(char* base, SymLayout lay, int N) {
-  SymHeader* h = hdr_of(base);
-  __shared__ int s_cnt[kSymMaxRanks];
-  if (threadIdx.x < N) s_cnt[threadIdx.x] = *reinterpret_cast<volatile int*>(&h->in_cnt[threadIdx.x]);
-  __syncthreads();
-  unsigned long long* ids = reinterpret_cast<unsigned long long*>(base + lay.off_inbox_ids);
-  const int64_t total = (int64_t)N * lay.cap;
+// ---- owner: the sampleNB input of batch g = the requests of source 0..N-1 for that batch, each zero-padded to rows_b
+// (id 0 = "exists nowhere": it takes no RNG draws and lands in no dedup table)  ->  pad[g][s][rows_b]
+__global__ void __launch_bounds__(256) k_sym_gather_pad(const char* base, SymLayout lay, int N, int nb, int64_t rows_b,
+                                                        const int32_t* __restrict__ seg_lo, unsigned long long* __restrict__ pad) {
+  const unsigned long long* ids = reinterpret_cast<const unsigned long long*>(base + lay.off_inbox_ids);
+  const int64_t total = (int64_t)nb * N * rows_b;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int s = (int)(i / lay.cap);
-    if (i - s * lay.cap >= s_cnt[s]) ids[i] = 0ull;
+    const int64_t gs = i / rows_b;
+    const int64_t k = i - gs * rows_b;
+    const int g = (int)(gs / N), s = (int)(gs - (int64_t)g * N);
+    const int32_t lo = seg_lo[s * (nb + 1) + g], hi = seg_lo[s * (nb + 1) + g + 1];
+    pad[i] = k < hi - lo ? ids[(int64_t)s * lay.cap + lo + k] : 0ull;
   }
 }
 
 // ---- owner: sampled rows of the padded inbox -> requester's outputs at the original positions (+ TF packing)
-__global__ void __launch_bounds__(256) k_sym_reply_sample(SymPeers peers, SymLayout lay, int me, int N, int32_t count,
+__global__ void __launch_bounds__(256) k_sym_reply_sample(SymPeers peers, SymLayout lay, int me, int N, int nb, int64_t rows_b,
+                                                          const int32_t* __restrict__ seg_lo, int32_t count,
                                                           long long default_node, const long long* __restrict__ r_ids,
                                                           const float* __restrict__ r_w, const int32_t* __restrict__ r_t,
                                                           bool want_packed) {
@@ -136,14 +156,16 @@ __global__ void __launch_bounds__(256) k_sym_reply_sample(SymPeers peers, SymLay
   SymHeader* mine = hdr_of(base);
   const int32_t* src = reinterpret_cast<const int32_t*>(base + lay.off_inbox_src);
   __shared__ bool s_last;
-  const int64_t slots = (int64_t)N * lay.cap * count;
+  const int64_t slots = (int64_t)nb * N * rows_b * count;
   for (int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; tid < slots; tid += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = tid / count;            // padded inbox row
+    const int64_t row = tid / count;            // padded row (g, s, k)
     const int32_t j = (int32_t)(tid - row * count);
-    const int s = (int)(row / lay.cap);
-    const int64_t k = row - (int64_t)s * lay.cap;
-    if (k < mine->in_cnt[s]) {
-      const int64_t dst = (int64_t)src[row] * count + j;
+    const int64_t gs = row / rows_b;
+    const int64_t k = row - gs * rows_b;
+    const int g = (int)(gs / N), s = (int)(gs - (int64_t)g * N);
+    const int32_t lo = seg_lo[s * (nb + 1) + g], hi = seg_lo[s * (nb + 1) + g + 1];
+    if (k < hi - lo) {
+      const int64_t dst = (int64_t)src[(int64_t)s * lay.cap + lo + k] * count + j;   // requester's flat slot [g][pos][j]
       const long long id = r_ids[tid];
       const bool keep = r_ids[row * count] != 0;   // tf_euler/kernels/sample_neighbor_op.cc:114-122
       char* pb = peers.base[s];
@@ -226,6 +248,10 @@ __device__ __forceinline__ int32_t warp_lower_bound(const int32_t* __restrict__ 
   return lo + __popc(__ballot_sync(0xffffffffu, b));
 }
 
+// One warp serves kSageR consecutive destinations of one source: one segment search, then a walk over their inbox
+// entries (id -> row lookups 32 at a time across the lanes, 4 feature rows in flight), flushing a partial row -- zeros
+// when this shard owns none of a destination's neighbors -- whenever the destination changes.
+static constexpr int kSageR = 8;
 template <int NV>   // feat_dim == dim == NV*128
 __global__ void __launch_bounds__(256) k_sym_reply_sage(DevGraph g, SymPeers peers, SymLayout lay, int me, int N, int64_t rows,
                                                         int32_t count) {
@@ -238,25 +264,33 @@ __global__ void __launch_bounds__(256) k_sym_reply_sage(DevGraph g, SymPeers pee
   constexpr int32_t fd = NV * 128;
   const float* __restrict__ feat = g.feat + lane * 4;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; w < (int64_t)N * rows; w += nwarps) {
-    const int s = (int)(w / rows);
-    const int64_t d = w - (int64_t)s * rows;
+  const int64_t gps = (rows + kSageR - 1) / kSageR;   // destination groups per source
+  for (int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; w < (int64_t)N * gps; w += nwarps) {
+    const int s = (int)(w / gps);
+    const int64_t d0 = (w - (int64_t)s * gps) * kSageR;
+    const int nd = (int)(rows - d0 < kSageR ? rows - d0 : kSageR);
     const int32_t n_s = mine->in_cnt[s];
     const int32_t* seg = src + (int64_t)s * lay.cap;
     const unsigned long long* sid = ids + (int64_t)s * lay.cap;
-    const int32_t key_hi = (int32_t)((d + 1) * count);
+    const int32_t key_lo = (int32_t)(d0 * count), key_hi = (int32_t)((d0 + nd) * count);
+    float* o = reinterpret_cast<float*>(peers.base[s] + lay.off_rows) + ((int64_t)me * rows + d0) * fd + lane * 4;
+    int cur = 0;   // next destination (relative to d0) whose partial row is still open
+    bool any = false;        // the open destination has at least one row of this shard
+    unsigned present = 0;    // bit d: a partial row was stored for destination d0 + d (empty partials are not sent)
     float4 acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int32_t e0 = warp_lower_bound(seg, n_s, (int32_t)(d * count), lane);; e0 += 32) {
+    for (int32_t e0 = warp_lower_bound(seg, n_s, key_lo, lane);; e0 += 32) {
       const int32_t e = e0 + lane;
-      const bool in = e < n_s && seg[e] < key_hi;
-      int32_t my = -1;
-      if (in) my = (int32_t)lookup_row(g, sid[e]);
+      int32_t sv = 0;
+      const bool in = e < n_s && (sv = seg[e]) < key_hi;
+      int32_t my = -1, md = 0;
+      if (in) { my = (int32_t)lookup_row(g, sid[e]); md = (sv - key_lo) / count; }
       const int nin = __popc(__ballot_sync(0xffffffffu, in));
       unsigned valid = __ballot_sync(0xffffffffu, my >= 0);
-      while (valid) {
+      while (valid) {   // warp-uniform
         float4 v[4][NV];
+        int dq[4];
         int n = 0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -264,6 +298,7 @@ __global__ void __launch_bounds__(256) k_sym_reply_sage(DevGraph g, SymPeers pee
             const int j = __ffs(valid) - 1;
             valid &= valid - 1;
             const int32_t row = __shfl_sync(0xffffffffu, my, j);
+            dq[q] = __shfl_sync(0xffffffffu, md, j);
             const float* p = feat + (int64_t)row * fd;
 #pragma unroll
             for (int t = 0; t < NV; ++t) v[q][t] = __ldg(reinterpret_cast<const float4*>(p + t * 128));
@@ -273,6 +308,16 @@ __global__ void __launch_bounds__(256) k_sym_reply_sage(DevGraph g, SymPeers pee
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           if (q < n) {
+            if (cur < dq[q]) {
+              if (any) {
+#pragma unroll
+                for (int t = 0; t < NV; ++t) { *reinterpret_cast<float4*>(o + (int64_t)cur * fd + t * 128) = acc[t]; acc[t] = make_float4(0.f, 0.f, 0.f, 0.f); }
+                present |= 1u << cur;
+                any = false;
+              }
+              cur = dq[q];
+            }
+            any = true;
 #pragma unroll
             for (int t = 0; t < NV; ++t) {
               acc[t].x = __fadd_rn(acc[t].x, v[q][t].x); acc[t].y = __fadd_rn(acc[t].y, v[q][t].y);
@@ -283,9 +328,12 @@ __global__ void __launch_bounds__(256) k_sym_reply_sage(DevGraph g, SymPeers pee
       }
       if (nin < 32) break;
     }
-    float* o = reinterpret_cast<float*>(peers.base[s] + lay.off_rows) + ((int64_t)me * rows + d) * fd + lane * 4;
+    if (any) {
 #pragma unroll
-    for (int t = 0; t < NV; ++t) *reinterpret_cast<float4*>(o + t * 128) = acc[t];
+      for (int t = 0; t < NV; ++t) *reinterpret_cast<float4*>(o + (int64_t)cur * fd + t * 128) = acc[t];
+      present |= 1u << cur;
+    }
+    if (lane == 0) reinterpret_cast<unsigned char*>(peers.base[s] + lay.off_flags)[(int64_t)me * gps + (w - (int64_t)s * gps)] = (unsigned char)present;
   }
   __threadfence_system();
   __syncthreads();
@@ -337,15 +385,26 @@ __global__ void __launch_bounds__(256) k_sym_reply_sage_generic(DevGraph g, SymP
   if (threadIdx.x < N) st_release_sys(&hdr_of(peers.base[threadIdx.x])->flagB[me], mine->epoch);
 }
 
+__device__ __forceinline__ float vadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float4 vadd(float4 a, float4 b) { return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w)); }
+__device__ __forceinline__ float vzero(float) { return 0.f; }
+__device__ __forceinline__ float4 vzero(float4) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float vdiv(float a, float d) { return __fdiv_rn(a, d); }
+__device__ __forceinline__ float4 vdiv(float4 a, float d) { return make_float4(__fdiv_rn(a.x, d), __fdiv_rn(a.y, d), __fdiv_rn(a.z, d), __fdiv_rn(a.w, d)); }
+
 // requester: out[d,:] = (part[0][d,:] + part[1][d,:] + ...) / (count + 1e-7), rank order
-__global__ void __launch_bounds__(256) k_sym_sage_reduce(const float* __restrict__ part, int N, int64_t rows, int32_t dim, int32_t count,
-                                                         float* __restrict__ out) {
+template <typename V>
+__global__ void __launch_bounds__(256) k_sym_sage_reduce(const V* __restrict__ part, const unsigned char* __restrict__ flags, int N,
+                                                         int64_t rows, int32_t vdim /* V units per row */, int32_t count, V* __restrict__ out) {
   const float denom = __fadd_rn((float)count, 1e-7f);
-  const int64_t total = rows * dim;
+  const int64_t total = rows * vdim;
+  const int64_t gps = (rows + kSageR - 1) / kSageR;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    float acc = part[i];
-    for (int o = 1; o < N; ++o) acc = __fadd_rn(acc, part[(int64_t)o * total + i]);
-    out[i] = __fdiv_rn(acc, denom);
+    const int64_t d = i / vdim;
+    V acc = vzero(V());
+    for (int o = 0; o < N; ++o)   // absent partial == a row of +0.0: skipping it is exact (acc is never -0.0)
+      if ((flags[(int64_t)o * gps + (d >> 3)] >> (d & 7)) & 1) acc = vadd(acc, __ldcs(part + (int64_t)o * total + i));
+    out[i] = vdiv(acc, denom);
   }
 }
 
@@ -367,7 +426,8 @@ struct eu_sym {
   // local scratch
   int64_t* d_sorted = nullptr; int32_t* d_src = nullptr; int64_t* d_counts = nullptr; int64_t* d_offs = nullptr;
   int64_t* d_rids = nullptr; float* d_rw = nullptr; int32_t* d_rt = nullptr;
-  int64_t scratch_rows = 0, scratch_slots = 0;
+  unsigned long long* d_pad = nullptr; int32_t* d_seglo = nullptr;
+  int64_t scratch_rows = 0, scratch_slots = 0, scratch_pad = 0;
 };
 
 using namespace eu;
@@ -394,6 +454,7 @@ int eu_sym_create(eu_ctx* c, int32_t rank, int32_t world, int64_t max_rows, int3
   L.off_w = off; off += a256(4 * L.max_out);
   L.off_t = off; off += a256(4 * L.max_out);
   L.off_rows = off; off += a256(4 * max_feat_rows * (int64_t)max_dim);
+  L.off_flags = off; off += a256((max_feat_rows / 8 + 1) * (int64_t)world);   // partial-row presence bits of eu_sym_sage_mean
   L.bytes = off;
   cudaError_t e = cudaMalloc(&s->base, (size_t)L.bytes);
   if (e != cudaSuccess) { set_error("cudaMalloc(%lld) -> %s", (long long)L.bytes, cudaGetErrorString(e)); delete s; return EU_ERR_CUDA; }
@@ -434,7 +495,7 @@ int eu_sym_destroy(eu_sym* s) {
     if (r != s->rank && s->peers.base[r]) cudaIpcCloseMemHandle(s->peers.base[r]);
   cudaFree(s->base);
   cudaFree(s->d_sorted); cudaFree(s->d_src); cudaFree(s->d_counts); cudaFree(s->d_offs);
-  cudaFree(s->d_rids); cudaFree(s->d_rw); cudaFree(s->d_rt);
+  cudaFree(s->d_rids); cudaFree(s->d_rw); cudaFree(s->d_rt); cudaFree(s->d_pad); cudaFree(s->d_seglo);
   delete s;
   return EU_OK;
 }
@@ -459,7 +520,14 @@ int eu_sym_error(eu_sym* s, int* err) {
   return EU_OK;
 }
 
-static int sym_scratch(eu_sym* s, int64_t rows, int64_t slots) {
+static int sym_scratch(eu_sym* s, int64_t rows, int64_t slots, int64_t pad_rows = 0) {
+  if (pad_rows > s->scratch_pad) {
+    EU_CUDA(cudaStreamSynchronize(s->c->stream));
+    cudaFree(s->d_pad);
+    EU_CUDA(cudaMalloc(&s->d_pad, 8 * (size_t)pad_rows));
+    if (!s->d_seglo) EU_CUDA(cudaMalloc(&s->d_seglo, 4 * (size_t)kSymMaxRanks * 66));
+    s->scratch_pad = pad_rows;
+  }
   if (rows > s->scratch_rows) {
     EU_CUDA(cudaStreamSynchronize(s->c->stream));
     cudaFree(s->d_sorted); cudaFree(s->d_src);
@@ -479,46 +547,54 @@ static int sym_scratch(eu_sym* s, int64_t rows, int64_t slots) {
   return EU_OK;
 }
 
-// One sharded sampleNB hop.  seeds: this rank's frontier (device, i64[rows]).  Results land in this rank's symmetric
-// output arrays (eu_sym_outputs): eng ids (the next frontier) always, TF-packed ids/w/t when want_packed.
-int eu_sym_sample_hop(eu_sym* s, const int64_t* seeds, int64_t rows, const int32_t* etypes, int32_t K, int32_t count,
-                      int64_t default_node, int32_t num_partitions, int32_t want_packed) {
-  if (!s || !s->connected || rows < 0 || count < 0 || (rows > 0 && !seeds)) { set_error("eu_sym_sample_hop: bad argument / not connected"); return EU_ERR_INVALID; }
+// One sharded sampleNB hop over nb independent batches.  seeds: this rank's frontiers (device, i64[nb][rows]).  Batch g is
+// sampled by every shard's engine g as ONE sampleNB call over the requests of rank 0..N-1 for that batch (own dedup scope,
+// own RNG stream) -- nb = 1 is Euler's sharded sampleNB; nb > 1 runs nb of them per exchange so that the ~10 kernels and
+// two NVLink round trips of an exchange are paid once per nb batches.  Results land in this rank's symmetric output arrays
+// (eu_sym_outputs) as [nb][rows][count]: eng ids (the next frontier) always, TF-packed ids/w/t when want_packed.
+int eu_sym_sample_hop_batched(eu_sym* s, const int64_t* seeds, int32_t nb, int64_t rows, const int32_t* etypes, int32_t K,
+                              int32_t count, int64_t default_node, int32_t num_partitions, int32_t want_packed) {
+  if (!s || !s->connected || nb < 1 || nb > 64 || rows < 0 || count < 0 || (rows > 0 && !seeds)) { set_error("eu_sym_sample_hop: bad argument / not connected"); return EU_ERR_INVALID; }
   eu_ctx* c = s->c;
   EU_CUDA(cudaSetDevice(c->g->device));
-  // segment stride of THIS exchange = the requester's row count (every rank issues the same exchange with the same
-  // `rows`: batches are equal-sized across ranks), so the padded inbox is N*rows, not N*capacity
+  // segment stride of THIS exchange = the requester's id count (every rank issues the same exchange with the same
+  // nb x rows: batches are equal-sized across ranks), so the padded sampleNB input is nb*N*rows, not N*capacity
   SymLayout L = s->lay;
   const int N = s->world;
-  if (rows > L.cap || rows * count > L.max_out) { set_error("eu_sym_sample_hop: %lld rows x %d exceed the symmetric region", (long long)rows, count); return EU_ERR_INVALID; }
-  L.cap = std::max<int64_t>(rows, 1);
-  const int64_t prow = (int64_t)N * L.cap;   // padded inbox rows
-  int rc = sym_scratch(s, std::max<int64_t>(rows, 1), std::max<int64_t>(prow * count, 1));
+  const int64_t total = (int64_t)nb * rows;
+  if (total > L.cap || total * count > L.max_out || total >= ((int64_t)1 << 31)) { set_error("eu_sym_sample_hop: %d x %lld rows x %d exceed the symmetric region", nb, (long long)rows, count); return EU_ERR_INVALID; }
+  if (nb > c->n_eng) { set_error("eu_sym_sample_hop: %d batches but the ctx has %d engines", nb, c->n_eng); return EU_ERR_INVALID; }
+  L.cap = std::max<int64_t>(total, 1);
+  const int64_t prow = (int64_t)N * total;   // padded sampleNB rows, all batches
+  int rc = sym_scratch(s, std::max<int64_t>(total, 1), std::max<int64_t>(prow * count, 1), std::max<int64_t>(prow, 1));
   if (rc) return rc;
   cudaStream_t st = c->stream;
-  rc = eu_shard_bucket(c, seeds, rows, num_partitions, N, s->rank, s->d_sorted, s->d_src, s->d_counts, s->d_offs);
+  rc = eu_shard_bucket(c, seeds, total, num_partitions, N, s->rank, s->d_sorted, s->d_src, s->d_counts, s->d_offs);
   if (rc) return rc;
-  { EuProfScope ps(c, "k_sym_push", rows);
-    k_sym_push<<<sym_grid(rows), 256, 0, st>>>(s->peers, L, s->rank, N, (const unsigned long long*)s->d_sorted,
-                                                                                    s->d_src, (const long long*)s->d_offs, rows); }
+  { EuProfScope ps(c, "k_sym_push", total);
+    k_sym_push<<<sym_grid(total), 256, 0, st>>>(s->peers, L, s->rank, N, (const unsigned long long*)s->d_sorted,
+                                                 s->d_src, (const long long*)s->d_offs, total); }
   EU_LAUNCHED();
-  { EuProfScope ps(c, "k_sym_wait_in", rows); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, N); }
+  { EuProfScope ps(c, "k_sym_wait_in", total); k_sym_wait_in<<<1, 256, 0, st>>>(s->base, L, N, nb, rows, s->d_seglo); }
   EU_LAUNCHED();
-  { EuProfScope ps(c, "k_sym_wait_pad", prow); k_sym_wait_pad<<<148, 256, 0, st>>>(s->base, L, N); }
+  { EuProfScope ps(c, "k_sym_gather_pad", prow); k_sym_gather_pad<<<sym_grid(prow), 256, 0, st>>>(s->base, L, N, nb, rows, s->d_seglo, s->d_pad); }
   EU_LAUNCHED();
-  if (count > 0) {
-    rc = hop(c, (const unsigned long long*)(s->base + L.off_inbox_ids), prow, etypes, K, count, /*default_node=*/0, nullptr,
-             s->d_rids, s->d_rw, s->d_rt, 0, false, false, 1);
+  if (count > 0 && rows > 0) {
+    rc = hop(c, s->d_pad, (int64_t)N * rows, etypes, K, count, /*default_node=*/0, nullptr, s->d_rids, s->d_rw, s->d_rt, 0, false, false, nb);
     if (rc) return rc;
   }
   { EuProfScope ps(c, "k_sym_reply_sample", prow);
-    k_sym_reply_sample<<<sym_grid(prow * count), 256, 0, st>>>(s->peers, L, s->rank, N, count, default_node,
-                                                                                                   (const long long*)s->d_rids, s->d_rw, s->d_rt,
-                                                                                                   want_packed != 0); }
+    k_sym_reply_sample<<<sym_grid(prow * count), 256, 0, st>>>(s->peers, L, s->rank, N, nb, rows, s->d_seglo, count, default_node,
+                                                               (const long long*)s->d_rids, s->d_rw, s->d_rt, want_packed != 0); }
   EU_LAUNCHED();
-  { EuProfScope ps(c, "k_sym_wait", rows); k_sym_wait<<<1, 32, 0, st>>>(s->base, N); }
+  { EuProfScope ps(c, "k_sym_wait", total); k_sym_wait<<<1, 32, 0, st>>>(s->base, N); }
   EU_LAUNCHED();
   return EU_OK;
+}
+
+int eu_sym_sample_hop(eu_sym* s, const int64_t* seeds, int64_t rows, const int32_t* etypes, int32_t K, int32_t count,
+                      int64_t default_node, int32_t num_partitions, int32_t want_packed) {
+  return eu_sym_sample_hop_batched(s, seeds, 1, rows, etypes, K, count, default_node, num_partitions, want_packed);
 }
 
 // Sharded dense feature fetch: rows land in this rank's symmetric `rows` output, [rows, dim], request order.
@@ -543,7 +619,7 @@ int eu_sym_get_dense_feature(eu_sym* s, const int64_t* ids, int64_t rows, int32_
     k_sym_push<<<sym_grid(rows), 256, 0, st>>>(s->peers, L, s->rank, N, (const unsigned long long*)s->d_sorted,
                                                                                     s->d_src, (const long long*)s->d_offs, rows); }
   EU_LAUNCHED();
-  { EuProfScope ps(c, "k_sym_wait_in(feat)", rows); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, N); }
+  { EuProfScope ps(c, "k_sym_wait_in(feat)", rows); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, L, N, 1, 0, nullptr); }
   EU_LAUNCHED();
   int G = 1;
   while (G < 32 && G < dim / 4) G <<= 1;
@@ -577,24 +653,32 @@ int eu_sym_sage_mean(eu_sym* s, const int64_t* nbr_ids, int64_t rows, int32_t co
   cudaStream_t st = c->stream;
   rc = eu_shard_bucket(c, nbr_ids, nid, num_partitions, N, s->rank, s->d_sorted, s->d_src, s->d_counts, s->d_offs);
   if (rc) return rc;
+  const bool fast = d.n < ((int64_t)1 << 31) && d.n_slots == 1 && dim == d.feat_dim && (dim == 128 || dim == 256);
+  if ((rows / 8 + 1) * (int64_t)N > a256((L.max_rows_f / 8 + 1) * (int64_t)N)) { set_error("eu_sym_sage_mean: presence bits exceed the symmetric region"); return EU_ERR_INVALID; }
+  // the generic-width owners store every partial row: the requester marks them all present before its push goes out
+  if (!fast) EU_CUDA(cudaMemsetAsync(s->base + L.off_flags, 0xFF, (size_t)(ceil_div(rows, kSageR) * N), st));
   { EuProfScope ps(c, "k_sym_push(sage)", nid);
     k_sym_push<<<sym_grid(nid), 256, 0, st>>>(s->peers, L, s->rank, N, (const unsigned long long*)s->d_sorted, s->d_src,
                                                (const long long*)s->d_offs, nid); }
   EU_LAUNCHED();
-  { EuProfScope ps(c, "k_sym_wait_in(sage)", nid); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, N); }
+  { EuProfScope ps(c, "k_sym_wait_in(sage)", nid); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, L, N, 1, 0, nullptr); }
   EU_LAUNCHED();
   { EuProfScope ps(c, "k_sym_reply_sage", (int64_t)N * rows);
-    const unsigned grid = sym_grid((int64_t)N * rows * 32);
-    const bool fast = d.n < ((int64_t)1 << 31) && d.n_slots == 1 && dim == d.feat_dim;
+    const unsigned grid = sym_grid((int64_t)N * ceil_div(rows, kSageR) * 32);
     if (fast && dim == 128) k_sym_reply_sage<1><<<grid, 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count);
     else if (fast && dim == 256) k_sym_reply_sage<2><<<grid, 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count);
-    else k_sym_reply_sage_generic<<<grid, 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count, dim); }
+    else k_sym_reply_sage_generic<<<sym_grid((int64_t)N * rows * 32), 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count, dim); }
   EU_LAUNCHED();
   { EuProfScope ps(c, "k_sym_wait(sage)", rows); k_sym_wait<<<1, 32, 0, st>>>(s->base, N); }
   EU_LAUNCHED();
   if (rows > 0) {
     EuProfScope ps(c, "k_sym_sage_reduce", rows);
-    k_sym_sage_reduce<<<sym_grid(rows * dim), 256, 0, st>>>((const float*)(s->base + L.off_rows), N, rows, dim, count, out);
+    const float* part = (const float*)(s->base + L.off_rows);
+    const unsigned char* flags = (const unsigned char*)(s->base + L.off_flags);
+    if ((dim & 3) == 0 && ((uintptr_t)out & 15) == 0)
+      k_sym_sage_reduce<float4><<<sym_grid(rows * dim / 4), 256, 0, st>>>((const float4*)part, flags, N, rows, dim / 4, count, (float4*)out);
+    else
+      k_sym_sage_reduce<float><<<sym_grid(rows * dim), 256, 0, st>>>(part, flags, N, rows, dim, count, out);
     EU_LAUNCHED();
   }
   return EU_OK;

@@ -10,7 +10,7 @@
 namespace eu {
 
 static constexpr int kMaxShards = 64;
-static constexpr int kBktBlock = 256;
+static constexpr int kBktBlock = 1024;
 
 // ids 0 (the engine's "no neighbor" placeholder, DEFAULT_UINT64) and 2^64-1 (default_node = -1 fed back as a
 // seed) exist on no shard: they resolve to empty rows wherever they are looked up, so they stay on the
@@ -29,7 +29,10 @@ __global__ void __launch_bounds__(kBktBlock) k_bucket_count(const unsigned long 
   if (threadIdx.x < N) s_cnt[threadIdx.x] = 0;
   __syncthreads();
   const int64_t i = blockIdx.x * (int64_t)kBktBlock + threadIdx.x;
-  if (i < rows) atomicAdd(&s_cnt[owner_of(ids[i], P, N, self)], 1u);
+  // warp-aggregated: N is small, so a plain shared atomic per row would serialise 256 threads on a few counters
+  const int o = i < rows ? owner_of(ids[i], P, N, self) : -1;
+  const unsigned same = __match_any_sync(0xffffffffu, o);
+  if (o >= 0 && (threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&s_cnt[o], (uint32_t)__popc(same));
   __syncthreads();
   if (threadIdx.x < N) blkcnt[(int64_t)blockIdx.x * N + threadIdx.x] = s_cnt[threadIdx.x];
   __threadfence();

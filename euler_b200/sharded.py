@@ -191,7 +191,8 @@ class PeerShardedGraph:
     torch.distributed is used once, at construction, to all_gather the cudaIpc handles."""
 
     def __init__(self, graph, rank, world, max_rows, max_count, max_feat_rows, max_dim, rng="minstd", seed=1,
-                 num_partitions=None, group=None):
+                 num_partitions=None, group=None, engines=1):
+        """max_rows / max_feat_rows count ALL batches of a batched call; engines = the largest nb used."""
         import torch
         import torch.distributed as dist
         from . import _lib
@@ -201,6 +202,8 @@ class PeerShardedGraph:
         self.P = num_partitions or world
         self.dev = torch.device("cuda", graph.device)
         self.ctx = Context(graph, rng, seed)
+        if engines > 1:
+            self.ctx.set_engines(engines)
         self.ctx.reserve(world * max_rows + 1024)
         self._h = C.c_void_p()
         handle = (C.c_char * 64)()
@@ -236,16 +239,32 @@ class PeerShardedGraph:
         self.check(self.lib.eu_sym_error(self._h, C.byref(e)))
         return e.value
 
-    def hop(self, frontier, etypes, count, default_node=-1, packed=True):
-        """frontier: device i64 tensor.  Returns (eng, ids, w, t) VIEWS into the symmetric outputs (overwritten by the
-        next hop; eng is what the next hop consumes)."""
+    def hop(self, frontier, etypes, count, default_node=-1, packed=True, nb=1):
+        """frontier: device i64 tensor, [nb * rows] (batch-major).  Returns (eng, ids, w, t) VIEWS into the symmetric
+        outputs (overwritten by the next hop; eng is what the next hop consumes), each [nb * rows * count]."""
         self._stream()
         et = np.ascontiguousarray(etypes, dtype=np.int32)
-        rows = frontier.numel()
-        self.check(self.lib.eu_sym_sample_hop(self._h, frontier.data_ptr(), rows, et.ctypes.data, len(et), int(count),
-                                              default_node, self.P, int(packed)))
-        n = rows * int(count)
+        total = frontier.numel()
+        assert total % nb == 0
+        self.check(self.lib.eu_sym_sample_hop_batched(self._h, frontier.data_ptr(), int(nb), total // nb, et.ctypes.data, len(et),
+                                                      int(count), default_node, self.P, int(packed)))
+        n = total * int(count)
         return self.o_eng[:n], self.o_ids[:n], self.o_w[:n], self.o_t[:n]
+
+    def sample_fanout_batched(self, nodes, edge_types, counts, default_node=-1):
+        """nodes: [nb, B].  Batch g == sample_fanout of nodes[g] with every shard on its engine g.  Returns lists of
+        [nb, B * prod(counts[:l])] tensors."""
+        t = self.torch
+        nodes = nodes if isinstance(nodes, t.Tensor) else t.as_tensor(np.asarray(nodes), dtype=t.int64)
+        nodes = nodes.to(device=self.dev, dtype=t.int64).contiguous()
+        nb = nodes.shape[0]
+        frontier = nodes.reshape(-1)
+        ids, ws, ts = [nodes], [], []
+        for et, c in zip(edge_types, counts):
+            eng, o_ids, o_w, o_t = self.hop(frontier, et, c, default_node, nb=nb)
+            ids.append(o_ids.clone().reshape(nb, -1)); ws.append(o_w.clone().reshape(nb, -1)); ts.append(o_t.clone().reshape(nb, -1))
+            frontier = eng.clone()
+        return ids, ws, ts
 
     def sample_fanout(self, nodes, edge_types, counts, default_node=-1):
         t = self.torch

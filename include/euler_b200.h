@@ -244,6 +244,10 @@ int eu_sym_outputs(eu_sym* s, int64_t** eng, int64_t** ids, float** w, int32_t**
 int eu_sym_error(eu_sym* s, int* err);   /* 1 if a bounded wait timed out (synchronises) */
 int eu_sym_sample_hop(eu_sym* s, const int64_t* seeds, int64_t rows, const int32_t* etypes, int32_t K, int32_t count,
                       int64_t default_node, int32_t num_partitions, int32_t want_packed);
+/* nb independent batches per exchange: seeds i64[nb][rows], outputs [nb][rows][count]; batch g is sampled by every
+ * shard's engine g (eu_ctx_set_engines) over the requests of rank 0..N-1 for that batch, its own dedup scope. */
+int eu_sym_sample_hop_batched(eu_sym* s, const int64_t* seeds, int32_t nb, int64_t rows, const int32_t* etypes, int32_t K,
+                              int32_t count, int64_t default_node, int32_t num_partitions, int32_t want_packed);
 int eu_sym_get_dense_feature(eu_sym* s, const int64_t* ids, int64_t rows, int32_t fid, int32_t dim, int32_t num_partitions);
 /* Sharded eu_sage_mean_aggregate: REMOTE get_dense_feature (euler/core/kernels/remote_op.cc:60-146) fused with the
  * scatter_mean that follows it (tf_euler/python/euler_ops/mp_ops.py:65-69 over sage_dataflow.py:43-46's edge_src).

@@ -75,6 +75,30 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     pg.close()
+    # ---- nb batches per exchange: batch b == the sharded fanout with every shard on its engine b (seed + b)
+    NB = 3
+    bs = [[g["ids"][np.random.RandomState(900 + 10 * r + b).randint(0, 30000, size=512)].astype(np.int64) for b in range(NB)] for r in range(world)]
+    for r in range(world):
+        bs[r][1][::5] = 0
+        bs[r][2][::9] = 31337
+        bs[r][0][:64] = bs[r][0][64:128]          # duplicates inside a batch
+    pgb = PeerShardedGraph(gr, rank, world, max_rows=NB * 512 * 25, max_count=25, max_feat_rows=NB * 512 * 25, max_dim=64, rng="minstd",
+                           seed=4100 + 100 * rank, engines=NB)
+    for rep in range(2):
+        b_ids, b_ws, b_ts = pgb.sample_fanout_batched(np.stack(bs[rank]), ets, counts, -1)
+    assert pgb.error() == 0
+    # expectation: per batch, an independent simulation whose shard engines are seeded seed_s + b and called twice
+    for b in range(NB):
+        ops_seeds = [4100 + 100 * s_ + b for s_ in range(world)]
+        exp_b = sc.simulate(shards, [bs[r][b] for r in range(world)], ets, counts, shard_seeds=ops_seeds, repeat=2)
+        for l in range(3):
+            cases.eq(b_ids[l][b].cpu().numpy(), exp_b[rank][0][l], "batched peer: rank %d batch %d ids hop %d" % (rank, b, l))
+        for l in range(2):
+            cases.eq(b_ws[l][b].cpu().numpy(), exp_b[rank][1][l], "batched peer: rank %d batch %d w hop %d" % (rank, b, l))
+            cases.eq(b_ts[l][b].cpu().numpy(), exp_b[rank][2][l], "batched peer: rank %d batch %d t hop %d" % (rank, b, l))
+    torch.cuda.synchronize()
+    dist.barrier()
+    pgb.close()
     # dim 128: the float4 warp kernel, fanout 40 > 32 (two lookup rounds per destination)
     g2 = graphs.random_graph(seed=92, n=8000, T=1, avg_deg=9, feat_dim=128, id_stride=3, id_base=1)
     sh2 = sc.partition(g2, world)

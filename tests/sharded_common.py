@@ -100,8 +100,9 @@ class OracleShardOps:
         return self.torch.from_numpy(out)
 
 
-def simulate(shards, seeds_per_rank, ets, counts, shard_seeds, default_node=-1, P=None):
-    """Single-process restatement: returns, per rank, (ids list per hop incl. hop 0, ws, ts)."""
+def simulate(shards, seeds_per_rank, ets, counts, shard_seeds, default_node=-1, P=None, repeat=1):
+    """Single-process restatement: returns, per rank, (ids list per hop incl. hop 0, ws, ts) of the LAST of `repeat`
+    identical calls (the shard engines keep running across calls)."""
     N = len(shards)
     P = P or N
     ogs = [graphs.oracle_graph(s) for s in shards]
@@ -109,6 +110,12 @@ def simulate(shards, seeds_per_rank, ets, counts, shard_seeds, default_node=-1, 
     for s in range(N):
         po.seed(shard_seeds[s])
         states.append(po.get_state())
+    for _ in range(repeat):
+        res = _simulate_once(ogs, states, seeds_per_rank, ets, counts, default_node, P, N)
+    return res
+
+
+def _simulate_once(ogs, states, seeds_per_rank, ets, counts, default_node, P, N):
     frontier = [np.asarray(x, np.int64) for x in seeds_per_rank]
     res = [([f.copy()], [], []) for f in frontier]
     for et, c in zip(ets, counts):
