@@ -30,8 +30,8 @@ import numpy as np  # noqa: E402
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=400)
-    p.add_argument("--warmup", type=int, default=20)
+    p.add_argument("--steps", type=int, default=4000)
+    p.add_argument("--warmup", type=int, default=64)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--rng", default="minstd", choices=["minstd", "philox"])
     p.add_argument("--nodes", type=int, default=10_000_000)
@@ -39,8 +39,8 @@ def parse():
     p.add_argument("--batch", type=int, default=1024)
     p.add_argument("--fanout", default="25,10")
     p.add_argument("--dim", type=int, default=128)
-    p.add_argument("--lanes", type=int, default=2, help="execution contexts (streams) with launch groups in flight")
-    p.add_argument("--group", type=int, default=8, help="steps (batches) per launch group: each batch keeps its own engine and "
+    p.add_argument("--lanes", type=int, default=4, help="execution contexts (streams) with launch groups in flight")
+    p.add_argument("--group", type=int, default=16, help="steps (batches) per launch group: each batch keeps its own engine and "
                                                           "dedup scope (eu_sample_fanout_batched), only the kernel launches are shared")
     p.add_argument("--no-fuse", action="store_true", help="get_dense_feature + scatter_mean instead of the fused kernel")
     p.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph per step")
@@ -111,11 +111,11 @@ def step_bytes(B, counts, D):
 class Lane:
     """One execution context: own stream, RNG engine, pinned input + output buffers."""
 
-    def __init__(self, eb, graph, args, counts, seed, torch):
+    def __init__(self, eb, graph, args, counts, seed, torch, G=None):
         self.t = torch
         self.stream = torch.cuda.Stream()
         self.ctx = eb.Context(graph, args.rng, seed, self.stream.cuda_stream)
-        B, D, G = args.batch, args.dim, args.group
+        B, D, G = args.batch, args.dim, G or args.group
         dev = "cuda"
         self.B, self.D, self.G, self.counts = B, D, G, counts
         self.ctx.set_engines(G, [seed * 1000 + b for b in range(G)])
@@ -186,29 +186,33 @@ def run_ours(args):
     lib = _lib.load()
     counts = [int(x) for x in args.fanout.split(",")]
     et = np.zeros((len(counts), 1), np.int32)
-    import math
-    args.group = max(1, math.gcd(args.group, args.steps))   # exactly K steps are timed: groups must tile K
+    # exactly K steps are timed: K // G full launch groups + one tail group of K % G batches (its own lane + graph)
+    args.group = max(1, min(args.group, args.steps))
     G = args.group
+    tail = args.steps % G
     t0 = time.time()
     graph = eb.Graph.rmat(args.nodes, args.edges, feat_dim=args.dim, device=local)
     torch.cuda.synchronize()
     t_graph = time.time() - t0
     lanes = [Lane(eb, graph, args, counts, 12345 + i, torch) for i in range(args.lanes)]
+    tail_lane = Lane(eb, graph, args, counts, 12345 + args.lanes, torch, G=tail) if tail else None
     raw_step = make_step(lib, C, args, counts, et)
     per_step_launches = None
     use_graphs = not args.no_graphs
     if use_graphs:
         # the step has static shapes and device-resident RNG state: capture it once per lane and
         # replay (one graph launch per step instead of ~14 kernel launches from Python)
-        for ln in lanes:
+        for ln in lanes + ([tail_lane] if tail_lane else []):
             with torch.cuda.stream(ln.stream):
+                ln.d_seeds.fill_(1)
                 raw_step(ln, ln.d_seeds)          # warm (also sizes every scratch buffer)
             ln.stream.synchronize()
             l_before = lib.eu_launch_count()
             ln.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(ln.graph, stream=ln.stream):
                 raw_step(ln, ln.d_seeds)
-            per_step_launches = (lib.eu_launch_count() - l_before) / G
+            ln.launches = lib.eu_launch_count() - l_before
+        per_step_launches = ((args.steps // G) * lanes[0].launches + (tail_lane.launches if tail_lane else 0)) / args.steps
 
     def step(ln, seeds_dev):
         if use_graphs:
@@ -236,16 +240,22 @@ def run_ours(args):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         ev0.record(main)
-        for ln in lanes:
+        rem = n_steps % G
+        use_tail = tail_lane is not None and rem == tail_lane.G
+        n_groups = n_steps // G + (1 if rem else 0)     # an untimed (warm-up) remainder is rounded up to a full group
+        for ln in lanes + ([tail_lane] if use_tail else []):
             ln.stream.wait_event(ev0)
-        for i in range(-(-n_steps // G)):     # launch groups of G steps
+        for i in range(n_groups):     # launch groups of G steps
             ln = lanes[i % len(lanes)]
             g0, sd = group_seeds(first, i)
+            if use_tail and i == n_groups - 1:
+                ln, sd = tail_lane, sd[:rem * args.batch]
+            Gl = ln.G
             with torch.cuda.stream(ln.stream):
                 if e2e:
                     # the lane's pinned buffers are reused every len(lanes) groups
                     ln.stream.synchronize() if i >= len(lanes) else None
-                    ln.h_seeds.copy_(torch.from_numpy(host_seeds[g0:g0 + G].reshape(-1)))
+                    ln.h_seeds.copy_(torch.from_numpy(host_seeds[g0:g0 + Gl].reshape(-1)))
                     ln.d_seeds.copy_(ln.h_seeds, non_blocking=True)
                     step(ln, ln.d_seeds)
                     for l in range(len(counts)):
@@ -254,13 +264,15 @@ def run_ours(args):
                         ln.h_agg[l].copy_(ln.agg[l], non_blocking=True)
                 else:
                     step(ln, sd)
-        for ln in lanes:
+        for ln in lanes + ([tail_lane] if use_tail else []):
             main.wait_stream(ln.stream)
         ev1.record(main)
         torch.cuda.synchronize()
         return ev0.elapsed_time(ev1)
 
     run(-(-args.warmup // G) * G, 0, False)
+    if tail_lane:
+        run(tail, 0, False)
     clocks = Clocks(local)
     clocks.start()
     time.sleep(0.3)
@@ -400,15 +412,18 @@ def run_sharded(args, world, rank, local):
     n_lanes = args.lanes if peer else 1
     # launch group: G batches share every exchange (peer path) -- the kernels and NVLink round trips of an exchange are paid
     # once per G steps; each batch keeps its own engine and dedup scope on every shard (eu_sym_sample_hop_batched)
-    G = max(1, math.gcd(args.group, args.steps)) if peer else 1
+    G = max(1, min(args.group, args.steps)) if peer else 1
+    tail = args.steps % G                 # exactly K steps: K // G full groups + one tail group of K % G batches
     src = [torch.arange(n[l], dtype=torch.int32, device="cuda").repeat_interleave(counts[l]) for l in range(L)]
     n_self = sum(n[:L])                   # rows whose own features are materialised (hop 0 .. L-1)
 
     class SLane:
         pass
     lanes = []
-    for i in range(n_lanes):
+    for i in range(n_lanes + (1 if tail else 0)):
         ln = SLane()
+        ln.G = G if i < n_lanes else tail
+        G_main, G = G, ln.G               # the buffers below are sized for this lane's group
         ln.stream = torch.cuda.Stream()
         seed = 12345 + rank * 1000 + i * 64
         if peer:
@@ -433,11 +448,15 @@ def run_sharded(args, world, rank, local):
         ln.h_ids = [torch.empty(G * x, dtype=torch.int64).pin_memory() for x in n[1:]]
         ln.h_x = torch.empty((G * n_self, D), dtype=torch.float32).pin_memory()
         ln.h_agg = [torch.empty((G * n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
+        G = G_main
         lanes.append(ln)
+    tail_lane = lanes.pop() if tail else None
+    all_lanes = lanes + ([tail_lane] if tail_lane else [])
 
     def raw_step(ln):
-        """one launch group = G steps; seeds are in ln.d_seeds"""
+        """one launch group = ln.G steps; seeds are in ln.d_seeds"""
         sg = ln.sg
+        G = ln.G
         if peer:
             frontier = ln.d_seeds.view(-1)
             for l in range(L):
@@ -474,13 +493,13 @@ def run_sharded(args, world, rank, local):
 
     use_graphs = peer and not args.no_graphs
     if use_graphs:
-        for ln in lanes:
+        for ln in all_lanes:
             with torch.cuda.stream(ln.stream):
-                ln.d_seeds.copy_(dev_seeds[0])
+                ln.d_seeds.copy_(dev_seeds[0][:ln.G])
                 raw_step(ln)
             ln.stream.synchronize()
         dist.barrier()
-        for ln in lanes:
+        for ln in all_lanes:
             ln.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(ln.graph, stream=ln.stream):
                 raw_step(ln)
@@ -500,15 +519,20 @@ def run_sharded(args, world, rank, local):
         dist.barrier()
         torch.cuda.synchronize()
         ev0.record(main)
-        for ln in lanes:
+        rem = n_steps % G
+        use_tail = tail_lane is not None and rem == tail_lane.G
+        n_groups = n_steps // G + (1 if rem else 0)     # an untimed (warm-up) remainder is rounded up to a full group
+        for ln in all_lanes:
             ln.stream.wait_event(ev0)
-        for i in range(-(-n_steps // G)):
+        for i in range(n_groups):
             ln = lanes[i % len(lanes)]
+            if use_tail and i == n_groups - 1:
+                ln = tail_lane
             sd = (first // G + i) % n_seed_groups
             with torch.cuda.stream(ln.stream):
                 if e2e:
                     ln.stream.synchronize() if i >= len(lanes) else None
-                    ln.h_seeds.copy_(torch.from_numpy(host_seeds[sd]))
+                    ln.h_seeds.copy_(torch.from_numpy(host_seeds[sd][:ln.G]))
                     ln.d_seeds.copy_(ln.h_seeds, non_blocking=True)
                     step(ln)
                     ln.h_x.copy_(ln.x_view, non_blocking=True)
@@ -516,9 +540,9 @@ def run_sharded(args, world, rank, local):
                         ln.h_ids[l].copy_(ln.ids[l], non_blocking=True)
                         ln.h_agg[l].copy_(ln.agg[l], non_blocking=True)
                 else:
-                    ln.d_seeds.copy_(dev_seeds[sd], non_blocking=True)
+                    ln.d_seeds.copy_(dev_seeds[sd][:ln.G], non_blocking=True)
                     step(ln)
-        for ln in lanes:
+        for ln in all_lanes:
             main.wait_stream(ln.stream)
         ev1.record(main)
         torch.cuda.synchronize()
@@ -527,7 +551,9 @@ def run_sharded(args, world, rank, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    run(max(args.warmup, G * len(lanes)), 0, False)
+    run(-(-max(args.warmup, G * len(lanes)) // G) * G, 0, False)
+    if tail_lane:
+        run(tail, 0, False)
     clocks = Clocks(local)
     clocks.start()
     time.sleep(0.3)
@@ -535,9 +561,9 @@ def run_sharded(args, world, rank, local):
     ms = run(args.steps, args.warmup, False)
     w1 = time.time()
     clk = clocks.stop(w0, w1)
-    run(min(max(args.warmup, G), 4 * G), 0, True)
+    run(G * min(len(lanes), 2), 0, True)
     ms_e2e = run(args.steps, args.warmup, True)
-    err = max(ln.sg.error() for ln in lanes) if peer else 0
+    err = max(ln.sg.error() for ln in all_lanes) if peer else 0
     # per-kernel breakdown + launch count on one lane (library-side CUDA events), serial, no graphs
     prof = {}
     ln = lanes[0]
@@ -595,7 +621,7 @@ def run_sharded(args, world, rank, local):
             "e2e": {"value": edges_step * args.steps / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 8 * B * world,
                     "d2h_bytes_per_step": world * (sum(8 * x for x in n[1:]) + 2 * sum(4 * n[l] * D for l in range(L))),
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(round(launches_per_group * (args.steps // G))), "clocks": clk,
+            "gpu_launches": int(round(launches_per_group * (args.steps // G + (1 if tail else 0)))), "clocks": clk,
             "roofline": {"bound": "nvlink", "kernel": "exchange kernels (k_sym_push / k_sym_reply_sample / k_sym_reply_sage / k_sym_reply_feature)" if peer else "NCCL all-to-all",
                          "achieved": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9, 2), "peak": 770.0, "unit": "GB/s",
                          "frac": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9 / 770.0, 4), "traffic": None,
@@ -609,7 +635,7 @@ def run_sharded(args, world, rank, local):
             out["config"]["launch"] = "one CUDA graph replay per launch group; gpu_launches counts this library's kernels inside the replays"
         emit(out)
     if peer:
-        for ln in lanes:
+        for ln in all_lanes:
             ln.sg.close()
     dist.destroy_process_group()
 
@@ -698,20 +724,31 @@ def run_reference(args):
     host_seeds = np.stack([np.random.RandomState(1000 + i).randint(1, args.nodes + 1, size=args.batch)
                            for i in range(nb)]).astype(np.int64)
     et = [[0]] * len(counts)
-    fn = (lambda s, it: po.ref_bench_step(s, et, counts, args.dim, cores, it)) if use_ref else \
-         (lambda s, it: po.oracle_bench_step(og, s, et, counts, args.dim, cores, it))
-    # a "step" of this arm = one bounded sample: every core runs one batch
-    fn(host_seeds[:64], 1)
-    steps = min(args.steps, 6)
-    warm = min(args.warmup, 1)
+
+    def fn(sd, it, th):
+        return po.ref_bench_step(sd, et, counts, args.dim, th, it) if use_ref else po.oracle_bench_step(og, sd, et, counts, args.dim, th, it)
+    # untimed: pick the thread count the reference runs fastest with on this host (it links jemalloc upstream,
+    # CMakeLists.txt:13,41-43; with glibc malloc more threads are not always faster) -- its best case is the baseline
+    best_th, best_v = cores, 0.0
+    for th in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 16), min(cores, 8)}, reverse=True):
+        sec, edges = fn(host_seeds[:64], 1, th)
+        sec, edges = fn(host_seeds[:64], 1, th)
+        if edges / sec > best_v:
+            best_th, best_v = th, edges / sec
+    cores_used = best_th
+    # a "step" of this arm = one bounded sample: every thread runs one batch
+    sec1, _ = fn(host_seeds[:64], 1, cores_used)
+    steps = max(1, min(args.steps, int(90.0 / max(sec1, 1e-3))))     # whole run bounded to ~1.5 minutes
+    warm = min(args.warmup, 2)
     for _ in range(warm):
-        fn(host_seeds[:64], 1)
+        fn(host_seeds[:64], 1, cores_used)
     t_edges, t_sec = 0, 0.0
     for _ in range(steps):
-        sec, edges = fn(host_seeds[:64], 1)
+        sec, edges = fn(host_seeds[:64], 1, cores_used)
         t_edges += edges
         t_sec += sec
     v = t_edges / t_sec
+    cores = cores_used
     out = {"impl": "reference", "metric": "sampled_edges_per_sec", "value": v, "unit": "edges/s",
            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_sec / steps,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 ids / f32", "data": "synthetic",

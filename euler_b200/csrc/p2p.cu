@@ -15,6 +15,7 @@
 //                                original position (TF packing done here), then flagB[me] <- epoch on the requester
 //   requester  k_sym_wait      : waits for flagB of every owner; its outputs are complete, already in request order.
 // Flags are monotonic epochs kept on the device; all waits are bounded (hdr->error is set on timeout instead of hanging).
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -411,6 +412,13 @@ __global__ void __launch_bounds__(256) k_sym_sage_reduce(const V* __restrict__ p
 static inline unsigned sym_grid(int64_t threads) {   // persistent: at most 8 CTAs of 256 per SM
   return (unsigned)std::min<int64_t>(std::max<int64_t>(ceil_div(threads, 256), 1), 148 * 8);
 }
+// reply kernels are NVLink-store bound: fewer resident CTAs keep the link busy and leave SM slots to the compute
+// kernels of the other lanes
+static inline unsigned reply_grid(int64_t threads) {
+  static int per_sm = 0;
+  if (!per_sm) { const char* e = getenv("EU_SYM_REPLY_CTAS"); per_sm = e ? std::max(1, atoi(e)) : 4; }
+  return (unsigned)std::min<int64_t>(std::max<int64_t>(ceil_div(threads, 256), 1), 148 * (int64_t)per_sm);
+}
 
 static inline int64_t a256(int64_t x) { return (x + 255) & ~(int64_t)255; }
 
@@ -584,7 +592,7 @@ int eu_sym_sample_hop_batched(eu_sym* s, const int64_t* seeds, int32_t nb, int64
     if (rc) return rc;
   }
   { EuProfScope ps(c, "k_sym_reply_sample", prow);
-    k_sym_reply_sample<<<sym_grid(prow * count), 256, 0, st>>>(s->peers, L, s->rank, N, nb, rows, s->d_seglo, count, default_node,
+    k_sym_reply_sample<<<reply_grid(prow * count), 256, 0, st>>>(s->peers, L, s->rank, N, nb, rows, s->d_seglo, count, default_node,
                                                                (const long long*)s->d_rids, s->d_rw, s->d_rt, want_packed != 0); }
   EU_LAUNCHED();
   { EuProfScope ps(c, "k_sym_wait", total); k_sym_wait<<<1, 32, 0, st>>>(s->base, N); }
@@ -625,7 +633,7 @@ int eu_sym_get_dense_feature(eu_sym* s, const int64_t* ids, int64_t rows, int32_
   while (G < 32 && G < dim / 4) G <<= 1;
   const int64_t prow = (int64_t)N * L.cap;
   { EuProfScope ps(c, "k_sym_reply_feature", prow);
-    k_sym_reply_feature<<<sym_grid(prow * G), 256, 0, st>>>(d, s->peers, L, s->rank, N, dim, soff, sdim, G); }
+    k_sym_reply_feature<<<reply_grid(prow * G), 256, 0, st>>>(d, s->peers, L, s->rank, N, dim, soff, sdim, G); }
   EU_LAUNCHED();
   { EuProfScope ps(c, "k_sym_wait(feat)", rows); k_sym_wait<<<1, 32, 0, st>>>(s->base, N); }
   EU_LAUNCHED();
@@ -664,7 +672,7 @@ int eu_sym_sage_mean(eu_sym* s, const int64_t* nbr_ids, int64_t rows, int32_t co
   { EuProfScope ps(c, "k_sym_wait_in(sage)", nid); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, L, N, 1, 0, nullptr); }
   EU_LAUNCHED();
   { EuProfScope ps(c, "k_sym_reply_sage", (int64_t)N * rows);
-    const unsigned grid = sym_grid((int64_t)N * ceil_div(rows, kSageR) * 32);
+    const unsigned grid = reply_grid((int64_t)N * ceil_div(rows, kSageR) * 32);
     if (fast && dim == 128) k_sym_reply_sage<1><<<grid, 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count);
     else if (fast && dim == 256) k_sym_reply_sage<2><<<grid, 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count);
     else k_sym_reply_sage_generic<<<sym_grid((int64_t)N * rows * 32), 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count, dim); }

@@ -301,7 +301,8 @@ struct SampleArgs {
   const uint32_t* blkmul;       // F^(eligible rows in earlier blocks of the batch)
   uint32_t F;                   // A^(2 * uniforms per row) mod M
   uint32_t lanepow[32];         // A^(2 * uniforms per draw * lane): a lane's jump from the row state
-  uint32_t stride;              // A^(2 * uniforms per draw * 32)
+  uint32_t stride;              // A^(2 * uniforms per draw * SG)
+  int sg_log;                   // log2 of the lanes per row (SG)
   HashSlot* clear_tab;          // dedup tables of THIS hop (all batches), cleared here for the next user
   int64_t clear_n;
   HashSlot* next_tabs;          // dedup tables of the NEXT hop: this hop's engine ids are its seeds (or null)
@@ -316,13 +317,13 @@ struct SampleArgs {
   int32_t* out_t;
 };
 
-// shuffle binary search over 32 lane-resident values c (non-decreasing, +inf padded):
+// shuffle binary search over the SG lane-resident values c of a lane group (non-decreasing, +inf padded):
 // first local index in [lo,hi] with (double)c > r, else hi.
-__device__ __forceinline__ int lane_upper_bound(float c, int lo, int hi, float thr) {
+__device__ __forceinline__ int lane_upper_bound(float c, int lo, int hi, float thr, unsigned gmask, int SG) {
 #pragma unroll
   for (int it = 0; it < 5; ++it) {
     int mid = (lo + hi) >> 1;
-    float v = __shfl_sync(0xffffffffu, c, mid);
+    float v = __shfl_sync(gmask, c, mid, SG);
     bool go = lo < hi;
     bool gt = v >= thr;   // (double)v > r, see gt_threshold
     hi = (go && gt) ? mid : hi;
@@ -331,6 +332,10 @@ __device__ __forceinline__ int lane_upper_bound(float c, int lo, int hi, float t
   return lo;
 }
 
+// One lane GROUP (SG lanes, SG = 2^k >= min(count, 32)) per sampling row, one lane per draw; a warp carries 32/SG
+// rows, and a persistent grid strides over the live rows: with fanout 10 two rows share a warp (the kernel is
+// issue-bound, profiles/r01_*: every instruction a lane group spares is throughput), and the per-block set-up
+// (jump tables, table wipe, parameter loads) is paid once per CTA instead of once per 8 rows.
 template <bool PHILOX>
 __global__ void __launch_bounds__(256, 8) k_sample(DevGraph g, SampleArgs a) {
   const int lane = threadIdx.x & 31;
@@ -345,187 +350,190 @@ __global__ void __launch_bounds__(256, 8) k_sample(DevGraph g, SampleArgs a) {
       s_fpow[threadIdx.x] = fp;
     }
     __syncthreads();
-  }
-  if (!PHILOX) {  // k_prepare (the only reader of this hop's dedup tables) has finished: wipe them
+    // k_prepare (the only reader of this hop's dedup tables) has finished: wipe them
     for (int64_t s = gtid; s < a.clear_n; s += (int64_t)gridDim.x * blockDim.x) { a.clear_tab[s].key = 0; a.clear_tab[s].row = kEmptyRow; }
   }
-  int64_t w = gtid >> 5;
-  if (!PHILOX) {
-    if (w >= (int64_t)__ldg(a.n_live)) return;   // empty rows were finished by k_prepare
-    w = a.live[w];
-  }
-  if (w >= a.gm.nb * a.gm.rows_b) return;
-  const int bidx = (int)(w / a.gm.rows_b);
-  const int64_t li = w - bidx * a.gm.rows_b;
+  const int SG = 1 << a.sg_log;
+  const int sl = lane & (SG - 1);                    // lane inside its group = draw index modulo SG
+  const unsigned gmask = SG == 32 ? 0xffffffffu : (((1u << SG) - 1u) << (lane - sl));
   const int32_t count = a.count;
   const int32_t T = g.T;
-  const int64_t obase = w * (int64_t)count;
-  const EuRngState* rng = a.rngs + bidx;
-  HashSlot* ntab = a.next_tabs ? a.next_tabs + (int64_t)bidx * (a.next_cap_b + 1) : nullptr;
-  const unsigned long long nmask = (unsigned long long)a.next_cap_b - 1;
-  const int64_t nbase = li * (int64_t)count;  // index of this row's first id inside the next hop's batch
+  const int64_t total = PHILOX ? a.gm.nb * a.gm.rows_b : (int64_t)__ldg(a.n_live);   // empty rows were finished by k_prepare
+  const int64_t qstride = (((int64_t)gridDim.x * blockDim.x) >> 5) << (5 - a.sg_log);
+  const uint32_t upd = a.mode == 0 ? 1u : 2u;        // uniforms per draw
+  const uint32_t stride = a.stride;                  // A^(2 * upd * SG): a lane's jump to its next draw
 
-  int64_t row;
-  bool ok;
-  uint32_t st = 0;
-  unsigned long long seed_id = 0;
-  if (PHILOX) {
-    seed_id = a.seeds[w];
-    row = lookup_row(g, seed_id);
-    ok = row_eligible(g, row, a.et, a.mode);
-  } else {
-    const int64_t ib = bidx * a.gm.rows_pad;
-    const int32_t f = a.first[ib + li];
-    const uint32_t m = a.emask[(ib + f) >> 5];
-    ok = (m >> (f & 31)) & 1u;
-    if (ok) {
-      row = a.rowof[ib + li];
-      st = modmul(modmul(rng->x_prev, a.blkmul[(int64_t)bidx * a.gm.nblk_b + f / kPrepBlock]),
-                  modmul(a.wmul[(ib + f) >> 5], s_fpow[__popc(m & ((1u << (f & 31)) - 1u))]));
-    } else {
-      row = -1;
-    }
-  }
-  if (!ok) {
-    for (int32_t j = lane; j < count; j += 32) {
-      if (a.eng_ids) a.eng_ids[obase + j] = 0ull;
-      if (a.out_ids) { a.out_ids[obase + j] = a.default_node; a.out_w[obase + j] = 0.f; a.out_t[obase + j] = -1; }
-    }
-    if (!PHILOX && ntab && lane == 0) dedup_insert_one(ntab, nmask, 0ull, nbase);  // `count` zeros
-    return;
-  }
+  for (int64_t q = ((gtid >> 5) << (5 - a.sg_log)) + (lane >> a.sg_log); q < total; q += qstride) {
+    const int64_t w = PHILOX ? q : (int64_t)a.live[q];
+    const int bidx = (int)(w / a.gm.rows_b);
+    const int64_t li = w - bidx * a.gm.rows_b;
+    const int64_t obase = w * (int64_t)count;
+    const EuRngState* rng = a.rngs + bidx;
+    HashSlot* ntab = a.next_tabs ? a.next_tabs + (int64_t)bidx * (a.next_cap_b + 1) : nullptr;
+    const unsigned long long nmask = (unsigned long long)a.next_cap_b - 1;
+    const int64_t nbase = li * (int64_t)count;  // index of this row's first id inside the next hop's batch
 
-  const int64_t* gp = g.grp_ptr + row * T;
-  const int64_t base = gp[0];
-  const int64_t rlen = gp[T] - base;  // whole row
-  // stage the row's cumulative weights in lanes when it fits one warp
-  const bool small_row = rlen <= 32;
-  float c = __int_as_float(0x7f800000);  // +inf
-  if (small_row && lane < rlen) c = __ldg(g.cum_w + base + lane);
-
-  // mode 0: fixed group
-  int64_t gb = 0, ge = 0;  // group [gb, ge] inclusive, global indices
-  float lim_b = 0.f, lim_e = 0.f;
-  if (a.mode == 0) {
-    const int32_t t = a.et.v[0];
-    gb = gp[t];
-    ge = gp[t + 1] - 1;
-    lim_b = gb == base ? 0.f : __ldg(g.cum_w + gb - 1);
-    lim_e = __ldg(g.cum_w + ge);
-  }
-  // modes 1/2: type-pick table in lanes: tc[k] = prefix over listed types (1) or grp_cum (2)
-  float tc = __int_as_float(0x7f800000);
-  int ntc = 0;
-  if (a.mode == 1) {
-    ntc = a.et.K;
-    float s = 0.f, mine = 0.f;
-    for (int32_t i = 0; i < ntc; ++i) {
-      int32_t t = a.et.v[i];
-      float pre = t > 0 ? grp_cum_at(g, row, t - 1) : 0.f;
-      s = __fadd_rn(s, __fsub_rn(grp_cum_at(g, row, t), pre));
-      if (i == lane) mine = s;
-    }
-    if (lane < ntc) tc = mine;
-  } else if (a.mode == 2) {
-    ntc = T;
-    if (lane < T) tc = grp_cum_at(g, row, lane);
-  }
-  const float tc_end = __shfl_sync(0xffffffffu, tc, ntc > 0 ? ntc - 1 : 0);
-
-  const uint32_t upd = a.mode == 0 ? 1u : 2u;  // uniforms per draw
-  // engine state before this lane's first draw, and the stride for draws lane+32, lane+64, ...
-  uint32_t x = 0;
-  const uint32_t stride = a.stride;
-  if (!PHILOX) x = modmul(st, s_lanepow[lane]);
-  const uint32_t salt = PHILOX ? (uint32_t)rng->calls : 0u;
-  const unsigned long long pkey = PHILOX ? a.key ^ rng->key : 0ull;
-
-  bool keep = true;
-  bool bad = false;
-  for (int32_t j0 = 0; j0 < count; j0 += 32) {
-    const int32_t j = j0 + lane;
-    const bool active = j < count;
-    double u_t = 0.0, u_n = 0.0;
+    int64_t row;
+    bool ok;
+    uint32_t st = 0;
+    unsigned long long seed_id = 0;
     if (PHILOX) {
-      philox_uniform2(seed_id, (uint32_t)j, salt, pkey, u_t, u_n);
+      seed_id = a.seeds[w];
+      row = lookup_row(g, seed_id);
+      ok = row_eligible(g, row, a.et, a.mode);
     } else {
-      uint32_t xs = x;
-      if (upd == 2u) u_t = minstd_uniform(xs);
-      u_n = minstd_uniform(xs);
-      x = modmul(x, stride);
-    }
-    int32_t etype = a.mode == 0 ? a.et.v[0] : 0;
-    int64_t b = gb, e = ge;
-    float lb = lim_b, le = lim_e;
-    if (a.mode != 0) {
-      // type pick: RandomSelect(sum_weights_, 0, n-1)
-      const float tt = gt_threshold(pick_r(u_t, 0.f, tc_end));
-      int k = lane_upper_bound(tc, 0, ntc - 1, tt);
-      etype = a.mode == 1 ? a.et.v[k] : k;
-      b = gp[etype];
-      e = gp[etype + 1] - 1;
-      if (e < b) {  // zero-weight group reached through the fall-through: UB in the reference (SURVEY A-17)
-        bad = bad || active;
-        b = base; e = base;  // keep addresses valid
-      }
-      lb = b == base ? 0.f : __ldg(g.cum_w + b - 1);
-      le = __ldg(g.cum_w + e);
-    }
-    const float thr = gt_threshold(pick_r(u_n, lb, le));
-    int64_t m;
-    float wgt;
-    if (small_row) {
-      int li2 = lane_upper_bound(c, (int)(b - base), (int)(e - base), thr);
-      float hi_v = __shfl_sync(0xffffffffu, c, li2);
-      float lo_v = __shfl_sync(0xffffffffu, c, li2 > 0 ? li2 - 1 : 0);
-      m = base + li2;
-      wgt = __fsub_rn(hi_v, li2 > 0 ? lo_v : 0.f);
-    } else {
-      m = b + upper_bound_clamped(g.cum_w + b, 0, (int32_t)(e - b), thr);
-      float hi_v = __ldg(g.cum_w + m);
-      float lo_v = m > base ? __ldg(g.cum_w + m - 1) : 0.f;
-      wgt = __fsub_rn(hi_v, lo_v);
-    }
-    const unsigned long long nid = active ? __ldg(g.nbr + m) : 0ull;
-    if (j0 == 0) {
-      // TF packing keeps the row iff its first engine id != DEFAULT_UINT64 (0)
-      unsigned long long first_id = __shfl_sync(0xffffffffu, nid, 0);
-      keep = first_id != 0ull;
-    }
-    if (active) {
-      if (a.eng_ids) a.eng_ids[obase + j] = nid;
-      if (a.out_ids) {
-        a.out_ids[obase + j] = keep ? (long long)nid : a.default_node;
-        a.out_w[obase + j] = keep ? wgt : 0.f;
-        a.out_t[obase + j] = keep ? etype : -1;
+      const int64_t ib = bidx * a.gm.rows_pad;
+      const int32_t f = a.first[ib + li];
+      const uint32_t m = a.emask[(ib + f) >> 5];
+      ok = (m >> (f & 31)) & 1u;
+      if (ok) {
+        row = a.rowof[ib + li];
+        st = modmul(modmul(rng->x_prev, a.blkmul[(int64_t)bidx * a.gm.nblk_b + f / kPrepBlock]),
+                    modmul(a.wmul[(ib + f) >> 5], s_fpow[__popc(m & ((1u << (f & 31)) - 1u))]));
+      } else {
+        row = -1;
       }
     }
-    if (!PHILOX && ntab && a.mode == 0) {
-      // mode 0 cannot hit the `bad` path: the ids are final, enter them into the next hop's dedup table now
-      const unsigned act = __ballot_sync(0xffffffffu, active);
-      if (active) {
-        const unsigned peers = __match_any_sync(act, nid);
-        if (lane == __ffs(peers) - 1) dedup_insert_one(ntab, nmask, nid, nbase + j);
+    if (!ok) {
+      for (int32_t j = sl; j < count; j += SG) {
+        if (a.eng_ids) a.eng_ids[obase + j] = 0ull;
+        if (a.out_ids) { a.out_ids[obase + j] = a.default_node; a.out_w[obase + j] = 0.f; a.out_t[obase + j] = -1; }
       }
+      if (!PHILOX && ntab && sl == 0) dedup_insert_one(ntab, nmask, 0ull, nbase);  // `count` zeros
+      continue;
     }
-  }
-  if (__any_sync(0xffffffffu, bad)) {
-    for (int32_t j = lane; j < count; j += 32) {
-      if (a.eng_ids) a.eng_ids[obase + j] = 0ull;
-      if (a.out_ids) { a.out_ids[obase + j] = a.default_node; a.out_w[obase + j] = 0.f; a.out_t[obase + j] = -1; }
+
+    const int64_t* gp = g.grp_ptr + row * T;
+    const int64_t base = gp[0];
+    const int64_t rlen = gp[T] - base;  // whole row
+    // stage the row's cumulative weights in the group's lanes when it fits
+    const bool small_row = rlen <= SG;
+    float c = __int_as_float(0x7f800000);  // +inf
+    if (small_row && sl < rlen) c = __ldg(g.cum_w + base + sl);
+
+    // mode 0: fixed group
+    int64_t gb = 0, ge = 0;  // group [gb, ge] inclusive, global indices
+    float lim_b = 0.f, lim_e = 0.f;
+    if (a.mode == 0) {
+      const int32_t t = a.et.v[0];
+      gb = gp[t];
+      ge = gp[t + 1] - 1;
+      lim_b = gb == base ? 0.f : __ldg(g.cum_w + gb - 1);
+      lim_e = __ldg(g.cum_w + ge);
     }
-  }
-  if (!PHILOX && ntab && a.mode != 0) {
-    // the engine ids just written are the next hop's seeds: enter them into its dedup table now
-    // (each lane re-reads its own stores), so the next hop needs no insert kernel
-    for (int32_t j0 = 0; j0 < count; j0 += 32) {
-      const int32_t j = j0 + lane;
+    // modes 1/2: type-pick table in the group's lanes (SG >= table size, see hop()): tc[k] = prefix over listed
+    // types (1) or grp_cum (2)
+    float tc = __int_as_float(0x7f800000);
+    int ntc = 0;
+    if (a.mode == 1) {
+      ntc = a.et.K;
+      float sum = 0.f, mine = 0.f;
+      for (int32_t i = 0; i < ntc; ++i) {
+        int32_t t = a.et.v[i];
+        float pre = t > 0 ? grp_cum_at(g, row, t - 1) : 0.f;
+        sum = __fadd_rn(sum, __fsub_rn(grp_cum_at(g, row, t), pre));
+        if (i == sl) mine = sum;
+      }
+      if (sl < ntc) tc = mine;
+    } else if (a.mode == 2) {
+      ntc = T;
+      if (sl < T) tc = grp_cum_at(g, row, sl);
+    }
+    const float tc_end = __shfl_sync(gmask, tc, ntc > 0 ? ntc - 1 : 0, SG);
+
+    // engine state before this lane's first draw
+    uint32_t x = 0;
+    if (!PHILOX) x = modmul(st, s_lanepow[sl]);
+    const uint32_t salt = PHILOX ? (uint32_t)rng->calls : 0u;
+    const unsigned long long pkey = PHILOX ? a.key ^ rng->key : 0ull;
+
+    bool keep = true;
+    bool bad = false;
+    for (int32_t j0 = 0; j0 < count; j0 += SG) {
+      const int32_t j = j0 + sl;
       const bool active = j < count;
-      const unsigned long long nid = active ? a.eng_ids[obase + j] : 0ull;
-      const unsigned act = __ballot_sync(0xffffffffu, active);
+      double u_t = 0.0, u_n = 0.0;
+      if (PHILOX) {
+        philox_uniform2(seed_id, (uint32_t)j, salt, pkey, u_t, u_n);
+      } else {
+        uint32_t xs = x;
+        if (upd == 2u) u_t = minstd_uniform(xs);
+        u_n = minstd_uniform(xs);
+        x = modmul(x, stride);
+      }
+      int32_t etype = a.mode == 0 ? a.et.v[0] : 0;
+      int64_t b = gb, e = ge;
+      float lb = lim_b, le = lim_e;
+      if (a.mode != 0) {
+        // type pick: RandomSelect(sum_weights_, 0, n-1)
+        const float tt = gt_threshold(pick_r(u_t, 0.f, tc_end));
+        int k = lane_upper_bound(tc, 0, ntc - 1, tt, gmask, SG);
+        etype = a.mode == 1 ? a.et.v[k] : k;
+        b = gp[etype];
+        e = gp[etype + 1] - 1;
+        if (e < b) {  // zero-weight group reached through the fall-through: UB in the reference (SURVEY A-17)
+          bad = bad || active;
+          b = base; e = base;  // keep addresses valid
+        }
+        lb = b == base ? 0.f : __ldg(g.cum_w + b - 1);
+        le = __ldg(g.cum_w + e);
+      }
+      const float thr = gt_threshold(pick_r(u_n, lb, le));
+      int64_t m;
+      float wgt;
+      if (small_row) {
+        int li2 = lane_upper_bound(c, (int)(b - base), (int)(e - base), thr, gmask, SG);
+        float hi_v = __shfl_sync(gmask, c, li2, SG);
+        float lo_v = __shfl_sync(gmask, c, li2 > 0 ? li2 - 1 : 0, SG);
+        m = base + li2;
+        wgt = __fsub_rn(hi_v, li2 > 0 ? lo_v : 0.f);
+      } else {
+        m = b + upper_bound_clamped(g.cum_w + b, 0, (int32_t)(e - b), thr);
+        float hi_v = __ldg(g.cum_w + m);
+        float lo_v = m > base ? __ldg(g.cum_w + m - 1) : 0.f;
+        wgt = __fsub_rn(hi_v, lo_v);
+      }
+      const unsigned long long nid = active ? __ldg(g.nbr + m) : 0ull;
+      if (j0 == 0) {
+        // TF packing keeps the row iff its first engine id != DEFAULT_UINT64 (0)
+        unsigned long long first_id = __shfl_sync(gmask, nid, 0, SG);
+        keep = first_id != 0ull;
+      }
       if (active) {
-        const unsigned peers = __match_any_sync(act, nid);
-        if (lane == __ffs(peers) - 1) dedup_insert_one(ntab, nmask, nid, nbase + j);
+        if (a.eng_ids) a.eng_ids[obase + j] = nid;
+        if (a.out_ids) {
+          a.out_ids[obase + j] = keep ? (long long)nid : a.default_node;
+          a.out_w[obase + j] = keep ? wgt : 0.f;
+          a.out_t[obase + j] = keep ? etype : -1;
+        }
+      }
+      if (!PHILOX && ntab && a.mode == 0) {
+        // mode 0 cannot hit the `bad` path: the ids are final, enter them into the next hop's dedup table now
+        const unsigned act = __ballot_sync(gmask, active);
+        if (active) {
+          const unsigned peers = __match_any_sync(act, nid);
+          if (lane == __ffs(peers) - 1) dedup_insert_one(ntab, nmask, nid, nbase + j);
+        }
+      }
+    }
+    if (__any_sync(gmask, bad)) {
+      for (int32_t j = sl; j < count; j += SG) {
+        if (a.eng_ids) a.eng_ids[obase + j] = 0ull;
+        if (a.out_ids) { a.out_ids[obase + j] = a.default_node; a.out_w[obase + j] = 0.f; a.out_t[obase + j] = -1; }
+      }
+    }
+    if (!PHILOX && ntab && a.mode != 0) {
+      // the engine ids just written are the next hop's seeds: enter them into its dedup table now
+      // (each lane re-reads its own stores), so the next hop needs no insert kernel
+      for (int32_t j0 = 0; j0 < count; j0 += SG) {
+        const int32_t j = j0 + sl;
+        const bool active = j < count;
+        const unsigned long long nid = active ? a.eng_ids[obase + j] : 0ull;
+        const unsigned act = __ballot_sync(gmask, active);
+        if (active) {
+          const unsigned peers = __match_any_sync(act, nid);
+          if (lane == __ffs(peers) - 1) dedup_insert_one(ntab, nmask, nid, nbase + j);
+        }
       }
     }
   }
@@ -650,7 +658,16 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
   a.seeds = seeds; a.gm = gm; a.count = count; a.default_node = default_node;
   a.eng_ids = eng_ids; a.out_ids = (long long*)out_ids; a.out_w = out_w; a.out_t = out_t;
   a.rngs = c->d_rng;
-  const unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
+  // lanes per row: the smallest power of two that holds a row's draws (and the type-pick table of modes 1/2)
+  {
+    int need = std::min<int>(count, 32);
+    if (a.mode == 1) need = std::max<int>(need, std::min<int>(a.et.K, 32));
+    if (a.mode == 2) need = std::max<int>(need, std::min<int>(d.T, 32));
+    a.sg_log = 0;
+    while ((1 << a.sg_log) < need) ++a.sg_log;
+  }
+  // persistent grid: 8 CTAs per SM stride over the (live) rows
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(ceil_div(rows * 32, (int64_t)(32 >> a.sg_log)), 256), 148 * 8);
   if (c->rng == EU_RNG_PHILOX) {
     a.key = c->seed;
     { EuProfScope ps(c, "k_sample<philox>", rows); k_sample<true><<<blocks, 256, 0, s>>>(d, a); }
@@ -694,7 +711,7 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
   a.F = F;
   const uint32_t upd = a.mode == 0 ? 1u : 2u;
   for (uint32_t k = 0; k < 32; ++k) a.lanepow[k] = modpow_a(2ull * upd * k);
-  a.stride = modpow_a(2ull * upd * 32ull);
+  a.stride = modpow_a(2ull * upd * (unsigned long long)(1u << a.sg_log));
   a.clear_tab = tabs;
   a.clear_n = (gm.cap_b + 1) * nb;
   if (chain) {
