@@ -176,15 +176,17 @@ __device__ __forceinline__ float gt_threshold(double r) {
 __device__ __forceinline__ int32_t upper_bound_clamped(const float* __restrict__ base, int32_t lo, int32_t hi,
                                                        float thr) {
   while (hi - lo >= 8) {
-    const uint32_t n = (uint32_t)(hi - lo);
+    // probes p_i = lo + (i+1)*s + min(i+1, r), s = n/8, r = n%8: lo < p_0 < .. < p_6 < hi (any increasing probe set
+    // gives the same answer; this one needs no 64-bit multiply)
+    const int32_t n = hi - lo, s = n >> 3, r = n & 7;
     float v[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) v[i] = __ldg(base + lo + (int32_t)(((uint64_t)(i + 1) * n) >> 3));  // lo < p_0 < .. < p_6 < hi
+    for (int i = 0; i < 7; ++i) v[i] = __ldg(base + lo + (i + 1) * s + min(i + 1, r));
     int c = 0;
 #pragma unroll
     for (int i = 0; i < 7; ++i) c += (v[i] >= thr) ? 0 : 1;                                          // monotone: a prefix is below thr
-    const int32_t nlo = c > 0 ? lo + (int32_t)(((uint64_t)c * n) >> 3) + 1 : lo;
-    const int32_t nhi = c < 7 ? lo + (int32_t)(((uint64_t)(c + 1) * n) >> 3) : hi;
+    const int32_t nlo = c > 0 ? lo + c * s + min(c, r) + 1 : lo;
+    const int32_t nhi = c < 7 ? lo + (c + 1) * s + min(c + 1, r) : hi;
     lo = nlo; hi = nhi;
   }
   if (lo < hi) {  // fewer than 8 candidates below hi: one round of independent probes

@@ -19,6 +19,8 @@
 // gather pass and the frontier (engine ids) stays in HBM between hops.
 #include <algorithm>
 
+#include <stdlib.h>
+
 #include "internal.h"
 
 namespace eu {
@@ -336,8 +338,8 @@ __device__ __forceinline__ int lane_upper_bound(float c, int lo, int hi, float t
 // rows, and a persistent grid strides over the live rows: with fanout 10 two rows share a warp (the kernel is
 // issue-bound, profiles/r01_*: every instruction a lane group spares is throughput), and the per-block set-up
 // (jump tables, table wipe, parameter loads) is paid once per CTA instead of once per 8 rows.
-template <bool PHILOX>
-__global__ void __launch_bounds__(256, 8) k_sample(DevGraph g, SampleArgs a) {
+template <bool PHILOX, int CTAS>
+__global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) {
   const int lane = threadIdx.x & 31;
   const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   __shared__ uint32_t s_lanepow[32];  // A^(2k*lane)
@@ -667,10 +669,12 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
     while ((1 << a.sg_log) < need) ++a.sg_log;
   }
   // persistent grid: 8 CTAs per SM stride over the (live) rows
-  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(ceil_div(rows * 32, (int64_t)(32 >> a.sg_log)), 256), 148 * 8);
+  static int ctas = 0;
+  if (!ctas) { const char* e = getenv("EU_SAMPLE_CTAS"); ctas = e && atoi(e) == 6 ? 6 : 8; }
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(ceil_div(rows * 32, (int64_t)(32 >> a.sg_log)), 256), 148 * ctas);
   if (c->rng == EU_RNG_PHILOX) {
     a.key = c->seed;
-    { EuProfScope ps(c, "k_sample<philox>", rows); k_sample<true><<<blocks, 256, 0, s>>>(d, a); }
+    { EuProfScope ps(c, "k_sample<philox>", rows); if (ctas == 6) k_sample<true, 6><<<blocks, 256, 0, s>>>(d, a); else k_sample<true, 8><<<blocks, 256, 0, s>>>(d, a); }
     EU_LAUNCHED();
     k_bump_calls<<<1, 64, 0, s>>>(c->d_rng, nb);
     EU_LAUNCHED();
@@ -718,7 +722,7 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
     a.next_tabs = ntabs;
     a.next_cap_b = ng.cap_b;
   }
-  { EuProfScope ps(c, "k_sample<minstd>", rows); k_sample<false><<<blocks, 256, 0, s>>>(d, a); }
+  { EuProfScope ps(c, "k_sample<minstd>", rows); if (ctas == 6) k_sample<false, 6><<<blocks, 256, 0, s>>>(d, a); else k_sample<false, 8><<<blocks, 256, 0, s>>>(d, a); }
   EU_LAUNCHED();
   return EU_OK;
 }

@@ -355,9 +355,3 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
   return EU_OK;
 }
 
-extern "C" int eu_get_full_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
-                                    int64_t cap, int64_t* out_ptr, int64_t* out_ids, float* out_w, int32_t* out_t) {
-  (void)c; (void)nodes; (void)B; (void)etypes; (void)K; (void)cap; (void)out_ptr; (void)out_ids; (void)out_w; (void)out_t;
-  set_error("eu_get_full_neighbor: not implemented yet (SURVEY section 8f next-1)");
-  return EU_ERR_UNSUPPORTED;
-}

@@ -234,6 +234,28 @@ def get_dense_feature(nodes, feature_names, dimensions, thread_num=1):
     return outs
 
 
+def get_full_neighbor(nodes, edge_types):
+    """neighbor_ops.get_full_neighbor (tf_euler/python/euler_ops/neighbor_ops.py; kernel get_full_neighbor_op.cc over
+    euler::GetFullNeighbor api.cc:208-221).  The reference returns three SparseTensors [N, max_degree] (ids, weights,
+    types) whose values are listed node by node; here the same values come back ragged: (indptr i64[N+1], ids i64[nnz],
+    weights f32[nnz], types i32[nnz]) -- SparseTensor indices are (i, k - indptr[i]) for k in [indptr[i], indptr[i+1])."""
+    nodes = _t(nodes, torch.int64).reshape(-1)
+    et = np.ascontiguousarray(edge_types, dtype=np.int32).reshape(-1)
+    ctx = _ctx_on_stream()
+    lib = _lib.load()
+    n = nodes.numel()
+    indptr = torch.empty(n + 1, dtype=torch.int64, device=nodes.device)
+    check(lib.eu_get_full_neighbor(ctx._h, nodes.data_ptr(), n, et.ctypes.data, len(et), 0, indptr.data_ptr(), None, None, None))
+    total = int(indptr[-1].item())
+    ids = torch.empty(total, dtype=torch.int64, device=nodes.device)
+    w = torch.empty(total, dtype=torch.float32, device=nodes.device)
+    t = torch.empty(total, dtype=torch.int32, device=nodes.device)
+    if total:
+        check(lib.eu_get_full_neighbor(ctx._h, nodes.data_ptr(), n, et.ctypes.data, len(et), total, indptr.data_ptr(),
+                                       ids.data_ptr(), w.data_ptr(), t.data_ptr()))
+    return indptr, ids, w, t
+
+
 def sage_mean_aggregate(neighbor_ids, count, dim):
     """Fused get_dense_feature + scatter_mean for fixed-fanout blocks (SAGEConv's neighbor mean,
     tf_euler/python/convolution/sage_conv.py:33-38 over sage_dataflow.py:43-46 blocks)."""

@@ -182,12 +182,19 @@ int eu_get_dense_feature(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid
                          float* out);
 int eu_get_dense_feature_host(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid, int32_t dim,
                               float* out);
-/* tf_euler.get_full_neighbor core (euler::GetFullNeighbor api.cc:208-221): CSR-style output.
- * out_ptr i64[B+1] (device); if cap < total only the first cap entries are written.  *total (host)
- * is filled by the _host variant only. */
+/* tf_euler.get_full_neighbor core (euler::GetFullNeighbor api.cc:208-221 over Node::GetFullNeighbor node.cc:176-198):
+ * for every node the edges of each requested type, in the order the types are given, as (id, weight, type); a missing
+ * node has an empty list.  CSR-style output: out_ptr i64[B+1] (device) -- entries of node i are
+ * [out_ptr[i], out_ptr[i+1]); only the first `cap` entries are written (cap = 0: lengths only; out_* may be NULL).
+ * The _host variant takes host buffers and also returns *total = out_ptr[B]: call it with cap = 0 to size the
+ * outputs, then again with cap >= *total (the reference's kernel sizes its SparseTensor the same way,
+ * tf_euler/kernels/get_full_neighbor_op.cc). */
 int eu_get_full_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
                          int64_t cap, int64_t* out_ptr, int64_t* out_ids, float* out_w,
                          int32_t* out_t);
+int eu_get_full_neighbor_host(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
+                              int64_t cap, int64_t* out_ptr, int64_t* out_ids, float* out_w, int32_t* out_t,
+                              int64_t* total);
 
 /* ------------------------------------------------------------------ message-passing ops ------ */
 /* MPGather / MPScatterAdd / MPScatterMax (tf_euler/ops/mp_ops.cc:22-81; kernels

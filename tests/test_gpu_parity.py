@@ -440,3 +440,59 @@ def test_rmat_large_properties():
     assert np.abs(f).max() <= 1.0 and f[valid].std() > 0.5 and not f[~valid].any()
     (f2,) = euler_b200.get_dense_feature(ids[1], [0], [32])
     assert np.array_equal(f, f2.cpu().numpy())
+
+
+# ---------------------------------------------------------------------------- get_full_neighbor (next-1)
+@pytest.mark.gpu
+def test_get_full_neighbor_tiny_graph_matches_reference_test_vector():
+    """neighbor_ops_test.py:46-57 on the tools/test_data graph + every node / type list against the oracle"""
+    import euler_b200
+    g = graphs.load_tiny_csr()
+    gr = graphs.cuda_graph(g)
+    og = graphs.oracle_graph(g)
+    euler_b200.set_graph(gr, seed=1)
+    for nodes, et in [([1, 2], [0, 1]), ([1, 2, 3, 4, 5, 6], [0]), ([6, 5, 99, 1, 1], [1, 0, 1]), ([3], []), ([], [0, 1]), ([2, 4], [7, 0])]:
+        indptr, ids, w, t = euler_b200.get_full_neighbor(np.asarray(nodes, np.int64), et)
+        lens, o_ids, o_w, o_t = og.get_full_neighbor(np.asarray(nodes, np.uint64), et)
+        cases.eq(np.diff(indptr.cpu().numpy()), np.asarray(lens, np.int64), "lens %s %s" % (nodes, et))
+        cases.eq(ids.cpu().numpy(), np.asarray(o_ids).astype(np.int64), "ids")
+        cases.eq(w.cpu().numpy(), o_w, "w")
+        cases.eq(t.cpu().numpy(), o_t, "t")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,stride", [(1, 1), (3, 7)])
+def test_get_full_neighbor_random_graph_and_host_entry(T, stride):
+    import euler_b200
+    g = graphs.random_graph(seed=77 + T, n=5000, T=T, avg_deg=9, id_stride=stride, id_base=3, hub=4000, zero_w_frac=0.1)
+    gr = graphs.cuda_graph(g)
+    og = graphs.oracle_graph(g)
+    euler_b200.set_graph(gr, seed=1)
+    rs = np.random.RandomState(5)
+    nodes = g["ids"][rs.randint(0, 5000, size=3000)].astype(np.int64)
+    nodes[::9] = 10 ** 15
+    nodes[0] = g["ids"][int(np.argmax(np.diff(g["grp_ptr"])) // T)]        # the hub
+    for et in ([0], list(range(T))[::-1], [T - 1, 0, T - 1]):
+        indptr, ids, w, t = euler_b200.get_full_neighbor(nodes, et)
+        lens, o_ids, o_w, o_t = og.get_full_neighbor(nodes.astype(np.uint64), et)
+        cases.eq(np.diff(indptr.cpu().numpy()), np.asarray(lens, np.int64), "lens")
+        cases.eq(ids.cpu().numpy(), np.asarray(o_ids).astype(np.int64), "ids")
+        cases.eq(w.cpu().numpy(), o_w, "w")
+        cases.eq(t.cpu().numpy(), o_t, "t")
+    # host entry point through the C ABI: size with cap = 0, then fetch
+    from euler_b200 import _lib
+    lib = _lib.load()
+    ctx = euler_b200.context()
+    et = np.asarray([0], np.int32)
+    ptr = np.zeros(len(nodes) + 1, np.int64)
+    total = C.c_int64(0)
+    _lib.check(lib.eu_get_full_neighbor_host(ctx._h, nodes.ctypes.data, len(nodes), et.ctypes.data, 1, 0, ptr.ctypes.data, None, None, None, C.byref(total)))
+    lens, o_ids, o_w, o_t = og.get_full_neighbor(nodes.astype(np.uint64), [0])
+    assert total.value == int(np.sum(lens))
+    h_ids, h_w, h_t = np.zeros(total.value, np.int64), np.zeros(total.value, np.float32), np.zeros(total.value, np.int32)
+    _lib.check(lib.eu_get_full_neighbor_host(ctx._h, nodes.ctypes.data, len(nodes), et.ctypes.data, 1, total.value, ptr.ctypes.data,
+                                             h_ids.ctypes.data, h_w.ctypes.data, h_t.ctypes.data, C.byref(total)))
+    cases.eq(np.diff(ptr), np.asarray(lens, np.int64), "host lens")
+    cases.eq(h_ids, np.asarray(o_ids).astype(np.int64), "host ids")
+    cases.eq(h_w, o_w, "host w")
+    cases.eq(h_t, o_t, "host t")
