@@ -178,7 +178,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
+    if world > 1 or os.environ.get("EU_BENCH_FORCE_SHARDED"):   # the env knob runs the sharded pipeline on one rank (no link): its compute-only cost
         return run_sharded(args, world, rank, local)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
@@ -347,9 +347,22 @@ def run_ours(args):
         k["achieved_gbs"] = round(k["algorithmic_bytes_per_launch"] / (k["ms_per_launch"] * 1e-3) / 1e9, 1)
         k["frac_of_measured_hbm_peak"] = round(k["achieved_gbs"] / peak, 4)
     dom = kernels[0]
+    # DRAM traffic of the dominant kernel from the committed ncu capture (same workload and launch shape only)
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        default_shape = (args.nodes, args.edges, args.batch, args.fanout, args.dim, args.rng) == (10_000_000, 100_000_000, 1024, "25,10", 128, "minstd")
+        ent = tj["kernels"].get(dom["kernel"].split("<")[0], {}).get(str(dom["rows"]))
+        if default_shape and ent:
+            traffic, traffic_src = ent["dram_bytes_per_launch"], "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": "%s over %d rows (largest share of the step)" % (dom["kernel"], dom["rows"]),
             "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac_of_measured_hbm_peak"],
-            "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 (B200_PROFILING.md)",
+            "traffic": traffic, "traffic_source": traffic_src,
+            "note": "achieved = algorithmic bytes / live kernel time; a feature-gathering kernel re-reads hub rows from the 126 MB L2, "
+                    "so its algorithmic rate can exceed the HBM peak while `traffic` (DRAM bytes) stays below the algorithmic bytes",
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 (B200_PROFILING.md)",
             "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "kernel_ms": round(dom["ms_per_launch"], 5),
             "valid_edge_fraction_per_hop": [round(v, 4) for v in valid_frac],
             "all_kernels": kernels}

@@ -6,9 +6,11 @@
 // Every rank owns one symmetric region (same layout everywhere, cudaIpc-mapped into every peer):
 //   header | inbox_ids[N][cap] | inbox_src[N][cap] | out_eng | out_ids | out_w | out_t | out_rows
 // One exchange =
-//   requester  k_sym_push      : its bucket for owner o goes straight into o's inbox segment [me] (+ the original row
-//                                index of every seed), then count + flagA[me] <- epoch on o
-//   owner      k_sym_wait_pad  : waits for flagA of every source, zero-pads each segment (id 0 = "exists nowhere")
+//   requester  k_bucket_count/place (shard.cu): stable bucket by owner whose placement pass writes each id (+ the original
+//                                row index of the seed) straight into owner o's inbox segment [me]; the last CTA publishes the
+//                                counts and raises flagA[me] <- epoch on every owner
+//   owner      k_sym_wait_in / k_sym_gather_pad : waits for flagA of every source, finds the batch boundaries, builds the
+//                                zero-padded sampleNB input (id 0 = "exists nowhere")
 //   owner      hop() / gather  : samples the padded inbox as ONE sampleNB call on its own engine (sources in rank order,
 //                                each in batch order: the order pinned in euler_b200/sharded.py) -- or, for features,
 //   owner      k_sym_reply_*   : writes every result row DIRECTLY into the requester's output arrays at the seed's
@@ -21,43 +23,9 @@
 #include <algorithm>
 
 #include "internal.h"
+#include "sym.cuh"
 
 namespace eu {
-
-static constexpr int kSymMaxRanks = 16;
-
-struct SymHeader {
-  unsigned int flagA[kSymMaxRanks];   // [src]   epoch of the last inbox segment pushed by src
-  unsigned int flagB[kSymMaxRanks];   // [owner] epoch of the last reply written by owner
-  int in_cnt[kSymMaxRanks];           // [src]   seeds in src's segment
-  unsigned int epoch;                 // local exchange counter
-  unsigned int done;                  // last-block ticket
-  int error;                          // 1 = a wait timed out
-  int pad;
-};
-
-struct SymLayout {
-  int64_t cap;          // inbox slots per source
-  int64_t max_out;      // rows * count slots of the sample outputs
-  int64_t max_rows_f;   // rows of the feature output
-  int32_t max_dim;
-  int64_t off_inbox_ids, off_inbox_src, off_eng, off_ids, off_w, off_t, off_rows, off_flags, bytes;
-};
-
-struct SymPeers {
-  char* base[kSymMaxRanks];
-};
-
-__device__ __forceinline__ SymHeader* hdr_of(char* base) { return reinterpret_cast<SymHeader*>(base); }
-
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 // bounded spin until *flag >= want
 __device__ __forceinline__ bool spin_until(const unsigned int* flag, unsigned int want, int* error) {
@@ -67,45 +35,6 @@ __device__ __forceinline__ bool spin_until(const unsigned int* flag, unsigned in
     if (clock64() - t0 > 4000000000LL) { *error = 1; return false; }   // ~2 s
   }
   return true;
-}
-
-// ---- requester: push my sorted bucket segments into the owners' inboxes
-__global__ void __launch_bounds__(256) k_sym_push(SymPeers peers, SymLayout lay, int me, int N,
-                                                  const unsigned long long* __restrict__ sorted_ids,
-                                                  const int32_t* __restrict__ src_index,
-                                                  const long long* __restrict__ offsets /*[N+1]*/, int64_t rows) {
-  __shared__ long long s_off[kSymMaxRanks + 1];
-  __shared__ bool s_last;
-  if (threadIdx.x <= N) s_off[threadIdx.x] = offsets[threadIdx.x];
-  __syncthreads();
-  // persistent grid: one system fence per block, not per 256 rows (a fence waits for the NVLink acks of the block's stores)
-  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < rows; k += (int64_t)gridDim.x * blockDim.x) {
-    int o = 0;
-    while (o + 1 < N && k >= s_off[o + 1]) ++o;
-    const int64_t pos = k - s_off[o];
-    char* pb = peers.base[o];
-    reinterpret_cast<unsigned long long*>(pb + lay.off_inbox_ids)[(int64_t)me * lay.cap + pos] = sorted_ids[k];
-    reinterpret_cast<int32_t*>(pb + lay.off_inbox_src)[(int64_t)me * lay.cap + pos] = src_index[k];
-  }
-  __threadfence_system();
-  __syncthreads();
-  SymHeader* mine = hdr_of(peers.base[me]);
-  if (threadIdx.x == 0) s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence_system();
-  unsigned int e = 0;
-  if (threadIdx.x == 0) { e = mine->epoch + 1; mine->epoch = e; mine->done = 0; }
-  __shared__ unsigned int s_e;
-  if (threadIdx.x == 0) s_e = e;
-  __syncthreads();
-  e = s_e;
-  if (threadIdx.x < N) {
-    SymHeader* h = hdr_of(peers.base[threadIdx.x]);
-    h->in_cnt[me] = (int)(s_off[threadIdx.x + 1] - s_off[threadIdx.x]);
-    __threadfence_system();
-    st_release_sys(&h->flagA[me], e);
-  }
 }
 
 // ---- owner: wait for every source (one small block spins; nothing else of the GPU is held).  A batched hop also
@@ -178,12 +107,11 @@ __global__ void __launch_bounds__(256) k_sym_reply_sample(SymPeers peers, SymLay
       }
     }
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1;
+  __syncthreads();   // CTA's stores happen-before thread 0's fence (barrier + cumulativity): one system fence per CTA
+  if (threadIdx.x == 0) { __threadfence_system(); s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1; }
   __syncthreads();
   if (!s_last) return;
-  __threadfence_system();
+  if (threadIdx.x < N) __threadfence_system();   // ticket observed (barrier) -> ordered before the flag stores
   if (threadIdx.x == 0) mine->done = 0;
   if (threadIdx.x < N) st_release_sys(&hdr_of(peers.base[threadIdx.x])->flagB[me], mine->epoch);
 }
@@ -212,12 +140,11 @@ __global__ void __launch_bounds__(256) k_sym_reply_feature(DevGraph g, SymPeers 
       }
     }
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1;
+  __syncthreads();   // CTA's stores happen-before thread 0's fence (barrier + cumulativity): one system fence per CTA
+  if (threadIdx.x == 0) { __threadfence_system(); s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1; }
   __syncthreads();
   if (!s_last) return;
-  __threadfence_system();
+  if (threadIdx.x < N) __threadfence_system();   // ticket observed (barrier) -> ordered before the flag stores
   if (threadIdx.x == 0) mine->done = 0;
   if (threadIdx.x < N) st_release_sys(&hdr_of(peers.base[threadIdx.x])->flagB[me], mine->epoch);
 }
@@ -336,12 +263,11 @@ __global__ void __launch_bounds__(256) k_sym_reply_sage(DevGraph g, SymPeers pee
     }
     if (lane == 0) reinterpret_cast<unsigned char*>(peers.base[s] + lay.off_flags)[(int64_t)me * gps + (w - (int64_t)s * gps)] = (unsigned char)present;
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1;
+  __syncthreads();   // CTA's stores happen-before thread 0's fence (barrier + cumulativity): one system fence per CTA
+  if (threadIdx.x == 0) { __threadfence_system(); s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1; }
   __syncthreads();
   if (!s_last) return;
-  __threadfence_system();
+  if (threadIdx.x < N) __threadfence_system();   // ticket observed (barrier) -> ordered before the flag stores
   if (threadIdx.x == 0) mine->done = 0;
   if (threadIdx.x < N) st_release_sys(&hdr_of(peers.base[threadIdx.x])->flagB[me], mine->epoch);
 }
@@ -376,12 +302,11 @@ __global__ void __launch_bounds__(256) k_sym_reply_sage_generic(DevGraph g, SymP
       if (col < dim) o[col] = acc;
     }
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1;
+  __syncthreads();   // CTA's stores happen-before thread 0's fence (barrier + cumulativity): one system fence per CTA
+  if (threadIdx.x == 0) { __threadfence_system(); s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1; }
   __syncthreads();
   if (!s_last) return;
-  __threadfence_system();
+  if (threadIdx.x < N) __threadfence_system();   // ticket observed (barrier) -> ordered before the flag stores
   if (threadIdx.x == 0) mine->done = 0;
   if (threadIdx.x < N) st_release_sys(&hdr_of(peers.base[threadIdx.x])->flagB[me], mine->epoch);
 }
@@ -410,7 +335,9 @@ __global__ void __launch_bounds__(256) k_sym_sage_reduce(const V* __restrict__ p
 }
 
 static inline unsigned sym_grid(int64_t threads) {   // persistent: at most 8 CTAs of 256 per SM
-  return (unsigned)std::min<int64_t>(std::max<int64_t>(ceil_div(threads, 256), 1), 148 * 8);
+  static int per_sm = 0;
+  if (!per_sm) { const char* e = getenv("EU_SYM_CTAS"); per_sm = e ? std::min(8, std::max(1, atoi(e))) : 8; }
+  return (unsigned)std::min<int64_t>(std::max<int64_t>(ceil_div(threads, 256), 1), 148 * (int64_t)per_sm);
 }
 // reply kernels are NVLink-store bound: fewer resident CTAs keep the link busy and leave SM slots to the compute
 // kernels of the other lanes
@@ -577,12 +504,8 @@ int eu_sym_sample_hop_batched(eu_sym* s, const int64_t* seeds, int32_t nb, int64
   int rc = sym_scratch(s, std::max<int64_t>(total, 1), std::max<int64_t>(prow * count, 1), std::max<int64_t>(prow, 1));
   if (rc) return rc;
   cudaStream_t st = c->stream;
-  rc = eu_shard_bucket(c, seeds, total, num_partitions, N, s->rank, s->d_sorted, s->d_src, s->d_counts, s->d_offs);
+  rc = bucket_push(c, seeds, total, num_partitions, N, s->rank, false, s->d_counts, s->d_offs, s->peers, L, "k_bucket_push");
   if (rc) return rc;
-  { EuProfScope ps(c, "k_sym_push", total);
-    k_sym_push<<<sym_grid(total), 256, 0, st>>>(s->peers, L, s->rank, N, (const unsigned long long*)s->d_sorted,
-                                                 s->d_src, (const long long*)s->d_offs, total); }
-  EU_LAUNCHED();
   { EuProfScope ps(c, "k_sym_wait_in", total); k_sym_wait_in<<<1, 256, 0, st>>>(s->base, L, N, nb, rows, s->d_seglo); }
   EU_LAUNCHED();
   { EuProfScope ps(c, "k_sym_gather_pad", prow); k_sym_gather_pad<<<sym_grid(prow), 256, 0, st>>>(s->base, L, N, nb, rows, s->d_seglo, s->d_pad); }
@@ -621,12 +544,8 @@ int eu_sym_get_dense_feature(eu_sym* s, const int64_t* ids, int64_t rows, int32_
   int rc = sym_scratch(s, std::max<int64_t>(rows, 1), 1);
   if (rc) return rc;
   cudaStream_t st = c->stream;
-  rc = eu_shard_bucket(c, ids, rows, num_partitions, N, s->rank, s->d_sorted, s->d_src, s->d_counts, s->d_offs);
+  rc = bucket_push(c, ids, rows, num_partitions, N, s->rank, false, s->d_counts, s->d_offs, s->peers, L, "k_bucket_push(feat)");
   if (rc) return rc;
-  { EuProfScope ps(c, "k_sym_push(feat)", rows);
-    k_sym_push<<<sym_grid(rows), 256, 0, st>>>(s->peers, L, s->rank, N, (const unsigned long long*)s->d_sorted,
-                                                                                    s->d_src, (const long long*)s->d_offs, rows); }
-  EU_LAUNCHED();
   { EuProfScope ps(c, "k_sym_wait_in(feat)", rows); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, L, N, 1, 0, nullptr); }
   EU_LAUNCHED();
   int G = 1;
@@ -659,16 +578,13 @@ int eu_sym_sage_mean(eu_sym* s, const int64_t* nbr_ids, int64_t rows, int32_t co
   int rc = sym_scratch(s, std::max<int64_t>(nid, 1), 1);
   if (rc) return rc;
   cudaStream_t st = c->stream;
-  rc = eu_shard_bucket(c, nbr_ids, nid, num_partitions, N, s->rank, s->d_sorted, s->d_src, s->d_counts, s->d_offs);
-  if (rc) return rc;
   const bool fast = d.n < ((int64_t)1 << 31) && d.n_slots == 1 && dim == d.feat_dim && (dim == 128 || dim == 256);
   if ((rows / 8 + 1) * (int64_t)N > a256((L.max_rows_f / 8 + 1) * (int64_t)N)) { set_error("eu_sym_sage_mean: presence bits exceed the symmetric region"); return EU_ERR_INVALID; }
   // the generic-width owners store every partial row: the requester marks them all present before its push goes out
   if (!fast) EU_CUDA(cudaMemsetAsync(s->base + L.off_flags, 0xFF, (size_t)(ceil_div(rows, kSageR) * N), st));
-  { EuProfScope ps(c, "k_sym_push(sage)", nid);
-    k_sym_push<<<sym_grid(nid), 256, 0, st>>>(s->peers, L, s->rank, N, (const unsigned long long*)s->d_sorted, s->d_src,
-                                               (const long long*)s->d_offs, nid); }
-  EU_LAUNCHED();
+  // ids that exist nowhere (0 / default fill) contribute nothing: they are dropped at the bucket, not shipped
+  rc = bucket_push(c, nbr_ids, nid, num_partitions, N, s->rank, true, s->d_counts, s->d_offs, s->peers, L, "k_bucket_push(sage)");
+  if (rc) return rc;
   { EuProfScope ps(c, "k_sym_wait_in(sage)", nid); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, L, N, 1, 0, nullptr); }
   EU_LAUNCHED();
   { EuProfScope ps(c, "k_sym_reply_sage", (int64_t)N * rows);

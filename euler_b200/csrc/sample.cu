@@ -669,9 +669,13 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
     while ((1 << a.sg_log) < need) ++a.sg_log;
   }
   // persistent grid: 8 CTAs per SM stride over the (live) rows
-  static int ctas = 0;
-  if (!ctas) { const char* e = getenv("EU_SAMPLE_CTAS"); ctas = e && atoi(e) == 6 ? 6 : 8; }
-  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(ceil_div(rows * 32, (int64_t)(32 >> a.sg_log)), 256), 148 * ctas);
+  static int ctas = 0, grid_ctas = 0;
+  if (!ctas) {
+    const char* e = getenv("EU_SAMPLE_CTAS");     // tuning knob: CTAs per SM of the persistent grid (1..8; 6 also relaxes the register cap)
+    grid_ctas = e ? std::min(8, std::max(1, atoi(e))) : 8;
+    ctas = grid_ctas == 6 ? 6 : 8;
+  }
+  const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(ceil_div(rows * 32, (int64_t)(32 >> a.sg_log)), 256), 148 * grid_ctas);
   if (c->rng == EU_RNG_PHILOX) {
     a.key = c->seed;
     { EuProfScope ps(c, "k_sample<philox>", rows); if (ctas == 6) k_sample<true, 6><<<blocks, 256, 0, s>>>(d, a); else k_sample<true, 8><<<blocks, 256, 0, s>>>(d, a); }

@@ -6,88 +6,196 @@
 // eu_shard_bucket is a STABLE counting sort by owner (the reference keeps batch order inside each shard's
 // request, id_split_op.cc:70-75), so every shard sees a deterministic seed order.
 #include "internal.h"
+#include "sym.cuh"
 
 namespace eu {
 
 static constexpr int kMaxShards = 64;
-static constexpr int kBktBlock = 1024;
+static constexpr int kBktWarps = 8;     // warps per CTA
+static constexpr int kChunk = 256;      // ids per warp: 8 coalesced rounds, all loads in flight before the first use
 
 // ids 0 (the engine's "no neighbor" placeholder, DEFAULT_UINT64) and 2^64-1 (default_node = -1 fed back as a
 // seed) exist on no shard: they resolve to empty rows wherever they are looked up, so they stay on the
-// requesting rank instead of all piling onto shard 0 / shard (2^64-1) % N.
-__device__ __forceinline__ int owner_of(unsigned long long id, int P, int N, int self) {
-  if (id == 0ull || id == ~0ull) return self;
+// requesting rank instead of all piling onto shard 0 / shard (2^64-1) % N -- or are dropped (-1) when the caller
+// needs nothing back for them (the fused aggregation).
+__device__ __forceinline__ int owner_of(unsigned long long id, int P, int N, int self, bool drop) {
+  if (id == 0ull || id == ~0ull) return drop ? -1 : self;
   return (int)((id % (unsigned long long)P) % (unsigned long long)N);
 }
 
-// pass 1: per-block histogram; the last block turns blkcnt[b][o] into exclusive bases in (owner, block) order
-__global__ void __launch_bounds__(kBktBlock) k_bucket_count(const unsigned long long* __restrict__ ids, int64_t rows, int P, int N, int self,
-                                                            uint32_t* blkcnt /*[nblk][N]*/, long long* counts /*[N]*/,
-                                                            long long* offsets /*[N+1]*/, unsigned int* done) {
+// Stable counting sort by owner.  Warp w of CTA b owns ids [(b*8+w)*256, +256).
+// pass 1: per-CTA histogram bcnt[b][o]; the last CTA turns it into each CTA's exclusive base INSIDE its owner's segment
+// (strip-serial + one block scan per owner) and writes counts[o] / offsets[o] (segment starts in the sorted array).
+__global__ void __launch_bounds__(kBktWarps * 32) k_bucket_count(const unsigned long long* __restrict__ ids, int64_t rows, int P, int N,
+                                                                 int self, bool drop, uint32_t* bcnt /*[nblk][N]*/,
+                                                                 long long* counts /*[N]*/, long long* offsets /*[N+1]*/,
+                                                                 unsigned int* done) {
   __shared__ uint32_t s_cnt[kMaxShards];
+  __shared__ uint32_t s_scan[kBktWarps * 32];
   __shared__ bool s_last;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x < N) s_cnt[threadIdx.x] = 0;
   __syncthreads();
-  const int64_t i = blockIdx.x * (int64_t)kBktBlock + threadIdx.x;
-  // warp-aggregated: N is small, so a plain shared atomic per row would serialise 256 threads on a few counters
-  const int o = i < rows ? owner_of(ids[i], P, N, self) : -1;
-  const unsigned same = __match_any_sync(0xffffffffu, o);
-  if (o >= 0 && (threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(&s_cnt[o], (uint32_t)__popc(same));
+  {
+    unsigned long long v[kChunk / 32];
+    const int64_t i0 = (blockIdx.x * (int64_t)kBktWarps + wid) * kChunk + lane;
+#pragma unroll
+    for (int r = 0; r < kChunk / 32; ++r) v[r] = i0 + r * 32 < rows ? ids[i0 + r * 32] : 0ull;
+#pragma unroll
+    for (int r = 0; r < kChunk / 32; ++r) {
+      const int o = i0 + r * 32 < rows ? owner_of(v[r], P, N, self, drop) : -1;
+      const unsigned m = __match_any_sync(0xffffffffu, o);
+      if (o >= 0 && lane == __ffs(m) - 1) atomicAdd(&s_cnt[o], (uint32_t)__popc(m));   // one leader per (warp, owner)
+    }
+  }
   __syncthreads();
-  if (threadIdx.x < N) blkcnt[(int64_t)blockIdx.x * N + threadIdx.x] = s_cnt[threadIdx.x];
-  __threadfence();
+  if (threadIdx.x < N) bcnt[(int64_t)blockIdx.x * N + threadIdx.x] = s_cnt[threadIdx.x];
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(done, 1u) == gridDim.x - 1;
+  if (threadIdx.x == 0) { __threadfence(); s_last = atomicAdd(done, 1u) == gridDim.x - 1; }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  // serial over owners (<= 64), parallel over blocks with a running carry: base[b][o]
-  __shared__ uint32_t s_scan[kBktBlock];
-  uint32_t carry = 0;
+  const int64_t nblk = gridDim.x;
+  const int64_t strip = (nblk + blockDim.x - 1) / blockDim.x;
+  const int64_t b = min((int64_t)threadIdx.x * strip, nblk), e = min(b + strip, nblk);
+  uint32_t start = 0;
   for (int o = 0; o < N; ++o) {
-    const uint32_t start = carry;
-    for (uint32_t b0 = 0; b0 < gridDim.x; b0 += kBktBlock) {
-      const uint32_t b = b0 + threadIdx.x;
-      const uint32_t v = b < gridDim.x ? __ldcg(blkcnt + (int64_t)b * N + o) : 0u;
-      s_scan[threadIdx.x] = v;
+    uint32_t sum = 0;
+    for (int64_t k = b; k < e; ++k) sum += __ldcg(bcnt + k * N + o);
+    s_scan[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < kBktWarps * 32; off <<= 1) {
+      const uint32_t t = (int)threadIdx.x >= off ? s_scan[threadIdx.x - off] : 0u;
       __syncthreads();
-      for (int off = 1; off < kBktBlock; off <<= 1) {
-        uint32_t t = threadIdx.x >= off ? s_scan[threadIdx.x - off] : 0u;
-        __syncthreads();
-        s_scan[threadIdx.x] += t;
-        __syncthreads();
-      }
-      if (b < gridDim.x) blkcnt[(int64_t)b * N + o] = carry + s_scan[threadIdx.x] - v;
-      carry += s_scan[kBktBlock - 1];
+      s_scan[threadIdx.x] += t;
       __syncthreads();
     }
-    if (threadIdx.x == 0) { counts[o] = (long long)(carry - start); offsets[o] = (long long)start; }
+    uint32_t run = s_scan[threadIdx.x] - sum;   // exclusive base of this thread's strip inside owner o's segment
+    const uint32_t total = s_scan[kBktWarps * 32 - 1];
+    for (int64_t k = b; k < e; ++k) {
+      const uint32_t c = __ldcg(bcnt + k * N + o);
+      bcnt[k * N + o] = run;
+      run += c;
+    }
+    if (threadIdx.x == 0) { counts[o] = (long long)total; offsets[o] = (long long)start; }
+    start += total;
+    __syncthreads();
   }
-  if (threadIdx.x == 0) { offsets[N] = (long long)carry; *done = 0; }
+  if (threadIdx.x == 0) { offsets[N] = (long long)start; *done = 0; }
 }
 
-// pass 2: stable placement.  rank inside the block = number of earlier lanes / warps with the same owner.
-__global__ void __launch_bounds__(kBktBlock) k_bucket_place(const unsigned long long* __restrict__ ids, int64_t rows, int P, int N, int self,
-                                                            const uint32_t* __restrict__ base /*[nblk][N]*/,
-                                                            unsigned long long* __restrict__ sorted_ids, int32_t* __restrict__ src_index) {
-  __shared__ uint32_t s_w[kBktBlock / 32][kMaxShards];
+// pass 2: every id goes to its owner's segment at CTA base + (ids of the same owner before it in the CTA).
+// Local mode: segment o = sorted[offsets[o] ..).  Remote mode (the peer-memory exchange): segment o IS owner o's inbox
+// slice for this rank, written over NVLink, and the last CTA publishes the counts and raises flagA -- the bucket and
+// the push are one kernel.
+struct BucketDst {
+  unsigned long long* sorted_ids;   // local mode
+  int32_t* src_index;
+  int remote;
+  SymPeers peers;                   // remote mode
+  SymLayout lay;
+  int me;
+};
+
+__global__ void __launch_bounds__(kBktWarps * 32) k_bucket_place(const unsigned long long* __restrict__ ids, int64_t rows, int P, int N,
+                                                                 int self, bool drop, const uint32_t* __restrict__ bbase,
+                                                                 const long long* __restrict__ counts,
+                                                                 const long long* __restrict__ offsets, BucketDst dst) {
+  __shared__ uint32_t s_w[kBktWarps][kMaxShards];   // per-warp counts, then per-warp running bases
+  __shared__ bool s_last;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int64_t i = blockIdx.x * (int64_t)kBktBlock + threadIdx.x;
-  const bool valid = i < rows;
-  const unsigned long long id = valid ? ids[i] : 0ull;
-  const int o = valid ? owner_of(id, P, N, self) : -1;
-  const unsigned peers = __match_any_sync(0xffffffffu, o);
-  const int before = __popc(peers & ((1u << lane) - 1u));
   for (int k = lane; k < N; k += 32) s_w[wid][k] = 0;
   __syncwarp();
-  if (valid && before == 0) s_w[wid][o] = __popc(peers);
-  __syncthreads();
-  if (valid) {
-    uint32_t pos = base[(int64_t)blockIdx.x * N + o] + before;
-    for (int w = 0; w < wid; ++w) pos += s_w[w][o];
-    sorted_ids[pos] = id;
-    src_index[pos] = (int32_t)i;
+  unsigned long long v[kChunk / 32];
+  int8_t ow[kChunk / 32];
+  unsigned mm[kChunk / 32];
+  const int64_t i0 = (blockIdx.x * (int64_t)kBktWarps + wid) * kChunk + lane;
+#pragma unroll
+  for (int r = 0; r < kChunk / 32; ++r) v[r] = i0 + r * 32 < rows ? ids[i0 + r * 32] : 0ull;
+#pragma unroll
+  for (int r = 0; r < kChunk / 32; ++r) {
+    const int o = i0 + r * 32 < rows ? owner_of(v[r], P, N, self, drop) : -1;
+    const unsigned m = __match_any_sync(0xffffffffu, o);
+    ow[r] = (int8_t)o; mm[r] = m;
+    if (o >= 0 && lane == __ffs(m) - 1) s_w[wid][o] += (uint32_t)__popc(m);
+    __syncwarp();
   }
+  __syncthreads();
+  // running base of warp wid for owner k = CTA base + counts of the warps before it
+  if (threadIdx.x < N) {
+    uint32_t run = bbase[(int64_t)blockIdx.x * N + threadIdx.x];
+    for (int w = 0; w < kBktWarps; ++w) { const uint32_t c = s_w[w][threadIdx.x]; s_w[w][threadIdx.x] = run; run += c; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kChunk / 32; ++r) {
+    const int o = ow[r];
+    const unsigned m = mm[r];
+    uint32_t rel = 0;
+    if (o >= 0) rel = s_w[wid][o] + (uint32_t)__popc(m & ((1u << lane) - 1u));
+    __syncwarp();
+    if (o >= 0 && lane == __ffs(m) - 1) s_w[wid][o] += (uint32_t)__popc(m);
+    __syncwarp();
+    if (o >= 0) {
+      const int64_t i = i0 + r * 32;
+      if (dst.remote) {
+        char* pb = dst.peers.base[o];
+        reinterpret_cast<unsigned long long*>(pb + dst.lay.off_inbox_ids)[(int64_t)dst.me * dst.lay.cap + rel] = v[r];
+        reinterpret_cast<int32_t*>(pb + dst.lay.off_inbox_src)[(int64_t)dst.me * dst.lay.cap + rel] = (int32_t)i;
+      } else {
+        const int64_t pos = offsets[o] + rel;
+        dst.sorted_ids[pos] = v[r];
+        dst.src_index[pos] = (int32_t)i;
+      }
+    }
+  }
+  if (!dst.remote) return;
+  // publish: one system fence per CTA (it waits for the NVLink acks of the CTA's stores), last CTA raises the flags
+  __syncthreads();   // CTA's stores happen-before thread 0's fence (barrier + cumulativity)
+  SymHeader* mine = hdr_of(dst.peers.base[dst.me]);
+  if (threadIdx.x == 0) { __threadfence_system(); s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1; }
+  __syncthreads();
+  if (!s_last) return;
+  if (threadIdx.x < N) __threadfence_system();   // ticket observed (barrier) -> ordered before the flag stores
+  __shared__ unsigned int s_e;
+  if (threadIdx.x == 0) { s_e = mine->epoch + 1; mine->epoch = s_e; mine->done = 0; }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    SymHeader* h = hdr_of(dst.peers.base[threadIdx.x]);
+    h->in_cnt[dst.me] = (int)counts[threadIdx.x];
+    __threadfence_system();
+    st_release_sys(&h->flagA[dst.me], s_e);
+  }
+}
+
+static int bucket_launch(eu_ctx* c, const int64_t* ids, int64_t rows, int P, int N, int self, bool drop, int64_t* counts,
+                         int64_t* offsets, const BucketDst& dst, const char* label) {
+  if (rows >= ((int64_t)1 << 31)) { set_error("rows >= 2^31"); return EU_ERR_UNSUPPORTED; }
+  const int64_t nblk = rows > 0 ? ceil_div(rows, (int64_t)kChunk * kBktWarps) : 1;
+  int rc = ctx_misc(c, 256 + 4 * nblk * N);
+  if (rc) return rc;
+  unsigned int* done = (unsigned int*)((char*)c->d_misc + 64);
+  uint32_t* wcnt = (uint32_t*)((char*)c->d_misc + 256);
+  cudaStream_t s = c->stream;
+  EU_CUDA(cudaMemsetAsync(done, 0, sizeof(unsigned int), s));
+  EuProfScope ps(c, label, rows);
+  k_bucket_count<<<(unsigned)nblk, kBktWarps * 32, 0, s>>>((const unsigned long long*)ids, rows, P, N, self, drop, wcnt,
+                                                           (long long*)counts, (long long*)offsets, done);
+  EU_LAUNCHED();
+  if (rows > 0 || dst.remote) {   // remote mode always runs: the flags must be raised even for an empty request
+    k_bucket_place<<<(unsigned)nblk, kBktWarps * 32, 0, s>>>((const unsigned long long*)ids, rows, P, N, self, drop, wcnt,
+                                                             (const long long*)counts, (const long long*)offsets, dst);
+    EU_LAUNCHED();
+  }
+  return EU_OK;
+}
+
+// bucket + push of the peer-memory exchange (p2p.cu): requests land in the owners' inboxes, counts and flagA follow
+int bucket_push(eu_ctx* c, const int64_t* ids, int64_t rows, int P, int N, int self, bool drop_placeholders, int64_t* counts,
+                int64_t* offsets, const SymPeers& peers, const SymLayout& lay, const char* label) {
+  BucketDst dst{};
+  dst.remote = 1; dst.peers = peers; dst.lay = lay; dst.me = self;
+  return bucket_launch(c, ids, rows, P, N, self, drop_placeholders, counts, offsets, dst, label);
 }
 
 // reply merge + TF packing for sampled rows: reply row k (sorted order) belongs to original row src_index[k].
@@ -154,24 +262,9 @@ int eu_shard_bucket(eu_ctx* c, const int64_t* ids, int64_t rows, int32_t num_par
     return EU_ERR_INVALID;
   }
   EU_CUDA(cudaSetDevice(c->g->device));
-  if (rows >= ((int64_t)1 << 31)) { set_error("rows >= 2^31"); return EU_ERR_UNSUPPORTED; }
-  const int64_t nblk = rows > 0 ? ceil_div(rows, kBktBlock) : 1;
-  int rc = ctx_misc(c, 256 + 4 * nblk * shard_num);
-  if (rc) return rc;
-  unsigned int* done = (unsigned int*)((char*)c->d_misc + 64);
-  uint32_t* blkcnt = (uint32_t*)((char*)c->d_misc + 256);
-  cudaStream_t s = c->stream;
-  EU_CUDA(cudaMemsetAsync(done, 0, sizeof(unsigned int), s));
-  EuProfScope ps(c, "k_bucket(count+place)", rows);
-  k_bucket_count<<<(unsigned)nblk, kBktBlock, 0, s>>>((const unsigned long long*)ids, rows, num_partitions, shard_num, self_shard, blkcnt,
-                                                      (long long*)counts, (long long*)offsets, done);
-  EU_LAUNCHED();
-  if (rows > 0) {
-    k_bucket_place<<<(unsigned)nblk, kBktBlock, 0, s>>>((const unsigned long long*)ids, rows, num_partitions, shard_num, self_shard, blkcnt,
-                                                        (unsigned long long*)sorted_ids, src_index);
-    EU_LAUNCHED();
-  }
-  return EU_OK;
+  BucketDst dst{};
+  dst.sorted_ids = (unsigned long long*)sorted_ids; dst.src_index = src_index;
+  return bucket_launch(c, ids, rows, num_partitions, shard_num, self_shard, false, counts, offsets, dst, "k_bucket(count+place)");
 }
 
 int eu_shard_pack_sample(eu_ctx* c, const int64_t* ids, const float* w, const int32_t* t, int64_t n, int64_t* packed) {
