@@ -179,10 +179,10 @@ __device__ __forceinline__ int32_t warp_lower_bound(const int32_t* __restrict__ 
 // One warp serves kSageR consecutive destinations of one source: one segment search, then a walk over their inbox
 // entries (id -> row lookups 32 at a time across the lanes, 4 feature rows in flight), flushing a partial row -- zeros
 // when this shard owns none of a destination's neighbors -- whenever the destination changes.
-static constexpr int kSageR = 8;
+static constexpr int kSageRMax = 32;   // destinations per warp: R = 8 or 32 (one 32-bit presence mask per group)
 template <int NV>   // feat_dim == dim == NV*128
 __global__ void __launch_bounds__(256) k_sym_reply_sage(DevGraph g, SymPeers peers, SymLayout lay, int me, int N, int64_t rows,
-                                                        int32_t count) {
+                                                        int32_t count, int kSageR) {
   char* base = peers.base[me];
   SymHeader* mine = hdr_of(base);
   const unsigned long long* ids = reinterpret_cast<const unsigned long long*>(base + lay.off_inbox_ids);
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) k_sym_reply_sage(DevGraph g, SymPeers pee
       for (int t = 0; t < NV; ++t) *reinterpret_cast<float4*>(o + (int64_t)cur * fd + t * 128) = acc[t];
       present |= 1u << cur;
     }
-    if (lane == 0) reinterpret_cast<unsigned char*>(peers.base[s] + lay.off_flags)[(int64_t)me * gps + (w - (int64_t)s * gps)] = (unsigned char)present;
+    if (lane == 0) reinterpret_cast<unsigned int*>(peers.base[s] + lay.off_flags)[(int64_t)me * gps + (w - (int64_t)s * gps)] = present;
   }
   __syncthreads();   // CTA's stores happen-before thread 0's fence (barrier + cumulativity): one system fence per CTA
   if (threadIdx.x == 0) { __threadfence_system(); s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1; }
@@ -320,8 +320,9 @@ __device__ __forceinline__ float4 vdiv(float4 a, float d) { return make_float4(_
 
 // requester: out[d,:] = (part[0][d,:] + part[1][d,:] + ...) / (count + 1e-7), rank order
 template <typename V>
-__global__ void __launch_bounds__(256) k_sym_sage_reduce(const V* __restrict__ part, const unsigned char* __restrict__ flags, int N,
-                                                         int64_t rows, int32_t vdim /* V units per row */, int32_t count, V* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_sym_sage_reduce(const V* __restrict__ part, const unsigned int* __restrict__ flags, int N,
+                                                         int64_t rows, int32_t vdim /* V units per row */, int32_t count, int kSageR,
+                                                         V* __restrict__ out) {
   const float denom = __fadd_rn((float)count, 1e-7f);
   const int64_t total = rows * vdim;
   const int64_t gps = (rows + kSageR - 1) / kSageR;
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(256) k_sym_sage_reduce(const V* __restrict__ p
     const int64_t d = i / vdim;
     V acc = vzero(V());
     for (int o = 0; o < N; ++o)   // absent partial == a row of +0.0: skipping it is exact (acc is never -0.0)
-      if ((flags[(int64_t)o * gps + (d >> 3)] >> (d & 7)) & 1) acc = vadd(acc, __ldcs(part + (int64_t)o * total + i));
+      if ((flags[(int64_t)o * gps + d / kSageR] >> (d % kSageR)) & 1u) acc = vadd(acc, __ldcs(part + (int64_t)o * total + i));
     out[i] = vdiv(acc, denom);
   }
 }
@@ -389,7 +390,7 @@ int eu_sym_create(eu_ctx* c, int32_t rank, int32_t world, int64_t max_rows, int3
   L.off_w = off; off += a256(4 * L.max_out);
   L.off_t = off; off += a256(4 * L.max_out);
   L.off_rows = off; off += a256(4 * max_feat_rows * (int64_t)max_dim);
-  L.off_flags = off; off += a256((max_feat_rows / 8 + 1) * (int64_t)world);   // partial-row presence bits of eu_sym_sage_mean
+  L.off_flags = off; off += a256((max_feat_rows / 8 + 1) * 4 * (int64_t)world);   // partial-row presence masks of eu_sym_sage_mean
   L.bytes = off;
   cudaError_t e = cudaMalloc(&s->base, (size_t)L.bytes);
   if (e != cudaSuccess) { set_error("cudaMalloc(%lld) -> %s", (long long)L.bytes, cudaGetErrorString(e)); delete s; return EU_ERR_CUDA; }
@@ -579,18 +580,21 @@ int eu_sym_sage_mean(eu_sym* s, const int64_t* nbr_ids, int64_t rows, int32_t co
   if (rc) return rc;
   cudaStream_t st = c->stream;
   const bool fast = d.n < ((int64_t)1 << 31) && d.n_slots == 1 && dim == d.feat_dim && (dim == 128 || dim == 256);
-  if ((rows / 8 + 1) * (int64_t)N > a256((L.max_rows_f / 8 + 1) * (int64_t)N)) { set_error("eu_sym_sage_mean: presence bits exceed the symmetric region"); return EU_ERR_INVALID; }
+  static int sage_r = 0;
+  if (!sage_r) { const char* e = getenv("EU_SAGE_R"); sage_r = e && atoi(e) == 8 ? 8 : 32; }
+  const int kSageR = sage_r;
+  if ((rows / 8 + 1) * (int64_t)N > (L.max_rows_f / 8 + 1) * (int64_t)N) { set_error("eu_sym_sage_mean: presence bits exceed the symmetric region"); return EU_ERR_INVALID; }
   // the generic-width owners store every partial row: the requester marks them all present before its push goes out
-  if (!fast) EU_CUDA(cudaMemsetAsync(s->base + L.off_flags, 0xFF, (size_t)(ceil_div(rows, kSageR) * N), st));
+  if (!fast) EU_CUDA(cudaMemsetAsync(s->base + L.off_flags, 0xFF, (size_t)(ceil_div(rows, kSageR) * N * 4), st));
   // ids that exist nowhere (0 / default fill) contribute nothing: they are dropped at the bucket, not shipped
   rc = bucket_push(c, nbr_ids, nid, num_partitions, N, s->rank, true, s->d_counts, s->d_offs, s->peers, L, "k_bucket_push(sage)");
   if (rc) return rc;
   { EuProfScope ps(c, "k_sym_wait_in(sage)", nid); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, L, N, 1, 0, nullptr); }
   EU_LAUNCHED();
   { EuProfScope ps(c, "k_sym_reply_sage", (int64_t)N * rows);
-    const unsigned grid = reply_grid((int64_t)N * ceil_div(rows, kSageR) * 32);
-    if (fast && dim == 128) k_sym_reply_sage<1><<<grid, 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count);
-    else if (fast && dim == 256) k_sym_reply_sage<2><<<grid, 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count);
+    const unsigned grid = sym_grid((int64_t)N * ceil_div(rows, kSageR) * 32);   // search-latency bound at large N: full occupancy
+    if (fast && dim == 128) k_sym_reply_sage<1><<<grid, 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count, kSageR);
+    else if (fast && dim == 256) k_sym_reply_sage<2><<<grid, 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count, kSageR);
     else k_sym_reply_sage_generic<<<sym_grid((int64_t)N * rows * 32), 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count, dim); }
   EU_LAUNCHED();
   { EuProfScope ps(c, "k_sym_wait(sage)", rows); k_sym_wait<<<1, 32, 0, st>>>(s->base, N); }
@@ -598,11 +602,11 @@ int eu_sym_sage_mean(eu_sym* s, const int64_t* nbr_ids, int64_t rows, int32_t co
   if (rows > 0) {
     EuProfScope ps(c, "k_sym_sage_reduce", rows);
     const float* part = (const float*)(s->base + L.off_rows);
-    const unsigned char* flags = (const unsigned char*)(s->base + L.off_flags);
+    const unsigned int* flags = (const unsigned int*)(s->base + L.off_flags);
     if ((dim & 3) == 0 && ((uintptr_t)out & 15) == 0)
-      k_sym_sage_reduce<float4><<<sym_grid(rows * dim / 4), 256, 0, st>>>((const float4*)part, flags, N, rows, dim / 4, count, (float4*)out);
+      k_sym_sage_reduce<float4><<<sym_grid(rows * dim / 4), 256, 0, st>>>((const float4*)part, flags, N, rows, dim / 4, count, kSageR, (float4*)out);
     else
-      k_sym_sage_reduce<float><<<sym_grid(rows * dim), 256, 0, st>>>(part, flags, N, rows, dim, count, out);
+      k_sym_sage_reduce<float><<<sym_grid(rows * dim), 256, 0, st>>>(part, flags, N, rows, dim, count, kSageR, out);
     EU_LAUNCHED();
   }
   return EU_OK;
