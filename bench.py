@@ -53,42 +53,75 @@ def parse():
 
 # ----------------------------------------------------------------------------- clocks sampler
 class Clocks:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML from a thread every few ms (the timed region of
+    the device-resident arm is ~0.1 s), nvidia-smi -lms as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nv, self.run = index, [], None, None, False
+        self.max_mhz = None
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            self.h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.nv, self.run = nv, True
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nv = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nv
+        names = [("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                 ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")]
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while self.run:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                bits = get(self.h)
+                self.rows.append((time.time(), float(mhz), [n for n, a in names if bits & getattr(nv, a, 0)]))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+            r = [x.strip() for x in line.split(",")]
+            try:
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                self.max_mhz = float(r[2])
+                self.rows.append((time.time(), float(r[1]), [nm for k, nm in enumerate(names) if len(r) > 5 + k and r[5 + k].lower().startswith("active")]))
+            except Exception:
+                pass
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2] or [r for _, r in self.rows[-3:]]
-        sm = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
+        if self.nv is None and self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml / nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.run = False
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for r in self.rows if t0 <= r[0] <= t1 + 0.02] or self.rows[-3:]
+        sm = sorted(r[1] for r in rows)
         reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
-            for k, nm in enumerate(names):
-                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": float(rows[0][2]) if rows and rows[0][2].replace(".", "").isdigit() else None,
-                "reasons": sorted(reasons), "samples": len(rows)}
+            reasons.update(r[2])
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(reasons), "samples": len(rows), "source": "nvml" if self.nv is not None else "nvidia-smi"}
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -749,15 +782,17 @@ def run_reference(args):
         if edges / sec > best_v:
             best_th, best_v = th, edges / sec
     cores_used = best_th
-    # a "step" of this arm = one bounded sample: every thread runs one batch
-    sec1, _ = fn(host_seeds[:64], 1, cores_used)
+    # a "step" of this arm = one bounded sample: every thread runs PER_STEP batches back to back (its first batch after a
+    # thread start pays the allocator warm-up; a single batch per step would understate the reference by ~2x)
+    PER_STEP = 4
+    sec1, _ = fn(host_seeds[:64], PER_STEP, cores_used)
     steps = max(1, min(args.steps, int(90.0 / max(sec1, 1e-3))))     # whole run bounded to ~1.5 minutes
     warm = min(args.warmup, 2)
     for _ in range(warm):
-        fn(host_seeds[:64], 1, cores_used)
+        fn(host_seeds[:64], PER_STEP, cores_used)
     t_edges, t_sec = 0, 0.0
     for _ in range(steps):
-        sec, edges = fn(host_seeds[:64], 1, cores_used)
+        sec, edges = fn(host_seeds[:64], PER_STEP, cores_used)
         t_edges += edges
         t_sec += sec
     v = t_edges / t_sec
@@ -767,9 +802,9 @@ def run_reference(args):
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 ids / f32", "data": "synthetic",
            "config": {"workload": "BASELINE configs[1]: RMAT %dM nodes/%dM edges, 2-hop sample_fanout %s batch=%d, GraphSAGE-mean "
                                   "aggregation, feat_dim=%d" % (args.nodes // 10**6, args.edges // 10**6, counts, args.batch, args.dim),
-                      "step": "one bounded sample = %d host threads x 1 batch each" % cores},
+                      "step": "one bounded sample = %d host threads x %d batches each" % (cores, PER_STEP)},
            "cpu_baseline": {"value": v, "unit": "edges/s", "cores": cores, "kind": "reference" if use_ref else "port",
-                            "sample": "%d steps of %d threads x 1 batch" % (steps, cores)},
+                            "sample": "%d steps of %d threads x %d batches" % (steps, cores, PER_STEP)},
            "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)

@@ -64,9 +64,44 @@ __global__ void __launch_bounds__(256) k_full_fill(DevGraph g, const unsigned lo
   }
 }
 
+// euler::GetNodeType (api.cc:50-61): the node's type, DEFAULT_INT32 (= INT32_MIN, data_types.cc:23) when the node is absent
+__global__ void k_node_type(DevGraph g, const unsigned long long* __restrict__ nodes, int64_t B, int32_t* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const int64_t row = lookup_row(g, nodes[i]);
+  out[i] = row >= 0 ? g.node_type[row] : (int32_t)0x80000000;
+}
+
 }  // namespace eu
 
 using namespace eu;
+
+extern "C" int eu_get_node_type(eu_ctx* c, const int64_t* nodes, int64_t B, int32_t* out) {
+  if (!c || B < 0 || (B > 0 && (!nodes || !out))) { set_error("eu_get_node_type: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  if (B == 0) return EU_OK;
+  k_node_type<<<(unsigned)ceil_div(B, 256), 256, 0, c->stream>>>(c->g->d, (const unsigned long long*)nodes, B, out);
+  EU_LAUNCHED();
+  return EU_OK;
+}
+
+extern "C" int eu_get_node_type_host(eu_ctx* c, const int64_t* nodes, int64_t B, int32_t* out) {
+  if (!c || B < 0 || (B > 0 && (!nodes || !out))) { set_error("eu_get_node_type_host: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  if (B == 0) return EU_OK;
+  unsigned long long* d_nodes = nullptr; int32_t* d_out = nullptr;
+  EU_CUDA(cudaMalloc(&d_nodes, 8 * (size_t)B));
+  cudaError_t e = cudaMalloc(&d_out, 4 * (size_t)B);
+  int rc = EU_OK;
+  if (e != cudaSuccess) rc = EU_ERR_CUDA;
+  if (!rc && cudaMemcpyAsync(d_nodes, nodes, 8 * (size_t)B, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) rc = EU_ERR_CUDA;
+  if (!rc) rc = eu_get_node_type(c, (const int64_t*)d_nodes, B, d_out);
+  if (!rc && (cudaMemcpyAsync(out, d_out, 4 * (size_t)B, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+              cudaStreamSynchronize(c->stream) != cudaSuccess)) rc = EU_ERR_CUDA;
+  cudaFree(d_nodes); cudaFree(d_out);
+  if (rc == EU_ERR_CUDA) set_error("eu_get_node_type_host: CUDA error %s", cudaGetErrorString(cudaGetLastError()));
+  return rc;
+}
 
 extern "C" int eu_get_full_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
                                     int64_t cap, int64_t* out_ptr, int64_t* out_ids, float* out_w, int32_t* out_t) {

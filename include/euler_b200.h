@@ -100,7 +100,7 @@ int eu_graph_create_rmat_shard(int64_t n_nodes, int64_t n_edges, double a, doubl
 int eu_graph_create_rmat_hetero(int64_t n_nodes, int64_t n_edges, int32_t n_edge_types, int32_t n_node_types, double a,
                                 double b, double c, uint64_t seed, int32_t feat_dim, uint64_t feat_seed, int device,
                                 int shard_index, int shard_number, eu_graph** out);
-/* Euler 2.0 on-disk format (euler.meta + Node/*.dat), shard `shard_index` of
+/* Euler 2.0 on-disk format (euler.meta + the Node and Edge partition files), shard `shard_index` of
  * `shard_number` with the reference's file filter (graph.cc:90-98).  = Graph::Init, graph.h:53-56. */
 int eu_graph_load(const char* data_path, int shard_index, int shard_number, int device,
                   eu_graph** out);
@@ -195,6 +195,11 @@ int eu_get_full_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32
 int eu_get_full_neighbor_host(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
                               int64_t cap, int64_t* out_ptr, int64_t* out_ids, float* out_w, int32_t* out_t,
                               int64_t* total);
+
+/* euler::GetNodeType (euler/core/api/api.cc:50-61; tf_euler get_node_type): type of every node, INT32_MIN
+ * (DEFAULT_INT32, euler/common/data_types.cc:23) for ids that are not in the graph. */
+int eu_get_node_type(eu_ctx* c, const int64_t* nodes, int64_t B, int32_t* out);
+int eu_get_node_type_host(eu_ctx* c, const int64_t* nodes, int64_t B, int32_t* out);
 
 /* ------------------------------------------------------------------ message-passing ops ------ */
 /* MPGather / MPScatterAdd / MPScatterMax (tf_euler/ops/mp_ops.cc:22-81; kernels

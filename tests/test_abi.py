@@ -70,3 +70,23 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "pyoracle" not in txt and "euler_oracle" not in txt and "libeuler_ref" not in txt, f
+
+
+def test_cpp_api_adapter_compiles_and_links():
+    """include/euler_b200_api.hpp (the reference's euler/core/api/api.h surface over the C ABI) compiles as C++11 and links
+    against the shared library; with no GPU the program refuses to start (no CPU fallback)."""
+    import shutil
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "euler_b200", "lib")
+    if shutil.which("g++") is None or not os.path.exists(os.path.join(lib, "libeuler_b200.so")):
+        pytest.skip("g++ or the built library is missing")
+    exe = os.path.join(tempfile.mkdtemp(), "api_adapter_main")
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "api_adapter_main.cc"), "-L" + lib, "-leuler_b200",
+                           "-Wl,-rpath," + lib, "-o", exe])
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe, os.path.join(root, "tests", "golden", "tiny_euler")], capture_output=True, text=True)
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr

@@ -496,3 +496,65 @@ def test_get_full_neighbor_random_graph_and_host_entry(T, stride):
     cases.eq(h_ids, np.asarray(o_ids).astype(np.int64), "host ids")
     cases.eq(h_w, o_w, "host w")
     cases.eq(h_t, o_t, "host t")
+
+
+# ---------------------------------------------------------------------------- C++ euler::api adapter (seam B3)
+@pytest.mark.gpu
+def test_cpp_api_adapter(tiny_dir):
+    """tests/cpp/api_adapter_main.cc calls include/euler_b200_api.hpp like a C++ user of euler/core/api/api.h; its printed
+    results must equal the oracle's on the tools/test_data graph (same seed -> same sampled neighbors)."""
+    import os
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "euler_b200", "lib")
+    exe = os.path.join(tempfile.mkdtemp(), "api_adapter_main")
+    subprocess.check_call(["g++", "-std=c++11", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp", "api_adapter_main.cc"),
+                           "-L" + lib, "-leuler_b200", "-Wl,-rpath," + lib, "-o", exe])
+    out = subprocess.run([exe, tiny_dir, "5"], capture_output=True, text=True, check=True).stdout
+    kv = {}
+    for line in out.strip().splitlines():
+        k, _, v = line.partition(":")
+        kv[k] = v.split()
+    g = graphs.load_tiny_csr()
+    og = graphs.oracle_graph(g)
+    type_of = {int(i): int(t) for i, t in zip(g["ids"], g["node_type"])}
+    assert [int(x) for x in kv["node_type"]] == [type_of.get(i, -2 ** 31) for i in [1, 2, 3, 4, 5, 6, 99]]
+    # full neighbors
+    lens, ids, w, t = og.get_full_neighbor(np.asarray([1, 2, 99, 6], np.uint64), [0, 1])
+    off = 0
+    for i, n in enumerate(lens):
+        got = kv["full[%d]" % i]
+        want = []
+        for k in range(off, off + n):
+            want += [str(int(ids[k])), "%.9g" % float(w[k]), str(int(t[k]))]
+        assert got == want, (i, got, want)
+        off += n
+    # sampled neighbors: engine stream seeded 4242, op semantics (duplicates share a row), empty vector for absent rows
+    po.seed(4242)
+    for key, nodes, et in [("sample", [1, 2, 3, 99, 1, 6], [0, 1]), ("sample2", [4, 5], [1])]:
+        o_ids, o_w, o_t = og.op_sample_neighbor(np.asarray(nodes, np.int64), et, 5, 0)
+        o_ids, o_w, o_t = o_ids.reshape(len(nodes), 5), o_w.reshape(len(nodes), 5), o_t.reshape(len(nodes), 5)
+        for i in range(len(nodes)):
+            want = []
+            if o_ids[i, 0] != 0:
+                for j in range(5):
+                    want += [str(int(o_ids[i, j])), "%.9g" % float(o_w[i, j]), str(int(o_t[i, j]))]
+            assert kv["%s[%d]" % (key, i)] == want, (key, i)
+    # dense features: node 1 and 3 per slot, absent node -> empty vectors, unknown slot -> empty
+    feat = g["feat"].reshape(len(g["ids"]), -1)
+    rows = {int(i): r for r, i in enumerate(g["ids"])}
+    dims = [int(d) for d in g["feat_slot_dims"]] if "feat_slot_dims" in g else None
+    for i, node in enumerate([1, 99, 3]):
+        for k in range(3):
+            vals = kv["feat[%d][%d]" % (i, k)]
+            if node not in rows or k == 2:
+                assert vals == []
+            elif dims is not None:
+                lo = sum(dims[:k])
+                assert vals == ["%.9g" % float(x) for x in feat[rows[node], lo:lo + dims[k]]]
+            else:
+                assert len(vals) > 0
+    assert len(kv["sample_node"]) == 8 and all(int(x) in rows for x in kv["sample_node"])
+    assert kv["names"] == ["1", "-1", "0", "-1"]
+    assert kv["out_of_scope"] == ["throws"]
