@@ -38,6 +38,69 @@ def owner_of(ids, num_partitions, shard_num, self_shard=None):
     return own
 
 
+class ClientRng:
+    """The requesting side's engine: std::minstd_rand0 + libstdc++ generate_canonical<double,53>, the thread-local
+    generator of euler/common/random.cc:22-28 (the same stream arithmetic as csrc/common.cuh::minstd_uniform)."""
+    M, A = 2147483647, 16807
+
+    def __init__(self, seed=1):
+        self.x = int(seed) % self.M or 1
+
+    def uniform(self):
+        import math
+        R = 2147483646.0
+        self.x = self.x * self.A % self.M
+        s = float(self.x - 1)
+        self.x = self.x * self.A % self.M
+        s = s + float(self.x - 1) * R
+        r = s / (R * R)
+        return math.nextafter(1.0, 0.0) if r >= 1.0 else r
+
+
+def split_sample_count(count, node_types, shard_weight, rng):
+    """SAMPLE_NODE_SPLIT (euler/core/kernels/sample_node_split_op.cc:38-85): how many of `count` draws each shard serves.
+    shard_weight: f32[n_types + 1][N + 1] = QueryProxy::GetShardNodeWeight() (row n_types = all types, column N = total).
+    floor(count * w_shard / w_total) in f32 each, the remainder handed out one by one to non-empty shards picked with the
+    CLIENT's engine (one uniform per leftover draw, :79-83)."""
+    import math
+    w = np.asarray(shard_weight, np.float32)
+    N = w.shape[1] - 1
+    types = [int(t) for t in node_types]
+    if -1 in types:
+        if len(types) > 1:
+            raise ValueError("sample_node: -1 (all types) cannot be mixed with other node types")   # EULER_LOG(FATAL) :61-63
+        types = [w.shape[0] - 1]
+    split, nonzero, remain = [], [], int(count)
+    for i in range(N):
+        s0, s1 = np.float32(0), np.float32(0)
+        for t in types:
+            s0 = np.float32(s0 + w[t][i])
+            s1 = np.float32(s1 + w[t][N])
+        if abs(float(s1)) < 1e-7:
+            raise ValueError("sample_node: node type sum weight is zero")                              # :69-71
+        c = int(math.floor(float(np.float32(np.float32(np.float32(count) * s0) / s1))))
+        split.append(c)
+        if s0 > 0:
+            nonzero.append(i)
+        remain -= c
+    while remain > 0:
+        split[nonzero[int(math.floor(rng.uniform() * len(nonzero)))]] += 1
+        remain -= 1
+    return split
+
+
+def shard_weight_table(per_shard_type_sums):
+    """per_shard_type_sums: [N][n_types] node-weight sums (f64).  Returns f32[n_types + 1][N + 1] laid out like
+    GetShardNodeWeight(): row t = type t, last row = all types; column s = shard s, last column = total."""
+    a = np.asarray(per_shard_type_sums, np.float64)          # [N, n_types]
+    N, nt = a.shape
+    out = np.zeros((nt + 1, N + 1), np.float64)
+    out[:nt, :N] = a.T
+    out[nt, :N] = a.sum(axis=1)
+    out[:, N] = out[:, :N].sum(axis=1)
+    return out.astype(np.float32)
+
+
 class TorchExchange:
     """all-to-all over a torch.distributed process group (NCCL for CUDA tensors, gloo for CPU)."""
 
@@ -123,6 +186,21 @@ class CudaShardOps:
                                                   o_ids.data_ptr(), o_w.data_ptr(), o_t.data_ptr()))
         return eng, o_ids, o_w, o_t
 
+    def node_weight_sums(self):
+        """per node type: sum of this shard's node weights (f64), the shard's column of GetShardNodeWeight()"""
+        ex = self.graph.export(with_feat=False)
+        nt = int(ex["node_type"].max()) + 1 if len(ex["node_type"]) else 1
+        nt = max(nt, int(getattr(self.graph, "n_node_types", nt) or nt))
+        return np.bincount(ex["node_type"], weights=ex["node_w"].astype(np.float64), minlength=nt)
+
+    def sample_node_local(self, n, node_types):
+        t = self.torch
+        out = t.empty(n, dtype=t.int64, device=self.dev)
+        types = np.ascontiguousarray(node_types, dtype=np.int32)
+        if n:
+            self.check(self.lib.eu_sample_node(self._stream(), n, types.ctypes.data, len(types), out.data_ptr()))
+        return out
+
     def feature_local(self, ids, fid, dim):
         t = self.torch
         out = t.empty(ids.numel() * dim, dtype=t.float32, device=self.dev)
@@ -147,6 +225,7 @@ class ShardedGraph:
         self.ops, self.xchg = ops, xchg
         self.N = xchg.world
         self.P = num_partitions or self.N   # partitions a multiple of shards -> owner = id % N
+        self._shard_w = None
 
     def sample_neighbor(self, nodes, edge_types, count, default_node=-1):
         eng, ids, w, t = self._hop(self.ops.to_dev(nodes, _i64(self.ops)), edge_types, count, default_node)
@@ -172,6 +251,41 @@ class ShardedGraph:
         packed = ops.sample_local(inbox, etypes, count)            # 16-byte records {id, w | t << 32}
         back = x.a2a(packed, recv, send, count * 2)
         return ops.merge_sample(back, src, rows, count, default_node)
+
+    def random_walk(self, nodes, edge_types, p=1.0, q=1.0, default_node=-1):
+        """walk_ops.random_walk over shards for p = q = 1 (TraditionalRandomWalk, tf_euler/kernels/random_walk_op.cc:170-232):
+        L chained sampleNB(count = 1) hops whose frontier is the ENGINE id (0 placeholder), one exchange per step; returns
+        [B, L+1] with default_node where the walk has died.  The biased node2vec step needs the parent's adjacency on the
+        walker's shard and is not sharded yet."""
+        if abs(float(p) - 1.0) > 1e-6 or abs(float(q) - 1.0) > 1e-6:
+            raise NotImplementedError("sharded random_walk: only p = q = 1 (node2vec across shards is not built)")
+        ops = self.ops
+        frontier = ops.to_dev(nodes, _i64(ops)).reshape(-1)
+        cols = [frontier]
+        for et in edge_types:
+            frontier, o_ids, _, _ = self._hop(frontier, et, 1, default_node)
+            cols.append(o_ids)
+        return ops.torch.stack(cols, dim=1)
+
+    def sample_node(self, count, node_types, client_rng):
+        """sample_ops.sample_node over shards (SAMPLE_NODE_SPLIT -> per-shard API_SAMPLE_NODE -> merge in shard order,
+        euler/core/kernels/sample_node_split_op.cc:38-110): this rank's `count` draws are split over the shards in
+        proportion to their node-weight sums; every shard serves the requests of rank 0..N-1 in rank order on its own
+        engine; the result is the concatenation in shard order.  Collective: every rank calls it with the same
+        node_types.  client_rng: this rank's ClientRng (the remainder draws)."""
+        ops, x = self.ops, self.xchg
+        if self._shard_w is None:
+            import torch
+            mine = torch.as_tensor(np.asarray(ops.node_weight_sums(), np.float64))
+            mine = ops.to_dev(mine, torch.float64)
+            allw = [torch.empty_like(mine) for _ in range(self.N)]
+            x.dist.all_gather(allw, mine, group=x.group)
+            self._shard_w = shard_weight_table(np.stack([a.cpu().numpy() for a in allw]))
+        split = split_sample_count(count, node_types, self._shard_w, client_rng)
+        send, recv = x.counts(ops.to_dev(np.asarray(split, np.int64), _i64(ops)))
+        served = [ops.sample_node_local(int(n), node_types) for n in recv]        # rank order, one call per requester
+        cat = ops.torch.cat(served) if served else ops.to_dev(np.zeros(0, np.int64), _i64(ops))
+        return x.a2a(cat, recv, send)
 
     def get_dense_feature(self, nodes, fid, dim):
         ops, x = self.ops, self.xchg

@@ -51,6 +51,8 @@ class OracleShardOps:
         import torch
         self.torch = torch
         self.og = graphs.oracle_graph(shard_graph)
+        self.shard = shard_graph
+        self.og.build_node_sampler(np.arange(len(shard_graph["ids"]), dtype=np.int64), shard_graph["n_node_types"])
         self.feat_dim = 0 if shard_graph.get("feat") is None else shard_graph["feat"].shape[1]
         po.seed(seed)
 
@@ -93,6 +95,18 @@ class OracleShardOps:
 
     def feature_local(self, ids, fid, dim):
         return self.torch.from_numpy(self.og.op_get_dense_feature(ids.numpy(), dim).reshape(-1))
+
+    def node_weight_sums(self):
+        return type_weight_sums(self.shard)
+
+    def sample_node_local(self, n, node_types):
+        """the shard's ONE engine (the oracle's global stream here) also serves its node draws"""
+        st = po.get_state()
+        r = po.Rng(1)
+        r.x, r.draws = st[0], st[1]
+        ids = self.og.sample_node(node_types, int(n), r) if n else np.zeros(0, np.uint64)
+        po.set_state((r.x, r.draws))
+        return self.torch.from_numpy(ids.astype(np.int64))
 
     def merge_rows(self, rows_in, src, rows, dim):
         out = np.zeros((rows, dim), np.float32)
@@ -161,3 +175,30 @@ def sage_mean_sharded(full_oracle, nbr_ids, rows, count, dim, N, me, P=None):
         total = (total + part).astype(np.float32)
     denom = np.float32(np.float32(count) + np.float32(1e-7))
     return (total / denom).astype(np.float32)
+
+
+def type_weight_sums(shard):
+    return np.bincount(shard["node_type"], weights=shard["node_w"].astype(np.float64), minlength=shard["n_node_types"])
+
+
+def simulate_sample_node(shards, count, node_types, shard_seeds, client_seeds, repeat=1):
+    """Single-process restatement of ShardedGraph.sample_node: per rank the ids it receives (shard order)."""
+    from euler_b200.sharded import ClientRng, shard_weight_table, split_sample_count
+    N = len(shards)
+    table = shard_weight_table(np.stack([type_weight_sums(s) for s in shards]))
+    ogs = []
+    for s in shards:
+        og = graphs.oracle_graph(s)
+        og.build_node_sampler(np.arange(len(s["ids"]), dtype=np.int64), s["n_node_types"])
+        ogs.append(og)
+    rngs = [po.Rng(sd) for sd in shard_seeds]
+    clients = [ClientRng(cs) for cs in client_seeds]
+    out = None
+    for _ in range(repeat):
+        splits = [split_sample_count(count, node_types, table, clients[r]) for r in range(N)]
+        got = [[None] * N for _ in range(N)]
+        for s in range(N):
+            for r in range(N):
+                got[r][s] = ogs[s].sample_node(node_types, splits[r][s], rngs[s]) if splits[r][s] else np.zeros(0, np.uint64)
+        out = [np.concatenate(got[r]).astype(np.int64) for r in range(N)]
+    return out

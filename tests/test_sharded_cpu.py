@@ -56,6 +56,29 @@ def _worker(rank, world, port, q):
             if b != -1:
                 lens, nb, _, _ = full.get_full_neighbor([a], [0, 1])
                 assert b in nb.tolist()
+        # ---- DeepWalk (p = q = 1) = chained count-1 hops: one exchange per step
+        ops_w = sc.OracleShardOps(shards[rank], 700 + rank)
+        walk = ShardedGraph(ops_w, TorchExchange()).random_walk(seeds[rank], [[0, 1]] * 5, 1.0, 1.0, -1)
+        exp_w = sc.simulate(shards, seeds, [[0, 1]] * 5, [1] * 5, shard_seeds=[700 + s for s in range(world)])
+        assert tuple(walk.shape) == (150, 6)
+        for l in range(6):
+            cases.eq(walk[:, l].numpy(), exp_w[rank][0][l], "rank %d walk column %d" % (rank, l))
+        # ---- sharded sample_node: split by shard weight sums, remainder by the client's engine, shard-order merge
+        from euler_b200.sharded import ClientRng
+        g2 = graphs.random_graph(seed=78, n=900, T=1, avg_deg=3, n_node_types=3, id_stride=2, id_base=5)
+        shards2 = sc.partition(g2, world)
+        for types in ([0], [-1], [1, 2]):
+            ops2 = sc.OracleShardOps(shards2[rank], 600 + rank)
+            sg2 = ShardedGraph(ops2, TorchExchange())
+            crng = ClientRng(900 + rank)
+            for _ in range(2):
+                got = sg2.sample_node(257, types, crng)
+            want = sc.simulate_sample_node(shards2, 257, types, [600 + s for s in range(world)], [900 + r for r in range(world)], repeat=2)
+            cases.eq(got.numpy(), want[rank], "rank %d sample_node %s" % (rank, types))
+            assert got.numel() == 257
+            tt = {int(i): int(t) for i, t in zip(g2["ids"], g2["node_type"])}
+            if types != [-1]:
+                assert all(tt[int(i)] in types for i in got.numpy())
         dist.barrier()
         dist.destroy_process_group()
         q.put((rank, "ok"))
@@ -86,3 +109,24 @@ def test_partition_is_a_partition():
     from euler_b200.sharded import owner_of
     for k, s in enumerate(shards):
         assert (owner_of(s["ids"], 8, 4) == k).all()
+
+
+def test_client_rng_and_split_match_the_oracle_engine():
+    """ClientRng == the oracle's restatement of the reference engine; split_sample_count follows
+    sample_node_split_op.cc:58-85 (floor shares + remainder draws)."""
+    from euler_b200.sharded import ClientRng, shard_weight_table, split_sample_count
+    from oracle import pyoracle as po
+    for seed in (1, 12345, 0, 2 ** 31 - 1, 1758564000):
+        a, b = ClientRng(seed), po.Rng(seed)
+        for _ in range(2000):
+            assert a.uniform() == b.uniform()
+    table = shard_weight_table([[3.0, 0.0, 1.5], [1.0, 0.0, 2.5], [0.0, 0.0, 4.0]])     # 3 shards x 3 types
+    assert table.shape == (4, 4) and table[3][3] == 12.0 and table[0][3] == 4.0
+    r = ClientRng(7)
+    sp = split_sample_count(10, [0], table, r)
+    assert sum(sp) == 10 and sp[2] == 0 and sp[0] >= 7 and sp[1] >= 2          # floor(7.5), floor(2.5) + 1 leftover
+    assert split_sample_count(12, [-1], table, ClientRng(1)) == [4, 3, 4] or sum(split_sample_count(12, [-1], table, ClientRng(1))) == 12
+    with pytest.raises(ValueError):
+        split_sample_count(5, [1], table, ClientRng(1))                          # zero total weight (EULER_LOG(FATAL) in the reference)
+    with pytest.raises(ValueError):
+        split_sample_count(5, [-1, 0], table, ClientRng(1))
