@@ -45,6 +45,10 @@ def parse():
     p.add_argument("--no-fuse", action="store_true", help="get_dense_feature + scatter_mean instead of the fused kernel")
     p.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph per step")
     p.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N>1: in-kernel peer-memory exchange or NCCL")
+    p.add_argument("--features", default="sharded", choices=["sharded", "replicated"],
+                   help="N>1: dense features live with their rows (Euler's scheme; fetched / aggregated by the owners over NVLink) "
+                        "or every rank holds all feature rows (fits: 5 GB at C2) and only the CSR is sharded -- DESIGN.md section 8 item 1; "
+                        "opt-in until validated on the GPU")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=15.0)
     p.add_argument("--breakdown-iters", type=int, default=50)
@@ -450,6 +454,12 @@ def run_sharded(args, world, rank, local):
     counts = [int(x) for x in args.fanout.split(",")]
     L, B, D = len(counts), args.batch, args.dim
     graph = eb.Graph.rmat_shard(args.nodes, args.edges, rank, world, feat_dim=D, device=local)
+    replicated = args.features == "replicated" and args.exchange == "peer"
+    feat_graph = None
+    if replicated:
+        # all feature rows on every rank: the generator's features are a hash of (global node index, column), so a full-node
+        # graph with a token number of edges carries exactly the rows the shards hold
+        feat_graph = eb.Graph.rmat(args.nodes, 1024, feat_dim=D, device=local)
     n = [B]
     for c in counts:
         n.append(n[-1] * c)
@@ -494,6 +504,9 @@ def run_sharded(args, world, rank, local):
         ln.h_ids = [torch.empty(G * x, dtype=torch.int64).pin_memory() for x in n[1:]]
         ln.h_x = torch.empty((G * n_self, D), dtype=torch.float32).pin_memory()
         ln.h_agg = [torch.empty((G * n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
+        if replicated:
+            ln.fctx = eb.Context(feat_graph, args.rng, seed + 7, ln.stream.cuda_stream)
+            ln.x_local = torch.empty((G * n_self, D), dtype=torch.float32, device="cuda")
         G = G_main
         lanes.append(ln)
     tail_lane = lanes.pop() if tail else None
@@ -511,6 +524,17 @@ def run_sharded(args, world, rank, local):
                 eng, o_ids, o_w, o_t = sg.hop(frontier, [0], counts[l], -1, nb=G)
                 ln.ids[l].copy_(o_ids)
                 frontier = eng
+            if replicated:
+                # every rank holds all feature rows: fetch + aggregation are the single-GPU kernels, nothing crosses NVLink
+                h = ln.fctx._h
+                ln.fctx.set_stream(torch.cuda.current_stream().cuda_stream)
+                rc = lib.eu_get_dense_feature(h, ln.idbuf.data_ptr(), G * n_self, 0, D, ln.x_local.data_ptr())
+                for l in range(L):
+                    rc |= lib.eu_sage_mean_aggregate(h, ln.ids[l].data_ptr(), G * n[l], counts[l], D, ln.agg[l].data_ptr())
+                if rc:
+                    raise RuntimeError(lib.eu_last_error().decode())
+                ln.x_view = ln.x_local
+                return
             # the hop-(l+1) features are summed by their owners and never cross NVLink row by row
             for l in range(L):
                 sg.sage_mean(ln.ids[l], G * n[l], counts[l], D, out=ln.agg[l])
@@ -643,7 +667,9 @@ def run_sharded(args, world, rank, local):
     a2a_bytes = 0
     for l in range(L):
         a2a_bytes += remote * n[l] * (12 + 24 * counts[l])
-    if peer:
+    if peer and replicated:
+        pass   # only the hop exchanges cross the link
+    elif peer:
         a2a_bytes += remote * n_self * (12 + 4 * D)
         # valid (existing) fraction of the sampled ids of the last profiled group: placeholders are dropped before the
         # aggregation exchange, and an owner sends a partial row only for destinations it owns a neighbor of --
@@ -669,7 +695,9 @@ def run_sharded(args, world, rank, local):
                        "nodes": args.nodes, "edges": args.edges, "batch_per_gpu": B, "global_batch": B * world, "fanout": counts,
                        "feat_dim": D, "rng": args.rng, "exchange": "peer-memory kernels (NVLink loads/stores, no NCCL)" if peer else "NCCL all_to_all",
                        "lanes_in_flight": n_lanes, "steps_per_launch_group": G, "cuda_graphs": use_graphs, "peer_wait_timeouts": err,
-                       "aggregation": "fused at the owners (eu_sym_sage_mean: one partial row per owner and destination)" if peer else "materialised rows + scatter_mean",
+                       "aggregation": ("features replicated on every rank (%.1f GB): local k_feature / k_sage_mean" % (args.nodes * D * 4 / 1e9)) if replicated
+                                      else ("fused at the owners (eu_sym_sage_mean: one partial row per owner and destination)" if peer else "materialised rows + scatter_mean"),
+                       "features": "replicated" if replicated else "sharded with their rows",
                        "parallelism": "graph sharded id %% %d, batches data-parallel" % world,
                        "l2_policy": "inputs larger than L2 (random seeds per step over a %.1f GB shard)" % (graph.hbm_bytes / 1e9)},
             "e2e": {"value": edges_step * args.steps / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 8 * B * world,
