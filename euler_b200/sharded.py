@@ -221,11 +221,15 @@ class CudaShardOps:
 class ShardedGraph:
     """tf_euler's sampling / feature ops over a graph partitioned across the ranks of `xchg`."""
 
-    def __init__(self, ops, xchg, num_partitions=None):
+    def __init__(self, ops, xchg, num_partitions=None, feature_ops=None):
+        """feature_ops: per-rank ops over a graph that holds EVERY node's dense features (replicated feature table: 5 GB at
+        BASELINE configs[1] against 180 GB of HBM); when given, get_dense_feature runs locally and only the sampling hops
+        use the exchange.  None = Euler's scheme: features live with their rows."""
         self.ops, self.xchg = ops, xchg
         self.N = xchg.world
         self.P = num_partitions or self.N   # partitions a multiple of shards -> owner = id % N
         self._shard_w = None
+        self.feature_ops = feature_ops
 
     def sample_neighbor(self, nodes, edge_types, count, default_node=-1):
         eng, ids, w, t = self._hop(self.ops.to_dev(nodes, _i64(self.ops)), edge_types, count, default_node)
@@ -291,6 +295,8 @@ class ShardedGraph:
         ops, x = self.ops, self.xchg
         ids = ops.to_dev(nodes, _i64(ops)).reshape(-1)
         rows = ids.numel()
+        if self.feature_ops is not None:     # replicated feature table: no exchange
+            return self.feature_ops.feature_local(ids, fid, dim).reshape(rows, dim)
         sorted_ids, src, counts = ops.bucket(ids, self.P, self.N, x.rank)
         send, recv = x.counts(counts)
         inbox = x.a2a(sorted_ids, send, recv)

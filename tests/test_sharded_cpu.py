@@ -56,6 +56,10 @@ def _worker(rank, world, port, q):
             if b != -1:
                 lens, nb, _, _ = full.get_full_neighbor([a], [0, 1])
                 assert b in nb.tolist()
+        # ---- replicated feature table: same rows without an exchange
+        full_ops = sc.OracleShardOps(g, 1)
+        f2 = ShardedGraph(sc.OracleShardOps(shards[rank], 501 + rank), TorchExchange(), feature_ops=full_ops).get_dense_feature(ids[2], 0, 6)
+        cases.eq(f2.numpy(), f.numpy(), "rank %d replicated features" % rank)
         # ---- DeepWalk (p = q = 1) = chained count-1 hops: one exchange per step
         ops_w = sc.OracleShardOps(shards[rank], 700 + rank)
         walk = ShardedGraph(ops_w, TorchExchange()).random_walk(seeds[rank], [[0, 1]] * 5, 1.0, 1.0, -1)
