@@ -704,7 +704,7 @@ def run_sharded(args, world, rank, local):
                     "d2h_bytes_per_step": world * (sum(8 * x for x in n[1:]) + 2 * sum(4 * n[l] * D for l in range(L))),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(round(launches_per_group * (args.steps // G + (1 if tail else 0)))), "clocks": clk,
-            "roofline": {"bound": "nvlink", "kernel": "exchange kernels (k_sym_push / k_sym_reply_sample / k_sym_reply_sage / k_sym_reply_feature)" if peer else "NCCL all-to-all",
+            "roofline": {"bound": "nvlink", "kernel": "exchange kernels (k_bucket_place / k_sym_reply_sample / k_sym_reply_sage / k_sym_reply_feature)" if peer else "NCCL all-to-all",
                          "achieved": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9, 2), "peak": 770.0, "unit": "GB/s",
                          "frac": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9 / 770.0, 4), "traffic": None,
                          "peak_source": "B200_PROFILING.md measured peer copy 770 GB/s per direction",
