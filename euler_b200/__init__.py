@@ -10,4 +10,4 @@ from .graph import Context, Graph  # noqa: F401
 from .ops import (context, gather, get_dense_feature, get_edge_type_id, get_full_neighbor, get_graph,  # noqa: F401
                   get_node_type_id, initialize_embedded_graph, initialize_graph, random_walk,
                   sage_mean_aggregate, sample_fanout, sample_fanout_batched, sample_neighbor, sample_node, scatter_,
-                  scatter_add, scatter_max, scatter_mean, scatter_softmax, seed, set_graph)
+                  scatter_add, scatter_max, scatter_mean, scatter_softmax, seed, set_graph, unique)

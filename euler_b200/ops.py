@@ -256,6 +256,18 @@ def get_full_neighbor(nodes, edge_types):
     return indptr, ids, w, t
 
 
+def unique(ids):
+    """tf.unique on the device (eu_unique): (values in first-occurrence order, inverse i32 with ids == values[inverse])."""
+    ids = _t(ids, torch.int64).reshape(-1)
+    n = ids.numel()
+    vals = torch.empty(n, dtype=torch.int64, device=ids.device)
+    inv = torch.empty(n, dtype=torch.int32, device=ids.device)
+    cnt = torch.zeros(1, dtype=torch.int64, device=ids.device)
+    ctx = _ctx_on_stream()
+    check(_lib.load().eu_unique(ctx._h, ids.data_ptr(), n, vals.data_ptr(), inv.data_ptr(), cnt.data_ptr()))
+    return vals[:int(cnt.item())], inv
+
+
 def sage_mean_aggregate(neighbor_ids, count, dim):
     """Fused get_dense_feature + scatter_mean for fixed-fanout blocks (SAGEConv's neighbor mean,
     tf_euler/python/convolution/sage_conv.py:33-38 over sage_dataflow.py:43-46 blocks)."""

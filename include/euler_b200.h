@@ -201,6 +201,11 @@ int eu_get_full_neighbor_host(eu_ctx* c, const int64_t* nodes, int64_t B, const 
 int eu_get_node_type(eu_ctx* c, const int64_t* nodes, int64_t B, int32_t* out);
 int eu_get_node_type_host(eu_ctx* c, const int64_t* nodes, int64_t B, int32_t* out);
 
+/* tf.unique on the device (UniqueDataFlow / SageDataFlow, tf_euler/python/dataflow/neighbor_dataflow.py:84-109): the
+ * distinct values of ids in order of FIRST occurrence and, per input, the index of its value in that list.
+ * uniq: device i64[n] (first *n_unique valid), inverse: device i32[n], n_unique: device i64[1] (may be NULL). */
+int eu_unique(eu_ctx* c, const int64_t* ids, int64_t n, int64_t* uniq, int32_t* inverse, int64_t* n_unique);
+
 /* ------------------------------------------------------------------ message-passing ops ------ */
 /* MPGather / MPScatterAdd / MPScatterMax (tf_euler/ops/mp_ops.cc:22-81; kernels
  * tf_euler/kernels/gather_op.cc:31-52, scatter_op.cc:32-92).  f32 data, i32 indices, as registered. */

@@ -558,3 +558,35 @@ def test_cpp_api_adapter(tiny_dir):
     assert len(kv["sample_node"]) == 8 and all(int(x) in rows for x in kv["sample_node"])
     assert kv["names"] == ["1", "-1", "0", "-1"]
     assert kv["out_of_scope"] == ["throws"]
+
+
+# ---------------------------------------------------------------------------- device-side unique + dataflow (next-1)
+@pytest.mark.gpu
+def test_unique_first_occurrence_and_sage_dataflow():
+    import euler_b200
+    from euler_b200.dataflow import SageDataFlow
+    from test_dataflow_cpu import CpuSampler, np_unique_first
+    g = graphs.random_graph(seed=11, n=800, T=2, avg_deg=4, id_stride=3, id_base=2, hub=90)
+    euler_b200.set_graph(graphs.cuda_graph(g), seed=77)
+    rs = np.random.RandomState(2)
+    for n in (1, 31, 1000, 70001):
+        x = rs.randint(-3, 400, size=n).astype(np.int64)
+        x[::17] = -1
+        x[5::29] = 0
+        v, inv = euler_b200.unique(x)
+        wv, winv = np_unique_first(x)
+        cases.eq(v.cpu().numpy(), wv, "unique values n=%d" % n)
+        cases.eq(inv.cpu().numpy().astype(np.int64), winv.astype(np.int64), "unique inverse n=%d" % n)
+    v, inv = euler_b200.unique(np.zeros(0, np.int64))
+    assert v.numel() == 0 and inv.numel() == 0
+    roots = g["ids"][rs.randint(0, 800, size=64)].astype(np.int64)
+    roots[::9] = 10 ** 9
+    for self_loops in (True, False):
+        euler_b200.seed(77)
+        flow = SageDataFlow([5, 3], [[0, 1], [1]], add_self_loops=self_loops, max_id=10 ** 7)(torch.as_tensor(roots, device="cuda"))
+        want = SageDataFlow([5, 3], [[0, 1], [1]], add_self_loops=self_loops, max_id=10 ** 7, sampler=CpuSampler(g, 77))(torch.from_numpy(roots))
+        for a, b in zip(flow, want):
+            cases.eq(a.n_id.cpu().numpy(), b.n_id.numpy(), "flow n_id")
+            cases.eq(a.res_n_id.cpu().numpy(), b.res_n_id.numpy(), "flow res_n_id")
+            cases.eq(a.edge_index.cpu().numpy(), b.edge_index.numpy(), "flow edge_index")
+            assert a.size == b.size
