@@ -1,19 +1,25 @@
 #!/usr/bin/env python
-"""bench.py -- the minibatch-construction step of BASELINE.json configs[1] on N B200s.
+"""bench.py -- the minibatch-construction step of alibaba/euler's hot path on N B200s.
 
-    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (host cores)
+    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path (default workload = the north-star config)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
+    python bench.py --config c2 ...                          # BASELINE configs[1] instead (RMAT 10M/100M, [25,10], B=1024, D=128)
 
-A "step" = one pass of the hot path over one batch of synthetic input (BASELINE.json configs[1]):
-  RMAT 10M nodes / 100M edges resident in HBM, batch 1024 seeds,
-  sample_fanout [25,10]  ->  dense features (dim 128) of the seeds and of hop 1 (self inputs)
-  ->  GraphSAGE neighbor mean of hop 1 per seed and of hop 2 per hop-1 node (fused gather+mean).
-metric = sampled edges/s (slots delivered: B*25 + B*250 per step); extra key agg_feat_gbs =
-algorithmic bytes of the feature gather + segment mean per second.
+Default workload = BASELINE.json's north-star headline (configs[3]'s graph and shape): synthetic power-law (R-MAT) graph of
+100M nodes / 1B edges resident in HBM -- whole on one GPU at N=1, CSR hash-partitioned by id over the GPUs at N>1 -- batch
+8192 seeds per GPU, 2-hop sample_fanout [15,10], dense features (dim 256) of the seeds and of hop 1, GraphSAGE neighbor
+mean of hop 1 per seed and of hop 2 per hop-1 node.  A "step" = one pass of that path over one batch.
+metric = sampled edges/s (slots delivered: B*15 + B*150 per step per GPU); agg_feat_gbs = algorithmic bytes of the feature
+gather + segment mean per second (BASELINE's second number).
+
+Before anything is timed a PARITY GATE runs one seeded launch group through the exact timed code path and compares it with
+the CPU oracle (sampling on the exported CSR of this very graph: ids / weights / types bit-exact for every batch of the
+group; features and neighbor means of one batch against independently generated feature rows, bit-exact); a mismatch aborts.
 
 One JSON line on stdout (rank 0).  See the task's bench contract for the keys.
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -26,39 +32,83 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
+CONFIGS = {
+    # north-star headline: BASELINE.json configs[3]'s graph and shape (at N=1 the whole graph lives on one GPU)
+    "c4": dict(nodes=100_000_000, edges=1_000_000_000, batch=8192, fanout="15,10", dim=256,
+               label="north-star headline (BASELINE configs[3])"),
+    "c2": dict(nodes=10_000_000, edges=100_000_000, batch=1024, fanout="25,10", dim=128, label="BASELINE configs[1]"),
+}
+CPU_GRAPH_MAX_NODES = 10_000_000   # the CPU arms build the reference's unordered_map<NodeID,Node*> graph: bounded so the arm fits the driver's time box
+GRAPH_SEED, FEAT_SEED = 42, 7
+
 
 def parse():
     p = argparse.ArgumentParser()
     p.add_argument("--gpus", type=int, default=1)
-    p.add_argument("--steps", type=int, default=4000)
-    p.add_argument("--warmup", type=int, default=64)
+    p.add_argument("--steps", type=int, default=40)
+    p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--config", default="c4", choices=sorted(CONFIGS))
     p.add_argument("--rng", default="minstd", choices=["minstd", "philox"])
-    p.add_argument("--nodes", type=int, default=10_000_000)
-    p.add_argument("--edges", type=int, default=100_000_000)
-    p.add_argument("--batch", type=int, default=1024)
-    p.add_argument("--fanout", default="25,10")
-    p.add_argument("--dim", type=int, default=128)
+    p.add_argument("--nodes", type=int, default=None)
+    p.add_argument("--edges", type=int, default=None)
+    p.add_argument("--batch", type=int, default=None)
+    p.add_argument("--fanout", default=None)
+    p.add_argument("--dim", type=int, default=None)
     p.add_argument("--lanes", type=int, default=4, help="execution contexts (streams) with launch groups in flight")
-    p.add_argument("--group", type=int, default=16, help="steps (batches) per launch group: each batch keeps its own engine and "
-                                                          "dedup scope (eu_sample_fanout_batched), only the kernel launches are shared")
+    p.add_argument("--group", type=int, default=0, help="steps (batches) per launch group, 0 = auto: ceil(steps / lanes) capped by a "
+                                                         "row budget.  Each batch keeps its own engine and dedup scope "
+                                                         "(eu_sample_fanout_batched), only the kernel launches are shared")
     p.add_argument("--no-fuse", action="store_true", help="get_dense_feature + scatter_mean instead of the fused kernel")
     p.add_argument("--no-graphs", action="store_true", help="launch every kernel from the host instead of replaying a CUDA graph per step")
     p.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N>1: in-kernel peer-memory exchange or NCCL")
-    p.add_argument("--features", default="sharded", choices=["sharded", "replicated"],
-                   help="N>1: dense features live with their rows (Euler's scheme; fetched / aggregated by the owners over NVLink) "
-                        "or every rank holds all feature rows (fits: 5 GB at C2) and only the CSR is sharded -- DESIGN.md section 8 item 1; "
-                        "opt-in until validated on the GPU")
+    p.add_argument("--features", default="replicated", choices=["sharded", "replicated"],
+                   help="N>1: every rank holds all feature rows (102 GB at the headline config, fits 180 GB of HBM) and only the CSR "
+                        "is sharded -- or Euler's scheme, features live with their rows and are fetched / aggregated by the owners")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--cpu-seconds", type=float, default=15.0)
-    p.add_argument("--breakdown-iters", type=int, default=50)
-    return p.parse_args()
+    p.add_argument("--no-gate", action="store_true", help="skip the pre-timing parity gate (debugging only)")
+    p.add_argument("--no-e2e-host", action="store_true", help="skip the e2e leg through the *_host C ABI")
+    p.add_argument("--cpu-seconds", type=float, default=12.0)
+    p.add_argument("--breakdown-iters", type=int, default=6)
+    a = p.parse_args()
+    cfg = CONFIGS[a.config]
+    for k in ("nodes", "edges", "batch", "fanout", "dim"):
+        if getattr(a, k) is None:
+            setattr(a, k, cfg[k])
+    a.label = cfg["label"] if all(getattr(a, k) == cfg[k] for k in ("nodes", "edges", "batch", "fanout", "dim")) else "custom"
+    return a
+
+
+def workload_string(args, counts, n_gpus):
+    """identical in both arms (ours / --impl reference)"""
+    return ("%s: synthetic power-law (R-MAT 0.57/0.19/0.19/0.05) graph %dM nodes/%dM edges, %d-hop sample_fanout %s "
+            "batch=%d per GPU, dense features + GraphSAGE-mean aggregation, feat_dim=%d, %d GPU(s)"
+            % (args.label, args.nodes // 10**6, args.edges // 10**6, len(counts), counts, args.batch, args.dim, n_gpus))
+
+
+def workload_config(args, counts, n_gpus):
+    """the `config` object both arms print (arm-specific details live under `arm`)"""
+    return {"workload": workload_string(args, counts, n_gpus), "nodes": args.nodes, "edges": args.edges, "batch": args.batch,
+            "fanout": counts, "feat_dim": args.dim, "rng": args.rng,
+            "l2_policy": "inputs larger than L2 (graph >> 126 MB, fresh random seeds every step)"}
+
+
+def auto_group(args, counts):
+    """steps per launch group: all lanes busy for a short driver run (G = ceil(steps / lanes)), bounded by a row budget
+    (the widest hop of a group stays under ~5M rows: 16 at configs[1], 4 at the headline config)"""
+    if args.group > 0:
+        return max(1, min(args.group, args.steps))
+    widest = args.batch
+    for c in counts:
+        widest *= c
+    cap = max(1, min(16, 5_000_000 // max(widest, 1)))
+    return max(1, min(cap, -(-args.steps // max(args.lanes, 1))))
 
 
 # ----------------------------------------------------------------------------- clocks sampler
 class Clocks:
-    """SM clock + throttle reasons sampled DURING the timed region: NVML from a thread every few ms (the timed region of
-    the device-resident arm is ~0.1 s), nvidia-smi -lms as the fallback."""
+    """SM clock + throttle reasons sampled DURING the timed region: NVML from a thread every few ms, nvidia-smi -lms as the
+    fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -146,16 +196,17 @@ def step_bytes(B, counts, D):
 
 
 class Lane:
-    """One execution context: own stream, RNG engine, pinned input + output buffers."""
+    """One execution context: own stream, RNG engines, device outputs, pinned host buffers."""
 
-    def __init__(self, eb, graph, args, counts, seed, torch, G=None):
+    def __init__(self, eb, graph, args, counts, seed, torch, G):
         self.t = torch
         self.stream = torch.cuda.Stream()
         self.ctx = eb.Context(graph, args.rng, seed, self.stream.cuda_stream)
-        B, D, G = args.batch, args.dim, G or args.group
+        B, D = args.batch, args.dim
         dev = "cuda"
-        self.B, self.D, self.G, self.counts = B, D, G, counts
-        self.ctx.set_engines(G, [seed * 1000 + b for b in range(G)])
+        self.B, self.D, self.G, self.counts, self.seed = B, D, G, counts, seed
+        self.engine_seeds = [seed * 1000 + b for b in range(G)]
+        self.ctx.set_engines(G, self.engine_seeds)
         rows = G * B                      # rows of one launch group = G batches
         self.n = [rows]
         for c in counts:
@@ -173,26 +224,34 @@ class Lane:
         if args.no_fuse:
             self.hop_feat = [torch.empty((self.n[l + 1], D), dtype=torch.float32, device=dev) for l in range(L)]
             self.src = [torch.arange(self.n[l], dtype=torch.int32, device=dev).repeat_interleave(counts[l]) for l in range(L)]
-        # host side of the e2e path
+        # host side of the e2e paths (page-locked: the *_host ABI DMAs pinned caller buffers in place)
         self.h_seeds = torch.empty(G * B, dtype=torch.int64).pin_memory()
         self.h_ids = [torch.empty(n, dtype=torch.int64).pin_memory() for n in self.n[1:]]
+        self.h_w = [torch.empty(n, dtype=torch.float32).pin_memory() for n in self.n[1:]]
+        self.h_t = [torch.empty(n, dtype=torch.int32).pin_memory() for n in self.n[1:]]
         self.h_x = [torch.empty((self.n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
         self.h_agg = [torch.empty((self.n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
         self.h2d = 8 * B                  # per step
         self.d2h = (sum(8 * n for n in self.n[1:]) + 2 * sum(4 * self.n[l] * D for l in range(L))) // G
+        # through the *_host ABI: seeds up; ids + weights + types down; per hop the source ids (features) and the neighbor
+        # ids (fused mean) go up again, self features and means come down
+        self.h2d_host = (8 * self.n[0] + sum(8 * self.n[l] + 8 * self.n[l + 1] for l in range(L))) // G
+        self.d2h_host = (sum(16 * n for n in self.n[1:]) + 2 * sum(4 * self.n[l] * D for l in range(L))) // G
 
 
-def make_step(lib, C, args, counts, et):
-    import ctypes
+def make_step(lib, args, counts, et):
     L = len(counts)
     cs = np.ascontiguousarray(counts, dtype=np.int32)
     P = ctypes.c_void_p * L
 
-    def step(lane, seeds_dev):
+    def sample(lane, seeds_dev):
+        return lib.eu_sample_fanout_batched(lane.ctx._h, seeds_dev.data_ptr(), lane.G, lane.B, et.ctypes.data, et.shape[1], cs.ctypes.data, L, -1,
+                                            P(*[x.data_ptr() for x in lane.ids]), P(*[x.data_ptr() for x in lane.w]),
+                                            P(*[x.data_ptr() for x in lane.ty]))
+
+    def aggregate(lane, seeds_dev):
         h = lane.ctx._h
-        rc = lib.eu_sample_fanout_batched(h, seeds_dev.data_ptr(), lane.G, lane.B, et.ctypes.data, et.shape[1], cs.ctypes.data, L, -1,
-                                          P(*[x.data_ptr() for x in lane.ids]), P(*[x.data_ptr() for x in lane.w]),
-                                          P(*[x.data_ptr() for x in lane.ty]))
+        rc = 0
         for l in range(L):
             src_ids = seeds_dev if l == 0 else lane.ids[l - 1]
             rc |= lib.eu_get_dense_feature(h, src_ids.data_ptr(), lane.n[l], 0, lane.D, lane.x[l].data_ptr())
@@ -202,16 +261,95 @@ def make_step(lib, C, args, counts, et):
                                           lane.n[l], lane.agg[l].data_ptr())
             else:
                 rc |= lib.eu_sage_mean_aggregate(h, lane.ids[l].data_ptr(), lane.n[l], counts[l], lane.D, lane.agg[l].data_ptr())
+        return rc
+
+    def step(lane, seeds_dev, what="all"):
+        rc = 0
+        if what in ("all", "sample"):
+            rc |= sample(lane, seeds_dev)
+        if what in ("all", "aggregate"):
+            rc |= aggregate(lane, seeds_dev)
         if rc:
             raise RuntimeError("euler_b200: " + lib.eu_last_error().decode())
+
+    def host_step(lane):
+        """the same step through the reference-facing *_host C ABI: HOST buffers in, HOST buffers out (each call returns when
+        its results have landed)"""
+        h = lane.ctx._h
+        rc = lib.eu_sample_fanout_batched_host(h, lane.h_seeds.data_ptr(), lane.G, lane.B, et.ctypes.data, et.shape[1], cs.ctypes.data, L, -1,
+                                               P(*[x.data_ptr() for x in lane.h_ids]), P(*[x.data_ptr() for x in lane.h_w]),
+                                               P(*[x.data_ptr() for x in lane.h_t]))
+        for l in range(L):
+            src = lane.h_seeds if l == 0 else lane.h_ids[l - 1]
+            rc |= lib.eu_get_dense_feature_host(h, src.data_ptr(), lane.n[l], 0, lane.D, lane.h_x[l].data_ptr())
+            rc |= lib.eu_sage_mean_aggregate_host(h, lane.h_ids[l].data_ptr(), lane.n[l], counts[l], lane.D, lane.h_agg[l].data_ptr())
+        if rc:
+            raise RuntimeError("euler_b200: " + lib.eu_last_error().decode())
+    step.host = host_step
     return step
+
+
+def parity_gate(args, counts, graph, lane, raw_step, host_seeds, torch):
+    """One seeded launch group through the timed code path vs the CPU oracle.  Sampling: every batch of the group, ids /
+    weights / types bit-exact, on the CSR exported from this very graph.  Features + neighbor means: batch 0 against feature
+    rows generated independently on the host (oracle/rmat_gen.c), bit-exact (sorted fixed-fanout segments sum in the
+    reference's order).  Raises on any mismatch."""
+    from oracle import pyoracle as po
+    t0 = time.time()
+    G, B, D, L = lane.G, lane.B, lane.D, len(counts)
+    ex = graph.export(with_feat=False)
+    t_export = time.time() - t0
+    og = po.OracleGraph(ex["ids"], ex["node_type"], ex["node_w"], 1, ex["grp_ptr"], ex["nbr"], ex["cum_w"],
+                        np.zeros(len(ex["ids"]), np.float32))
+    seeds = host_seeds[:G].copy()
+    seeds[0, :8] = [0, -1, args.nodes + 12345, seeds[0, 9], seeds[0, 9], 1, args.nodes, seeds[0, 20]]   # placeholders, absent, duplicates, range ends
+    lane.ctx.set_engines(G, lane.engine_seeds)
+    with torch.cuda.stream(lane.stream):
+        lane.d_seeds.copy_(torch.from_numpy(seeds.reshape(-1)))
+        raw_step(lane, lane.d_seeds)
+    lane.stream.synchronize()
+    et = [[0]] * L
+    checked = 0
+    for b in range(G):
+        po.seed(lane.engine_seeds[b])
+        o_ids, o_w, o_t = og.op_sample_fanout(seeds[b], et, counts)
+        for l in range(L):
+            per = lane.n[l + 1] // G
+            sl = slice(b * per, (b + 1) * per)
+            for name, got, want in (("ids", lane.ids[l], o_ids[l]), ("weights", lane.w[l], o_w[l]), ("types", lane.ty[l], o_t[l])):
+                gnp = got[sl].cpu().numpy()
+                if not np.array_equal(gnp, want):
+                    bad = np.nonzero(gnp != want)[0]
+                    raise SystemExit("PARITY GATE FAILED: %s of hop %d, batch %d differ from the oracle at %d of %d slots (first %d: got %r want %r)"
+                                     % (name, l + 1, b, len(bad), len(want), bad[0], gnp[bad[0]], want[bad[0]]))
+            checked += 3 * per
+        if b == 0:
+            feats = [po.rmat_feat_rows(seeds[0], args.nodes, D, FEAT_SEED)] + \
+                    [po.rmat_feat_rows(o_ids[l], args.nodes, D, FEAT_SEED) for l in range(L)]
+            for l in range(L):
+                per = lane.n[l] // G
+                x = lane.x[l][:per].cpu().numpy()
+                if not np.array_equal(x, feats[l]):
+                    raise SystemExit("PARITY GATE FAILED: dense features of hop %d differ from the independently generated rows" % l)
+                want = po.scatter_mean(feats[l + 1], np.repeat(np.arange(per, dtype=np.int32), counts[l]), per)
+                a = lane.agg[l][:per].cpu().numpy()
+                if not np.array_equal(a, want):
+                    err = float(np.max(np.abs(a - want) / (np.abs(want) + 1e-6)))
+                    raise SystemExit("PARITY GATE FAILED: neighbor means of hop %d differ from the oracle (max rel err %.3g)" % (l + 1, err))
+                checked += 2 * per * D
+    lane.ctx.set_engines(G, lane.engine_seeds)
+    del og, ex
+    return {"passed": True, "batches": G, "values_compared": int(checked), "seconds": round(time.time() - t0, 2),
+            "csr_export_seconds": round(t_export, 2),
+            "what": "one launch group of %d batches through the timed code path vs oracle/euler_oracle.c on the exported CSR of the bench "
+                    "graph: ids/weights/types of every hop bit-exact; dense features + fused neighbor means of batch 0 bit-exact vs "
+                    "oracle/rmat_gen.c feature rows + the oracle's scatter_mean" % G}
 
 
 def run_ours(args):
     import torch
     import euler_b200 as eb
     from euler_b200 import _lib
-    import ctypes as C
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -224,21 +362,31 @@ def run_ours(args):
     counts = [int(x) for x in args.fanout.split(",")]
     et = np.zeros((len(counts), 1), np.int32)
     # exactly K steps are timed: K // G full launch groups + one tail group of K % G batches (its own lane + graph)
-    args.group = max(1, min(args.group, args.steps))
-    G = args.group
+    G = auto_group(args, counts)
     tail = args.steps % G
     t0 = time.time()
-    graph = eb.Graph.rmat(args.nodes, args.edges, feat_dim=args.dim, device=local)
+    graph = eb.Graph.rmat(args.nodes, args.edges, seed=GRAPH_SEED, feat_dim=args.dim, feat_seed=FEAT_SEED, device=local)
     torch.cuda.synchronize()
     t_graph = time.time() - t0
-    lanes = [Lane(eb, graph, args, counts, 12345 + i, torch) for i in range(args.lanes)]
-    tail_lane = Lane(eb, graph, args, counts, 12345 + args.lanes, torch, G=tail) if tail else None
-    raw_step = make_step(lib, C, args, counts, et)
+    n_lanes = max(1, min(args.lanes, args.steps // G if args.steps >= G else 1))
+    lanes = [Lane(eb, graph, args, counts, 12345 + i, torch, G) for i in range(n_lanes)]
+    tail_lane = Lane(eb, graph, args, counts, 12345 + n_lanes, torch, tail) if tail else None
+    raw_step = make_step(lib, args, counts, et)
+    nb = args.warmup + args.steps
+    n_seed_batches = -(-max(nb, 4 * G) // G) * G
+    host_seeds = np.stack([np.random.RandomState(1000 + i).randint(1, args.nodes + 1, size=args.batch)
+                           for i in range(n_seed_batches)]).astype(np.int64)
+    gate = {"passed": None, "skipped": "--no-gate"}
+    if not args.no_gate:
+        if args.rng != "minstd":
+            gate = {"passed": None, "skipped": "philox mode has no bit-exact oracle stream (statistical tests only)"}
+        else:
+            gate = parity_gate(args, counts, graph, lanes[0], raw_step, host_seeds, torch)
     per_step_launches = None
     use_graphs = not args.no_graphs
     if use_graphs:
         # the step has static shapes and device-resident RNG state: capture it once per lane and
-        # replay (one graph launch per step instead of ~14 kernel launches from Python)
+        # replay (one graph launch per launch group instead of ~14 kernel launches from Python)
         for ln in lanes + ([tail_lane] if tail_lane else []):
             with torch.cuda.stream(ln.stream):
                 ln.d_seeds.fill_(1)
@@ -258,10 +406,6 @@ def run_ours(args):
             ln.graph.replay()
         else:
             raw_step(ln, seeds_dev)
-    nb = args.warmup + args.steps
-    n_seed_batches = -(-max(nb, 64) // G) * G
-    host_seeds = np.stack([np.random.RandomState(1000 + i).randint(1, args.nodes + 1, size=args.batch)
-                           for i in range(n_seed_batches)]).astype(np.int64)
     dev_seeds = torch.from_numpy(host_seeds).cuda()
     n_groups_avail = n_seed_batches // G
 
@@ -270,67 +414,99 @@ def run_ours(args):
         return g0, dev_seeds[g0:g0 + G].reshape(-1)
     bts = step_bytes(args.batch, counts, args.dim)
     main = torch.cuda.current_stream()
+    all_lanes = lanes + ([tail_lane] if tail_lane else [])
 
-    def run(n_steps, first, e2e):
-        """n_steps steps round-robin over the lanes; returns device ms (events on the main stream,
-        lanes fork from / join into it)."""
+    def run(n_steps, first, mode):
+        """n_steps steps round-robin over the lanes; returns device ms (events on the main stream, lanes fork from / join
+        into it).  mode: "dev" = seeds resident in HBM; "e2e" = device entry points + pinned H2D / D2H copies;
+        "host" = the *_host C ABI, one host thread per lane (the reference's client pool, query_proxy.cc:205-210)."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        ev0.record(main)
         rem = n_steps % G
         use_tail = tail_lane is not None and rem == tail_lane.G
         n_groups = n_steps // G + (1 if rem else 0)     # an untimed (warm-up) remainder is rounded up to a full group
-        for ln in lanes + ([tail_lane] if use_tail else []):
-            ln.stream.wait_event(ev0)
-        for i in range(n_groups):     # launch groups of G steps
+        work = []                                        # (lane, first seed batch, batches)
+        for i in range(n_groups):
             ln = lanes[i % len(lanes)]
             g0, sd = group_seeds(first, i)
             if use_tail and i == n_groups - 1:
                 ln, sd = tail_lane, sd[:rem * args.batch]
-            Gl = ln.G
-            with torch.cuda.stream(ln.stream):
-                if e2e:
-                    # the lane's pinned buffers are reused every len(lanes) groups
-                    ln.stream.synchronize() if i >= len(lanes) else None
-                    ln.h_seeds.copy_(torch.from_numpy(host_seeds[g0:g0 + Gl].reshape(-1)))
-                    ln.d_seeds.copy_(ln.h_seeds, non_blocking=True)
-                    step(ln, ln.d_seeds)
-                    for l in range(len(counts)):
-                        ln.h_ids[l].copy_(ln.ids[l], non_blocking=True)
-                        ln.h_x[l].copy_(ln.x[l], non_blocking=True)
-                        ln.h_agg[l].copy_(ln.agg[l], non_blocking=True)
-                else:
-                    step(ln, sd)
-        for ln in lanes + ([tail_lane] if use_tail else []):
+            work.append((ln, g0, sd))
+        torch.cuda.synchronize()
+        ev0.record(main)
+        for ln in all_lanes:
+            ln.stream.wait_event(ev0)
+        if mode == "host":
+            def worker(ln):
+                for (l2, g0, _) in work:
+                    if l2 is ln:
+                        ln.h_seeds.copy_(torch.from_numpy(host_seeds[g0:g0 + ln.G].reshape(-1)))
+                        raw_step.host(ln)
+            ths = [threading.Thread(target=worker, args=(ln,)) for ln in all_lanes]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        else:
+            for i, (ln, g0, sd) in enumerate(work):
+                with torch.cuda.stream(ln.stream):
+                    if mode == "e2e":
+                        # the lane's pinned buffers are reused every len(lanes) groups
+                        ln.stream.synchronize() if i >= len(lanes) else None
+                        ln.h_seeds.copy_(torch.from_numpy(host_seeds[g0:g0 + ln.G].reshape(-1)))
+                        ln.d_seeds.copy_(ln.h_seeds, non_blocking=True)
+                        step(ln, ln.d_seeds)
+                        for l in range(len(counts)):
+                            ln.h_ids[l].copy_(ln.ids[l], non_blocking=True)
+                            ln.h_x[l].copy_(ln.x[l], non_blocking=True)
+                            ln.h_agg[l].copy_(ln.agg[l], non_blocking=True)
+                    else:
+                        step(ln, sd)
+        for ln in all_lanes:
             main.wait_stream(ln.stream)
         ev1.record(main)
         torch.cuda.synchronize()
         return ev0.elapsed_time(ev1)
 
-    run(-(-args.warmup // G) * G, 0, False)
+    run(-(-args.warmup // G) * G, 0, "dev")
     if tail_lane:
-        run(tail, 0, False)
+        run(tail, 0, "dev")
     clocks = Clocks(local)
     clocks.start()
     time.sleep(0.3)
     l0 = lib.eu_launch_count()
     w0 = time.time()
-    ms = run(args.steps, args.warmup, False)
+    ms = run(args.steps, args.warmup, "dev")
     w1 = time.time()
     launches = lib.eu_launch_count() - l0
     if use_graphs:
         launches = int(per_step_launches * args.steps)  # kernels of ours inside the replayed graphs
     clk = clocks.stop(w0, w1)
-    run(min(args.warmup, 8), 0, True)
-    ms_e2e = run(args.steps, args.warmup, True)
+    run(min(args.warmup, 2 * G), 0, "e2e")
+    ms_e2e = run(args.steps, args.warmup, "e2e")
+    ms_host = None
+    if not args.no_e2e_host:
+        run(min(args.warmup, 2 * G), 0, "host")
+        ms_host = run(args.steps, args.warmup, "host")
     edges_step = bts["edges"]
     value = edges_step * args.steps / (ms * 1e-3)
-    e2e_value = edges_step * args.steps / (ms_e2e * 1e-3)
+
+    # ---- sub-rates (BASELINE's metric is two numbers): sampling only and feature gather + aggregation only, one lane, serial
+    ln = lanes[0]
+    sub = {}
+    for what in ("sample", "aggregate"):
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        with torch.cuda.stream(ln.stream):
+            raw_step(ln, group_seeds(0, 0)[1], "sample")
+            raw_step(ln, group_seeds(0, 0)[1], what)
+            evs[0].record(ln.stream)
+            for it in range(args.breakdown_iters):
+                raw_step(ln, group_seeds(0, it)[1] if what == "sample" else ln.d_seeds, what)
+            evs[1].record(ln.stream)
+        ln.stream.synchronize()
+        sub[what] = evs[0].elapsed_time(evs[1]) / (args.breakdown_iters * G)   # ms per step
 
     # ---- per-kernel breakdown on one lane, serial: the library brackets each of its kernels with CUDA
     # events on the lane's stream (eu_ctx_profile); explains `value` and feeds the roofline
-    import ctypes
-    ln = lanes[0]
     Lh = len(counts)
     valid_edges = [0] * Lh
     lib.eu_ctx_profile(ln.ctx._h, 1)
@@ -357,7 +533,7 @@ def run_ours(args):
         exist (default-filled slots read nothing) and sampling reads only for rows that sample."""
         nm, rows = k["kernel"], k["rows"]
         hop = ln.n.index(rows) if rows in ln.n else 0
-        if nm == "k_sage_mean":
+        if nm.startswith("k_sage_mean"):
             c = counts[hop]
             return rows * c * 8 + valid_frac[hop] * rows * c * 4 * D + rows * 4 * D
         if nm == "k_feature":
@@ -385,20 +561,20 @@ def run_ours(args):
         k["frac_of_measured_hbm_peak"] = round(k["achieved_gbs"] / peak, 4)
     dom = kernels[0]
     # DRAM traffic of the dominant kernel from the committed ncu capture (same workload and launch shape only)
-    traffic, traffic_src = None, None
+    traffic, traffic_src, l2_hit = None, None, None
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-        default_shape = (args.nodes, args.edges, args.batch, args.fanout, args.dim, args.rng) == (10_000_000, 100_000_000, 1024, "25,10", 128, "minstd")
-        ent = tj["kernels"].get(dom["kernel"].split("<")[0], {}).get(str(dom["rows"]))
-        if default_shape and ent:
-            traffic, traffic_src = ent["dram_bytes_per_launch"], "profiles/r01_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        ent = tj.get(args.config, {}).get("kernels", {}).get(dom["kernel"].split("<")[0], {}).get(str(dom["rows"]))
+        if args.label != "custom" and ent:
+            traffic, l2_hit = ent["dram_bytes_per_launch"], ent.get("l2_hit_rate")
+            traffic_src = "profiles/r02_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": "%s over %d rows (largest share of the step)" % (dom["kernel"], dom["rows"]),
             "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac_of_measured_hbm_peak"],
-            "traffic": traffic, "traffic_source": traffic_src,
+            "traffic": traffic, "traffic_source": traffic_src, "l2_hit_rate": l2_hit,
             "note": "achieved = algorithmic bytes / live kernel time; a feature-gathering kernel re-reads hub rows from the 126 MB L2, "
-                    "so its algorithmic rate can exceed the HBM peak while `traffic` (DRAM bytes) stays below the algorithmic bytes",
+                    "so `traffic` (DRAM bytes) stays below the algorithmic bytes",
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 (B200_PROFILING.md)",
             "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "kernel_ms": round(dom["ms_per_launch"], 5),
             "valid_edge_fraction_per_hop": [round(v, 4) for v in valid_frac],
@@ -410,20 +586,33 @@ def run_ours(args):
         vf = 1.0 if l == 0 else valid_frac[l - 1]
         agg_bytes += ln.n[l] * 8 + vf * ln.n[l] * 4 * D + ln.n[l] * 4 * D
     agg_bytes /= G   # ln.n counts the rows of a whole launch group
+    cfg = workload_config(args, counts, 1)
+    e2e_dev = {"value": edges_step * args.steps / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / args.steps,
+               "api": "device entry points + pinned-tensor copies issued by the caller"}
+    if ms_host is not None:
+        e2e = {"value": edges_step * args.steps / (ms_host * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": lanes[0].h2d_host,
+               "d2h_bytes_per_step": lanes[0].d2h_host, "ms_per_step": ms_host / args.steps,
+               "api": "eu_sample_fanout_batched_host + eu_get_dense_feature_host + eu_sage_mean_aggregate_host (HOST buffers in and out; "
+                      "one host thread per lane); PCIe-bound: %.0f MB D2H per step" % (lanes[0].d2h_host / 1e6),
+               "pcie_gbs": round((lanes[0].d2h_host + lanes[0].h2d_host) * args.steps / (ms_host * 1e-3) / 1e9, 1),
+               "device_api_variant": e2e_dev}
+    else:
+        e2e = {"value": e2e_dev["value"], "unit": "edges/s", "h2d_bytes_per_step": lanes[0].h2d, "d2h_bytes_per_step": lanes[0].d2h,
+               "ms_per_step": e2e_dev["ms_per_step"], "api": e2e_dev["api"]}
     out = {
         "metric": "sampled_edges_per_sec", "value": value, "unit": "edges/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64 ids / f32 weights+features (f64 CDF compare)", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: RMAT %dM nodes/%dM edges in HBM, 2-hop sample_fanout %s batch=%d, "
-                               "GraphSAGE-mean aggregation, feat_dim=%d" % (args.nodes // 10**6, args.edges // 10**6, counts, args.batch, args.dim),
-                   "nodes": args.nodes, "edges": args.edges, "batch": args.batch, "fanout": counts, "feat_dim": args.dim,
-                   "rng": args.rng, "lanes_in_flight": args.lanes, "steps_per_launch_group": G, "cuda_graphs": use_graphs, "fused_aggregation": not args.no_fuse,
-                   "l2_policy": "inputs larger than L2 (%.1f GB graph, random seeds per step)" % (graph.hbm_bytes / 1e9),
-                   "parallelism": "1 GPU, %d streams x groups of %d independent batches per launch" % (args.lanes, G)},
+        "config": cfg,
+        "arm": {"lanes_in_flight": len(lanes), "steps_per_launch_group": G, "cuda_graphs": use_graphs, "fused_aggregation": not args.no_fuse,
+                "graph_hbm_gb": round(graph.hbm_bytes / 1e9, 1),
+                "parallelism": "1 GPU, %d streams x groups of %d independent batches per launch" % (len(lanes), G)},
+        "parity_gate": gate,
         "agg_feat_gbs": agg_bytes * args.steps / (ms * 1e-3) / 1e9,
-        "e2e": {"value": e2e_value, "unit": "edges/s", "h2d_bytes_per_step": lanes[0].h2d, "d2h_bytes_per_step": lanes[0].d2h,
-                "ms_per_step": ms_e2e / args.steps,
-                "note": "host seeds -> pinned -> H2D; D2H of hop ids + self features + neighbor means every step"},
+        "sub_rates": {"sampling_only_edges_per_s": edges_step / (sub["sample"] * 1e-3),
+                      "aggregation_only_gbs": agg_bytes / (sub["aggregate"] * 1e-3) / 1e9,
+                      "ms_per_step": {k: round(v, 5) for k, v in sub.items()}, "how": "one lane, serial launch groups, device-timed"},
+        "e2e": e2e,
         "gpu_launches": int(launches),
         "clocks": clk,
         "roofline": roof,
@@ -432,45 +621,104 @@ def run_ours(args):
         "graph_build_s": round(t_graph, 2), "hbm_graph_bytes": graph.hbm_bytes,
     }
     if not args.no_cpu_baseline and rank == 0:
-        out["cpu_baseline"] = cpu_baseline(graph, args, counts, host_seeds)
+        for ln_ in all_lanes:
+            del ln_.h_x, ln_.h_agg
+        out["cpu_baseline"] = cpu_baseline(args, counts)
     emit(out)
 
 
 # ----------------------------------------------------------------------------- sharded arm (N > 1)
+def sharded_gate(args, counts, graph, rank, world, torch, dist):
+    """N > 1 parity gate: one seeded batch per rank through the peer-memory exchange (csrc/p2p.cu) vs the SAME sharded
+    orchestration run with the CPU oracle as every shard's engine over a gloo group (euler_b200/sharded.py::ShardedGraph +
+    tests/sharded_common.py::OracleShardOps): ids / weights / types of every hop bit-exact on every rank."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import sharded_common as sc
+    from oracle import pyoracle as po
+    from euler_b200.sharded import PeerShardedGraph, ShardedGraph, TorchExchange
+    t0 = time.time()
+    B, L = args.batch, len(counts)
+    n = [B]
+    for c in counts:
+        n.append(n[-1] * c)
+    ex = graph.export(with_feat=False)
+
+    class GateOps(sc.OracleShardOps):
+        def __init__(self, seed):
+            self.torch = torch
+            self.og = po.OracleGraph(ex["ids"], ex["node_type"], ex["node_w"], 1, ex["grp_ptr"], ex["nbr"], ex["cum_w"],
+                                     np.zeros(len(ex["ids"]), np.float32))
+            po.seed(seed)
+    seeds = np.random.RandomState(777 + rank).randint(1, args.nodes + 1, size=B).astype(np.int64)
+    seeds[:4] = [0, -1, args.nodes + 99, seeds[5]]
+    ets = [[0]] * L
+    pg = PeerShardedGraph(graph, rank, world, max_rows=max(n[:-1]), max_count=max(counts), max_feat_rows=1, max_dim=4, rng="minstd",
+                          seed=9100 + rank)
+    p_ids, p_ws, p_ts = pg.sample_fanout(seeds, ets, counts, -1)
+    torch.cuda.synchronize()
+    err = pg.error()
+    gl = dist.new_group(backend="gloo")
+    sg = ShardedGraph(GateOps(9100 + rank), TorchExchange(gl))
+    o_ids, o_ws, o_ts = sg.sample_fanout(torch.from_numpy(seeds), ets, counts, -1)
+    bad = []
+    if err:
+        bad.append("peer exchange timed out")
+    for l in range(L):
+        for name, got, want in (("ids", p_ids[l + 1], o_ids[l + 1]), ("weights", p_ws[l], o_ws[l]), ("types", p_ts[l], o_ts[l])):
+            if not np.array_equal(got.cpu().numpy().reshape(-1), want.numpy().reshape(-1)):
+                bad.append("rank %d: %s of hop %d differ from the oracle-backed sharded run" % (rank, name, l + 1))
+    allbad = [None] * world
+    dist.all_gather_object(allbad, bad)
+    pg.close()
+    flat = [b for x in allbad for b in x]
+    if flat:
+        raise SystemExit("PARITY GATE FAILED: " + "; ".join(flat))
+    return {"passed": True, "ranks": world, "values_compared_per_rank": int(3 * sum(n[1:])), "seconds": round(time.time() - t0, 2),
+            "what": "one seeded batch per rank through the peer-memory exchange vs ShardedGraph over gloo with the C oracle as every "
+                    "shard's engine (same per-shard seeds): ids/weights/types of every hop bit-exact on every rank"}
+
+
 def run_sharded(args, world, rank, local):
-    """Weak scaling: the graph is hash-partitioned by id over the ranks (owner = id % N, Euler's shard scheme), every
-    rank constructs its own batch per step; each hop and the feature fetch resolve remote ids through an all-to-all over
-    NVLink -- by default done by the kernels themselves on peer memory (csrc/p2p.cu: no NCCL call, no host sync; the
-    whole step is one CUDA graph per lane), or with NCCL (--exchange nccl, euler_b200/sharded.py::ShardedGraph)."""
-    import ctypes
+    """Weak scaling: the graph's CSR is hash-partitioned by id over the ranks (owner = id % N, Euler's shard scheme), every
+    rank constructs its own batch per step; each hop resolves remote ids through an all-to-all over NVLink -- by default
+    done by the kernels themselves on peer memory (csrc/p2p.cu: no NCCL call, no host sync; the whole step is one CUDA graph
+    per lane), or with NCCL (--exchange nccl, euler_b200/sharded.py::ShardedGraph).  Dense features: replicated on every
+    rank by default (local fetch + aggregation), or sharded with their rows (--features sharded)."""
     import torch
     import torch.distributed as dist
     import euler_b200 as eb
     from euler_b200 import _lib
     from euler_b200.sharded import CudaShardOps, PeerShardedGraph, ShardedGraph, TorchExchange
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     counts = [int(x) for x in args.fanout.split(",")]
     L, B, D = len(counts), args.batch, args.dim
-    graph = eb.Graph.rmat_shard(args.nodes, args.edges, rank, world, feat_dim=D, device=local)
+    t0 = time.time()
     replicated = args.features == "replicated" and args.exchange == "peer"
+    graph = eb.Graph.rmat_shard(args.nodes, args.edges, rank, world, seed=GRAPH_SEED, feat_dim=0 if replicated else D,
+                                feat_seed=FEAT_SEED, device=local)
     feat_graph = None
     if replicated:
         # all feature rows on every rank: the generator's features are a hash of (global node index, column), so a full-node
-        # graph with a token number of edges carries exactly the rows the shards hold
-        feat_graph = eb.Graph.rmat(args.nodes, 1024, feat_dim=D, device=local)
+        # graph with a token number of edges carries exactly the rows the shards would hold
+        feat_graph = eb.Graph.rmat(args.nodes, 1024, seed=GRAPH_SEED, feat_dim=D, feat_seed=FEAT_SEED, device=local)
+    torch.cuda.synchronize()
+    t_graph = time.time() - t0
     n = [B]
     for c in counts:
         n.append(n[-1] * c)
-    import math
     peer = args.exchange == "peer"
-    n_lanes = args.lanes if peer else 1
+    gate = {"passed": None, "skipped": "--no-gate"}
+    if not args.no_gate and peer and args.rng == "minstd":
+        gate = sharded_gate(args, counts, graph, rank, world, torch, dist)
     # launch group: G batches share every exchange (peer path) -- the kernels and NVLink round trips of an exchange are paid
     # once per G steps; each batch keeps its own engine and dedup scope on every shard (eu_sym_sample_hop_batched)
-    G = max(1, min(args.group, args.steps)) if peer else 1
+    G = auto_group(args, counts) if peer else 1
+    n_lanes = max(1, min(args.lanes, args.steps // G if args.steps >= G else 1)) if peer else 1
     tail = args.steps % G                 # exactly K steps: K // G full groups + one tail group of K % G batches
-    src = [torch.arange(n[l], dtype=torch.int32, device="cuda").repeat_interleave(counts[l]) for l in range(L)]
+    src = [torch.arange(n[l], dtype=torch.int32, device="cuda").repeat_interleave(counts[l]) for l in range(L)] if not peer else None
     n_self = sum(n[:L])                   # rows whose own features are materialised (hop 0 .. L-1)
 
     class SLane:
@@ -483,8 +731,9 @@ def run_sharded(args, world, rank, local):
         ln.stream = torch.cuda.Stream()
         seed = 12345 + rank * 1000 + i * 64
         if peer:
+            feat_rows = 1 if replicated else G * max(max(n), world * max(n[:-1]))
             ln.sg = PeerShardedGraph(graph, rank, world, max_rows=G * max(n[:-1]), max_count=max(counts),
-                                     max_feat_rows=G * max(max(n), world * max(n[:-1])), max_dim=D, rng=args.rng, seed=seed, engines=G)
+                                     max_feat_rows=feat_rows, max_dim=4 if replicated else D, rng=args.rng, seed=seed, engines=G)
             ln.ctx = ln.sg.ctx
         else:
             ln.ops = CudaShardOps(graph, args.rng, seed)
@@ -506,7 +755,6 @@ def run_sharded(args, world, rank, local):
         ln.h_agg = [torch.empty((G * n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
         if replicated:
             ln.fctx = eb.Context(feat_graph, args.rng, seed + 7, ln.stream.cuda_stream)
-            ln.x_local = torch.empty((G * n_self, D), dtype=torch.float32, device="cuda")
         G = G_main
         lanes.append(ln)
     tail_lane = lanes.pop() if tail else None
@@ -528,12 +776,12 @@ def run_sharded(args, world, rank, local):
                 # every rank holds all feature rows: fetch + aggregation are the single-GPU kernels, nothing crosses NVLink
                 h = ln.fctx._h
                 ln.fctx.set_stream(torch.cuda.current_stream().cuda_stream)
-                rc = lib.eu_get_dense_feature(h, ln.idbuf.data_ptr(), G * n_self, 0, D, ln.x_local.data_ptr())
+                rc = lib.eu_get_dense_feature(h, ln.idbuf.data_ptr(), G * n_self, 0, D, ln.x.data_ptr())
                 for l in range(L):
                     rc |= lib.eu_sage_mean_aggregate(h, ln.ids[l].data_ptr(), G * n[l], counts[l], D, ln.agg[l].data_ptr())
                 if rc:
                     raise RuntimeError(lib.eu_last_error().decode())
-                ln.x_view = ln.x_local
+                ln.x_view = ln.x
                 return
             # the hop-(l+1) features are summed by their owners and never cross NVLink row by row
             for l in range(L):
@@ -556,7 +804,7 @@ def run_sharded(args, world, rank, local):
             if rc:
                 raise RuntimeError(lib.eu_last_error().decode())
 
-    n_seed_groups = max(-(-(args.warmup + args.steps) // G), 16)
+    n_seed_groups = max(-(-(args.warmup + args.steps) // G), 8)
     host_seeds = np.stack([np.random.RandomState(1000 + rank * 100003 + i).randint(1, args.nodes + 1, size=(G, B))
                            for i in range(n_seed_groups)]).astype(np.int64)
     dev_seeds = torch.from_numpy(host_seeds).cuda()
@@ -637,8 +885,10 @@ def run_sharded(args, world, rank, local):
     # per-kernel breakdown + launch count on one lane (library-side CUDA events), serial, no graphs
     prof = {}
     ln = lanes[0]
-    reps = 4
+    reps = 3
     lib.eu_ctx_profile(ln.ctx._h, 1)
+    if replicated:
+        lib.eu_ctx_profile(ln.fctx._h, 1)
     l0 = lib.eu_launch_count()
     with torch.cuda.stream(ln.stream):
         for it in range(reps):
@@ -646,12 +896,13 @@ def run_sharded(args, world, rank, local):
             raw_step(ln)
     ln.stream.synchronize()
     launches_per_group = (lib.eu_launch_count() - l0) / reps
-    buf = ctypes.create_string_buffer(1 << 16)
-    lib.eu_ctx_profile_read(ln.ctx._h, buf, len(buf))
-    lib.eu_ctx_profile(ln.ctx._h, 0)
-    for line in buf.value.decode().strip().splitlines():
-        nm, rows_, cnt_, ms_tot = line.split(",")
-        prof["%s[rows=%s]" % (nm, rows_)] = round(float(ms_tot) / reps / G, 4)
+    for hctx in [ln.ctx] + ([ln.fctx] if replicated else []):
+        buf = ctypes.create_string_buffer(1 << 16)
+        lib.eu_ctx_profile_read(hctx._h, buf, len(buf))
+        lib.eu_ctx_profile(hctx._h, 0)
+        for line in buf.value.decode().strip().splitlines():
+            nm, rows_, cnt_, ms_tot = line.split(",")
+            prof["%s[rows=%s]" % (nm, rows_)] = round(float(ms_tot) / reps / G, 4)
     all_prof = [None] * world
     dist.all_gather_object(all_prof, prof)
     if os.environ.get("EU_BENCH_DEBUG") and rank == 0:
@@ -684,38 +935,44 @@ def run_sharded(args, world, rank, local):
     else:
         a2a_bytes += remote * sum(n) * (12 + 4 * D)
     if rank == 0:
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+            ent = tj.get(args.config, {}).get("nvlink", {}).get(str(world))
+            if ent and args.label != "custom":
+                traffic, traffic_src = ent["nvlink_bytes_per_step_per_rank"], ent.get("source")
+        except Exception:
+            pass
         out = {
             "metric": "sampled_edges_per_sec", "value": edges_step * args.steps / (ms * 1e-3), "unit": "edges/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u64 ids / f32 weights+features (f64 CDF compare)", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1] sharded: RMAT %dM nodes/%dM edges hash-partitioned by id over %d GPUs, per rank "
-                                   "2-hop sample_fanout %s batch=%d + dense features (dim %d) + GraphSAGE mean, all-to-all per hop"
-                                   % (args.nodes // 10**6, args.edges // 10**6, world, counts, B, D),
-                       "nodes": args.nodes, "edges": args.edges, "batch_per_gpu": B, "global_batch": B * world, "fanout": counts,
-                       "feat_dim": D, "rng": args.rng, "exchange": "peer-memory kernels (NVLink loads/stores, no NCCL)" if peer else "NCCL all_to_all",
-                       "lanes_in_flight": n_lanes, "steps_per_launch_group": G, "cuda_graphs": use_graphs, "peer_wait_timeouts": err,
-                       "aggregation": ("features replicated on every rank (%.1f GB): local k_feature / k_sage_mean" % (args.nodes * D * 4 / 1e9)) if replicated
-                                      else ("fused at the owners (eu_sym_sage_mean: one partial row per owner and destination)" if peer else "materialised rows + scatter_mean"),
-                       "features": "replicated" if replicated else "sharded with their rows",
-                       "parallelism": "graph sharded id %% %d, batches data-parallel" % world,
-                       "l2_policy": "inputs larger than L2 (random seeds per step over a %.1f GB shard)" % (graph.hbm_bytes / 1e9)},
+            "config": workload_config(args, counts, world),
+            "arm": {"global_batch": B * world, "exchange": "peer-memory kernels (NVLink loads/stores, no NCCL)" if peer else "NCCL all_to_all",
+                    "lanes_in_flight": n_lanes, "steps_per_launch_group": G, "cuda_graphs": use_graphs, "peer_wait_timeouts": err,
+                    "aggregation": ("features replicated on every rank (%.1f GB): local k_feature / k_sage_mean" % (args.nodes * D * 4 / 1e9)) if replicated
+                                   else ("fused at the owners (eu_sym_sage_mean: one partial row per owner and destination)" if peer else "materialised rows + scatter_mean"),
+                    "features": "replicated" if replicated else "sharded with their rows",
+                    "parallelism": "CSR sharded id %% %d, batches data-parallel" % world,
+                    "hbm_gb_per_rank": round((graph.hbm_bytes + (feat_graph.hbm_bytes if feat_graph else 0)) / 1e9, 1)},
+            "parity_gate": gate,
             "e2e": {"value": edges_step * args.steps / (ms_e2e * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": 8 * B * world,
                     "d2h_bytes_per_step": world * (sum(8 * x for x in n[1:]) + 2 * sum(4 * n[l] * D for l in range(L))),
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(round(launches_per_group * (args.steps // G + (1 if tail else 0)))), "clocks": clk,
-            "roofline": {"bound": "nvlink", "kernel": "exchange kernels (k_bucket_place / k_sym_reply_sample / k_sym_reply_sage / k_sym_reply_feature)" if peer else "NCCL all-to-all",
+            "roofline": {"bound": "nvlink", "kernel": "exchange kernels (k_bucket_place / k_sym_reply_sample%s)" % ("" if replicated else " / k_sym_reply_sage / k_sym_reply_feature") if peer else "NCCL all-to-all",
                          "achieved": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9, 2), "peak": 770.0, "unit": "GB/s",
-                         "frac": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9 / 770.0, 4), "traffic": None,
+                         "frac": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9 / 770.0, 4), "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "B200_PROFILING.md measured peer copy 770 GB/s per direction",
                          "algorithmic_bytes_per_step_per_rank": int(a2a_bytes),
-                         "note": "achieved = algorithmic exchange bytes per rank per step / whole step time (the exchange is not timed alone); "
-                                 "partial aggregation rows counted at their expected presence-pruned number"},
-            "hbm_graph_bytes_per_rank": graph.hbm_bytes,
+                         "note": "achieved = algorithmic exchange bytes per rank per step / whole step time (the exchange overlaps the local "
+                                 "kernels of the other lanes and is not timed alone)"},
+            "graph_build_s": round(t_graph, 2),
             "kernel_ms_per_step_single_lane": dict(sorted(prof.items(), key=lambda kv: -kv[1])),
         }
         if use_graphs:
-            out["config"]["launch"] = "one CUDA graph replay per launch group; gpu_launches counts this library's kernels inside the replays"
+            out["arm"]["launch"] = "one CUDA graph replay per launch group; gpu_launches counts this library's kernels inside the replays"
         emit(out)
     if peer:
         for ln in all_lanes:
@@ -731,117 +988,140 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def build_cpu_graph(ex, args, use_ref):
+def cpu_graph(args):
+    """The CPU arms' input: the same generator (oracle/rmat_gen.c restates euler_b200/csrc/graph.cu bit-exactly; nothing of
+    the product is loaded), at the bench's size when the reference's in-memory graph can be built inside the time box, else
+    down-scaled at constant mean degree -- which favours the CPU (its working set shrinks; the GPU arm keeps the full graph)."""
     from oracle import pyoracle as po
-    n = len(ex["ids"])
+    nodes, edges = args.nodes, args.edges
+    scale = 1.0
+    if nodes > CPU_GRAPH_MAX_NODES:
+        scale = CPU_GRAPH_MAX_NODES / nodes
+        nodes, edges = CPU_GRAPH_MAX_NODES, int(edges * scale)
+    t0 = time.time()
+    ex = po.rmat_graph(nodes, edges, seed=GRAPH_SEED, feat_dim=args.dim, feat_seed=FEAT_SEED)
+    use_ref = po.have_ref()
     if use_ref:
         # raw weights are needed by Node::Init; de-cumulate exactly as stored differences
-        cum = ex["cum_w"]
-        ptr = ex["grp_ptr"]
+        cum, ptr = ex["cum_w"], ex["grp_ptr"]
         w = np.diff(cum, prepend=np.float32(0)).astype(np.float32)
         first = ptr[:-1][np.diff(ptr) > 0]
         w[first] = cum[first]
-        return po.RefGraph.build(ex["ids"], ex["node_type"], ex["node_w"], 1, ptr, ex["nbr"], w, 1,
-                                 ex["feat"], sampler=False), None
-    og = po.OracleGraph(ex["ids"], ex["node_type"], ex["node_w"], 1, ex["grp_ptr"], ex["nbr"], ex["cum_w"],
-                        np.zeros(n, np.float32), ex["feat"])
-    return None, og
+        rg = po.RefGraph.build(ex["ids"], ex["node_type"], ex["node_w"], 1, ptr, ex["nbr"], w, 1, ex["feat"], sampler=False)
+        og = None
+    else:
+        rg = None
+        og = po.OracleGraph(ex["ids"], ex["node_type"], ex["node_w"], 1, ex["grp_ptr"], ex["nbr"], ex["cum_w"],
+                            np.zeros(nodes, np.float32), ex["feat"])
+    info = {"nodes": nodes, "edges": edges, "scale_vs_gpu_arm": scale, "build_s": round(time.time() - t0, 1),
+            "note": "full size" if scale == 1.0 else "down-scaled on the CPU side only (same generator, same mean degree): the reference's "
+                    "unordered_map<NodeID,Node*> graph of the full size does not build inside the bench's time box"}
+    return rg, og, ex, nodes, info
 
 
-def time_cpu(rg, og, args, counts, host_seeds, threads, target_s):
-    from oracle import pyoracle as po
-    et = [[0]] * len(counts)
-    seeds = host_seeds[:64]
-    fn = (lambda it: po.ref_bench_step(seeds, et, counts, args.dim, threads, it)) if rg is not None else \
-         (lambda it: po.oracle_bench_step(og, seeds, et, counts, args.dim, threads, it))
-    sec, edges = fn(1)
-    iters = max(1, min(200, int(target_s / max(sec, 1e-3))))
-    if iters > 1:
-        sec, edges = fn(iters)
-    return edges / sec, sec, iters
+class CpuStep:
+    def __init__(self, args, counts, rg, og, nodes):
+        from oracle import pyoracle as po
+        self.po, self.rg, self.og, self.args, self.counts = po, rg, og, args, counts
+        self.et = [[0]] * len(counts)
+        self.seeds = np.stack([np.random.RandomState(1000 + i).randint(1, nodes + 1, size=args.batch) for i in range(64)]).astype(np.int64)
+
+    def step(self, threads, iters):
+        """(seconds, edges): every thread runs `iters` full steps (sample_fanout + dense features of every hop + neighbor means)"""
+        po = self.po
+        if self.rg is not None:
+            return po.ref_bench_step(self.seeds, self.et, self.counts, self.args.dim, threads, iters)
+        return po.oracle_bench_step(self.og, self.seeds, self.et, self.counts, self.args.dim, threads, iters)
+
+    def fanout(self, threads, iters):
+        """(seconds, edges): sampling only"""
+        po = self.po
+        if self.rg is not None:
+            return self.rg.bench_fanout(self.seeds, self.et, self.counts, threads, iters)
+        return self.og.bench_fanout(self.seeds, self.et, self.counts, threads, iters)
+
+    def best_threads(self, cores):
+        """the reference links jemalloc (CMakeLists.txt:13,41-43), absent here: with glibc malloc its
+        vector<vector<vector<float>>> feature path scales badly, so sweep thread counts and keep the best"""
+        sweep, best = {}, (0.0, 1)
+        for th in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 16), min(cores, 8), 1}, reverse=True):
+            self.step(th, 1)
+            sec, edges = self.step(th, 1)
+            sweep[str(th)] = edges / sec
+            if edges / sec > best[0]:
+                best = (edges / sec, th)
+        return best[1], sweep
 
 
-def cpu_baseline(graph, args, counts, host_seeds):
+def cpu_sub_rates(cs, args, counts, th, iters):
+    """sampling-only edges/s and aggregation-only GB/s (algorithmic bytes) of the CPU path at `th` threads"""
+    bts = step_bytes(args.batch, counts, args.dim)
+    cs.fanout(th, 1)
+    f_sec, f_edges = cs.fanout(th, iters)
+    s_sec, s_edges = cs.step(th, iters)
+    agg_sec = max(s_sec - f_sec, 1e-9)
+    batches = s_edges / bts["edges"]
+    return {"sampling_only_edges_per_s": f_edges / f_sec, "aggregation_only_gbs": (bts["agg"] + bts["self_feat"]) * batches / agg_sec / 1e9,
+            "how": "%d threads x %d batches: sampling-only loop timed alone; aggregation = full-step time minus sampling-only time" % (th, iters)}
+
+
+def cpu_baseline(args, counts):
     """cpu_baseline leg: the reference's own sources (oracle/_ref, kind "reference") when the prebuilt
-    shim travelled with the repo, else the C restatement (kind "port"); all host cores, bounded sample."""
-    from oracle import pyoracle as po
-    use_ref = po.have_ref()
-    ex = graph.export(with_feat=True)
-    rg, og = build_cpu_graph(ex, args, use_ref)
+    shim travelled with the repo, else the C restatement (kind "port"); best thread count, bounded sample."""
+    rg, og, ex, nodes, info = cpu_graph(args)
+    cs = CpuStep(args, counts, rg, og, nodes)
     cores = host_cores()
-    # the reference links jemalloc (CMakeLists.txt:13,41-43), absent here: with glibc malloc its
-    # vector<vector<vector<float>>> feature path scales badly, so sweep thread counts and keep the best
-    sweep = {}
-    best = (0.0, 0, 0.0, 0)
-    for th in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 16), min(cores, 8), 1}, reverse=True):
-        v, sec, iters = time_cpu(rg, og, args, counts, host_seeds, th, args.cpu_seconds / 5.0)
-        sweep[str(th)] = v
-        if v > best[0]:
-            best = (v, th, sec, iters)
-    v, th, sec, iters = best
-    return {"value": v, "unit": "edges/s", "cores": th, "host_cores": cores, "kind": "reference" if use_ref else "port",
-            "sample": "best of a thread sweep: %d threads x %d batches of the same step (sample_fanout + dense features "
-                      "of every hop + neighbor means) on the same exported graph, %.1f s" % (th, iters, sec),
-            "threads_sweep_edges_per_s": sweep}
+    th, sweep = cs.best_threads(cores)
+    sec1, _ = cs.step(th, 1)
+    iters = max(1, min(50, int(args.cpu_seconds / max(sec1, 1e-3))))
+    sec, edges = cs.step(th, iters)
+    one_sec, one_edges = cs.step(1, 1)
+    return {"value": edges / sec, "unit": "edges/s", "cores": th, "host_cores": cores, "kind": "reference" if rg is not None else "port",
+            "sample": "best of a thread sweep: %d threads x %d batches of the same step (sample_fanout + dense features of every hop + "
+                      "neighbor means), %.1f s" % (th, iters, sec),
+            "one_thread_edges_per_s": one_edges / one_sec,
+            "threads_sweep_edges_per_s": sweep, "sub_rates": cpu_sub_rates(cs, args, counts, th, max(1, iters // 2)), "cpu_graph": info}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the same step on the host cores."""
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+    """--impl reference: the reference's CPU implementation of the same step on the host cores.  Loads nothing of the
+    product: the input graph comes from oracle/rmat_gen.c."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    import euler_b200 as eb
-    from oracle import pyoracle as po
     counts = [int(x) for x in args.fanout.split(",")]
-    # inputs: the same synthetic graph, generated on the device and exported (not timed)
-    graph = eb.Graph.rmat(args.nodes, args.edges, feat_dim=args.dim, device=0)
-    ex = graph.export(with_feat=True)
-    graph.close()
-    torch.cuda.empty_cache()
-    use_ref = po.have_ref()
-    rg, og = build_cpu_graph(ex, args, use_ref)
+    rg, og, ex, nodes, info = cpu_graph(args)
+    cs = CpuStep(args, counts, rg, og, nodes)
     cores = host_cores()
-    nb = max(args.warmup + args.steps, 64)
-    host_seeds = np.stack([np.random.RandomState(1000 + i).randint(1, args.nodes + 1, size=args.batch)
-                           for i in range(nb)]).astype(np.int64)
-    et = [[0]] * len(counts)
-
-    def fn(sd, it, th):
-        return po.ref_bench_step(sd, et, counts, args.dim, th, it) if use_ref else po.oracle_bench_step(og, sd, et, counts, args.dim, th, it)
-    # untimed: pick the thread count the reference runs fastest with on this host (it links jemalloc upstream,
-    # CMakeLists.txt:13,41-43; with glibc malloc more threads are not always faster) -- its best case is the baseline
-    best_th, best_v = cores, 0.0
-    for th in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 16), min(cores, 8)}, reverse=True):
-        sec, edges = fn(host_seeds[:64], 1, th)
-        sec, edges = fn(host_seeds[:64], 1, th)
-        if edges / sec > best_v:
-            best_th, best_v = th, edges / sec
-    cores_used = best_th
+    # untimed: pick the thread count the reference runs fastest with on this host -- its best case is the baseline
+    th, sweep = cs.best_threads(cores)
     # a "step" of this arm = one bounded sample: every thread runs PER_STEP batches back to back (its first batch after a
-    # thread start pays the allocator warm-up; a single batch per step would understate the reference by ~2x)
-    PER_STEP = 4
-    sec1, _ = fn(host_seeds[:64], PER_STEP, cores_used)
-    steps = max(1, min(args.steps, int(90.0 / max(sec1, 1e-3))))     # whole run bounded to ~1.5 minutes
-    warm = min(args.warmup, 2)
+    # thread start pays the allocator warm-up; a single batch per step would understate the reference)
+    PER_STEP = 2
+    sec1, _ = cs.step(th, PER_STEP)
+    budget = 150.0                                    # seconds for warm-up + timed steps
+    steps = max(1, min(args.steps, int(budget / max(sec1, 1e-3)) - args.warmup))
+    warm = args.warmup if steps == args.steps else min(args.warmup, 1)
     for _ in range(warm):
-        fn(host_seeds[:64], PER_STEP, cores_used)
+        cs.step(th, PER_STEP)
     t_edges, t_sec = 0, 0.0
     for _ in range(steps):
-        sec, edges = fn(host_seeds[:64], PER_STEP, cores_used)
+        sec, edges = cs.step(th, PER_STEP)
         t_edges += edges
         t_sec += sec
     v = t_edges / t_sec
-    cores = cores_used
+    sub = cpu_sub_rates(cs, args, counts, th, PER_STEP)
+    bts = step_bytes(args.batch, counts, args.dim)
     out = {"impl": "reference", "metric": "sampled_edges_per_sec", "value": v, "unit": "edges/s",
            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * t_sec / steps,
-           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 ids / f32", "data": "synthetic",
-           "config": {"workload": "BASELINE configs[1]: RMAT %dM nodes/%dM edges, 2-hop sample_fanout %s batch=%d, GraphSAGE-mean "
-                                  "aggregation, feat_dim=%d" % (args.nodes // 10**6, args.edges // 10**6, counts, args.batch, args.dim),
-                      "step": "one bounded sample = %d host threads x %d batches each" % (cores, PER_STEP)},
-           "cpu_baseline": {"value": v, "unit": "edges/s", "cores": cores, "kind": "reference" if use_ref else "port",
-                            "sample": "%d steps of %d threads x %d batches" % (steps, cores, PER_STEP)},
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 ids / f32 weights+features (f64 CDF compare)",
+           "data": "synthetic", "config": workload_config(args, counts, args.gpus),
+           "arm": {"step": "one bounded sample = %d host threads x %d batches each" % (th, PER_STEP), "cpu_graph": info,
+                   "threads_sweep_edges_per_s": sweep, "host_cores": cores},
+           "agg_feat_gbs": (bts["agg"] + bts["self_feat"]) * (t_edges / bts["edges"]) / t_sec / 1e9,
+           "sub_rates": sub,
+           "cpu_baseline": {"value": v, "unit": "edges/s", "cores": th, "kind": "reference" if rg is not None else "port",
+                            "sample": "%d steps of %d threads x %d batches" % (steps, th, PER_STEP)},
            "e2e": {"value": v, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     emit(out)

@@ -171,22 +171,25 @@ __global__ void k_check_adj_sorted(int64_t n_groups, const int64_t* grp_ptr, con
 
 static int build_hash(eu_graph* g) {
   DevGraph& d = g->d;
-  unsigned long long cap = 64;
-  while (cap < (unsigned long long)d.n * 2) cap <<= 1;
-  HashSlot* tab = nullptr;
-  int rc = g->alloc(&tab, (int64_t)cap);
-  if (rc) return rc;
   const int tb = 256;
-  k_hash_clear<<<(unsigned)ceil_div(cap, tb), tb>>>(tab, cap);
-  EU_LAUNCHED();
-  if (d.n > 0) {
-    k_hash_insert<<<(unsigned)ceil_div(d.n, tb), tb>>>(tab, cap - 1, d.ids, d.n);
+  if (!d.dense_ids) {   // ids in arithmetic progression resolve by arithmetic (lookup_row): no table (4.3 GB at 100M nodes)
+    unsigned long long cap = 64;
+    while (cap < (unsigned long long)d.n * 2) cap <<= 1;
+    HashSlot* tab = nullptr;
+    int rc = g->alloc(&tab, (int64_t)cap);
+    if (rc) return rc;
+    k_hash_clear<<<(unsigned)ceil_div(cap, tb), tb>>>(tab, cap);
     EU_LAUNCHED();
+    if (d.n > 0) {
+      k_hash_insert<<<(unsigned)ceil_div(d.n, tb), tb>>>(tab, cap - 1, d.ids, d.n);
+      EU_LAUNCHED();
+    }
+    k_hash_finalize<<<(unsigned)ceil_div(cap, tb), tb>>>(tab, cap);
+    EU_LAUNCHED();
+    EU_CUDA(cudaDeviceSynchronize());
+    d.htab = tab;
+    d.hmask = cap - 1;
   }
-  k_hash_finalize<<<(unsigned)ceil_div(cap, tb), tb>>>(tab, cap);
-  EU_LAUNCHED();
-  EU_CUDA(cudaDeviceSynchronize());
-  d.htab = tab;
   {
     int* flag = nullptr;
     EU_CUDA(cudaMalloc(&flag, sizeof(int)));
@@ -200,7 +203,6 @@ static int build_hash(eu_graph* g) {
     cudaFree(flag);
     d.adj_sorted = h ? 0 : 1;
   }
-  d.hmask = cap - 1;
   return EU_OK;
 }
 
@@ -337,6 +339,10 @@ int eu_graph_create(const eu_graph_desc* desc, int device, eu_graph** out) {
     set_error("eu_graph_create: invalid descriptor");
     return EU_ERR_INVALID;
   }
+  // id 2^64-1 cannot be a node: the id -> row table stores id + 1 with 0 = "slot not published yet" (and the reference's own
+  // id 0 is unusable the same way, DEFAULT_UINT64)
+  for (int64_t r = 0; r < desc->n_nodes; ++r)
+    if (desc->ids[r] == ~0ull) { set_error("eu_graph_create: node id 2^64-1 is not supported"); return EU_ERR_UNSUPPORTED; }
   int rc = check_device(device);
   if (rc) return rc;
   eu_graph* g = new eu_graph();

@@ -15,8 +15,9 @@
  *     stream-ordered; different ctxs may run concurrently; the graph is immutable after creation;
  *   - functions without a `_host` suffix take DEVICE pointers and only enqueue work on the ctx
  *     stream (no host synchronisation, capturable in a CUDA graph);
- *   - `_host` variants take HOST pointers, stage through pinned buffers owned by the ctx, and
- *     return after the results have landed (this is what a CPU-tensor framework binds);
+ *   - `_host` variants take HOST pointers and return after the results have landed (this is what a
+ *     CPU-tensor framework binds): pageable buffers are staged through pinned memory owned by the ctx,
+ *     buffers that are already page-locked (cudaHostAlloc / cudaHostRegister) are DMA'd in place;
  *   - edge-type / count lists are HOST arrays (they are op attributes / tiny tensors upstream).
  */
 #ifndef EULER_B200_H_
@@ -164,6 +165,9 @@ int eu_sample_fanout_batched(eu_ctx* c, const int64_t* nodes, int32_t nb, int64_
 int eu_sample_fanout_host(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes,
                           int32_t K, const int32_t* counts, int32_t L, int64_t default_node,
                           int64_t* const* out_ids, float* const* out_w, int32_t* const* out_t);
+int eu_sample_fanout_batched_host(eu_ctx* c, const int64_t* nodes, int32_t nb, int64_t B, const int32_t* etypes,
+                                  int32_t K, const int32_t* counts, int32_t L, int64_t default_node,
+                                  int64_t* const* out_ids, float* const* out_w, int32_t* const* out_t);
 /* tf_euler.sample_node -- TF op SampleNode (tf_euler/ops/sample_ops.cc:22-37, kernel
  * tf_euler/kernels/sample_node_op.cc:39-96; euler::SampleNode api.cc:32-37).  types i32[n_types]
  * (host); a single -1 means all types.  out i64[count]. */
@@ -223,6 +227,8 @@ int eu_scatter_mean(eu_ctx* c, const float* updates, int64_t D, const int32_t* i
  * divisor; ids not in the graph (default fill) contribute zeros, as get_dense_feature would. */
 int eu_sage_mean_aggregate(eu_ctx* c, const int64_t* nbr_ids, int64_t rows, int32_t count,
                            int32_t dim, float* out);
+int eu_sage_mean_aggregate_host(eu_ctx* c, const int64_t* nbr_ids, int64_t rows, int32_t count,
+                                int32_t dim, float* out);
 int eu_gather_host(eu_ctx* c, const float* params, int64_t N, int64_t D, const int32_t* idx,
                    int64_t E, float* out);
 int eu_scatter_add_host(eu_ctx* c, const float* updates, int64_t D, const int32_t* idx, int64_t E,

@@ -67,6 +67,10 @@ struct eo_graph {
   uint64_t cap;
   uint64_t* hkey;
   int64_t* hval;
+  /* ids[r] == id_base + r * id_stride for all r (synthetic graphs, shards of them): the lookup is arithmetic and no
+   * table is built (a 100M-node table would take minutes to fill; the answer is the same) */
+  int dense;
+  uint64_t id_base, id_stride;
 };
 
 static inline uint64_t eo_mix(uint64_t k) {
@@ -82,6 +86,12 @@ eo_graph* eo_graph_create(int64_t n, int32_t T, const uint64_t* ids, const int32
   g->n = n; g->T = T; g->ids = ids; g->node_type = node_type; g->node_w = node_w;
   g->grp_ptr = grp_ptr; g->nbr = nbr; g->cum_w = cum_w; g->grp_cum = grp_cum;
   g->feat_dim = feat_dim; g->feat = feat;
+  if (n > 1 && ids[1] > ids[0]) {
+    const uint64_t st = ids[1] - ids[0];
+    int dense = 1;
+    for (int64_t r = 2; r < n && dense; ++r) dense = ids[r] == ids[0] + (uint64_t)r * st;
+    if (dense) { g->dense = 1; g->id_base = ids[0]; g->id_stride = st; return g; }
+  }
   uint64_t cap = 16;
   while (cap < (uint64_t)n * 2) cap <<= 1;
   g->cap = cap;
@@ -103,6 +113,11 @@ void eo_graph_destroy(eo_graph* g) {
 }
 
 int64_t eo_graph_row(const eo_graph* g, uint64_t id) {
+  if (g->dense) {
+    if (id < g->id_base || (id - g->id_base) % g->id_stride) return -1;
+    const uint64_t r = (id - g->id_base) / g->id_stride;
+    return r < (uint64_t)g->n ? (int64_t)r : -1;
+  }
   uint64_t h = eo_mix(id) & (g->cap - 1);
   while (g->hval[h] >= 0) {
     if (g->hkey[h] == id) return g->hval[h];

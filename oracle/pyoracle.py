@@ -26,8 +26,8 @@ f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
 
 def build(force=False):
     """Compile the C restatement (and, if /root/reference exists, the reference shim)."""
-    if force or not os.path.exists(ORACLE_SO) or (
-            os.path.getmtime(ORACLE_SO) < os.path.getmtime(os.path.join(_HERE, "euler_oracle.c"))):
+    srcs = [os.path.join(_HERE, f) for f in ("euler_oracle.c", "rmat_gen.c", "euler_oracle.h")]
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "oracle"], stdout=subprocess.DEVNULL)
     if os.path.exists("/root/reference/euler/core/api/api.cc"):
         subprocess.check_call(["make", "-C", _HERE, "-j8", "ref"], stdout=subprocess.DEVNULL)
@@ -112,8 +112,37 @@ def lib():
         L.eo_bench_step.restype = C.c_double
         L.eo_bench_step.argtypes = [C.c_void_p, i64p, C.c_int64, C.c_int64, i32p, C.c_int32, i32p,
                                     C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
+        L.eo_rmat_csr.restype = C.c_int
+        L.eo_rmat_csr.argtypes = [C.c_int64, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_int32,
+                                  C.c_int32, C.c_int32, u64p, i32p, f32p, i64p, u64p, f32p, C.c_void_p]
+        L.eo_rmat_feat_rows.argtypes = [i64p, C.c_int64, C.c_int64, C.c_int32, C.c_uint64, f32p]
+        L.eo_rmat_feat_full.argtypes = [C.c_int64, C.c_int32, C.c_uint64, C.c_int32, f32p]
         _lib = L
     return _lib
+
+
+def rmat_graph(n_nodes, n_edges, a=0.57, b=0.19, c=0.19, seed=42, feat_dim=0, feat_seed=7, T=1, NT=1, threads=None):
+    """Host copy of euler_b200.Graph.rmat / rmat_hetero (oracle/rmat_gen.c): the same dict Graph.export() returns."""
+    threads = threads or max(1, len(os.sched_getaffinity(0)))
+    out = dict(ids=np.zeros(n_nodes, np.uint64), node_type=np.zeros(n_nodes, np.int32), node_w=np.zeros(n_nodes, np.float32),
+               grp_ptr=np.zeros(n_nodes * T + 1, np.int64), nbr=np.zeros(n_edges, np.uint64),
+               cum_w=np.zeros(n_edges, np.float32), grp_cum=np.zeros(n_nodes * T, np.float32) if T > 1 else None, feat=None, T=T)
+    rc = lib().eo_rmat_csr(n_nodes, n_edges, a, b, c, seed, T, NT, threads, out["ids"], out["node_type"], out["node_w"],
+                           out["grp_ptr"], out["nbr"], out["cum_w"], None if T == 1 else out["grp_cum"].ctypes.data)
+    if rc:
+        raise RuntimeError("eo_rmat_csr failed")
+    if feat_dim:
+        out["feat"] = np.zeros((n_nodes, feat_dim), np.float32)
+        lib().eo_rmat_feat_full(n_nodes, feat_dim, feat_seed, threads, out["feat"].reshape(-1))
+    return out
+
+
+def rmat_feat_rows(ids, n_nodes, dim, feat_seed=7):
+    """feature rows of the synthetic graph for `ids` (zeros for ids that are not nodes), f32[len(ids), dim]"""
+    ids = _arr(ids, np.int64).reshape(-1)
+    out = np.zeros((len(ids), dim), np.float32)
+    lib().eo_rmat_feat_rows(ids, len(ids), n_nodes, dim, feat_seed, out.reshape(-1))
+    return out
 
 
 class Rng(C.Structure):
