@@ -733,7 +733,8 @@ def run_sharded(args, world, rank, local):
         if peer:
             feat_rows = 1 if replicated else G * max(max(n), world * max(n[:-1]))
             ln.sg = PeerShardedGraph(graph, rank, world, max_rows=G * max(n[:-1]), max_count=max(counts),
-                                     max_feat_rows=feat_rows, max_dim=4 if replicated else D, rng=args.rng, seed=seed, engines=G)
+                                     max_feat_rows=feat_rows, max_dim=4 if replicated else D, rng=args.rng, seed=seed, engines=G,
+                                     feature_graph=feat_graph)
             ln.ctx = ln.sg.ctx
         else:
             ln.ops = CudaShardOps(graph, args.rng, seed)
@@ -753,8 +754,6 @@ def run_sharded(args, world, rank, local):
         ln.h_ids = [torch.empty(G * x, dtype=torch.int64).pin_memory() for x in n[1:]]
         ln.h_x = torch.empty((G * n_self, D), dtype=torch.float32).pin_memory()
         ln.h_agg = [torch.empty((G * n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
-        if replicated:
-            ln.fctx = eb.Context(feat_graph, args.rng, seed + 7, ln.stream.cuda_stream)
         G = G_main
         lanes.append(ln)
     tail_lane = lanes.pop() if tail else None
@@ -773,14 +772,11 @@ def run_sharded(args, world, rank, local):
                 ln.ids[l].copy_(o_ids)
                 frontier = eng
             if replicated:
-                # every rank holds all feature rows: fetch + aggregation are the single-GPU kernels, nothing crosses NVLink
-                h = ln.fctx._h
-                ln.fctx.set_stream(torch.cuda.current_stream().cuda_stream)
-                rc = lib.eu_get_dense_feature(h, ln.idbuf.data_ptr(), G * n_self, 0, D, ln.x.data_ptr())
+                # every rank holds all feature rows (PeerShardedGraph(feature_graph=...)): fetch + aggregation are the
+                # single-GPU kernels, nothing crosses NVLink
+                sg.get_dense_feature(ln.idbuf[:G * n_self], 0, D, out=ln.x)
                 for l in range(L):
-                    rc |= lib.eu_sage_mean_aggregate(h, ln.ids[l].data_ptr(), G * n[l], counts[l], D, ln.agg[l].data_ptr())
-                if rc:
-                    raise RuntimeError(lib.eu_last_error().decode())
+                    sg.sage_mean(ln.ids[l], G * n[l], counts[l], D, out=ln.agg[l])
                 ln.x_view = ln.x
                 return
             # the hop-(l+1) features are summed by their owners and never cross NVLink row by row
@@ -882,13 +878,15 @@ def run_sharded(args, world, rank, local):
     run(G * min(len(lanes), 2), 0, True)
     ms_e2e = run(args.steps, args.warmup, True)
     err = max(ln.sg.error() for ln in all_lanes) if peer else 0
+    if err:
+        raise SystemExit("bench: the peer exchange was poisoned (a bounded wait timed out): the timed numbers are invalid")
     # per-kernel breakdown + launch count on one lane (library-side CUDA events), serial, no graphs
     prof = {}
     ln = lanes[0]
     reps = 3
     lib.eu_ctx_profile(ln.ctx._h, 1)
     if replicated:
-        lib.eu_ctx_profile(ln.fctx._h, 1)
+        lib.eu_ctx_profile(ln.sg.fctx._h, 1)
     l0 = lib.eu_launch_count()
     with torch.cuda.stream(ln.stream):
         for it in range(reps):
@@ -896,7 +894,7 @@ def run_sharded(args, world, rank, local):
             raw_step(ln)
     ln.stream.synchronize()
     launches_per_group = (lib.eu_launch_count() - l0) / reps
-    for hctx in [ln.ctx] + ([ln.fctx] if replicated else []):
+    for hctx in [ln.ctx] + ([ln.sg.fctx] if replicated else []):
         buf = ctypes.create_string_buffer(1 << 16)
         lib.eu_ctx_profile_read(hctx._h, buf, len(buf))
         lib.eu_ctx_profile(hctx._h, 0)

@@ -42,8 +42,21 @@ static int regrow(T** p, int64_t count) {
   return EU_OK;
 }
 
+// growing scratch frees and re-allocates under a stream synchronise: impossible while the stream is being captured into
+// a CUDA graph -- fail loudly and say what to do instead of invalidating the capture
+static int refuse_if_capturing(eu_ctx* c, const char* what) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(c->stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+    set_error("%s must grow while the ctx stream is being captured: run the op once (or call eu_ctx_reserve) before the capture", what);
+    return EU_ERR_STATE;
+  }
+  cudaGetLastError();
+  return EU_OK;
+}
+
 int ctx_reserve(eu_ctx* c, int64_t rows, int64_t table_slots) {
   int rc;
+  if ((table_slots > c->tab_set_slots || rows > c->cap_rows) && (rc = refuse_if_capturing(c, "the sampling scratch"))) return rc;
   if (table_slots > c->tab_set_slots) {
     EU_CUDA(cudaStreamSynchronize(c->stream));  // growing while the stream still uses the old buffers would be a race
     const int64_t slots = table_slots + 64;
@@ -76,6 +89,7 @@ int ctx_reserve(eu_ctx* c, int64_t rows, int64_t table_slots) {
 
 int ctx_misc(eu_ctx* c, int64_t bytes) {
   if (bytes <= c->misc_bytes) return EU_OK;
+  if (int rc0 = refuse_if_capturing(c, "the op scratch")) return rc0;
   EU_CUDA(cudaStreamSynchronize(c->stream));
   char* p = (char*)c->d_misc;
   int rc = regrow(&p, bytes);

@@ -27,23 +27,50 @@
 
 namespace eu {
 
-// bounded spin until *flag >= want
-__device__ __forceinline__ bool spin_until(const unsigned int* flag, unsigned int want, int* error) {
+// Bounded spin until *flag >= want.  A wait that runs out of time POISONS the exchange instead of letting stale data
+// through: it sets error in this rank's header, the wait kernel then stores error into every peer's header, every later
+// kernel of a poisoned region returns at once (no replies, no flags), and every spin polls its own error word, so the
+// whole group drains within microseconds and eu_sym_error() is nonzero on every rank.  A poisoned eu_sym is dead: destroy it.
+__device__ __forceinline__ bool spin_until(const unsigned int* flag, unsigned int want, SymHeader* h, long long limit) {
   const long long t0 = clock64();
   while ((int)(ld_acquire_sys(flag) - want) < 0) {
     __nanosleep(200);
-    if (clock64() - t0 > 4000000000LL) { *error = 1; return false; }   // ~2 s
+    if (ld_volatile_i32(&h->error)) return false;
+    if (clock64() - t0 > limit) { h->error = 1; return false; }
   }
   return true;
+}
+
+__device__ __forceinline__ void propagate_error(SymHeader* h, char* const* pb_tab, int N) {
+  // called by threads 0..N-1 after a barrier that follows the spins
+  if (threadIdx.x < N && ld_volatile_i32(&h->error)) {
+    *reinterpret_cast<volatile int*>(&hdr_of(pb_tab[threadIdx.x])->error) = 1;
+    __threadfence_system();
+  }
 }
 
 // ---- owner: wait for every source (one small block spins; nothing else of the GPU is held).  A batched hop also
 // needs the batch boundaries inside every source's segment: the bucket is stable and src = g*rows_b + position, so
 // batch g of source s is the slice [seg_lo[s][g], seg_lo[s][g+1]) -- N*(nb+1) binary searches, done here.
-__global__ void __launch_bounds__(256) k_sym_wait_in(char* base, SymLayout lay, int N, int nb, int64_t rows_b,
-                                                     int32_t* __restrict__ seg_lo /* [N][nb+1] or null */) {
+__global__ void __launch_bounds__(256) k_sym_wait_in(char* base, char* const* pb_tab, SymLayout lay, int N, int nb, int64_t rows_b,
+                                                     int expect_total /* every source must have bucketed this many ids; -1 = any */,
+                                                     int32_t* __restrict__ seg_lo /* [N][nb+1] or null */,
+                                                     int32_t* __restrict__ boff /* [nb][N+1] or null */,
+                                                     int32_t* __restrict__ act /* [nb] or null */) {
   SymHeader* h = hdr_of(base);
-  if (threadIdx.x < N) spin_until(&h->flagA[threadIdx.x], h->epoch, &h->error);
+  if (threadIdx.x < N) {
+    const bool ok = spin_until(&h->flagA[threadIdx.x], h->epoch, h, lay.timeout_cycles);
+    // the segment stride is fixed at creation, but the batch geometry (nb x rows) must be the same on every rank
+    if (ok && expect_total >= 0 && ld_volatile_i32(&h->in_total[threadIdx.x]) != expect_total) h->error = 2;
+  }
+  __syncthreads();
+  propagate_error(h, pb_tab, N);
+  if (ld_volatile_i32(&h->error)) {   // poisoned: the hop that follows samples nothing
+    if (act) for (int g = threadIdx.x; g < nb; g += blockDim.x) act[g] = 0;
+    if (boff) for (int i = threadIdx.x; i < nb * (N + 1); i += blockDim.x) boff[i] = 0;
+    if (seg_lo) for (int i = threadIdx.x; i < N * (nb + 1); i += blockDim.x) seg_lo[i] = 0;
+    return;
+  }
   if (!seg_lo) return;
   __syncthreads();
   const int32_t* src = reinterpret_cast<const int32_t*>(base + lay.off_inbox_src);
@@ -59,46 +86,74 @@ __global__ void __launch_bounds__(256) k_sym_wait_in(char* base, SymLayout lay, 
     }
     seg_lo[i] = lo;
   }
+  if (!boff) return;
+  __syncthreads();
+  // batch g of the owner's sampleNB input = the requests of source 0..N-1 for g, back to back: boff[g][s] = where source
+  // s starts, act[g] = how many rows the batch really has (the launch is sized for N * rows_b)
+  for (int g = threadIdx.x; g < nb; g += blockDim.x) {
+    int32_t run = 0;
+    for (int s = 0; s < N; ++s) {
+      boff[g * (N + 1) + s] = run;
+      run += seg_lo[s * (nb + 1) + g + 1] - seg_lo[s * (nb + 1) + g];
+    }
+    boff[g * (N + 1) + N] = run;
+    act[g] = run;
+  }
 }
 
-// ---- owner: the sampleNB input of batch g = the requests of source 0..N-1 for that batch, each zero-padded to rows_b
-// (id 0 = "exists nowhere": it takes no RNG draws and lands in no dedup table)  ->  pad[g][s][rows_b]
+// ---- owner: the sampleNB input of batch g = the requests of source 0..N-1 for that batch, back to back (compact: the
+// kernels of hop() learn the real row count of every batch from act[g]; nothing is zero-padded)  ->  pad[g][0 .. act[g])
+__device__ __forceinline__ int src_of(const int32_t* __restrict__ bo /* [N+1] */, int N, int32_t p) {
+  int s = 0;
+  while (s + 1 < N && p >= bo[s + 1]) ++s;
+  return s;
+}
+
 __global__ void __launch_bounds__(256) k_sym_gather_pad(const char* base, SymLayout lay, int N, int nb, int64_t rows_b,
-                                                        const int32_t* __restrict__ seg_lo, unsigned long long* __restrict__ pad) {
+                                                        const int32_t* __restrict__ seg_lo, const int32_t* __restrict__ boff,
+                                                        unsigned long long* __restrict__ pad) {
   const unsigned long long* ids = reinterpret_cast<const unsigned long long*>(base + lay.off_inbox_ids);
-  const int64_t total = (int64_t)nb * N * rows_b;
+  const int64_t cap_b = (int64_t)N * rows_b;
+  const int64_t total = (int64_t)nb * cap_b;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t gs = i / rows_b;
-    const int64_t k = i - gs * rows_b;
-    const int g = (int)(gs / N), s = (int)(gs - (int64_t)g * N);
-    const int32_t lo = seg_lo[s * (nb + 1) + g], hi = seg_lo[s * (nb + 1) + g + 1];
-    pad[i] = k < hi - lo ? ids[(int64_t)s * lay.cap + lo + k] : 0ull;
+    const int g = (int)(i / cap_b);
+    const int32_t p = (int32_t)(i - (int64_t)g * cap_b);
+    const int32_t* bo = boff + g * (N + 1);
+    if (p >= bo[N]) continue;
+    const int s = src_of(bo, N, p);
+    pad[i] = ids[(int64_t)s * lay.cap + seg_lo[s * (nb + 1) + g] + (p - bo[s])];
   }
 }
 
 // ---- owner: sampled rows of the padded inbox -> requester's outputs at the original positions (+ TF packing)
-__global__ void __launch_bounds__(256) k_sym_reply_sample(SymPeers peers, SymLayout lay, int me, int N, int nb, int64_t rows_b,
-                                                          const int32_t* __restrict__ seg_lo, int32_t count,
+__global__ void __launch_bounds__(256) k_sym_reply_sample(char* const* __restrict__ pb_tab, SymLayout lay, int me, int N, int nb, int64_t rows_b,
+                                                          const int32_t* __restrict__ seg_lo, const int32_t* __restrict__ boff,
+                                                          int32_t count,
                                                           long long default_node, const long long* __restrict__ r_ids,
                                                           const float* __restrict__ r_w, const int32_t* __restrict__ r_t,
                                                           bool want_packed) {
-  char* base = peers.base[me];
+  char* base = pb_tab[me];
   SymHeader* mine = hdr_of(base);
   const int32_t* src = reinterpret_cast<const int32_t*>(base + lay.off_inbox_src);
   __shared__ bool s_last;
+  __shared__ int s_err;
+  if (threadIdx.x == 0) s_err = ld_volatile_i32(&mine->error);
+  __syncthreads();
+  if (s_err) return;   // poisoned exchange: no replies, no flags
   const int64_t slots = (int64_t)nb * N * rows_b * count;
   for (int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; tid < slots; tid += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = tid / count;            // padded row (g, s, k)
+    const int64_t row = tid / count;            // row (g, p) of the owner's compact input
     const int32_t j = (int32_t)(tid - row * count);
-    const int64_t gs = row / rows_b;
-    const int64_t k = row - gs * rows_b;
-    const int g = (int)(gs / N), s = (int)(gs - (int64_t)g * N);
-    const int32_t lo = seg_lo[s * (nb + 1) + g], hi = seg_lo[s * (nb + 1) + g + 1];
-    if (k < hi - lo) {
-      const int64_t dst = (int64_t)src[(int64_t)s * lay.cap + lo + k] * count + j;   // requester's flat slot [g][pos][j]
+    const int64_t cap_b = (int64_t)N * rows_b;
+    const int g = (int)(row / cap_b);
+    const int32_t p = (int32_t)(row - (int64_t)g * cap_b);
+    const int32_t* bo = boff + g * (N + 1);
+    if (p < bo[N]) {
+      const int s = src_of(bo, N, p);
+      const int64_t dst = (int64_t)src[(int64_t)s * lay.cap + seg_lo[s * (nb + 1) + g] + (p - bo[s])] * count + j;   // requester's flat slot [g][pos][j]
       const long long id = r_ids[tid];
       const bool keep = r_ids[row * count] != 0;   // tf_euler/kernels/sample_neighbor_op.cc:114-122
-      char* pb = peers.base[s];
+      char* pb = pb_tab[s];
       reinterpret_cast<long long*>(pb + lay.off_eng)[dst] = id;
       if (want_packed) {
         reinterpret_cast<long long*>(pb + lay.off_ids)[dst] = keep ? id : default_node;
@@ -113,26 +168,31 @@ __global__ void __launch_bounds__(256) k_sym_reply_sample(SymPeers peers, SymLay
   if (!s_last) return;
   if (threadIdx.x < N) __threadfence_system();   // ticket observed (barrier) -> ordered before the flag stores
   if (threadIdx.x == 0) mine->done = 0;
-  if (threadIdx.x < N) st_release_sys(&hdr_of(peers.base[threadIdx.x])->flagB[me], mine->epoch);
+  if (threadIdx.x < N) st_release_sys(&hdr_of(pb_tab[threadIdx.x])->flagB[me], mine->epoch);
 }
 
 // ---- owner: feature rows gathered from the local shard straight into the requester's output (G lanes per row)
-__global__ void __launch_bounds__(256) k_sym_reply_feature(DevGraph g, SymPeers peers, SymLayout lay, int me, int N,
+__global__ void __launch_bounds__(256) k_sym_reply_feature(DevGraph g, char* const* __restrict__ pb_tab, SymLayout lay, int me, int N,
                                                            int32_t dim, int32_t soff, int32_t sdim, int G) {
-  char* base = peers.base[me];
+  char* base = pb_tab[me];
   SymHeader* mine = hdr_of(base);
   const unsigned long long* ids = reinterpret_cast<const unsigned long long*>(base + lay.off_inbox_ids);
   const int32_t* src = reinterpret_cast<const int32_t*>(base + lay.off_inbox_src);
   __shared__ bool s_last;
+  __shared__ int s_err;
+  if (threadIdx.x == 0) s_err = ld_volatile_i32(&mine->error);
+  __syncthreads();
+  if (s_err) return;
   const int sh = 31 - __clz(G);
   const int sub = (int)(threadIdx.x & (G - 1));
-  for (int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> sh; row < (int64_t)N * lay.cap;
-       row += ((int64_t)gridDim.x * blockDim.x) >> sh) {
-    const int s = (int)(row / lay.cap);
-    if (row - (int64_t)s * lay.cap < mine->in_cnt[s]) {
+  for (int s = 0; s < N; ++s) {   // segment s holds in_cnt[s] requests (the stride lay.cap is fixed at creation)
+    const int64_t n_s = mine->in_cnt[s];
+    float* obase = reinterpret_cast<float*>(pb_tab[s] + lay.off_rows);
+    for (int64_t k = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> sh; k < n_s; k += ((int64_t)gridDim.x * blockDim.x) >> sh) {
+      const int64_t row = (int64_t)s * lay.cap + k;
       const int64_t gr = sdim > 0 ? lookup_row(g, ids[row]) : -1;
       const float* f = gr >= 0 ? g.feat + gr * (int64_t)g.feat_dim + soff : nullptr;
-      float* o = reinterpret_cast<float*>(peers.base[s] + lay.off_rows) + (int64_t)src[row] * dim;
+      float* o = obase + (int64_t)src[row] * dim;
       for (int32_t d = sub * 4; d < dim; d += G * 4) {   // dim, sdim, soff multiples of 4 (checked by the launcher)
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (f && d < sdim) v = __ldg(reinterpret_cast<const float4*>(f + d));
@@ -146,13 +206,15 @@ __global__ void __launch_bounds__(256) k_sym_reply_feature(DevGraph g, SymPeers 
   if (!s_last) return;
   if (threadIdx.x < N) __threadfence_system();   // ticket observed (barrier) -> ordered before the flag stores
   if (threadIdx.x == 0) mine->done = 0;
-  if (threadIdx.x < N) st_release_sys(&hdr_of(peers.base[threadIdx.x])->flagB[me], mine->epoch);
+  if (threadIdx.x < N) st_release_sys(&hdr_of(pb_tab[threadIdx.x])->flagB[me], mine->epoch);
 }
 
 // ---- requester: wait for every owner's replies
-__global__ void k_sym_wait(char* base, int N) {
+__global__ void k_sym_wait(char* base, char* const* pb_tab, SymLayout lay, int N) {
   SymHeader* h = hdr_of(base);
-  if (threadIdx.x < N) spin_until(&h->flagB[threadIdx.x], h->epoch, &h->error);
+  if (threadIdx.x < N) spin_until(&h->flagB[threadIdx.x], h->epoch, h, lay.timeout_cycles);
+  __syncthreads();
+  propagate_error(h, pb_tab, N);
 }
 
 // ---- fused sharded SAGE mean.  The requester pushes the neighbor ids of its fixed-fanout block (flat [rows*count],
@@ -181,13 +243,17 @@ __device__ __forceinline__ int32_t warp_lower_bound(const int32_t* __restrict__ 
 // when this shard owns none of a destination's neighbors -- whenever the destination changes.
 static constexpr int kSageRMax = 32;   // destinations per warp: R = 8 or 32 (one 32-bit presence mask per group)
 template <int NV>   // feat_dim == dim == NV*128
-__global__ void __launch_bounds__(256) k_sym_reply_sage(DevGraph g, SymPeers peers, SymLayout lay, int me, int N, int64_t rows,
+__global__ void __launch_bounds__(256) k_sym_reply_sage(DevGraph g, char* const* __restrict__ pb_tab, SymLayout lay, int me, int N, int64_t rows,
                                                         int32_t count, int kSageR) {
-  char* base = peers.base[me];
+  char* base = pb_tab[me];
   SymHeader* mine = hdr_of(base);
   const unsigned long long* ids = reinterpret_cast<const unsigned long long*>(base + lay.off_inbox_ids);
   const int32_t* src = reinterpret_cast<const int32_t*>(base + lay.off_inbox_src);
   __shared__ bool s_last;
+  __shared__ int s_err;
+  if (threadIdx.x == 0) s_err = ld_volatile_i32(&mine->error);
+  __syncthreads();
+  if (s_err) return;
   const int lane = threadIdx.x & 31;
   constexpr int32_t fd = NV * 128;
   const float* __restrict__ feat = g.feat + lane * 4;
@@ -201,7 +267,7 @@ __global__ void __launch_bounds__(256) k_sym_reply_sage(DevGraph g, SymPeers pee
     const int32_t* seg = src + (int64_t)s * lay.cap;
     const unsigned long long* sid = ids + (int64_t)s * lay.cap;
     const int32_t key_lo = (int32_t)(d0 * count), key_hi = (int32_t)((d0 + nd) * count);
-    float* o = reinterpret_cast<float*>(peers.base[s] + lay.off_rows) + ((int64_t)me * rows + d0) * fd + lane * 4;
+    float* o = reinterpret_cast<float*>(pb_tab[s] + lay.off_rows) + ((int64_t)me * rows + d0) * fd + lane * 4;
     int cur = 0;   // next destination (relative to d0) whose partial row is still open
     bool any = false;        // the open destination has at least one row of this shard
     unsigned present = 0;    // bit d: a partial row was stored for destination d0 + d (empty partials are not sent)
@@ -261,7 +327,7 @@ __global__ void __launch_bounds__(256) k_sym_reply_sage(DevGraph g, SymPeers pee
       for (int t = 0; t < NV; ++t) *reinterpret_cast<float4*>(o + (int64_t)cur * fd + t * 128) = acc[t];
       present |= 1u << cur;
     }
-    if (lane == 0) reinterpret_cast<unsigned int*>(peers.base[s] + lay.off_flags)[(int64_t)me * gps + (w - (int64_t)s * gps)] = present;
+    if (lane == 0) reinterpret_cast<unsigned int*>(pb_tab[s] + lay.off_flags)[(int64_t)me * gps + (w - (int64_t)s * gps)] = present;
   }
   __syncthreads();   // CTA's stores happen-before thread 0's fence (barrier + cumulativity): one system fence per CTA
   if (threadIdx.x == 0) { __threadfence_system(); s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1; }
@@ -269,17 +335,21 @@ __global__ void __launch_bounds__(256) k_sym_reply_sage(DevGraph g, SymPeers pee
   if (!s_last) return;
   if (threadIdx.x < N) __threadfence_system();   // ticket observed (barrier) -> ordered before the flag stores
   if (threadIdx.x == 0) mine->done = 0;
-  if (threadIdx.x < N) st_release_sys(&hdr_of(peers.base[threadIdx.x])->flagB[me], mine->epoch);
+  if (threadIdx.x < N) st_release_sys(&hdr_of(pb_tab[threadIdx.x])->flagB[me], mine->epoch);
 }
 
 // any width: lanes over columns, entries serial (slow path, same sums)
-__global__ void __launch_bounds__(256) k_sym_reply_sage_generic(DevGraph g, SymPeers peers, SymLayout lay, int me, int N, int64_t rows,
+__global__ void __launch_bounds__(256) k_sym_reply_sage_generic(DevGraph g, char* const* __restrict__ pb_tab, SymLayout lay, int me, int N, int64_t rows,
                                                                 int32_t count, int32_t dim) {
-  char* base = peers.base[me];
+  char* base = pb_tab[me];
   SymHeader* mine = hdr_of(base);
   const unsigned long long* ids = reinterpret_cast<const unsigned long long*>(base + lay.off_inbox_ids);
   const int32_t* src = reinterpret_cast<const int32_t*>(base + lay.off_inbox_src);
   __shared__ bool s_last;
+  __shared__ int s_err;
+  if (threadIdx.x == 0) s_err = ld_volatile_i32(&mine->error);
+  __syncthreads();
+  if (s_err) return;
   const int lane = threadIdx.x & 31;
   const int32_t fd = g.feat_dim;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -291,7 +361,7 @@ __global__ void __launch_bounds__(256) k_sym_reply_sage_generic(DevGraph g, SymP
     const unsigned long long* sid = ids + (int64_t)s * lay.cap;
     const int32_t key_hi = (int32_t)((d + 1) * count);
     const int32_t e_lo = warp_lower_bound(seg, n_s, (int32_t)(d * count), lane);
-    float* o = reinterpret_cast<float*>(peers.base[s] + lay.off_rows) + ((int64_t)me * rows + d) * dim;
+    float* o = reinterpret_cast<float*>(pb_tab[s] + lay.off_rows) + ((int64_t)me * rows + d) * dim;
     for (int32_t c0 = 0; c0 < dim; c0 += 32) {
       const int32_t col = c0 + lane;
       float acc = 0.f;
@@ -308,7 +378,7 @@ __global__ void __launch_bounds__(256) k_sym_reply_sage_generic(DevGraph g, SymP
   if (!s_last) return;
   if (threadIdx.x < N) __threadfence_system();   // ticket observed (barrier) -> ordered before the flag stores
   if (threadIdx.x == 0) mine->done = 0;
-  if (threadIdx.x < N) st_release_sys(&hdr_of(peers.base[threadIdx.x])->flagB[me], mine->epoch);
+  if (threadIdx.x < N) st_release_sys(&hdr_of(pb_tab[threadIdx.x])->flagB[me], mine->epoch);
 }
 
 __device__ __forceinline__ float vadd(float a, float b) { return __fadd_rn(a, b); }
@@ -357,12 +427,13 @@ struct eu_sym {
   int rank = 0, world = 1;
   eu::SymLayout lay{};
   eu::SymPeers peers{};
+  char** d_peers = nullptr;   // device copy of peers.base (what the kernels index)
   char* base = nullptr;
   bool connected = false;
   // local scratch
   int64_t* d_sorted = nullptr; int32_t* d_src = nullptr; int64_t* d_counts = nullptr; int64_t* d_offs = nullptr;
   int64_t* d_rids = nullptr; float* d_rw = nullptr; int32_t* d_rt = nullptr;
-  unsigned long long* d_pad = nullptr; int32_t* d_seglo = nullptr;
+  unsigned long long* d_pad = nullptr; int32_t* d_seglo = nullptr; int32_t* d_boff = nullptr; int32_t* d_act = nullptr;
   int64_t scratch_rows = 0, scratch_slots = 0, scratch_pad = 0;
 };
 
@@ -382,6 +453,15 @@ int eu_sym_create(eu_ctx* c, int32_t rank, int32_t world, int64_t max_rows, int3
   L.max_out = max_rows * max_count;
   L.max_rows_f = max_feat_rows;
   L.max_dim = max_dim;
+  {
+    // bound of every flag wait: generous (a peer may sit in a cudaMalloc, a GC pause or a data-loader stall), and when it
+    // does expire the exchange is poisoned on every rank instead of continuing on stale data (spin_until)
+    const char* e = getenv("EU_SYM_TIMEOUT_S");
+    const double sec = e && atof(e) > 0 ? atof(e) : 30.0;
+    int khz = 1900000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->g->device);
+    L.timeout_cycles = (long long)(sec * 1e3 * (double)khz);
+  }
   int64_t off = a256(sizeof(SymHeader));
   L.off_inbox_ids = off; off += a256(8 * L.cap * world);
   L.off_inbox_src = off; off += a256(4 * L.cap * world);
@@ -401,6 +481,8 @@ int eu_sym_create(eu_ctx* c, int32_t rank, int32_t world, int64_t max_rows, int3
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
   memcpy(handle_out, &h, 64);
   s->peers.base[rank] = s->base;
+  EU_CUDA(cudaMalloc(&s->d_peers, sizeof(char*) * kSymMaxRanks));
+  EU_CUDA(cudaMemcpy(s->d_peers, s->peers.base, sizeof(char*) * kSymMaxRanks, cudaMemcpyHostToDevice));
   EU_CUDA(cudaDeviceSynchronize());
   *out = s;
   return EU_OK;
@@ -419,6 +501,7 @@ int eu_sym_connect(eu_sym* s, const void* handles) {
     if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle(rank %d) -> %s", r, cudaGetErrorString(e)); return EU_ERR_CUDA; }
     s->peers.base[r] = (char*)p;
   }
+  EU_CUDA(cudaMemcpy(s->d_peers, s->peers.base, sizeof(char*) * kSymMaxRanks, cudaMemcpyHostToDevice));
   s->connected = true;
   return EU_OK;
 }
@@ -429,9 +512,9 @@ int eu_sym_destroy(eu_sym* s) {
   cudaDeviceSynchronize();
   for (int r = 0; r < s->world; ++r)
     if (r != s->rank && s->peers.base[r]) cudaIpcCloseMemHandle(s->peers.base[r]);
-  cudaFree(s->base);
+  cudaFree(s->base); cudaFree(s->d_peers);
   cudaFree(s->d_sorted); cudaFree(s->d_src); cudaFree(s->d_counts); cudaFree(s->d_offs);
-  cudaFree(s->d_rids); cudaFree(s->d_rw); cudaFree(s->d_rt); cudaFree(s->d_pad); cudaFree(s->d_seglo);
+  cudaFree(s->d_rids); cudaFree(s->d_rw); cudaFree(s->d_rt); cudaFree(s->d_pad); cudaFree(s->d_seglo); cudaFree(s->d_boff); cudaFree(s->d_act);
   delete s;
   return EU_OK;
 }
@@ -461,7 +544,11 @@ static int sym_scratch(eu_sym* s, int64_t rows, int64_t slots, int64_t pad_rows 
     EU_CUDA(cudaStreamSynchronize(s->c->stream));
     cudaFree(s->d_pad);
     EU_CUDA(cudaMalloc(&s->d_pad, 8 * (size_t)pad_rows));
-    if (!s->d_seglo) EU_CUDA(cudaMalloc(&s->d_seglo, 4 * (size_t)kSymMaxRanks * 66));
+    if (!s->d_seglo) {
+      EU_CUDA(cudaMalloc(&s->d_seglo, 4 * (size_t)kSymMaxRanks * 66));
+      EU_CUDA(cudaMalloc(&s->d_boff, 4 * (size_t)(kSymMaxRanks + 1) * 64));
+      EU_CUDA(cudaMalloc(&s->d_act, 4 * (size_t)64));
+    }
     s->scratch_pad = pad_rows;
   }
   if (rows > s->scratch_rows) {
@@ -493,33 +580,32 @@ int eu_sym_sample_hop_batched(eu_sym* s, const int64_t* seeds, int32_t nb, int64
   if (!s || !s->connected || nb < 1 || nb > 64 || rows < 0 || count < 0 || (rows > 0 && !seeds)) { set_error("eu_sym_sample_hop: bad argument / not connected"); return EU_ERR_INVALID; }
   eu_ctx* c = s->c;
   EU_CUDA(cudaSetDevice(c->g->device));
-  // segment stride of THIS exchange = the requester's id count (every rank issues the same exchange with the same
-  // nb x rows: batches are equal-sized across ranks), so the padded sampleNB input is nb*N*rows, not N*capacity
-  SymLayout L = s->lay;
+  // The inbox segment stride is the creation-time capacity (identical on every rank by construction); every rank must
+  // issue the same exchange shape (nb x rows) -- the owners verify it (k_sym_wait_in, error 2) instead of trusting it.
+  const SymLayout& L = s->lay;
   const int N = s->world;
   const int64_t total = (int64_t)nb * rows;
   if (total > L.cap || total * count > L.max_out || total >= ((int64_t)1 << 31)) { set_error("eu_sym_sample_hop: %d x %lld rows x %d exceed the symmetric region", nb, (long long)rows, count); return EU_ERR_INVALID; }
   if (nb > c->n_eng) { set_error("eu_sym_sample_hop: %d batches but the ctx has %d engines", nb, c->n_eng); return EU_ERR_INVALID; }
-  L.cap = std::max<int64_t>(total, 1);
   const int64_t prow = (int64_t)N * total;   // padded sampleNB rows, all batches
   int rc = sym_scratch(s, std::max<int64_t>(total, 1), std::max<int64_t>(prow * count, 1), std::max<int64_t>(prow, 1));
   if (rc) return rc;
   cudaStream_t st = c->stream;
-  rc = bucket_push(c, seeds, total, num_partitions, N, s->rank, false, s->d_counts, s->d_offs, s->peers, L, "k_bucket_push");
+  rc = bucket_push(c, seeds, total, num_partitions, N, s->rank, false, s->d_counts, s->d_offs, s->d_peers, L, "k_bucket_push");
   if (rc) return rc;
-  { EuProfScope ps(c, "k_sym_wait_in", total); k_sym_wait_in<<<1, 256, 0, st>>>(s->base, L, N, nb, rows, s->d_seglo); }
+  { EuProfScope ps(c, "k_sym_wait_in", total); k_sym_wait_in<<<1, 256, 0, st>>>(s->base, s->d_peers, L, N, nb, rows, (int)total, s->d_seglo, s->d_boff, s->d_act); }
   EU_LAUNCHED();
-  { EuProfScope ps(c, "k_sym_gather_pad", prow); k_sym_gather_pad<<<sym_grid(prow), 256, 0, st>>>(s->base, L, N, nb, rows, s->d_seglo, s->d_pad); }
+  { EuProfScope ps(c, "k_sym_gather_pad", prow); k_sym_gather_pad<<<sym_grid(prow), 256, 0, st>>>(s->base, L, N, nb, rows, s->d_seglo, s->d_boff, s->d_pad); }
   EU_LAUNCHED();
   if (count > 0 && rows > 0) {
-    rc = hop(c, s->d_pad, (int64_t)N * rows, etypes, K, count, /*default_node=*/0, nullptr, s->d_rids, s->d_rw, s->d_rt, 0, false, false, nb);
+    rc = hop(c, s->d_pad, (int64_t)N * rows, etypes, K, count, /*default_node=*/0, nullptr, s->d_rids, s->d_rw, s->d_rt, 0, false, false, nb, s->d_act);
     if (rc) return rc;
   }
   { EuProfScope ps(c, "k_sym_reply_sample", prow);
-    k_sym_reply_sample<<<reply_grid(prow * count), 256, 0, st>>>(s->peers, L, s->rank, N, nb, rows, s->d_seglo, count, default_node,
+    k_sym_reply_sample<<<reply_grid(prow * count), 256, 0, st>>>(s->d_peers, L, s->rank, N, nb, rows, s->d_seglo, s->d_boff, count, default_node,
                                                                (const long long*)s->d_rids, s->d_rw, s->d_rt, want_packed != 0); }
   EU_LAUNCHED();
-  { EuProfScope ps(c, "k_sym_wait", total); k_sym_wait<<<1, 32, 0, st>>>(s->base, N); }
+  { EuProfScope ps(c, "k_sym_wait", total); k_sym_wait<<<1, 32, 0, st>>>(s->base, s->d_peers, L, N); }
   EU_LAUNCHED();
   return EU_OK;
 }
@@ -534,28 +620,27 @@ int eu_sym_get_dense_feature(eu_sym* s, const int64_t* ids, int64_t rows, int32_
   if (!s || !s->connected || rows < 0 || dim <= 0 || (rows > 0 && !ids)) { set_error("eu_sym_get_dense_feature: bad argument / not connected"); return EU_ERR_INVALID; }
   eu_ctx* c = s->c;
   EU_CUDA(cudaSetDevice(c->g->device));
-  SymLayout L = s->lay;
+  const SymLayout& L = s->lay;
   const DevGraph& d = c->g->d;
   const int N = s->world;
   if (rows > L.cap || rows > L.max_rows_f || dim > L.max_dim) { set_error("eu_sym_get_dense_feature: request exceeds the symmetric region"); return EU_ERR_INVALID; }
   const bool have = fid >= 0 && fid < d.n_slots;
   const int32_t soff = have ? d.slot_off[fid] : 0, sdim = have ? d.slot_dim[fid] : 0;
   if ((dim & 3) || (soff & 3) || (sdim & 3) || (d.feat_dim & 3)) { set_error("eu_sym_get_dense_feature: widths must be multiples of 4 floats"); return EU_ERR_UNSUPPORTED; }
-  L.cap = std::max<int64_t>(rows, 1);
   int rc = sym_scratch(s, std::max<int64_t>(rows, 1), 1);
   if (rc) return rc;
   cudaStream_t st = c->stream;
-  rc = bucket_push(c, ids, rows, num_partitions, N, s->rank, false, s->d_counts, s->d_offs, s->peers, L, "k_bucket_push(feat)");
+  rc = bucket_push(c, ids, rows, num_partitions, N, s->rank, false, s->d_counts, s->d_offs, s->d_peers, L, "k_bucket_push(feat)");
   if (rc) return rc;
-  { EuProfScope ps(c, "k_sym_wait_in(feat)", rows); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, L, N, 1, 0, nullptr); }
+  { EuProfScope ps(c, "k_sym_wait_in(feat)", rows); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, s->d_peers, L, N, 1, 0, -1, nullptr, nullptr, nullptr); }
   EU_LAUNCHED();
   int G = 1;
   while (G < 32 && G < dim / 4) G <<= 1;
-  const int64_t prow = (int64_t)N * L.cap;
+  const int64_t prow = rows;   // on average a shard serves as many rows as it requests
   { EuProfScope ps(c, "k_sym_reply_feature", prow);
-    k_sym_reply_feature<<<reply_grid(prow * G), 256, 0, st>>>(d, s->peers, L, s->rank, N, dim, soff, sdim, G); }
+    k_sym_reply_feature<<<reply_grid(prow * G), 256, 0, st>>>(d, s->d_peers, L, s->rank, N, dim, soff, sdim, G); }
   EU_LAUNCHED();
-  { EuProfScope ps(c, "k_sym_wait(feat)", rows); k_sym_wait<<<1, 32, 0, st>>>(s->base, N); }
+  { EuProfScope ps(c, "k_sym_wait(feat)", rows); k_sym_wait<<<1, 32, 0, st>>>(s->base, s->d_peers, L, N); }
   EU_LAUNCHED();
   return EU_OK;
 }
@@ -567,7 +652,7 @@ int eu_sym_sage_mean(eu_sym* s, const int64_t* nbr_ids, int64_t rows, int32_t co
   if (!s || !s->connected || rows < 0 || count < 1 || dim <= 0 || (rows > 0 && (!nbr_ids || !out))) { set_error("eu_sym_sage_mean: bad argument / not connected"); return EU_ERR_INVALID; }
   eu_ctx* c = s->c;
   EU_CUDA(cudaSetDevice(c->g->device));
-  SymLayout L = s->lay;
+  const SymLayout& L = s->lay;
   const DevGraph& d = c->g->d;
   const int N = s->world;
   const int64_t nid = rows * count;
@@ -575,7 +660,6 @@ int eu_sym_sage_mean(eu_sym* s, const int64_t* nbr_ids, int64_t rows, int32_t co
     set_error("eu_sym_sage_mean: %lld x %d ids / %d partial blocks exceed the symmetric region", (long long)rows, count, N);
     return EU_ERR_INVALID;
   }
-  L.cap = std::max<int64_t>(nid, 1);
   int rc = sym_scratch(s, std::max<int64_t>(nid, 1), 1);
   if (rc) return rc;
   cudaStream_t st = c->stream;
@@ -587,17 +671,17 @@ int eu_sym_sage_mean(eu_sym* s, const int64_t* nbr_ids, int64_t rows, int32_t co
   // the generic-width owners store every partial row: the requester marks them all present before its push goes out
   if (!fast) EU_CUDA(cudaMemsetAsync(s->base + L.off_flags, 0xFF, (size_t)(ceil_div(rows, kSageR) * N * 4), st));
   // ids that exist nowhere (0 / default fill) contribute nothing: they are dropped at the bucket, not shipped
-  rc = bucket_push(c, nbr_ids, nid, num_partitions, N, s->rank, true, s->d_counts, s->d_offs, s->peers, L, "k_bucket_push(sage)");
+  rc = bucket_push(c, nbr_ids, nid, num_partitions, N, s->rank, true, s->d_counts, s->d_offs, s->d_peers, L, "k_bucket_push(sage)");
   if (rc) return rc;
-  { EuProfScope ps(c, "k_sym_wait_in(sage)", nid); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, L, N, 1, 0, nullptr); }
+  { EuProfScope ps(c, "k_sym_wait_in(sage)", nid); k_sym_wait_in<<<1, 32, 0, st>>>(s->base, s->d_peers, L, N, 1, 0, (int)nid, nullptr, nullptr, nullptr); }
   EU_LAUNCHED();
   { EuProfScope ps(c, "k_sym_reply_sage", (int64_t)N * rows);
     const unsigned grid = sym_grid((int64_t)N * ceil_div(rows, kSageR) * 32);   // search-latency bound at large N: full occupancy
-    if (fast && dim == 128) k_sym_reply_sage<1><<<grid, 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count, kSageR);
-    else if (fast && dim == 256) k_sym_reply_sage<2><<<grid, 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count, kSageR);
-    else k_sym_reply_sage_generic<<<sym_grid((int64_t)N * rows * 32), 256, 0, st>>>(d, s->peers, L, s->rank, N, rows, count, dim); }
+    if (fast && dim == 128) k_sym_reply_sage<1><<<grid, 256, 0, st>>>(d, s->d_peers, L, s->rank, N, rows, count, kSageR);
+    else if (fast && dim == 256) k_sym_reply_sage<2><<<grid, 256, 0, st>>>(d, s->d_peers, L, s->rank, N, rows, count, kSageR);
+    else k_sym_reply_sage_generic<<<sym_grid((int64_t)N * rows * 32), 256, 0, st>>>(d, s->d_peers, L, s->rank, N, rows, count, dim); }
   EU_LAUNCHED();
-  { EuProfScope ps(c, "k_sym_wait(sage)", rows); k_sym_wait<<<1, 32, 0, st>>>(s->base, N); }
+  { EuProfScope ps(c, "k_sym_wait(sage)", rows); k_sym_wait<<<1, 32, 0, st>>>(s->base, s->d_peers, L, N); }
   EU_LAUNCHED();
   if (rows > 0) {
     EuProfScope ps(c, "k_sym_sage_reduce", rows);

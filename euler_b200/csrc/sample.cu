@@ -39,6 +39,8 @@ struct Geom {
   int64_t rows_b;    // seeds per batch (dense in the seed / output arrays)
   int64_t rows_pad;  // nblk_b * 256: stride of the per-row scratch arrays
   int64_t cap_b;     // dedup slots per batch (power of two) ; region stride = cap_b + 1
+  const int32_t* rows_act;  // device, [nb] or null: only the first rows_act[b] (<= rows_b) seeds of batch b exist -- the
+                            // sharded owner path sizes a launch for the worst case and learns the real counts on the device
 };
 
 // ---------------------------------------------------------------------------- 1. seed dedup
@@ -66,6 +68,7 @@ __global__ void k_dedup_insert(HashSlot* tabs, Geom gm, const unsigned long long
   if (i >= gm.nb * gm.rows_b) return;
   const int b = (int)(i / gm.rows_b);
   const int64_t li = i - b * gm.rows_b;
+  if (gm.rows_act && li >= gm.rows_act[b]) return;
   const unsigned long long id = seeds[i];
   // Warp-aggregate: frontiers are full of runs of equal ids (a default row is `count` zeros, hubs repeat)
   // and equal ids hammer one slot.  The lowest lane of each (batch, id) group carries the group's minimum
@@ -156,7 +159,8 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSl
   EuRngState* rng = rngs + b;
   bool e = false;      // eligible FIRST occurrence: takes a slot of the serial draw order
   bool own = false;    // this row samples (its id is eligible, whether or not it is the first occurrence)
-  if (li < gm.rows_b) {
+  const int64_t rows_here = gm.rows_act ? (int64_t)gm.rows_act[b] : gm.rows_b;
+  if (li < rows_here) {
     const int64_t w = b * gm.rows_b + li;
     const unsigned long long id = seeds[w];
     const int64_t f = dedup_first(tabs + (int64_t)b * (gm.cap_b + 1), (unsigned long long)gm.cap_b - 1, id);
@@ -369,6 +373,7 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
     const int64_t w = PHILOX ? q : (int64_t)a.live[q];
     const int bidx = (int)(w / a.gm.rows_b);
     const int64_t li = w - bidx * a.gm.rows_b;
+    if (PHILOX && a.gm.rows_act && li >= a.gm.rows_act[bidx]) continue;   // rows past the batch's real count do not exist
     const int64_t obase = w * (int64_t)count;
     const EuRngState* rng = a.rngs + bidx;
     HashSlot* ntab = a.next_tabs ? a.next_tabs + (int64_t)bidx * (a.next_cap_b + 1) : nullptr;
@@ -635,6 +640,7 @@ static Geom make_geom(int nb, int64_t rows_b) {
   gm.rows_pad = (int64_t)gm.nblk_b * kPrepBlock;
   gm.cap_b = 64;
   while (gm.cap_b < rows_b * 2) gm.cap_b <<= 1;
+  gm.rows_act = nullptr;
   return gm;
 }
 
@@ -646,7 +652,8 @@ int64_t hop_table_slots(int nb, int64_t rows_b) { return (make_geom(nb, rows_b).
 // be null) and TF-packed outputs (may be null).  Batch b uses engine b of the ctx.
 int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_t* etypes,
         int32_t K, int32_t count, int64_t default_node, unsigned long long* eng_ids,
-        int64_t* out_ids, float* out_w, int32_t* out_t, int hop_index, bool pre_inserted, bool insert_next, int nb) {
+        int64_t* out_ids, float* out_w, int32_t* out_t, int hop_index, bool pre_inserted, bool insert_next, int nb,
+        const int32_t* rows_act) {
   const int64_t rows = rows_b * nb;
   if (rows == 0 || count == 0) return EU_OK;
   if (nb < 1 || nb > c->n_eng) { set_error("hop: %d batches but the ctx has %d engines", nb, c->n_eng); return EU_ERR_INVALID; }
@@ -656,7 +663,8 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
   if (rc) return rc;
   if (a.mode != 0 && d.T > 32) { set_error("T > 32 unsupported"); return EU_ERR_UNSUPPORTED; }
   cudaStream_t s = c->stream;
-  const Geom gm = make_geom(nb, rows_b);
+  Geom gm = make_geom(nb, rows_b);
+  gm.rows_act = rows_act;
   a.seeds = seeds; a.gm = gm; a.count = count; a.default_node = default_node;
   a.eng_ids = eng_ids; a.out_ids = (long long*)out_ids; a.out_w = out_w; a.out_t = out_t;
   a.rngs = c->d_rng;
@@ -668,13 +676,10 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
     a.sg_log = 0;
     while ((1 << a.sg_log) < need) ++a.sg_log;
   }
-  // persistent grid: 8 CTAs per SM stride over the (live) rows
-  static int ctas = 0, grid_ctas = 0;
-  if (!ctas) {
-    const char* e = getenv("EU_SAMPLE_CTAS");     // tuning knob: CTAs per SM of the persistent grid (1..8; 6 also relaxes the register cap)
-    grid_ctas = e ? std::min(8, std::max(1, atoi(e))) : 8;
-    ctas = grid_ctas == 6 ? 6 : 8;
-  }
+  // persistent grid: 8 CTAs per SM stride over the (live) rows.  EU_SAMPLE_CTAS = CTAs per SM (1..8; 6 also relaxes the
+  // register cap); read once (C++11 static initialisation is thread-safe: the ABI is re-entrant across ctxs)
+  static const int grid_ctas = [] { const char* e = getenv("EU_SAMPLE_CTAS"); return e ? std::min(8, std::max(1, atoi(e))) : 8; }();
+  const int ctas = grid_ctas == 6 ? 6 : 8;
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(ceil_div(rows * 32, (int64_t)(32 >> a.sg_log)), 256), 148 * grid_ctas);
   if (c->rng == EU_RNG_PHILOX) {
     a.key = c->seed;
@@ -751,9 +756,15 @@ int eu_sample_fanout_batched(eu_ctx* c, const int64_t* nodes, int32_t nb, int64_
   if (!c || nb < 1 || B < 0 || L < 0 || !counts || (K > 0 && !etypes)) { set_error("eu_sample_fanout: bad argument"); return EU_ERR_INVALID; }
   EU_CUDA(cudaSetDevice(c->g->device));
   if (nb > c->n_eng) { set_error("eu_sample_fanout_batched: %d batches but the ctx has %d engines (eu_ctx_set_engines)", nb, c->n_eng); return EU_ERR_INVALID; }
+  for (int l = 0; l < L; ++l)
+    if (counts[l] < 0) { set_error("negative count"); return EU_ERR_INVALID; }
+  // a hop with count 0 delivers nothing and neither does any hop after it: stop the chain BEFORE it, so that no hop enters
+  // ids into a dedup table that nobody would consume and wipe (the tables must be all-free when an op returns)
+  for (int l = 0; l < L; ++l)
+    if (counts[l] == 0) { L = l; break; }
+  if (B == 0) return EU_OK;
   int64_t rows_b = B, max_rows = hop_scratch_rows(nb, B), max_slots = hop_table_slots(nb, B), widest = B * nb;
   for (int l = 0; l < L; ++l) {
-    if (counts[l] < 0) { set_error("negative count"); return EU_ERR_INVALID; }
     rows_b *= counts[l];
     if (l + 1 < L) { max_rows = std::max(max_rows, hop_scratch_rows(nb, rows_b)); max_slots = std::max(max_slots, hop_table_slots(nb, rows_b)); }
     widest = std::max(widest, rows_b * nb);

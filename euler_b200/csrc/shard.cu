@@ -92,7 +92,7 @@ struct BucketDst {
   unsigned long long* sorted_ids;   // local mode
   int32_t* src_index;
   int remote;
-  SymPeers peers;                   // remote mode
+  char* const* pb_tab;              // remote mode: device table of the peers' region bases
   SymLayout lay;
   int me;
 };
@@ -103,7 +103,13 @@ __global__ void __launch_bounds__(kBktWarps * 32) k_bucket_place(const unsigned 
                                                                  const long long* __restrict__ offsets, BucketDst dst) {
   __shared__ uint32_t s_w[kBktWarps][kMaxShards];   // per-warp counts, then per-warp running bases
   __shared__ bool s_last;
+  __shared__ int s_err;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (dst.remote) {   // a timed-out exchange poisons the region (p2p.cu): push nothing, raise nothing
+    if (threadIdx.x == 0) s_err = ld_volatile_i32(&hdr_of(dst.pb_tab[dst.me])->error);
+    __syncthreads();
+    if (s_err) return;
+  }
   for (int k = lane; k < N; k += 32) s_w[wid][k] = 0;
   __syncwarp();
   unsigned long long v[kChunk / 32];
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(kBktWarps * 32) k_bucket_place(const unsigned 
     if (o >= 0) {
       const int64_t i = i0 + r * 32;
       if (dst.remote) {
-        char* pb = dst.peers.base[o];
+        char* pb = dst.pb_tab[o];
         reinterpret_cast<unsigned long long*>(pb + dst.lay.off_inbox_ids)[(int64_t)dst.me * dst.lay.cap + rel] = v[r];
         reinterpret_cast<int32_t*>(pb + dst.lay.off_inbox_src)[(int64_t)dst.me * dst.lay.cap + rel] = (int32_t)i;
       } else {
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(kBktWarps * 32) k_bucket_place(const unsigned 
   if (!dst.remote) return;
   // publish: one system fence per CTA (it waits for the NVLink acks of the CTA's stores), last CTA raises the flags
   __syncthreads();   // CTA's stores happen-before thread 0's fence (barrier + cumulativity)
-  SymHeader* mine = hdr_of(dst.peers.base[dst.me]);
+  SymHeader* mine = hdr_of(dst.pb_tab[dst.me]);
   if (threadIdx.x == 0) { __threadfence_system(); s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1; }
   __syncthreads();
   if (!s_last) return;
@@ -161,8 +167,9 @@ __global__ void __launch_bounds__(kBktWarps * 32) k_bucket_place(const unsigned 
   if (threadIdx.x == 0) { s_e = mine->epoch + 1; mine->epoch = s_e; mine->done = 0; }
   __syncthreads();
   if (threadIdx.x < N) {
-    SymHeader* h = hdr_of(dst.peers.base[threadIdx.x]);
+    SymHeader* h = hdr_of(dst.pb_tab[threadIdx.x]);
     h->in_cnt[dst.me] = (int)counts[threadIdx.x];
+    h->in_total[dst.me] = (int)rows;
     __threadfence_system();
     st_release_sys(&h->flagA[dst.me], s_e);
   }
@@ -192,9 +199,9 @@ static int bucket_launch(eu_ctx* c, const int64_t* ids, int64_t rows, int P, int
 
 // bucket + push of the peer-memory exchange (p2p.cu): requests land in the owners' inboxes, counts and flagA follow
 int bucket_push(eu_ctx* c, const int64_t* ids, int64_t rows, int P, int N, int self, bool drop_placeholders, int64_t* counts,
-                int64_t* offsets, const SymPeers& peers, const SymLayout& lay, const char* label) {
+                int64_t* offsets, char* const* pb_tab, const SymLayout& lay, const char* label) {
   BucketDst dst{};
-  dst.remote = 1; dst.peers = peers; dst.lay = lay; dst.me = self;
+  dst.remote = 1; dst.pb_tab = pb_tab; dst.lay = lay; dst.me = self;
   return bucket_launch(c, ids, rows, P, N, self, drop_placeholders, counts, offsets, dst, label);
 }
 

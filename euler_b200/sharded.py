@@ -189,8 +189,7 @@ class CudaShardOps:
     def node_weight_sums(self):
         """per node type: sum of this shard's node weights (f64), the shard's column of GetShardNodeWeight()"""
         ex = self.graph.export(with_feat=False)
-        nt = int(ex["node_type"].max()) + 1 if len(ex["node_type"]) else 1
-        nt = max(nt, int(getattr(self.graph, "n_node_types", nt) or nt))
+        nt = int(self.graph.num_node_types)
         return np.bincount(ex["node_type"], weights=ex["node_w"].astype(np.float64), minlength=nt)
 
     def sample_node_local(self, n, node_types):
@@ -311,8 +310,12 @@ class PeerShardedGraph:
     torch.distributed is used once, at construction, to all_gather the cudaIpc handles."""
 
     def __init__(self, graph, rank, world, max_rows, max_count, max_feat_rows, max_dim, rng="minstd", seed=1,
-                 num_partitions=None, group=None, engines=1):
-        """max_rows / max_feat_rows count ALL batches of a batched call; engines = the largest nb used."""
+                 num_partitions=None, group=None, engines=1, feature_graph=None):
+        """max_rows / max_feat_rows count ALL batches of a batched call; engines = the largest nb used.
+        feature_graph: a Graph on this rank's GPU that holds EVERY node's dense features (replicated feature table: 102 GB at
+        the 100M-node / dim-256 config against 180 GB of HBM per B200).  When given, get_dense_feature and sage_mean are the
+        single-GPU kernels on it and only the sampling hops cross NVLink; None = Euler's scheme (features live with their
+        rows and are fetched / aggregated by the owners)."""
         import torch
         import torch.distributed as dist
         from . import _lib
@@ -325,6 +328,8 @@ class PeerShardedGraph:
         if engines > 1:
             self.ctx.set_engines(engines)
         self.ctx.reserve(world * max_rows + 1024)
+        self.feature_graph = feature_graph
+        self.fctx = Context(feature_graph, rng, seed + 7) if feature_graph is not None else None
         self._h = C.c_void_p()
         handle = (C.c_char * 64)()
         self.check(self.lib.eu_sym_create(self.ctx._h, rank, world, max_rows, max_count, max_feat_rows, max_dim,
@@ -355,9 +360,16 @@ class PeerShardedGraph:
         self.ctx.set_stream(self.torch.cuda.current_stream(self.dev).cuda_stream)
 
     def error(self):
+        """nonzero if a bounded wait of this exchange group timed out (or the ranks disagreed on a batch shape): the region is
+        poisoned on EVERY rank -- results since then are invalid and the object must be closed.  Synchronises."""
         e = C.c_int(0)
         self.check(self.lib.eu_sym_error(self._h, C.byref(e)))
         return e.value
+
+    def raise_on_error(self):
+        if self.error():
+            raise EulerErrorSharded("peer exchange poisoned: a rank did not answer within EU_SYM_TIMEOUT_S (default 30 s) "
+                                    "or issued a different batch shape; results of this PeerShardedGraph are invalid")
 
     def hop(self, frontier, etypes, count, default_node=-1, packed=True, nb=1):
         """frontier: device i64 tensor, [nb * rows] (batch-major).  Returns (eng, ids, w, t) VIEWS into the symmetric
@@ -371,7 +383,7 @@ class PeerShardedGraph:
         n = total * int(count)
         return self.o_eng[:n], self.o_ids[:n], self.o_w[:n], self.o_t[:n]
 
-    def sample_fanout_batched(self, nodes, edge_types, counts, default_node=-1):
+    def sample_fanout_batched(self, nodes, edge_types, counts, default_node=-1, check=True):
         """nodes: [nb, B].  Batch g == sample_fanout of nodes[g] with every shard on its engine g.  Returns lists of
         [nb, B * prod(counts[:l])] tensors."""
         t = self.torch
@@ -384,9 +396,13 @@ class PeerShardedGraph:
             eng, o_ids, o_w, o_t = self.hop(frontier, et, c, default_node, nb=nb)
             ids.append(o_ids.clone().reshape(nb, -1)); ws.append(o_w.clone().reshape(nb, -1)); ts.append(o_t.clone().reshape(nb, -1))
             frontier = eng.clone()
+        if check:
+            self.raise_on_error()
         return ids, ws, ts
 
-    def sample_fanout(self, nodes, edge_types, counts, default_node=-1):
+    def sample_fanout(self, nodes, edge_types, counts, default_node=-1, check=True):
+        """check=True synchronises and raises if the exchange was poisoned (pass False inside a CUDA-graph capture and call
+        raise_on_error() at your own sync point)."""
         t = self.torch
         frontier = nodes if isinstance(nodes, t.Tensor) else t.as_tensor(np.asarray(nodes), dtype=t.int64, device=self.dev)
         frontier = frontier.to(device=self.dev, dtype=t.int64).reshape(-1).contiguous()
@@ -395,11 +411,19 @@ class PeerShardedGraph:
             eng, o_ids, o_w, o_t = self.hop(frontier, et, c, default_node)
             ids.append(o_ids.clone()); ws.append(o_w.clone()); ts.append(o_t.clone())
             frontier = eng.clone()
+        if check:
+            self.raise_on_error()
         return ids, ws, ts
 
-    def get_dense_feature(self, nodes, fid, dim, clone=True):
+    def get_dense_feature(self, nodes, fid, dim, clone=True, out=None):
         t = self.torch
         ids = nodes.to(device=self.dev, dtype=t.int64).reshape(-1).contiguous()
+        if self.fctx is not None:      # replicated feature table: the single-GPU kernel, nothing crosses NVLink
+            if out is None:
+                out = t.empty(ids.numel(), dim, dtype=t.float32, device=self.dev)
+            self.fctx.set_stream(t.cuda.current_stream(self.dev).cuda_stream)
+            self.check(self.lib.eu_get_dense_feature(self.fctx._h, ids.data_ptr(), ids.numel(), int(fid), int(dim), out.data_ptr()))
+            return out
         self._stream()
         self.check(self.lib.eu_sym_get_dense_feature(self._h, ids.data_ptr(), ids.numel(), int(fid), int(dim), self.P))
         out = self.o_rows[:ids.numel() * dim].reshape(ids.numel(), dim)
@@ -412,15 +436,29 @@ class PeerShardedGraph:
         assert ids.numel() == rows * count
         if out is None:
             out = t.empty(rows, dim, dtype=t.float32, device=self.dev)
+        if self.fctx is not None:      # replicated feature table: eu_sage_mean_aggregate, bit-identical to the single-GPU path
+            self.fctx.set_stream(t.cuda.current_stream(self.dev).cuda_stream)
+            self.check(self.lib.eu_sage_mean_aggregate(self.fctx._h, ids.data_ptr(), int(rows), int(count), int(dim), out.data_ptr()))
+            return out
         self._stream()
         self.check(self.lib.eu_sym_sage_mean(self._h, ids.data_ptr(), int(rows), int(count), int(dim), self.P, out.data_ptr()))
         return out
 
     def close(self):
+        """destroys the symmetric region; raises if the exchange had been poisoned (results before the close are invalid)"""
         if self._h:
             self.torch.cuda.synchronize()
+            bad = self.error()
             self.lib.eu_sym_destroy(self._h)
             self._h = None
+            if self.fctx is not None:
+                self.fctx.close()
+            if bad:
+                raise EulerErrorSharded("peer exchange was poisoned (timeout or batch-shape mismatch) before close()")
+
+
+class EulerErrorSharded(RuntimeError):
+    pass
 
 
 def _i64(ops):

@@ -118,8 +118,64 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     pg2.close()
+    # ---- replicated feature table (PeerShardedGraph(feature_graph=...)): the fetch and the fused mean are the single-GPU
+    # kernels on a graph that holds every node's row -> bit-identical to the unsharded ops / the oracle's scatter_mean
+    full_gr = graphs.cuda_graph(g, device=local)
+    pr = PeerShardedGraph(gr, rank, world, max_rows=n1, max_count=25, max_feat_rows=1, max_dim=4, rng="minstd", seed=700 + rank,
+                          feature_graph=full_gr)
+    r_ids, r_ws, r_ts = pr.sample_fanout(seeds[rank], ets, counts, -1)
+    for l in range(3):
+        cases.eq(r_ids[l].cpu().numpy(), expect[rank][0][l], "replicated: rank %d ids hop %d" % (rank, l))
+    rf = pr.get_dense_feature(r_ids[1], 0, 64)
+    cases.eq(rf.cpu().numpy(), full.op_get_dense_feature(r_ids[1].cpu().numpy(), 64), "replicated: features")
+    ra = pr.sage_mean(r_ids[2], n1, 10, 64)
+    from oracle import pyoracle as po
+    want_a = po.scatter_mean(full.op_get_dense_feature(r_ids[2].cpu().numpy(), 64), np.repeat(np.arange(n1, dtype=np.int32), 10), n1)
+    cases.eq(ra.cpu().numpy(), want_a, "replicated: fused sage mean == oracle scatter_mean (bit-exact)")
+    torch.cuda.synchronize()
+    dist.barrier()
+    pr.close()
+    # ---- a rank that issues a different batch shape poisons the exchange on EVERY rank instead of corrupting it silently
+    pz = PeerShardedGraph(gr, rank, world, max_rows=4096, max_count=4, max_feat_rows=1, max_dim=4, rng="minstd", seed=1 + rank)
+    odd = seeds[rank][:1000 if rank == 0 else 1001]
+    try:
+        pz.sample_fanout(odd, [[0]], [4], -1)
+        poisoned = False
+    except Exception:
+        poisoned = True
+    assert poisoned, "rank %d: a batch-shape mismatch went undetected" % rank
+    torch.cuda.synchronize()
+    dist.barrier()
+    try:
+        pz.close()
+    except Exception:
+        pass
+    # ---- sharded DeepWalk (p = q = 1) and sample_node on the CUDA per-shard ops over NCCL (host logic pinned over gloo in
+    # tests/test_sharded_cpu.py with the oracle ops; here the same expectations with the real kernels)
+    from euler_b200.sharded import ClientRng
+    ops_w = CudaShardOps(gr, "minstd", 700 + rank)
+    wseeds = [s_[:150] for s_ in seeds]
+    walk = ShardedGraph(ops_w, TorchExchange()).random_walk(wseeds[rank], [[0, 1]] * 5, 1.0, 1.0, -1)
+    exp_w = sc.simulate(shards, wseeds, [[0, 1]] * 5, [1] * 5, shard_seeds=[700 + s_ for s_ in range(world)])
+    assert tuple(walk.shape) == (150, 6)
+    for l in range(6):
+        cases.eq(walk[:, l].cpu().numpy(), exp_w[rank][0][l], "cuda sharded walk: rank %d column %d" % (rank, l))
+    g3 = graphs.random_graph(seed=78, n=900, T=1, avg_deg=3, n_node_types=3, id_stride=2, id_base=5)
+    shards3 = sc.partition(g3, world)
+    gr3 = graphs.cuda_graph(shards3[rank], device=local)
+    for types in ([0], [-1], [1, 2]):
+        ops3 = CudaShardOps(gr3, "minstd", 600 + rank)
+        sg3 = ShardedGraph(ops3, TorchExchange())
+        crng = ClientRng(900 + rank)
+        for _ in range(2):
+            got = sg3.sample_node(257, types, crng)
+        want = sc.simulate_sample_node(shards3, 257, types, [600 + s_ for s_ in range(world)], [900 + r for r in range(world)], repeat=2)
+        cases.eq(got.cpu().numpy(), want[rank], "cuda sharded sample_node: rank %d types %s" % (rank, types))
+    torch.cuda.synchronize()
+    dist.barrier()
     if rank == 0:
-        print("SHARDED_GPU_OK world=%d" % world)
+        print("SHARDED_GPU_OK world=%d (peer exchange, batched, fused sage, replicated features, poison on shape mismatch, "
+              "sharded walk + sample_node on CUDA ops)" % world)
     dist.destroy_process_group()
 
 

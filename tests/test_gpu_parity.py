@@ -590,3 +590,88 @@ def test_unique_first_occurrence_and_sage_dataflow():
             cases.eq(a.res_n_id.cpu().numpy(), b.res_n_id.numpy(), "flow res_n_id")
             cases.eq(a.edge_index.cpu().numpy(), b.edge_index.numpy(), "flow edge_index")
             assert a.size == b.size
+
+
+# ------------------------------------------------------------------ round 2: generator restatement, pinned host buffers
+@pytest.mark.parametrize("n,E,T,NT", [(50_000, 600_000, 1, 1), (30_011, 250_000, 5, 3)])
+def test_device_rmat_generator_equals_host_restatement(n, E, T, NT):
+    """euler_b200/csrc/graph.cu (k_rmat_edges, k_rmat_fill, k_build_cum, k_fill_feat) vs oracle/rmat_gen.c: bit-identical
+    CSR, cumulative weights and features -- bench.py's CPU arms and its parity gate rely on this equality."""
+    import euler_b200
+    if T == 1:
+        gr = euler_b200.Graph.rmat(n, E, seed=42, feat_dim=24, feat_seed=7)
+    else:
+        gr = euler_b200.Graph.rmat_hetero(n, E, T, NT, seed=42, feat_dim=24, feat_seed=7)
+    ex = gr.export()
+    host = po.rmat_graph(n, E, seed=42, feat_dim=24, feat_seed=7, T=T, NT=NT, threads=3)
+    for k in ("ids", "node_type", "node_w", "grp_ptr", "nbr", "cum_w", "feat") + (("grp_cum",) if T > 1 else ()):
+        cases.eq(ex[k], host[k], "rmat " + k)
+    ids = np.array([1, n, n + 1, 0, -1, 17], np.int64)
+    want = np.where(((ids >= 1) & (ids <= n))[:, None], host["feat"][np.clip(ids - 1, 0, n - 1)], 0).astype(np.float32)
+    cases.eq(po.rmat_feat_rows(ids, n, 24, 7), want, "rmat_feat_rows")
+
+
+def test_host_entry_points_dma_pinned_buffers_in_place():
+    """*_host with page-locked caller buffers (no staging copy) == the same calls with pageable buffers == device entry points"""
+    import euler_b200
+    from euler_b200 import _lib
+    lib = _lib.load()
+    g = graphs.random_graph(seed=77, n=20000, T=2, avg_deg=8, feat_dim=128, hub=400)
+    gr = graphs.cuda_graph(g)
+    B, counts, nb = 300, [6, 5], 3
+    cs = np.asarray(counts, np.int32)
+    et = np.asarray([[0, 1], [1, 0]], np.int32)
+    seeds = g["ids"][np.random.RandomState(5).randint(0, 20000, size=nb * B)].astype(np.int64)
+    seeds[::7] = 0
+    n1, n2 = nb * B * 6, nb * B * 30
+    P = C.c_void_p * 2
+    outs = {}
+    for mode in ("pinned", "pageable"):
+        ctx = euler_b200.Context(gr, "minstd", 99)
+        ctx.set_engines(nb, [500 + b for b in range(nb)])
+        mk = (lambda n_, dt: torch.empty(n_, dtype=dt).pin_memory()) if mode == "pinned" else (lambda n_, dt: torch.empty(n_, dtype=dt))
+        h_seeds = mk(nb * B, torch.int64); h_seeds.copy_(torch.from_numpy(seeds))
+        ids = [mk(n1, torch.int64), mk(n2, torch.int64)]
+        ws = [mk(n1, torch.float32), mk(n2, torch.float32)]
+        ts = [mk(n1, torch.int32), mk(n2, torch.int32)]
+        _lib.check(lib.eu_sample_fanout_batched_host(ctx._h, h_seeds.data_ptr(), nb, B, et.ctypes.data, 2, cs.ctypes.data, 2, -1,
+                                                     P(*[x.data_ptr() for x in ids]), P(*[x.data_ptr() for x in ws]), P(*[x.data_ptr() for x in ts])))
+        x = mk(n1 * 128, torch.float32)
+        _lib.check(lib.eu_get_dense_feature_host(ctx._h, ids[0].data_ptr(), n1, 0, 128, x.data_ptr()))
+        agg = mk(n1 * 128, torch.float32)
+        _lib.check(lib.eu_sage_mean_aggregate_host(ctx._h, ids[1].data_ptr(), n1, 5, 128, agg.data_ptr()))
+        outs[mode] = [t.clone().numpy() for t in ids + ws + ts + [x, agg]]
+    for a, b in zip(outs["pinned"], outs["pageable"]):
+        cases.eq(a, b, "pinned vs pageable host buffers")
+    # device entry points, same engines
+    ctx = euler_b200.Context(gr, "minstd", 99)
+    ctx.set_engines(nb, [500 + b for b in range(nb)])
+    d_seeds = torch.from_numpy(seeds).cuda()
+    d_ids = [torch.empty(n1, dtype=torch.int64, device="cuda"), torch.empty(n2, dtype=torch.int64, device="cuda")]
+    d_ws = [torch.empty(n1, dtype=torch.float32, device="cuda"), torch.empty(n2, dtype=torch.float32, device="cuda")]
+    d_ts = [torch.empty(n1, dtype=torch.int32, device="cuda"), torch.empty(n2, dtype=torch.int32, device="cuda")]
+    _lib.check(lib.eu_sample_fanout_batched(ctx._h, d_seeds.data_ptr(), nb, B, et.ctypes.data, 2, cs.ctypes.data, 2, -1,
+                                            P(*[x.data_ptr() for x in d_ids]), P(*[x.data_ptr() for x in d_ws]), P(*[x.data_ptr() for x in d_ts])))
+    d_agg = torch.empty(n1 * 128, dtype=torch.float32, device="cuda")
+    _lib.check(lib.eu_sage_mean_aggregate(ctx._h, d_ids[1].data_ptr(), n1, 5, 128, d_agg.data_ptr()))
+    ctx.sync()
+    cases.eq(outs["pinned"][0], d_ids[0].cpu().numpy(), "host vs device ids hop 1")
+    cases.eq(outs["pinned"][1], d_ids[1].cpu().numpy(), "host vs device ids hop 2")
+    cases.eq(outs["pinned"][7], d_agg.cpu().numpy(), "host vs device sage mean")
+
+
+def test_fanout_with_zero_count_leaves_the_dedup_tables_clean():
+    """counts = [5, 0]: the chain stops before the empty hop; the next op on the same ctx still matches the oracle"""
+    import euler_b200
+    g = graphs.random_graph(seed=78, n=3000, T=1, avg_deg=5)
+    euler_b200.set_graph(graphs.cuda_graph(g), rng="minstd", seed=31)
+    og = graphs.oracle_graph(g)
+    seeds = g["ids"][np.random.RandomState(1).randint(0, 3000, size=200)].astype(np.int64)
+    po.seed(31)
+    ids, ws, ts = euler_b200.sample_fanout(seeds, [[0], [0]], [5, 0])
+    o_ids, _, _ = og.op_sample_fanout(seeds, [[0]], [5])
+    cases.eq(ids[1].cpu().numpy(), o_ids[0], "hop 1 of [5, 0]")
+    assert ids[2].numel() == 0
+    ids2, _, _ = euler_b200.sample_fanout(seeds, [[0], [0]], [4, 3])
+    o2, _, _ = og.op_sample_fanout(seeds, [[0], [0]], [4, 3])
+    cases.eq(ids2[2].cpu().numpy(), o2[1], "fanout after a zero-count call")

@@ -119,3 +119,30 @@ def test_tiny_dense_feature_golden():
 def test_shard_routing():
     # euler/core/kernels/id_split_op.cc:46-49
     assert [po.shard_of(i, 8, 2) for i in range(10)] == [(i % 8) % 2 for i in range(10)]
+
+
+def test_rmat_generator_restatement_invariants_and_pin():
+    """oracle/rmat_gen.c (the host restatement of the device graph generator): structure, determinism across thread
+    counts, and a pinned digest so that a silent change of either generator is caught on CPU (the GPU test compares the
+    device generator against this one array by array)."""
+    import hashlib
+    a = po.rmat_graph(20_000, 150_000, seed=42, feat_dim=8, feat_seed=7, threads=1)
+    b = po.rmat_graph(20_000, 150_000, seed=42, feat_dim=8, feat_seed=7, threads=5)
+    for k in ("ids", "grp_ptr", "nbr", "cum_w", "feat"):
+        assert np.array_equal(a[k], b[k]), k
+    ptr, nbr, cum = a["grp_ptr"], a["nbr"], a["cum_w"]
+    assert ptr[0] == 0 and ptr[-1] == 150_000 and np.all(np.diff(ptr) >= 0)
+    assert nbr.min() >= 1 and nbr.max() <= 20_000
+    rows = np.repeat(np.arange(20_000), np.diff(ptr))
+    same = rows[1:] == rows[:-1]
+    assert np.all(nbr[1:][same] >= nbr[:-1][same])                      # adjacency sorted by neighbor id
+    w = np.diff(cum, prepend=np.float32(0)); w[ptr[:-1][np.diff(ptr) > 0]] = cum[ptr[:-1][np.diff(ptr) > 0]]
+    assert w.min() > 0.99 and w.max() < 11.0                            # 1 + (h % 100) / 10, up to f32 rounding of the prefix
+    assert np.abs(a["feat"]).max() <= 1.0
+    h = hashlib.sha256()
+    for k in ("grp_ptr", "nbr", "cum_w", "feat"):
+        h.update(np.ascontiguousarray(a[k]).tobytes())
+    assert h.hexdigest() == RMAT_DIGEST, h.hexdigest()
+
+
+RMAT_DIGEST = "f0374b5e0a692cfbe72b1ece86e00b32787a7b1b4ff12d355e454958e95cc3b6"
