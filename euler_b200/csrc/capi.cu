@@ -44,7 +44,7 @@ static int regrow(T** p, int64_t count) {
 
 // growing scratch frees and re-allocates under a stream synchronise: impossible while the stream is being captured into
 // a CUDA graph -- fail loudly and say what to do instead of invalidating the capture
-static int refuse_if_capturing(eu_ctx* c, const char* what) {
+int refuse_growth_in_capture(eu_ctx* c, const char* what) {
   cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(c->stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
     set_error("%s must grow while the ctx stream is being captured: run the op once (or call eu_ctx_reserve) before the capture", what);
@@ -56,7 +56,7 @@ static int refuse_if_capturing(eu_ctx* c, const char* what) {
 
 int ctx_reserve(eu_ctx* c, int64_t rows, int64_t table_slots) {
   int rc;
-  if ((table_slots > c->tab_set_slots || rows > c->cap_rows) && (rc = refuse_if_capturing(c, "the sampling scratch"))) return rc;
+  if ((table_slots > c->tab_set_slots || rows > c->cap_rows) && (rc = refuse_growth_in_capture(c, "the sampling scratch"))) return rc;
   if (table_slots > c->tab_set_slots) {
     EU_CUDA(cudaStreamSynchronize(c->stream));  // growing while the stream still uses the old buffers would be a race
     const int64_t slots = table_slots + 64;
@@ -89,7 +89,7 @@ int ctx_reserve(eu_ctx* c, int64_t rows, int64_t table_slots) {
 
 int ctx_misc(eu_ctx* c, int64_t bytes) {
   if (bytes <= c->misc_bytes) return EU_OK;
-  if (int rc0 = refuse_if_capturing(c, "the op scratch")) return rc0;
+  if (int rc0 = refuse_growth_in_capture(c, "the op scratch")) return rc0;
   EU_CUDA(cudaStreamSynchronize(c->stream));
   char* p = (char*)c->d_misc;
   int rc = regrow(&p, bytes);
@@ -165,7 +165,7 @@ int eu_ctx_destroy(eu_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaFree(c->d_rng); cudaFree(c->d_dedup); cudaFree(c->d_first); cudaFree(c->d_rowof);
   cudaFree(c->d_elig); cudaFree(c->d_state); cudaFree(c->d_emask); cudaFree(c->d_woff); cudaFree(c->d_blkpre); cudaFree(c->d_blkmul); cudaFree(c->d_live); cudaFree(c->d_nlive); cudaFree(c->d_front[0]); cudaFree(c->d_front[1]);
-  cudaFree(c->d_misc); cudaFree(c->d_stage);
+  cudaFree(c->d_misc); cudaFree(c->d_stage); cudaFree(c->d_walkv);
   if (c->h_pin) cudaFreeHost(c->h_pin);
   delete c;
   return EU_OK;

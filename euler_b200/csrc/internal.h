@@ -117,6 +117,8 @@ struct eu_ctx {
   // extra scratch for walks / scatter
   void* d_misc = nullptr;
   int64_t misc_bytes = 0;
+  float* d_walkv = nullptr;          // node2vec: biased weights of the big rows of one step (walk.cu)
+  long long walkv_cap = 0;
   // pinned staging for *_host calls
   void* h_pin = nullptr;
   int64_t pin_bytes = 0;
@@ -147,6 +149,7 @@ int ctx_reserve(eu_ctx* c, int64_t rows, int64_t table_slots);
 int64_t hop_scratch_rows(int nb, int64_t rows_b);
 int64_t hop_table_slots(int nb, int64_t rows_b);
 int ctx_misc(eu_ctx* c, int64_t bytes);
+int refuse_growth_in_capture(eu_ctx* c, const char* what);   // EU_ERR_STATE if the ctx stream is being captured
 int ctx_stage(eu_ctx* c, int64_t host_bytes, int64_t dev_bytes);
 int graph_build_sampler(eu_graph* g);
 int launch_state_scan(eu_ctx* c, int64_t rows, unsigned long long uniforms_per_row);

@@ -10,6 +10,8 @@
 //                                               sequential f32 prefix + one RandomSelect draw.
 // The reference makes one host round trip (a GQL query) per step; here a step is two small kernels
 // and the frontier never leaves HBM.  Exact-RNG order: one uniform per LIVE walker, in walker order.
+#include <stdlib.h>
+
 #include "internal.h"
 
 namespace eu {
@@ -169,7 +171,8 @@ __global__ void __launch_bounds__(128) k_walk_step(DevGraph g, int64_t B, int32_
 // biased (/p if it is the parent id, /q otherwise).  That is a per-element predicate, so 32 lanes classify 32
 // children at once by streaming P in 32-wide chunks next to C; only the f32 prefix sum (CompactWeightedCollection
 // ::Init, compact_weighted_collection.h:82-97) stays serial -- it is evaluated left to right through shuffles,
-// ~5 cycles per neighbor, which is the floor for a bit-exact sum.  Pass 1 = total, pass 2 = select.
+// ~5 cycles per neighbor.  Pass 1 = total, pass 2 = select.  Used for rows of up to kWalkBig edges (k_walk_prefix); longer
+// rows go through k_walk_weights + block_exact_prefix, which evaluates the same sequential sum 1024 elements at a time.
 struct WarpWalk {
   const DevGraph* g;
   int64_t cb, ce, cbase;   // child group [cb, ce), first edge of the child's row
@@ -235,18 +238,371 @@ struct WarpWalk {
   }
 };
 
-__global__ void __launch_bounds__(256) k_walk_step_warp(DevGraph g, int64_t B, int32_t L, int32_t step, int32_t ctype,
-                                                        int32_t ptype, float p, float q, long long default_node,
-                                                        WalkState s, const uint8_t* __restrict__ live,
-                                                        const uint32_t* __restrict__ state, bool philox,
-                                                        unsigned long long key, long long* __restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+// ---------------------------------------------------------------------------------------------
+// Exact node2vec step for BIG rows (deg > kWalkBig), split so that nothing latency-heavy sits inside the sequential part:
+//   k_walk_plan     one block: RNG engine states of the live walkers (the reference draws one uniform per live walker, in
+//                   walker order), the big / small work lists, offsets of the big rows in the weight scratch V
+//   k_walk_weights  fully parallel over (big walker, neighbor): BuildWeights' bias (:140-168) per element -- membership of
+//                   the child in the parent's sorted list by binary search, multiset rule as in WarpWalk -- written to V
+//   k_walk_prefix   CTA per big walker: the SEQUENTIAL f32 prefix of CompactWeightedCollection::Init (:82-97) evaluated
+//                   1024 elements per iteration without changing a single rounding (block_exact_prefix below), total ->
+//                   one uniform -> RandomSelect; then warp per small walker (WarpWalk, as before)
+//
+// block_exact_prefix: S_k = fl(S_{k-1} + v_k) for v_k >= 0.  While S stays in one binade (ulp u = 2^(e-23), S = M u with
+// 2^23 <= M < 2^24) and v_k's exponent does not exceed e, fl(S + v) = (M + a + c) u with a = floor(v / u) and c = 1 iff the
+// discarded part of v exceeds u / 2 -- an INTEGER increment that does not depend on M, except (i) exact ties (discarded
+// part == u / 2: round-half-even needs M's parity), (ii) M reaching 2^24 (the binade changes) and (iii) v above S's binade.
+// So the block computes the increments of 1024 elements in parallel, prefix-sums them as integers, accepts everything
+// before the first exception, lets one thread redo the next 32 elements with real FADDs, and continues.  Exceptions are
+// common only while S is within a few binades of the addends (the first dozens of elements of a row); a 137K-edge hub row
+// of the R-MAT graph takes 143 iterations instead of 137K dependent FADDs.  Checked against the plain sequential sum on
+// random, tie-heavy, zero-laden and wide-exponent inputs (the same arithmetic in Python) and by the oracle parity tests.
+static constexpr int kWalkBig = 512;        // rows longer than this take the V path
+static constexpr int kWalkChunk = 256;      // elements per k_walk_weights chunk
+static constexpr int kPrefT = 256;          // threads of a k_walk_prefix CTA
+static constexpr int kPrefE = 4;            // elements per thread and iteration
+static constexpr int kPrefCH = kPrefT * kPrefE;
+static constexpr int kPrefSer = 32;         // elements redone serially after an exception
+static constexpr int kPrefCk = 256;         // checkpoints kept per row
+
+struct WalkPlan {
+  int32_t* deg;         // [B] length of the walker's child list (single type), 0 if dead
+  int32_t* big_list;    // [B] walkers on the V path, walker order
+  int32_t* small_list;  // [B] the rest of the live walkers
+  long long* voff;      // [B+1] V offset of big walker k (k = position in big_list)
+  int32_t* coff;        // [B+1] first k_walk_weights chunk of big walker k
+  unsigned int* ctr;    // [8]: 0 n_big, 1 n_small, 2 n_chunks, 3 big ticket, 4 small ticket
+  float* V;
+  long long capV;
+};
+
+__global__ void k_walk_deg(DevGraph g, int64_t B, int32_t ctype, WalkState s, uint8_t* live, int32_t* deg) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= B) return;
-  const long long cur = s.cur[i];
-  const int64_t crow = s.cur_row[i];
-  long long next = default_node;
-  if (live[i]) {
+  const int64_t row = lookup_row(g, (unsigned long long)s.cur[i]);
+  s.cur_row[i] = row;
+  int64_t d = 0;
+  if (row >= 0) d = g.grp_ptr[row * g.T + ctype + 1] - g.grp_ptr[row * g.T + ctype];
+  live[i] = d > 0 ? 1 : 0;
+  deg[i] = (int32_t)min(d, (int64_t)0x7fffffff);
+}
+
+// one block of 1024 threads; thread t owns a contiguous stretch of walkers
+__global__ void __launch_bounds__(1024) k_walk_plan(int64_t B, const uint8_t* __restrict__ live, bool minstd, uint32_t F,
+                                                    uint32_t* __restrict__ state, EuRngState* rng, WalkPlan wp) {
+  __shared__ uint32_t s_prod[1024];
+  __shared__ uint32_t s_cnt[1024];
+  __shared__ uint32_t s_big[1024];
+  __shared__ uint32_t s_small[1024];
+  __shared__ uint32_t s_chunks[1024];
+  __shared__ unsigned long long s_el[1024];
+  const int t = threadIdx.x;
+  if (t == 0) wp.ctr[5] = 0;   // walkers demoted to the warp path because V is full
+  const int64_t per = (B + 1023) / 1024;
+  const int64_t b = min((int64_t)t * per, B), e = min(b + per, B);
+  uint32_t prod = 1, cnt = 0, nbig = 0, nsmall = 0, chunks = 0;
+  unsigned long long el = 0;
+  for (int64_t i = b; i < e; ++i) {
+    if (!live[i]) continue;
+    prod = modmul(prod, F); ++cnt;
+    const int32_t d = wp.deg[i];
+    if (d > kWalkBig) { ++nbig; el += (unsigned long long)d; chunks += (uint32_t)((d + kWalkChunk - 1) / kWalkChunk); }
+    else ++nsmall;
+  }
+  s_prod[t] = prod; s_cnt[t] = cnt; s_big[t] = nbig; s_small[t] = nsmall; s_chunks[t] = chunks; s_el[t] = el;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {   // inclusive Hillis-Steele scans (modmul is associative and commutative)
+    uint32_t v = 1, c = 0, g1 = 0, g2 = 0, g3 = 0; unsigned long long g4 = 0;
+    if (t >= off) { v = s_prod[t - off]; c = s_cnt[t - off]; g1 = s_big[t - off]; g2 = s_small[t - off]; g3 = s_chunks[t - off]; g4 = s_el[t - off]; }
+    __syncthreads();
+    if (t >= off) { s_prod[t] = modmul(s_prod[t], v); s_cnt[t] += c; s_big[t] += g1; s_small[t] += g2; s_chunks[t] += g3; s_el[t] += g4; }
+    __syncthreads();
+  }
+  const uint32_t x0 = minstd ? rng->x : 0u;
+  uint32_t run = minstd ? modmul(x0, t > 0 ? s_prod[t - 1] : 1u) : 0u;
+  uint32_t kb = t > 0 ? s_big[t - 1] : 0u, ks = t > 0 ? s_small[t - 1] : 0u, kc = t > 0 ? s_chunks[t - 1] : 0u;
+  unsigned long long ke = t > 0 ? s_el[t - 1] : 0ull;
+  const uint32_t n_small_scan = s_small[1023];
+  for (int64_t i = b; i < e; ++i) {
+    if (minstd) state[i] = run;
+    if (!live[i]) continue;
+    if (minstd) run = modmul(run, F);
+    const int32_t d = wp.deg[i];
+    if (d > kWalkBig) {
+      if (ke + (unsigned long long)d <= (unsigned long long)wp.capV) {
+        wp.big_list[kb] = (int32_t)i; wp.voff[kb] = (long long)ke; wp.coff[kb] = (int32_t)kc;
+      } else {
+        // V is full (offsets are monotone, so this is a suffix of the big walkers): the warp path serves it
+        wp.small_list[n_small_scan + atomicAdd(&wp.ctr[5], 1u)] = (int32_t)i;
+      }
+      ++kb; ke += (unsigned long long)d; kc += (uint32_t)((d + kWalkChunk - 1) / kWalkChunk);
+    } else {
+      wp.small_list[ks++] = (int32_t)i;
+    }
+  }
+  __syncthreads();
+  if (t == 1023) {
+    // big walkers that fit: the prefix whose end offset is within capV -- recount from the scanned stretch ends
+    if (minstd) { rng->x = modmul(x0, s_prod[1023]); rng->draws += (unsigned long long)s_cnt[1023]; }
+  }
+  // n_big = big walkers whose V range fits.  Thread t knows how many of ITS big walkers fit; sum them.
+  __shared__ unsigned int s_fit, s_fitchunks;
+  if (t == 0) { s_fit = 0; s_fitchunks = 0; }
+  __syncthreads();
+  {
+    unsigned long long ke2 = t > 0 ? s_el[t - 1] : 0ull;
+    unsigned int fit = 0, fc = 0;
+    for (int64_t i = b; i < e; ++i) {
+      if (!live[i]) continue;
+      const int32_t d = wp.deg[i];
+      if (d > kWalkBig) {
+        if (ke2 + (unsigned long long)d <= (unsigned long long)wp.capV) { ++fit; fc += (uint32_t)((d + kWalkChunk - 1) / kWalkChunk); }
+        ke2 += (unsigned long long)d;
+      }
+    }
+    if (fit) { atomicAdd(&s_fit, fit); atomicAdd(&s_fitchunks, fc); }
+  }
+  __syncthreads();
+  if (t == 0) {
+    wp.ctr[0] = s_fit;
+    wp.ctr[1] = n_small_scan + (s_big[1023] - s_fit);
+    wp.ctr[2] = s_fitchunks;
+    wp.ctr[3] = 0; wp.ctr[4] = 0;
+    wp.coff[s_fit] = (int32_t)s_fitchunks;
+  }
+}
+
+// first j in [lo, hi) with (signed) a[j] >= key
+__device__ __forceinline__ int64_t lower_bound_ll(const unsigned long long* __restrict__ a, int64_t lo, int64_t hi, long long key) {
+  while (lo < hi) {
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    if ((long long)__ldg(a + mid) < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kWalkChunk) k_walk_weights(DevGraph g, int32_t ctype, int32_t ptype, float p, float q, WalkState s,
+                                                             WalkPlan wp) {
+  __shared__ int s_k;
+  const unsigned int n_chunks = wp.ctr[2], n_big = wp.ctr[0];
+  for (unsigned int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    if (threadIdx.x == 0) {   // big walker of chunk c: last k with coff[k] <= c
+      int lo = 0, hi = (int)n_big;
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((unsigned int)wp.coff[mid] <= c) lo = mid; else hi = mid; }
+      s_k = lo;
+    }
+    __syncthreads();
+    const int k = s_k;
+    const int64_t i = wp.big_list[k];
+    const int64_t crow = s.cur_row[i];
+    const int64_t cbase = g.grp_ptr[crow * g.T];
+    const int64_t cb = g.grp_ptr[crow * g.T + ctype];
+    const int64_t off = (int64_t)(c - (unsigned int)wp.coff[k]) * kWalkChunk + threadIdx.x;
+    const int32_t d = wp.deg[i];
+    if (off < d) {
+      const int64_t j = cb + off;
+      const long long cv = (long long)__ldg(g.nbr + j);
+      const float hi_w = __ldg(g.cum_w + j);
+      const float lo_w = j == cbase ? 0.f : __ldg(g.cum_w + j - 1);
+      float w = __fsub_rn(hi_w, lo_w);
+      // m = copies of cv that precede this one in the child list (sorted: they are adjacent)
+      int64_t m = 0;
+      while (j - 1 - m >= cb && (long long)__ldg(g.nbr + j - 1 - m) == cv) ++m;
+      bool shared = false;
+      const int64_t prow = s.parent_row[i];
+      if (prow >= 0 && ptype >= 0 && ptype < g.T) {
+        const int64_t pb = g.grp_ptr[prow * g.T + ptype], pe = g.grp_ptr[prow * g.T + ptype + 1];
+        const int64_t lb = lower_bound_ll(g.nbr, pb, pe, cv);
+        shared = lb + m < pe && (long long)__ldg(g.nbr + lb + m) == cv;   // the parent holds more than m copies
+      }
+      if (!shared) w = cv != s.parent[i] ? __fdiv_rn(w, q) : __fdiv_rn(w, p);   // d_tx = 2 / d_tx = 0
+      wp.V[wp.voff[k] + off] = w;
+    }
+    __syncthreads();
+  }
+}
+
+struct PrefShared {
+  float v[kPrefCH];
+  unsigned int warp_tot[kPrefT / 32];
+  float ck_S[kPrefCk];
+  int32_t ck_pos[kPrefCk];
+  int n_ck;
+  float S;
+  int32_t pos;
+  int first, hit;
+  unsigned int m_prev;
+  double r;
+  int32_t answer;
+};
+
+// Runs the exact prefix over V[0, n) from (sh.pos, sh.S).  select: stop at the first k with (double)S_k > r and leave k in
+// sh.answer (-1 if none).  record: store a checkpoint every ck_stride iterations.  Returns with sh.S = S_{n-1} when !select.
+__device__ void block_exact_prefix(PrefShared& sh, const float* __restrict__ V, int32_t n, bool select, bool record, int ck_stride) {
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  int it = 0;
+  while (true) {
+    __syncthreads();
+    const int32_t pos = sh.pos;
+    if (pos >= n || (select && sh.answer >= 0)) break;
+    const float S = sh.S;
+    if (record && t == 0 && (it % ck_stride) == 0 && sh.n_ck < kPrefCk) { sh.ck_pos[sh.n_ck] = pos; sh.ck_S[sh.n_ck] = S; ++sh.n_ck; }
+    ++it;
+    const int32_t n_it = min((int32_t)kPrefCH, n - pos);
+    const uint32_t sb = __float_as_uint(S);
+    const uint32_t eS = (sb >> 23) & 0xffu;
+    const uint32_t M_in = eS ? ((sb & 0x7fffffu) | 0x800000u) : 0u;
+    // select threshold in units of this binade's ulp: S_k > r  <=>  M_k > floor(r / ulp)
+    uint32_t Mthr = 0x1000000u;
+    if (select && eS) {
+      const double x = ldexp(sh.r, 150 - (int)eS);   // r / 2^(eS-127-23)
+      if (x < 16777216.0) Mthr = (uint32_t)floor(x);
+    }
+    uint32_t inc[kPrefE];
+    bool flg[kPrefE];
+    uint32_t l = 0;
+    int myfirst = kPrefCH;
+#pragma unroll
+    for (int e = 0; e < kPrefE; ++e) {
+      const int32_t k = t * kPrefE + e;
+      float v = 0.f;
+      if (k < n_it) v = V[pos + k];
+      sh.v[k] = v;
+      const uint32_t vb = __float_as_uint(v);
+      uint32_t in = 0; bool f = false;
+      if (vb != 0u) {
+        if (vb >> 31) f = true;                       // a negative weight: never speculated
+        else {
+          uint32_t ev = vb >> 23;
+          const uint32_t mant = ev ? ((vb & 0x7fffffu) | 0x800000u) : (vb & 0x7fffffu);
+          if (ev == 0u) ev = 1u;
+          if (eS == 0u || ev > eS) f = true;
+          else {
+            const uint32_t sft = eS - ev;
+            if (sft == 0u) in = mant;
+            else if (sft <= 24u) {
+              const uint32_t rem = mant & ((1u << sft) - 1u), half = 1u << (sft - 1u);
+              in = (mant >> sft) + (rem > half ? 1u : 0u);
+              f = rem == half;
+            }
+          }
+        }
+      }
+      inc[e] = in; flg[e] = f;
+      l += in;
+    }
+    // warp inclusive scan of the thread sums (l <= 4 * 2^24)
+    uint32_t ws = l;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += y; }
+    if (lane == 31) sh.warp_tot[wid] = min(ws, 0x2000000u);   // anything >= 2^24 means "crossed": clamp so that sums stay in 32 bits
+    if (t == 0) { sh.first = kPrefCH; sh.hit = kPrefCH; }
+    __syncthreads();
+    uint32_t base = M_in + (ws - l);
+    for (int w2 = 0; w2 < wid; ++w2) base += sh.warp_tot[w2];
+    uint32_t Mk = base, Mbefore = base;
+    int myhit = kPrefCH;
+#pragma unroll
+    for (int e = 0; e < kPrefE; ++e) {
+      const int32_t k = t * kPrefE + e;
+      const uint32_t prev = Mk;
+      Mk += inc[e];
+      if (k < n_it) {
+        if ((flg[e] || Mk >= 0x1000000u) && myfirst == kPrefCH) { myfirst = k; Mbefore = prev; }
+        if (select && Mk > Mthr && myhit == kPrefCH) myhit = k;
+      }
+    }
+    if (myfirst < kPrefCH) atomicMin(&sh.first, myfirst);
+    if (myhit < kPrefCH) atomicMin(&sh.hit, myhit);
+    __syncthreads();
+    const int f = sh.first, h = sh.hit;
+    if (select && h < f) {   // every element before the first exception is final: the hit is real
+      if (t == 0) sh.answer = pos + h;
+      continue;
+    }
+    if (f >= n_it) {         // no exception: the whole stretch is accepted
+      if (t * kPrefE < n_it && (t + 1) * kPrefE >= n_it) {   // owner of the last element: Mk of element n_it-1
+        uint32_t Ml = base;
+#pragma unroll
+        for (int e = 0; e < kPrefE; ++e) if (t * kPrefE + e < n_it) Ml += inc[e];
+        if (eS) sh.S = __uint_as_float((eS << 23) | (Ml & 0x7fffffu));
+        sh.pos = pos + n_it;
+      }
+      continue;
+    }
+    if (myfirst == f) sh.m_prev = Mbefore;   // M before element f
+    __syncthreads();
+    if (t == 0) {
+      float Sc = eS ? __uint_as_float((eS << 23) | (sh.m_prev & 0x7fffffu)) : S;
+      int32_t k = f;
+      const int32_t kend = min(f + kPrefSer, n_it);
+      int32_t ans = -1;
+      for (; k < kend; ++k) {
+        Sc = __fadd_rn(Sc, sh.v[k]);
+        if (select && (double)Sc > sh.r) { ans = pos + k; ++k; break; }
+      }
+      sh.S = Sc;
+      sh.pos = pos + k;
+      if (ans >= 0) sh.answer = ans;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kPrefT) k_walk_prefix(DevGraph g, int64_t B, int32_t L, int32_t step, int32_t ctype, int32_t ptype,
+                                                        float p, float q, long long default_node, WalkState s,
+                                                        const uint8_t* __restrict__ live, const uint32_t* __restrict__ state,
+                                                        bool philox, unsigned long long key, WalkPlan wp, long long* __restrict__ out) {
+  __shared__ PrefShared sh;
+  __shared__ unsigned int s_tk;
+  const int t = threadIdx.x, lane = t & 31;
+  const unsigned int n_big = wp.ctr[0], n_small = wp.ctr[1];
+  // ---- big walkers: one CTA each
+  while (true) {
+    if (t == 0) s_tk = atomicAdd(&wp.ctr[3], 1u);
+    __syncthreads();
+    const unsigned int k = s_tk;
+    __syncthreads();
+    if (k >= n_big) break;
+    const int64_t i = wp.big_list[k];
+    const int32_t n = wp.deg[i];
+    const float* V = wp.V + wp.voff[k];
+    if (t == 0) { sh.pos = 0; sh.S = 0.f; sh.n_ck = 0; sh.answer = -1; }
+    const int ck_stride = 1 + (n / kPrefCH) / (kPrefCk / 2);
+    block_exact_prefix(sh, V, n, false, true, ck_stride);
+    if (t == 0) {
+      const float total = sh.S;
+      double u, u2;
+      if (philox) philox_uniform2((unsigned long long)i, (uint32_t)step, 0x77616C6Bu, key, u, u2);
+      else { uint32_t x = state[i]; u = minstd_uniform(x); }
+      const double r = pick_r(u, 0.f, total);
+      sh.r = r;
+      // resume from the last checkpoint whose prefix does not exceed r (prefixes are non-decreasing; checkpoint 0 is 0)
+      int c = 0;
+      for (int j = 1; j < sh.n_ck; ++j) if (!((double)sh.ck_S[j] > r)) c = j; else break;
+      sh.pos = sh.ck_pos[c]; sh.S = sh.ck_S[c]; sh.answer = -1;
+    }
+    block_exact_prefix(sh, V, n, true, false, 1);
+    if (t == 0) {
+      const int64_t crow = s.cur_row[i];
+      const int64_t cb = g.grp_ptr[crow * g.T + ctype];
+      const int32_t a = sh.answer >= 0 ? sh.answer : n - 1;    // RandomSelect's fall-through: the last entry
+      const long long next = (long long)__ldg(g.nbr + cb + a);
+      out[i * (L + 1) + step + 1] = next;
+      s.parent[i] = s.cur[i];
+      s.parent_row[i] = crow;
+      s.cur[i] = next;
+    }
+    __syncthreads();
+  }
+  // ---- small walkers: one warp each
+  while (true) {
+    unsigned int k = 0;
+    if (lane == 0) k = atomicAdd(&wp.ctr[4], 1u);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (k >= n_small) break;
+    const int64_t i = wp.small_list[k];
+    const long long cur = s.cur[i];
+    const int64_t crow = s.cur_row[i];
     const int64_t prow = s.parent_row[i];
     WarpWalk ww;
     ww.g = &g; ww.lane = lane; ww.p = p; ww.q = q; ww.parent_id = s.parent[i];
@@ -257,20 +613,28 @@ __global__ void __launch_bounds__(256) k_walk_step_warp(DevGraph g, int64_t B, i
     if (prow >= 0 && ptype >= 0 && ptype < g.T) { ww.pb = g.grp_ptr[prow * g.T + ptype]; ww.pe = g.grp_ptr[prow * g.T + ptype + 1]; }
     const float total = ww.pass(false, 0.0, nullptr);
     double u, u2;
-    if (philox) {
-      philox_uniform2((unsigned long long)i, (uint32_t)step, 0x77616C6Bu, key, u, u2);
-    } else {
-      uint32_t x = state[i];
-      u = minstd_uniform(x);
-    }
+    if (philox) philox_uniform2((unsigned long long)i, (uint32_t)step, 0x77616C6Bu, key, u, u2);
+    else { uint32_t x = state[i]; u = minstd_uniform(x); }
+    long long next = default_node;
     ww.pass(true, pick_r(u, 0.f, total), &next);
+    if (lane == 0) {
+      out[i * (L + 1) + step + 1] = next;
+      s.parent[i] = cur;
+      s.parent_row[i] = crow;
+      s.cur[i] = next;
+    }
   }
-  if (lane == 0) {
-    out[i * (L + 1) + step + 1] = next;
-    s.parent[i] = cur;
-    s.parent_row[i] = crow;
-    s.cur[i] = next;
-  }
+}
+
+// dead walkers: default_node forever (:232-241); parent bookkeeping as for the live ones
+__global__ void k_walk_dead(int64_t B, int32_t L, int32_t step, long long default_node, WalkState s, const uint8_t* __restrict__ live,
+                            long long* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B || live[i]) return;
+  out[i * (L + 1) + step + 1] = default_node;
+  s.parent[i] = s.cur[i];
+  s.parent_row[i] = s.cur_row[i];
+  s.cur[i] = default_node;
 }
 
 __global__ void k_walk_col(const unsigned long long* __restrict__ eng, int64_t B, int32_t L, int32_t col,
@@ -316,40 +680,73 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
     return EU_OK;
   }
   // node2vec
-  rc = ctx_misc(c, 256 + B * (8 + 8 + 8 + 8));
+  const int64_t plan_bytes = B * (4 + 4 + 4) + (B + 1) * (8 + 4) + 64 + 256;
+  rc = ctx_misc(c, 256 + B * (8 + 8 + 8 + 8) + plan_bytes);
   if (rc) return rc;
   char* m = (char*)c->d_misc + 256;
   WalkState ws;
   ws.cur = (long long*)m; m += 8 * B;
   ws.parent = (long long*)m; m += 8 * B;
   ws.cur_row = (int64_t*)m; m += 8 * B;
-  ws.parent_row = (int64_t*)m;
+  ws.parent_row = (int64_t*)m; m += 8 * B;
+  WalkPlan wp{};
+  wp.voff = (long long*)m; m += 8 * (B + 1);
+  wp.deg = (int32_t*)m; m += 4 * B;
+  wp.big_list = (int32_t*)m; m += 4 * B;
+  wp.small_list = (int32_t*)m; m += 4 * B;
+  wp.coff = (int32_t*)m; m += 4 * (B + 1);
+  m = (char*)(((uintptr_t)m + 63) & ~(uintptr_t)63);
+  wp.ctr = (unsigned int*)m;
   k_walk_init<<<(unsigned)ceil_div(B, tb), tb, 0, s>>>((const long long*)nodes, B, L, ws, (long long*)out);
   EU_LAUNCHED();
   ETypes2 pet{};
   pet.K = 0;
+  const bool philox = c->rng == EU_RNG_PHILOX;
+  const unsigned long long wkey = c->seed ^ 0x6E32766563ull;
   for (int l = 0; l < L; ++l) {
     ETypes2 cet{};
     cet.K = K;
     for (int k = 0; k < K; ++k) cet.v[k] = etypes[(int64_t)l * K + k];
-    k_walk_live<<<(unsigned)ceil_div(B, tb), tb, 0, s>>>(d, B, cet, ws, c->d_elig);
-    EU_LAUNCHED();
-    if (c->rng == EU_RNG_MINSTD) {
-      rc = launch_state_scan(c, B, 1);
-      if (rc) return rc;
-    }
-    const bool one_sorted_type = d.adj_sorted && cet.K == 1 && pet.K <= 1 && cet.v[0] >= 0 && cet.v[0] < d.T;
+    const bool one_sorted_type = d.adj_sorted && cet.K == 1 && pet.K <= 1 && cet.v[0] >= 0 && cet.v[0] < d.T && B < ((int64_t)1 << 31);
     if (one_sorted_type) {
-      k_walk_step_warp<<<(unsigned)ceil_div(B * 32, 256), 256, 0, s>>>(d, B, L, l, cet.v[0], pet.K == 1 ? pet.v[0] : -1, p, q,
-                                                                       default_node, ws, c->d_elig, c->d_state,
-                                                                       c->rng == EU_RNG_PHILOX, c->seed ^ 0x6E32766563ull,
-                                                                       (long long*)out);
+      // V: biased weights of the big rows of this step (k_walk_weights -> k_walk_prefix); walkers that do not fit take the
+      // warp path, so the capacity bounds memory, not correctness
+      if (!c->d_walkv) {
+        const char* e = getenv("EU_WALK_V_ELEMS");
+        const long long want = e && atoll(e) > 0 ? atoll(e) : (32ll << 20);
+        if ((rc = refuse_growth_in_capture(c, "the node2vec weight scratch"))) return rc;
+        EU_CUDA(cudaMalloc(&c->d_walkv, sizeof(float) * (size_t)want));
+        c->walkv_cap = want;
+      }
+      wp.V = c->d_walkv; wp.capV = c->walkv_cap;
+      const int32_t ctype = cet.v[0], ptype = pet.K == 1 ? pet.v[0] : -1;
+      { EuProfScope ps(c, "k_walk_deg", B);
+        k_walk_deg<<<(unsigned)ceil_div(B, tb), tb, 0, s>>>(d, B, ctype, ws, c->d_elig, wp.deg); }
+      EU_LAUNCHED();
+      { EuProfScope ps(c, "k_walk_plan", B);
+        k_walk_plan<<<1, 1024, 0, s>>>(B, c->d_elig, !philox, modpow_a(2ull), c->d_state, c->d_rng, wp); }
+      EU_LAUNCHED();
+      { EuProfScope ps(c, "k_walk_weights", B);
+        k_walk_weights<<<148 * 8, kWalkChunk, 0, s>>>(d, ctype, ptype, p, q, ws, wp); }
+      EU_LAUNCHED();
+      { EuProfScope ps(c, "k_walk_prefix", B);
+        k_walk_prefix<<<148 * 4, kPrefT, 0, s>>>(d, B, L, l, ctype, ptype, p, q, default_node, ws, c->d_elig, c->d_state, philox, wkey, wp,
+                                               (long long*)out); }
+      EU_LAUNCHED();
+      k_walk_dead<<<(unsigned)ceil_div(B, tb), tb, 0, s>>>(B, L, l, default_node, ws, c->d_elig, (long long*)out);
+      EU_LAUNCHED();
     } else {
+      k_walk_live<<<(unsigned)ceil_div(B, tb), tb, 0, s>>>(d, B, cet, ws, c->d_elig);
+      EU_LAUNCHED();
+      if (!philox) {
+        rc = launch_state_scan(c, B, 1);
+        if (rc) return rc;
+      }
+      EuProfScope ps(c, "k_walk_step(sequential)", B);
       k_walk_step<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(d, B, L, l, cet, pet, p, q, default_node, ws, c->d_elig,
-                                                             c->d_state, c->rng == EU_RNG_PHILOX, c->seed ^ 0x6E32766563ull,
-                                                             (long long*)out);
+                                                             c->d_state, philox, wkey, (long long*)out);
+      EU_LAUNCHED();
     }
-    EU_LAUNCHED();
     pet = cet;
   }
   return EU_OK;
