@@ -37,6 +37,8 @@ CONFIGS = {
     "c4": dict(nodes=100_000_000, edges=1_000_000_000, batch=8192, fanout="15,10", dim=256,
                label="north-star headline (BASELINE configs[3])"),
     "c2": dict(nodes=10_000_000, edges=100_000_000, batch=1024, fanout="25,10", dim=128, label="BASELINE configs[1]"),
+    # node2vec biased walk (deepwalk / line example path): metric = walker-steps/s
+    "c3": dict(nodes=10_000_000, edges=100_000_000, batch=4096, fanout="80", dim=0, label="BASELINE configs[2]"),
 }
 CPU_GRAPH_MAX_NODES = 10_000_000   # the CPU arms build the reference's unordered_map<NodeID,Node*> graph: bounded so the arm fits the driver's time box
 GRAPH_SEED, FEAT_SEED = 42, 7
@@ -70,6 +72,8 @@ def parse():
     p.add_argument("--no-e2e-host", action="store_true", help="skip the e2e leg through the *_host C ABI")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
     p.add_argument("--breakdown-iters", type=int, default=6)
+    p.add_argument("--p", type=float, default=0.5, help="config c3: node2vec return parameter")
+    p.add_argument("--q", type=float, default=2.0, help="config c3: node2vec in-out parameter")
     a = p.parse_args()
     cfg = CONFIGS[a.config]
     for k in ("nodes", "edges", "batch", "fanout", "dim"):
@@ -1081,6 +1085,264 @@ def cpu_baseline(args, counts):
             "threads_sweep_edges_per_s": sweep, "sub_rates": cpu_sub_rates(cs, args, counts, th, max(1, iters // 2)), "cpu_graph": info}
 
 
+# ----------------------------------------------------------------------------- config c3: node2vec walk
+def walk_workload(args, L, n_gpus):
+    return ("%s: synthetic power-law (R-MAT 0.57/0.19/0.19/0.05) graph %dM nodes/%dM edges, node2vec biased walk p=%g q=%g "
+            "walk_len=%d batch=%d, %d GPU(s)" % (args.label, args.nodes // 10**6, args.edges // 10**6, args.p, args.q, L, args.batch, n_gpus))
+
+
+def walk_config(args, L, n_gpus):
+    return {"workload": walk_workload(args, L, n_gpus), "nodes": args.nodes, "edges": args.edges, "batch": args.batch, "walk_len": L,
+            "p": args.p, "q": args.q, "rng": args.rng,
+            "l2_policy": "inputs larger than L2 (graph >> 126 MB, fresh random start nodes every step)"}
+
+
+def run_walk(args):
+    """A step = one random_walk op call: `batch` walkers x walk_len node2vec steps (tf_euler/kernels/random_walk_op.cc:83-289).
+    metric = walker-steps/s.  Parity gate: a smaller batch bit-exact against the oracle's restatement of the reference walk."""
+    import torch
+    import euler_b200 as eb
+    from euler_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (no CPU fallback)")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    lib = _lib.load()
+    L, B = int(args.fanout), args.batch
+    et = np.zeros((L, 1), np.int32)
+    t0 = time.time()
+    graph = eb.Graph.rmat(args.nodes, args.edges, seed=GRAPH_SEED, feat_dim=0, device=local)
+    torch.cuda.synchronize()
+    t_graph = time.time() - t0
+    ex = graph.export(with_feat=False)
+    deg = torch.from_numpy(np.diff(ex["grp_ptr"]).astype(np.int64)).cuda()
+    gate = {"passed": None, "skipped": "--no-gate"}
+    if not args.no_gate and args.rng == "minstd":
+        from oracle import pyoracle as po
+        tg = time.time()
+        og = po.OracleGraph(ex["ids"], ex["node_type"], ex["node_w"], 1, ex["grp_ptr"], ex["nbr"], ex["cum_w"], np.zeros(len(ex["ids"]), np.float32))
+        Bg, Lg = 1024, 12
+        gs = np.random.RandomState(5).randint(1, args.nodes + 1, size=Bg).astype(np.int64)
+        gs[:3] = [0, -1, args.nodes + 5]
+        ctx = eb.Context(graph, "minstd", 4242)
+        d_s = torch.from_numpy(gs).cuda()
+        d_o = torch.empty((Bg, Lg + 1), dtype=torch.int64, device="cuda")
+        _lib.check(lib.eu_random_walk(ctx._h, d_s.data_ptr(), Bg, et.ctypes.data, 1, Lg, args.p, args.q, -1, d_o.data_ptr()))
+        ctx.sync()
+        po.seed(4242)
+        want = og.op_random_walk(gs, et[:Lg], args.p, args.q, -1)
+        got = d_o.cpu().numpy()
+        if not np.array_equal(got, want):
+            bad = np.argwhere(got != want)
+            raise SystemExit("PARITY GATE FAILED: node2vec walk differs from the oracle at %d of %d positions (first: walker %d step %d got %d want %d)"
+                             % (len(bad), want.size, bad[0][0], bad[0][1], got[bad[0][0], bad[0][1]], want[bad[0][0], bad[0][1]]))
+        gate = {"passed": True, "walkers": Bg, "steps": Lg, "values_compared": int(want.size), "seconds": round(time.time() - tg, 2),
+                "what": "eu_random_walk (exact-RNG mode) vs oracle/euler_oracle.c eo_op_random_walk on the exported CSR of the bench graph, bit-exact"}
+        ctx.close()
+        del og
+
+    class WLane:
+        pass
+    lanes = []
+    for i in range(max(1, args.lanes)):
+        ln = WLane()
+        ln.stream = torch.cuda.Stream()
+        ln.ctx = eb.Context(graph, args.rng, 777 + i, ln.stream.cuda_stream)
+        ln.d_seeds = torch.empty(B, dtype=torch.int64, device="cuda")
+        ln.out = torch.empty((B, L + 1), dtype=torch.int64, device="cuda")
+        ln.h_seeds = torch.empty(B, dtype=torch.int64).pin_memory()
+        ln.h_out = torch.empty((B, L + 1), dtype=torch.int64).pin_memory()
+        lanes.append(ln)
+    n_sb = max(args.warmup + args.steps, 8)
+    host_seeds = np.stack([np.random.RandomState(3000 + i).randint(1, args.nodes + 1, size=B) for i in range(n_sb)]).astype(np.int64)
+    dev_seeds = torch.from_numpy(host_seeds).cuda()
+
+    def raw(ln):
+        rc = lib.eu_random_walk(ln.ctx._h, ln.d_seeds.data_ptr(), B, et.ctypes.data, 1, L, args.p, args.q, -1, ln.out.data_ptr())
+        if rc:
+            raise RuntimeError(lib.eu_last_error().decode())
+    use_graphs = not args.no_graphs
+    for ln in lanes:
+        with torch.cuda.stream(ln.stream):
+            ln.d_seeds.copy_(dev_seeds[0])
+            raw(ln)
+        ln.stream.synchronize()
+        if use_graphs:
+            l_before = lib.eu_launch_count()
+            ln.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ln.graph, stream=ln.stream):
+                raw(ln)
+            ln.launches = lib.eu_launch_count() - l_before
+    main = torch.cuda.current_stream()
+
+    def run(n_steps, first, mode):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record(main)
+        for ln in lanes:
+            ln.stream.wait_event(ev0)
+        if mode == "host":
+            def worker(k, ln):
+                for i in range(k, n_steps, len(lanes)):
+                    ln.h_seeds.copy_(torch.from_numpy(host_seeds[(first + i) % n_sb]))
+                    rc = lib.eu_random_walk_host(ln.ctx._h, ln.h_seeds.data_ptr(), B, et.ctypes.data, 1, L, args.p, args.q, -1, ln.h_out.data_ptr())
+                    if rc:
+                        raise RuntimeError(lib.eu_last_error().decode())
+            ths = [threading.Thread(target=worker, args=(k, ln)) for k, ln in enumerate(lanes)]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        else:
+            for i in range(n_steps):
+                ln = lanes[i % len(lanes)]
+                with torch.cuda.stream(ln.stream):
+                    ln.d_seeds.copy_(dev_seeds[(first + i) % n_sb], non_blocking=True)
+                    ln.graph.replay() if use_graphs else raw(ln)
+        for ln in lanes:
+            main.wait_stream(ln.stream)
+        ev1.record(main)
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1)
+    run(max(args.warmup, 3), 0, "dev")
+    clocks = Clocks(local)
+    clocks.start()
+    time.sleep(0.3)
+    w0 = time.time()
+    ms = run(args.steps, args.warmup, "dev")
+    w1 = time.time()
+    clk = clocks.stop(w0, w1)
+    run(2, 0, "host")
+    ms_host = run(args.steps, args.warmup, "host")
+    # measured sum of degrees: per walker-step 12 * deg(cur) + 8 * deg(prev) + 32 bytes (SURVEY.md section 8d)
+    ln = lanes[0]
+    with torch.cuda.stream(ln.stream):
+        ln.d_seeds.copy_(dev_seeds[1])
+        raw(ln)
+    ln.stream.synchronize()
+    o = ln.out
+    row = (o - 1).clamp_(0, args.nodes - 1)
+    dcur = torch.where(o > 0, deg[row], torch.zeros_like(o))
+    live = (dcur[:, :L] > 0)
+    dprev = torch.cat([torch.zeros_like(dcur[:, :1]), dcur[:, :L - 1]], dim=1)
+    sum_cur, sum_prev = int(dcur[:, :L].sum().item()), int((dprev * live).sum().item())
+    alg_bytes = 12 * sum_cur + 8 * sum_prev + 32 * B * L
+    # per-kernel times of one batch (library-side events)
+    lib.eu_ctx_profile(ln.ctx._h, 1)
+    with torch.cuda.stream(ln.stream):
+        raw(ln)
+    buf = ctypes.create_string_buffer(1 << 16)
+    lib.eu_ctx_profile_read(ln.ctx._h, buf, len(buf))
+    lib.eu_ctx_profile(ln.ctx._h, 0)
+    prof = {}
+    for line in buf.value.decode().strip().splitlines():
+        nm, rows_, cnt_, ms_tot = line.split(",")
+        prof[nm] = round(float(ms_tot), 4)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ws = B * L
+    value = ws * args.steps / (ms * 1e-3)
+    ach = alg_bytes * args.steps / (ms * 1e-3) / 1e9
+    out = {"metric": "walker_steps_per_sec", "value": value, "unit": "walker-steps/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u64 ids / f32 weights (sequential f32 prefix, f64 compare)", "data": "synthetic", "config": walk_config(args, L, 1),
+           "arm": {"lanes_in_flight": len(lanes), "cuda_graphs": use_graphs, "graph_hbm_gb": round(graph.hbm_bytes / 1e9, 1),
+                   "mode": "exact (bit-exact with the reference's serial engine stream and sequential f32 prefix)" if args.rng == "minstd" else "philox"},
+           "parity_gate": gate,
+           "e2e": {"value": ws * args.steps / (ms_host * 1e-3), "unit": "walker-steps/s", "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 8 * B * (L + 1),
+                   "ms_per_step": ms_host / args.steps, "api": "eu_random_walk_host (HOST buffers in and out), one host thread per lane"},
+           "gpu_launches": int(sum(getattr(x, "launches", 0) for x in lanes) / len(lanes) * args.steps) if use_graphs else None,
+           "clocks": clk,
+           "roofline": {"bound": "hbm", "kernel": "k_walk_weights + k_walk_prefix (whole op: the walk is one chain of dependent steps)",
+                        "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+                        "algorithmic_bytes_per_batch": int(alg_bytes), "sum_deg_cur": sum_cur, "sum_deg_prev": sum_prev,
+                        "mean_deg_cur_per_live_step": round(sum_cur / max(int(live.sum().item()), 1), 1),
+                        "note": "achieved = (12 deg(cur) + 8 deg(prev) + 32) bytes summed over the walker-steps of a batch / batch time; hub "
+                                "rows are L2-resident, so this is an algorithmic rate"},
+           "kernel_ms_per_batch_single_lane": dict(sorted(prof.items(), key=lambda kv: -kv[1])),
+           "graph_build_s": round(t_graph, 2)}
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_walk_baseline(args, L, ex)
+    emit(out)
+
+
+def cpu_walk_graph(args, ex):
+    from oracle import pyoracle as po
+    if ex is None:
+        ex = po.rmat_graph(args.nodes, args.edges, seed=GRAPH_SEED, feat_dim=0)
+    if po.have_ref():
+        cum, ptr = ex["cum_w"], ex["grp_ptr"]
+        w = np.diff(cum, prepend=np.float32(0)).astype(np.float32)
+        first = ptr[:-1][np.diff(ptr) > 0]
+        w[first] = cum[first]
+        return po.RefGraph.build(ex["ids"], ex["node_type"], ex["node_w"], 1, ptr, ex["nbr"], w, 1, None, sampler=False), None
+    return None, po.OracleGraph(ex["ids"], ex["node_type"], ex["node_w"], 1, ex["grp_ptr"], ex["nbr"], ex["cum_w"], np.zeros(len(ex["ids"]), np.float32))
+
+
+def cpu_walk_time(args, L, rg, og, threads, walkers):
+    """every thread walks `walkers` walkers for L steps (its own engine); returns (seconds, walker-steps)"""
+    et = np.zeros((L, 1), np.int32)
+    g = rg if rg is not None else og
+
+    def worker(k):
+        sd = np.random.RandomState(9000 + k).randint(1, args.nodes + 1, size=walkers).astype(np.int64)
+        g.op_random_walk(sd, et, args.p, args.q, -1)
+    ths = [threading.Thread(target=worker, args=(k,)) for k in range(threads)]
+    t0 = time.time()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return time.time() - t0, threads * walkers * L
+
+
+def cpu_walk_baseline(args, L, ex):
+    rg, og = cpu_walk_graph(args, ex)
+    cores = host_cores()
+    th = cores if rg is not None else 1     # the C restatement walks on one global engine: one thread
+    sec, n = cpu_walk_time(args, L, rg, og, th, 8)
+    walkers = max(8, min(256, int(8 * args.cpu_seconds / max(sec, 1e-3))))
+    sec, n = cpu_walk_time(args, L, rg, og, th, walkers)
+    one_sec, one_n = cpu_walk_time(args, L, rg, og, 1, max(8, walkers // 4))
+    return {"value": n / sec, "unit": "walker-steps/s", "cores": th, "host_cores": cores, "kind": "reference" if rg is not None else "port",
+            "one_thread_walker_steps_per_s": one_n / one_sec,
+            "sample": "%d host threads x %d walkers x %d steps of the reference's node2vec step (ref_shim restatement of random_walk_op.cc:83-168 "
+                      "over the reference's own GetFullNeighbor), %.1f s" % (th, walkers, L, sec)}
+
+
+def run_walk_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    L = int(args.fanout)
+    rg, og = cpu_walk_graph(args, None)
+    cores = host_cores()
+    th = cores if rg is not None else 1
+    walkers = 16
+    sec1, _ = cpu_walk_time(args, L, rg, og, th, walkers)
+    steps = max(1, min(args.steps, int(120.0 / max(sec1, 1e-3)) - args.warmup))
+    warm = args.warmup if steps == args.steps else min(args.warmup, 1)
+    for _ in range(warm):
+        cpu_walk_time(args, L, rg, og, th, walkers)
+    tn, ts = 0, 0.0
+    for _ in range(steps):
+        sec, n = cpu_walk_time(args, L, rg, og, th, walkers)
+        tn += n
+        ts += sec
+    v = tn / ts
+    emit({"impl": "reference", "metric": "walker_steps_per_sec", "value": v, "unit": "walker-steps/s", "n_gpus": args.gpus, "steps": steps,
+          "warmup": warm, "ms_per_step": 1e3 * ts / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "u64 ids / f32 weights (sequential f32 prefix, f64 compare)", "data": "synthetic", "config": walk_config(args, L, args.gpus),
+          "arm": {"step": "one bounded sample = %d host threads x %d walkers x %d steps" % (th, walkers, L), "host_cores": cores},
+          "cpu_baseline": {"value": v, "unit": "walker-steps/s", "cores": th, "kind": "reference" if rg is not None else "port",
+                           "sample": "%d steps of %d threads x %d walkers" % (steps, th, walkers)},
+          "e2e": {"value": v, "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the same step on the host cores.  Loads nothing of the
     product: the input graph comes from oracle/rmat_gen.c."""
@@ -1139,7 +1401,9 @@ if __name__ == "__main__":
     _REAL_STDOUT = os.dup(1)
     os.dup2(2, 1)
     a = parse()
-    if a.impl == "reference":
+    if a.config == "c3":
+        run_walk_reference(a) if a.impl == "reference" else run_walk(a)
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_ours(a)
