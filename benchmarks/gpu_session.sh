@@ -12,7 +12,7 @@ for s in "$@"; do
     bench_c4_nocpu) (time timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $out/bench_c4.json 2> $out/bench_c4.err) > $out/bench_c4.time 2>&1 ;;
     bench_c2) (time timeout 600 python bench.py --config c2 --steps 64 --warmup 16 --no-cpu-baseline > $out/bench_c2.json 2> $out/bench_c2.err) > $out/bench_c2.time 2>&1 ;;
     ref) (time timeout 900 python bench.py --impl reference --steps 20 --warmup 5 > $out/ref_c4.json 2> $out/ref_c4.err) > $out/ref.time 2>&1 ;;
-    walk) (time timeout 600 python benchmarks/bench_walk.py > $out/walk.json 2> $out/walk.err) > $out/walk.time 2>&1 ;;
+    walk) (time timeout 900 python bench.py --config c3 --steps 8 --warmup 2 > $out/walk.json 2> $out/walk.err) > $out/walk.time 2>&1 ;;
     *) echo "unknown step $s" ;;
   esac
   echo "== $s done rc=$?" >> $out/steps.log

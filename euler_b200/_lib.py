@@ -66,6 +66,12 @@ SIGNATURES = {
     "eu_ctx_profile_read": (C.c_int, [_P, C.c_char_p, _I64]),
     "eu_sample_neighbor": (C.c_int, [_P, _P, _I64, _P, _I32, _I32, _I64, _P, _P, _P]),
     "eu_sample_neighbor_host": (C.c_int, [_P, _P, _I64, _P, _I32, _I32, _I64, _P, _P, _P]),
+    "eu_sample_neighbor_raw": (C.c_int, [_P, _P, _I64, _P, _I32, _I32, _P, _P, _P]),
+    "eu_sample_neighbor_raw_host": (C.c_int, [_P, _P, _I64, _P, _I32, _I32, _P, _P, _P]),
+    "eu_get_sorted_full_neighbor": (C.c_int, [_P, _P, _I64, _P, _I32, _I64, _P, _P, _P, _P]),
+    "eu_get_top_k_neighbor": (C.c_int, [_P, _P, _I64, _P, _I32, _I32, _I64, _P, _P, _P]),
+    "eu_gen_pair_count": (_I64, [_I32, _I32, _I32]),
+    "eu_gen_pair": (C.c_int, [_P, _P, _I64, _I32, _I32, _I32, _P]),
     "eu_sample_fanout": (C.c_int, [_P, _P, _I64, _P, _I32, _P, _I32, _I64, _P, _P, _P]),
     "eu_sample_fanout_batched": (C.c_int, [_P, _P, _I32, _I64, _P, _I32, _P, _I32, _I64, _P, _P, _P]),
     "eu_sample_fanout_host": (C.c_int, [_P, _P, _I64, _P, _I32, _P, _I32, _I64, _P, _P, _P]),
@@ -81,6 +87,7 @@ SIGNATURES = {
     "eu_unique": (C.c_int, [_P, _P, _I64, _P, _P, _P]),
     "eu_get_node_type": (C.c_int, [_P, _P, _I64, _P]),
     "eu_get_node_type_host": (C.c_int, [_P, _P, _I64, _P]),
+    "eu_get_node_weight_host": (C.c_int, [_P, _P, _I64, _P]),
     "eu_get_full_neighbor_host": (C.c_int, [_P, _P, _I64, _P, _I32, _I64, _P, _P, _P, _P, _P]),
     "eu_gather": (C.c_int, [_P, _P, _I64, _I64, _P, _I64, _P]),
     "eu_scatter_add": (C.c_int, [_P, _P, _I64, _P, _I64, _I64, _P]),

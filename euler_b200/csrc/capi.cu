@@ -361,6 +361,22 @@ int eu_sample_neighbor_host(eu_ctx* c, const int64_t* nodes, int64_t B, const in
   return eu_sample_fanout_host(c, nodes, B, etypes, K, &count, 1, default_node, &out_ids, &out_w, &out_t);
 }
 
+int eu_sample_neighbor_raw_host(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K, int32_t count,
+                                int64_t* out_ids, float* out_w, int32_t* out_t) {
+  if (!c || B < 0 || count < 0 || (B > 0 && (!nodes || (count > 0 && (!out_ids || !out_w || !out_t))))) { set_error("eu_sample_neighbor_raw_host: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  HostIO io{c};
+  const int64_t n = B * count;
+  const int64_t o_nodes = io.take(8 * B), o_ids = io.take(8 * n), o_w = io.take(4 * n), o_t = io.take(4 * n);
+  int rc = io.begin({nodes, out_ids, out_w, out_t});
+  if (rc) return rc;
+  if ((rc = io.in(o_nodes, nodes, 8 * B))) return rc;
+  rc = eu_sample_neighbor_raw(c, (const int64_t*)io.dev(o_nodes), B, etypes, K, count, (int64_t*)io.dev(o_ids), (float*)io.dev(o_w), (int32_t*)io.dev(o_t));
+  if (rc) return rc;
+  if ((rc = io.out(o_ids, out_ids, 8 * n)) || (rc = io.out(o_w, out_w, 4 * n)) || (rc = io.out(o_t, out_t, 4 * n))) return rc;
+  return io.finish();
+}
+
 int eu_sample_node_host(eu_ctx* c, int32_t count, const int32_t* types, int32_t n_types, int64_t* out) {
   if (!c || count < 0 || (count > 0 && !out)) { set_error("eu_sample_node_host: bad argument"); return EU_ERR_INVALID; }
   EU_CUDA(cudaSetDevice(c->g->device));

@@ -158,5 +158,5 @@ int launch_state_scan(eu_ctx* c, int64_t rows, unsigned long long uniforms_per_r
 int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows, const int32_t* etypes, int32_t K,
         int32_t count, int64_t default_node, unsigned long long* eng_ids, int64_t* out_ids,
         float* out_w, int32_t* out_t, int hop_index, bool pre_inserted, bool insert_next, int nb,
-        const int32_t* rows_act = nullptr);
+        const int32_t* rows_act = nullptr, bool raw = false);
 }  // namespace eu

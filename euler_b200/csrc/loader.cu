@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <map>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -122,8 +123,9 @@ extern "C" int eu_graph_load(const char* data_path, int shard_index, int shard_n
     slot_off[s] = width;
     width += slot_dims[s];
   }
-  // ---- node files of this shard, in name order
-  std::vector<std::string> files;
+  // ---- node files of this shard, in name order (rows are laid out in this order); the order readdir returned them in is
+  // kept as well: it is the reference's insert order into node_map_ (see the sampler order below)
+  std::vector<std::string> files, readdir_files;
   {
     DIR* d = opendir((dir + "/Node").c_str());
     if (!d) { set_error("no such directory %s/Node", data_path); return EU_ERR_IO; }
@@ -133,8 +135,10 @@ extern "C" int eu_graph_load(const char* data_path, int shard_index, int shard_n
       if (tok.size() == 3 && tok[2] == "dat" && atoi(tok[1].c_str()) % shard_number == shard_index) files.push_back(fn);
     }
     closedir(d);
+    readdir_files = files;
     std::sort(files.begin(), files.end());
   }
+  std::map<std::string, std::pair<int64_t, int64_t>> file_rows;   // file -> [first row, end row)
   std::vector<uint64_t> ids, nbr;
   std::vector<int32_t> ntype;
   std::vector<float> nw, cum, gcum, feat;
@@ -145,6 +149,7 @@ extern "C" int eu_graph_load(const char* data_path, int shard_index, int shard_n
   for (const auto& fn : files) {
     if (!read_file(dir + "/Node/" + fn, &buf)) { set_error("cannot read %s", fn.c_str()); return EU_ERR_IO; }
     Reader f{buf.data(), buf.data() + buf.size()};
+    file_rows[fn].first = (int64_t)ids.size();
     while (f.p < f.end) {
       uint32_t len = f.get<uint32_t>();
       if (!f.ok || f.p + len > f.end) { set_error("truncated record in %s", fn.c_str()); return EU_ERR_IO; }
@@ -188,6 +193,29 @@ extern "C" int eu_graph_load(const char* data_path, int shard_index, int shard_n
         if (len > 0) memcpy(&feat[fbase + slot_off[s]], &fv[b], sizeof(float) * len);
       }
     }
+    file_rows[fn].second = (int64_t)ids.size();
+  }
+  // Global node sampler order = iteration order of the reference's node_map_ (Graph::BuildGlobalSampler, graph.cc:349-354):
+  // a std::unordered_map<NodeID, Node*> filled by GraphBuilder::AddToGraph (graph_builder.cc:160-166) task by task, i.e.
+  // file by file in ListDirectory (readdir) order (local_file_io.cc:102-119), record by record, with insert() (the first
+  // occurrence of an id wins, graph.cc:174-179).  The same container from the same libstdc++, fed the same sequence, iterates
+  // in the same order: replay it on the host.
+  std::vector<int64_t> order;
+  {
+    std::unordered_map<uint64_t, int64_t> node_map;
+    for (const auto& fn : readdir_files) {
+      const auto& rr = file_rows[fn];
+      for (int64_t r = rr.first; r < rr.second; ++r) node_map.insert({ids[r], r});
+    }
+    order.reserve(node_map.size());
+    for (const auto& kv : node_map) order.push_back(kv.second);
+    // ids stored twice keep the FIRST record in node_map_ but the id -> row table of the device graph resolves to the last:
+    // the sampler needs one entry per row, so duplicate rows (absent from the map) are appended; a converter never emits them
+    if (order.size() != ids.size()) {
+      std::vector<char> seen(ids.size(), 0);
+      for (int64_t r : order) seen[r] = 1;
+      for (int64_t r = 0; r < (int64_t)ids.size(); ++r) if (!seen[r]) order.push_back(r);
+    }
   }
   eu_graph_desc d{};
   d.n_nodes = (int64_t)ids.size();
@@ -197,6 +225,7 @@ extern "C" int eu_graph_load(const char* data_path, int shard_index, int shard_n
   d.grp_ptr = gptr.data(); d.nbr = nbr.data(); d.cum_w = cum.data(); d.grp_cum = gcum.data();
   d.feat_dim = width; d.feat = width > 0 ? feat.data() : nullptr;
   d.n_feat_slots = width > 0 ? n_slots : 0; d.feat_slot_dims = slot_dims.data();
+  d.sampler_order = order.data();
   int rc = eu_graph_create(&d, device, out);
   if (rc) return rc;
   eu_graph* g = *out;

@@ -163,7 +163,8 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSl
   if (li < rows_here) {
     const int64_t w = b * gm.rows_b + li;
     const unsigned long long id = seeds[w];
-    const int64_t f = dedup_first(tabs + (int64_t)b * (gm.cap_b + 1), (unsigned long long)gm.cap_b - 1, id);
+    // raw mode (tabs == null): euler::SampleNeighbor draws every occurrence of an id independently (api.cc:223-236)
+    const int64_t f = tabs ? dedup_first(tabs + (int64_t)b * (gm.cap_b + 1), (unsigned long long)gm.cap_b - 1, id) : li;
     first[ii] = (int32_t)f;
     // A duplicate has the same id, hence the same graph row and eligibility as its first occurrence: every row
     // resolves its own, so rows that cannot sample are finished right here and never reach k_sample.
@@ -653,7 +654,7 @@ int64_t hop_table_slots(int nb, int64_t rows_b) { return (make_geom(nb, rows_b).
 int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_t* etypes,
         int32_t K, int32_t count, int64_t default_node, unsigned long long* eng_ids,
         int64_t* out_ids, float* out_w, int32_t* out_t, int hop_index, bool pre_inserted, bool insert_next, int nb,
-        const int32_t* rows_act) {
+        const int32_t* rows_act, bool raw) {
   const int64_t rows = rows_b * nb;
   if (rows == 0 || count == 0) return EU_OK;
   if (nb < 1 || nb > c->n_eng) { set_error("hop: %d batches but the ctx has %d engines", nb, c->n_eng); return EU_ERR_INVALID; }
@@ -701,11 +702,12 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
   // (pre_inserted), so only the first hop of a chain needs the insert kernel.
   HashSlot* tabs = c->d_dedup + (hop_index & 1) * c->tab_set_slots;
   HashSlot* ntabs = c->d_dedup + ((hop_index + 1) & 1) * c->tab_set_slots;
-  if (!pre_inserted) {
+  if (raw && (pre_inserted || insert_next)) { set_error("hop: raw mode does not chain"); return EU_ERR_INVALID; }
+  if (!pre_inserted && !raw) {
     EuProfScope ps(c, "k_dedup_insert", rows);
     k_dedup_insert<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(tabs, gm, seeds);
+    EU_LAUNCHED();
   }
-  EU_LAUNCHED();
   const unsigned long long upr = (unsigned long long)count * (a.mode == 0 ? 1 : 2);
   const uint32_t F = modpow_a(2ull * upr);
   { EuProfScope ps(c, "k_prepare", rows);
@@ -715,7 +717,7 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
     if (chain) { po.next_tabs = ntabs; po.next_cap_b = ng.cap_b; }
     po.live = c->d_live; po.n_live = c->d_nlive;
     EU_CUDA(cudaMemsetAsync(c->d_nlive, 0, sizeof(unsigned int), s));
-    k_prepare<<<dim3((unsigned)gm.nblk_b, (unsigned)nb), tb, 0, s>>>(d, tabs, gm, seeds, a.et, a.mode, F, upr, c->d_first,
+    k_prepare<<<dim3((unsigned)gm.nblk_b, (unsigned)nb), tb, 0, s>>>(d, raw ? nullptr : tabs, gm, seeds, a.et, a.mode, F, upr, c->d_first,
                                                                      c->d_rowof, c->d_emask, c->d_woff, c->d_blkpre, c->d_blkmul,
                                                                      c->d_rng, po); }
   EU_LAUNCHED();
@@ -726,7 +728,7 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
   for (uint32_t k = 0; k < 32; ++k) a.lanepow[k] = modpow_a(2ull * upd * k);
   a.stride = modpow_a(2ull * upd * (unsigned long long)(1u << a.sg_log));
   a.clear_tab = tabs;
-  a.clear_n = (gm.cap_b + 1) * nb;
+  a.clear_n = raw ? 0 : (gm.cap_b + 1) * nb;   // raw mode never touched the dedup tables
   if (chain) {
     a.next_tabs = ntabs;
     a.next_cap_b = ng.cap_b;
@@ -748,6 +750,19 @@ int eu_sample_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t
   if (!c || B < 0 || count < 0 || (K > 0 && !etypes)) { set_error("eu_sample_neighbor: bad argument"); return EU_ERR_INVALID; }
   EU_CUDA(cudaSetDevice(c->g->device));
   return hop(c, (const unsigned long long*)nodes, B, etypes, K, count, default_node, nullptr, out_ids, out_w, out_t, 0, false, false, 1);
+}
+
+// euler::SampleNeighbor (euler/core/api/api.cc:223-236): one Node::SampleNeighbor per element of node_ids, in order --
+// NO unique / gather (that is the engine's rule, euler/parser/compiler.cc:76-90, which the op entry points above apply):
+// a repeated id draws again and consumes its own uniforms.  Engine-form outputs: a row that has no result (absent node, no
+// edge of the requested types) is `count` x (0, 0.0, -1); out_ids is what api.cc callers get as std::get<0>.
+int eu_sample_neighbor_raw(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
+                           int32_t count, int64_t* out_ids, float* out_w, int32_t* out_t) {
+  if (!c || B < 0 || count < 0 || (K > 0 && !etypes)) { set_error("eu_sample_neighbor_raw: bad argument"); return EU_ERR_INVALID; }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  if (c->rng != EU_RNG_MINSTD) { set_error("eu_sample_neighbor_raw: exact-RNG contexts only (philox rows are keyed on the node id: duplicates would repeat)"); return EU_ERR_UNSUPPORTED; }
+  return hop(c, (const unsigned long long*)nodes, B, etypes, K, count, /*default_node=*/0, nullptr, out_ids, out_w, out_t, 0, false, false, 1,
+             nullptr, /*raw=*/true);
 }
 
 int eu_sample_fanout_batched(eu_ctx* c, const int64_t* nodes, int32_t nb, int64_t B, const int32_t* etypes, int32_t K,

@@ -645,9 +645,66 @@ __global__ void k_walk_col(const unsigned long long* __restrict__ eng, int64_t B
   out[i * (L + 1) + col] = v == 0ull ? default_node : (long long)v;
 }
 
+// tf_euler gen_pair (tf_euler/kernels/gen_pair_op.cc:41-100): skip-gram pairs of every path.  For position j the pairs
+// (path[j], path[j-1]), ..., (path[j], path[j-lw]) then (path[j], path[j+1]), ..., (path[j], path[j+rw]), clipped to the
+// path; positions in ascending j.  pairs_before(j) is a closed form, so every (path, j) writes independently.
+__device__ __forceinline__ long long pairs_before(long long j, long long len, long long lw, long long rw) {
+  // sum_{x<j} min(x, lw) + sum_{x<j} min(len-1-x, rw)
+  const long long a = j <= lw ? j * (j - 1) / 2 : lw * (lw - 1) / 2 + (j - lw) * lw;
+  // right: y = len-1-x runs over len-1 .. len-j ; min(y, rw)
+  const long long hi = len - 1, lo = len - j;              // y in [lo, hi], j terms
+  long long b = 0;
+  if (j > 0) {
+    if (lo >= rw) b = j * rw;
+    else {
+      const long long full = hi >= rw ? hi - rw + 1 : 0;   // y in [rw, hi] -> rw each
+      const long long top = hi >= rw ? rw - 1 : hi;        // y in [lo, top] -> y each
+      b = full * rw + (top >= lo ? (lo + top) * (top - lo + 1) / 2 : 0);
+    }
+  }
+  return a + b;
+}
+
+__global__ void k_gen_pair(const long long* __restrict__ paths, int64_t B, int32_t len, int32_t lw, int32_t rw, long long pair_count,
+                           long long* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B * (int64_t)len) return;
+  const int64_t r = i / len;
+  const int32_t j = (int32_t)(i - r * len);
+  const long long* path = paths + r * len;
+  long long* o = out + (r * pair_count + pairs_before(j, len, lw, rw)) * 2;
+  const long long me = path[j];
+  for (int32_t k = 0; j - k - 1 >= 0 && k < lw; ++k) { *o++ = me; *o++ = path[j - k - 1]; }
+  for (int32_t k = 0; j + k + 1 < len && k < rw; ++k) { *o++ = me; *o++ = path[j + k + 1]; }
+}
+
 }  // namespace eu
 
 using namespace eu;
+
+// pairs per path, exactly as the kernel counts them (gen_pair_op.cc:47-53)
+extern "C" int64_t eu_gen_pair_count(int32_t path_len, int32_t left_win_size, int32_t right_win_size) {
+  long long pc = (long long)path_len * ((long long)left_win_size + right_win_size);
+  for (int i = left_win_size, j = 0; i > 0 && j < path_len; --i, ++j) pc -= i;
+  for (int i = right_win_size, j = 0; i > 0 && j < path_len; --i, ++j) pc -= i;
+  return pc;
+}
+
+// tf_euler.gen_pair: paths i64[B, path_len] -> out i64[B, eu_gen_pair_count(...), 2]   (device pointers)
+extern "C" int eu_gen_pair(eu_ctx* c, const int64_t* paths, int64_t B, int32_t path_len, int32_t left_win_size, int32_t right_win_size,
+                           int64_t* out) {
+  if (!c || B < 0 || path_len < 0 || left_win_size < 0 || right_win_size < 0 || (B > 0 && path_len > 0 && (!paths || !out))) {
+    set_error("eu_gen_pair: bad argument");
+    return EU_ERR_INVALID;
+  }
+  EU_CUDA(cudaSetDevice(c->g->device));
+  const long long pc = eu_gen_pair_count(path_len, left_win_size, right_win_size);
+  if (B == 0 || path_len == 0 || pc == 0) return EU_OK;
+  k_gen_pair<<<(unsigned)ceil_div(B * (int64_t)path_len, 256), 256, 0, c->stream>>>((const long long*)paths, B, path_len, left_win_size,
+                                                                                    right_win_size, pc, (long long*)out);
+  EU_LAUNCHED();
+  return EU_OK;
+}
 
 extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
                               int32_t L, float p, float q, int64_t default_node, int64_t* out) {

@@ -64,6 +64,7 @@ def context():
     if ctx is None or ctx.graph is not _default["graph"]:
         ctx = Context(get_graph(), _default["rng"], _default["seed"])
         _state.ctx = ctx
+        _state.stream = None    # a fresh Context is not bound to any torch stream yet
     return ctx
 
 
@@ -77,8 +78,19 @@ def _dev():
 
 
 def _ctx_on_stream():
+    """This thread's Context, bound to torch's current stream.  All ops of a Context share its scratch (dedup tables, engine
+    state, staging), so when the current stream CHANGES the new stream is first ordered after everything the Context issued on
+    the old one (an event, no host sync)."""
     ctx = context()
-    ctx.set_stream(torch.cuda.current_stream(_dev()).cuda_stream)
+    cur = torch.cuda.current_stream(_dev())
+    prev = getattr(_state, "stream", None)
+    if prev is not None and prev.cuda_stream != cur.cuda_stream:
+        ev = torch.cuda.Event()
+        ev.record(prev)
+        cur.wait_event(ev)
+    if prev is None or prev.cuda_stream != cur.cuda_stream:
+        ctx.set_stream(cur.cuda_stream)
+        _state.stream = cur
     return ctx
 
 
@@ -254,6 +266,75 @@ def get_full_neighbor(nodes, edge_types):
         check(lib.eu_get_full_neighbor(ctx._h, nodes.data_ptr(), n, et.ctypes.data, len(et), total, indptr.data_ptr(),
                                        ids.data_ptr(), w.data_ptr(), t.data_ptr()))
     return indptr, ids, w, t
+
+
+def get_sorted_full_neighbor(nodes, edge_types, condition=''):
+    """neighbor_ops.get_sorted_full_neighbor (neighbor_ops.py:100-119): get_full_neighbor with every node's entries ordered by
+    neighbor id; same ragged return."""
+    if condition:
+        raise EulerError("get_sorted_full_neighbor: `condition` (index queries) is outside this path")
+    nodes = _t(nodes, torch.int64).reshape(-1)
+    et = get_edge_type_id(edge_types)
+    ctx = _ctx_on_stream()
+    lib = _lib.load()
+    n = nodes.numel()
+    indptr = torch.empty(n + 1, dtype=torch.int64, device=nodes.device)
+    check(lib.eu_get_sorted_full_neighbor(ctx._h, nodes.data_ptr(), n, et.ctypes.data, len(et), 0, indptr.data_ptr(), None, None, None))
+    total = int(indptr[-1].item())
+    ids = torch.empty(total, dtype=torch.int64, device=nodes.device)
+    w = torch.empty(total, dtype=torch.float32, device=nodes.device)
+    t = torch.empty(total, dtype=torch.int32, device=nodes.device)
+    if total:
+        check(lib.eu_get_sorted_full_neighbor(ctx._h, nodes.data_ptr(), n, et.ctypes.data, len(et), total, indptr.data_ptr(),
+                                              ids.data_ptr(), w.data_ptr(), t.data_ptr()))
+    return indptr, ids, w, t
+
+
+def get_top_k_neighbor(nodes, edge_types, k, default_node=-1, condition=''):
+    """neighbor_ops.get_top_k_neighbor (neighbor_ops.py:44-46): (ids i64[N,k], weights f32[N,k], types i32[N,k]), the k
+    heaviest edges of each node, heaviest first, filled with default_node / 0 / -1."""
+    if condition:
+        raise EulerError("get_top_k_neighbor: `condition` (index queries) is outside this path")
+    nodes = _t(nodes, torch.int64).reshape(-1)
+    et = get_edge_type_id(edge_types)
+    n, k = nodes.numel(), int(k)
+    ids = torch.empty((n, k), dtype=torch.int64, device=nodes.device)
+    w = torch.empty((n, k), dtype=torch.float32, device=nodes.device)
+    t = torch.empty((n, k), dtype=torch.int32, device=nodes.device)
+    ctx = _ctx_on_stream()
+    check(_lib.load().eu_get_top_k_neighbor(ctx._h, nodes.data_ptr(), n, et.ctypes.data, len(et), k, default_node,
+                                            ids.data_ptr(), w.data_ptr(), t.data_ptr()))
+    return ids, w, t
+
+
+def gen_pair(paths, left_win_size, right_win_size):
+    """walk_ops.gen_pair (tf_euler/kernels/gen_pair_op.cc): skip-gram pairs i64[B, n_pairs, 2] of walks i64[B, path_len]."""
+    paths = _t(paths, torch.int64)
+    if paths.dim() != 2:
+        raise EulerError("gen_pair: paths must be [batch, path_len]")
+    paths = paths.contiguous()
+    B, plen = paths.shape
+    lib = _lib.load()
+    pc = lib.eu_gen_pair_count(plen, int(left_win_size), int(right_win_size))
+    out = torch.empty((B, pc, 2), dtype=torch.int64, device=paths.device)
+    ctx = _ctx_on_stream()
+    check(lib.eu_gen_pair(ctx._h, paths.data_ptr(), B, plen, int(left_win_size), int(right_win_size), out.data_ptr()))
+    return out
+
+
+def sample_neighbor_api(nodes, edge_types, count):
+    """euler::SampleNeighbor of the C++ api (api.cc:223-236): NO unique / gather -- a repeated id draws again.  Returns
+    engine-form (ids i64[N,count], w, t); rows without a result are (0, 0.0, -1)."""
+    nodes = _t(nodes, torch.int64).reshape(-1)
+    et = get_edge_type_id(edge_types)
+    n, count = nodes.numel(), int(count)
+    ids = torch.empty((n, count), dtype=torch.int64, device=nodes.device)
+    w = torch.empty((n, count), dtype=torch.float32, device=nodes.device)
+    t = torch.empty((n, count), dtype=torch.int32, device=nodes.device)
+    ctx = _ctx_on_stream()
+    check(_lib.load().eu_sample_neighbor_raw(ctx._h, nodes.data_ptr(), n, et.ctypes.data, len(et), count,
+                                             ids.data_ptr(), w.data_ptr(), t.data_ptr()))
+    return ids, w, t
 
 
 def unique(ids):

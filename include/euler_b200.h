@@ -152,6 +152,13 @@ int eu_sample_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t
 int eu_sample_neighbor_host(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes,
                             int32_t K, int32_t count, int64_t default_node, int64_t* out_ids,
                             float* out_w, int32_t* out_t);
+/* euler::SampleNeighbor of the C++ api (euler/core/api/api.cc:223-236): one Node::SampleNeighbor per element of `nodes`,
+ * in order, WITHOUT the engine's unique/gather rule -- a repeated id draws again.  Engine-form outputs [B,count]: rows
+ * without a result (absent node / no edge of the requested types) are (0, 0.0, -1).  Exact-RNG contexts only. */
+int eu_sample_neighbor_raw(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
+                           int32_t count, int64_t* out_ids, float* out_w, int32_t* out_t);
+int eu_sample_neighbor_raw_host(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
+                                int32_t count, int64_t* out_ids, float* out_w, int32_t* out_t);
 /* tf_euler.sample_fanout -- TF op SampleFanout (tf_euler/ops/neighbor_ops.cc:228-280, kernel
  * tf_euler/kernels/sample_fanout_op.cc:60-145).  etypes i32[L,K] (host), counts i32[L] (host);
  * out_*[l] point to B*prod(counts[0..l]) elements.  The frontier never leaves the device. */
@@ -200,10 +207,28 @@ int eu_get_full_neighbor_host(eu_ctx* c, const int64_t* nodes, int64_t B, const 
                               int64_t cap, int64_t* out_ptr, int64_t* out_ids, float* out_w, int32_t* out_t,
                               int64_t* total);
 
+/* tf_euler.get_sorted_full_neighbor (neighbor_ops.py:100-119; Node::GetSortedFullNeighbor node.cc:210-262; engine
+ * "order_by id asc", euler/core/kernels/get_neighbor_op.cc:128-141): eu_get_full_neighbor with every node's entries ordered
+ * by neighbor id ascending (ties keep the listing order).  Same convention (cap = 0: lengths only; cap must cover the listing). */
+int eu_get_sorted_full_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
+                                int64_t cap, int64_t* out_ptr, int64_t* out_ids, float* out_w, int32_t* out_t);
+/* tf_euler.get_top_k_neighbor (neighbor_ops.py:44-46; tf_euler/kernels/get_top_k_neighbor_op.cc:54-121; engine "order_by
+ * weight desc, limit k"): dense [B,k] outputs, heaviest edge first, default_node / 0.0 / -1 fill.  Device pointers; synchronises
+ * the stream once (scratch is sized from the listing length). */
+int eu_get_top_k_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K, int32_t k,
+                          int64_t default_node, int64_t* out_ids, float* out_w, int32_t* out_t);
+/* tf_euler.gen_pair (tf_euler/kernels/gen_pair_op.cc:41-100): skip-gram pairs of walks.  paths i64[B,path_len] ->
+ * out i64[B, eu_gen_pair_count(path_len, lw, rw), 2] (device pointers). */
+int64_t eu_gen_pair_count(int32_t path_len, int32_t left_win_size, int32_t right_win_size);
+int eu_gen_pair(eu_ctx* c, const int64_t* paths, int64_t B, int32_t path_len, int32_t left_win_size, int32_t right_win_size,
+                int64_t* out);
+
 /* euler::GetNodeType (euler/core/api/api.cc:50-61; tf_euler get_node_type): type of every node, INT32_MIN
  * (DEFAULT_INT32, euler/common/data_types.cc:23) for ids that are not in the graph. */
 int eu_get_node_type(eu_ctx* c, const int64_t* nodes, int64_t B, int32_t* out);
 int eu_get_node_type_host(eu_ctx* c, const int64_t* nodes, int64_t B, int32_t* out);
+/* Node::GetWeight (euler/core/graph/node.h:78) of every node, 0.0 for ids that are not in the graph (host buffers). */
+int eu_get_node_weight_host(eu_ctx* c, const int64_t* nodes, int64_t B, float* out);
 
 /* tf.unique on the device (UniqueDataFlow / SageDataFlow, tf_euler/python/dataflow/neighbor_dataflow.py:84-109): the
  * distinct values of ids in order of FIRST occurrence and, per input, the index of its value in that list.

@@ -10,25 +10,35 @@
 //   FloatFeatureVec GetNodeFloat32Feature(ids,fids):50    eu_get_dense_feature_host, one call per slot
 //   FloatFeatureVec GetNodeFloat32Feature(ids,names):57   names -> slots (eu_graph_dense_feature_id), then the above
 //   IdWeightPairVec GetFullNeighbor(ids, etypes)   :78    eu_get_full_neighbor_host
-//   IdWeightPairVec SampleNeighbor(ids, etypes, n) :80    eu_sample_neighbor_host
+//   IdWeightPairVec SampleNeighbor(ids, etypes, n) :80    eu_sample_neighbor_raw_host (api.cc:223-236: every occurrence of an id
+//                                                         draws independently, in order -- results identical to the reference's
+//                                                         serial loop under the same seed)
 //   bool GetNodeType / GetEdgeType (names)         :83-89 eu_graph_node_type_id / eu_graph_edge_type_id
-//   graph start-up (Graph::Init, graph.h:53-60)           euler::InitGraph(data_path, shard_index, shard_number, device)
+//   class Graph (euler/core/graph/graph.h:41-93)          euler::Graph: Instance(), Init(...), SampleNode(type|types, count),
+//                                                         GetNodeByID(id) -> Node* proxy (nullptr when absent)
+//   class Node  (euler/core/graph/node.h:63-110)          euler::Node: GetID/GetType/GetWeight, SampleNeighbor, GetFullNeighbor,
+//                                                         GetSortedFullNeighbor, GetTopKNeighbor
+//   graph start-up (Graph::Init, graph.h:53-60)           euler::InitGraph(data_path, shard_index, shard_number, device) / Graph::Init
 //   SampleEdge, EdgeExist, edge / uint64 / binary features: not on the path -> std::runtime_error
 //
-// Two behaviours differ from api.cc and are deliberate:
-//   * SampleNeighbor has the OP semantics every tf_euler op observes (engine rule ID_UNIQUE, euler/parser/compiler.cc:76-90):
-//     duplicate ids in one call share one sampled row; api.cc:223-236 would draw them independently.
-//   * results are deterministic under eu_ctx_seed (one serial minstd_rand0 stream per context), where api.cc's OpenMP loop
-//     interleaves thread-local engines.
+//   euler::SampleNeighborUnique(ids, etypes, n)            the OP semantics every tf_euler op observes (engine rule ID_UNIQUE,
+//                                                         euler/parser/compiler.cc:76-90): duplicate ids share one sampled row
+//
+// One behaviour differs from api.cc and is deliberate: results are deterministic under eu_ctx_seed
+// (one serial minstd_rand0 stream per context), where api.cc's OpenMP build interleaves thread-local engines.
 #ifndef EULER_B200_API_HPP_
 #define EULER_B200_API_HPP_
 
 #include <stdint.h>
 
+#include <algorithm>
 #include <limits>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <tuple>
+#include <unordered_map>
 #include <vector>
 
 #include "euler_b200.h"
@@ -127,8 +137,27 @@ inline IdWeightPairVec GetFullNeighbor(const NodeIdVec& node_ids, const std::vec
   return out;
 }
 
-// neighbor[i] has `count` entries, or none when node i is absent / has no edge of the requested types (node.cc:98-161)
+// neighbor[i] has `count` entries, or none when node i is absent / has no edge of the requested types (node.cc:98-161).
+// api.cc:223-236: one Node::SampleNeighbor per element, in order; a repeated id draws again.
 inline IdWeightPairVec SampleNeighbor(const NodeIdVec& node_ids, const std::vector<int>& edge_types, int count) {
+  const size_t n = node_ids.size();
+  IdWeightPairVec out(n);
+  if (n == 0 || count <= 0) return out;
+  std::vector<int32_t> et(edge_types.begin(), edge_types.end());
+  std::vector<int64_t> ids(n * (size_t)count);
+  std::vector<float> w(ids.size());
+  std::vector<int32_t> t(ids.size());
+  b200_detail::check(eu_sample_neighbor_raw_host(b200_detail::ctx(), b200_detail::i64(node_ids), (int64_t)n, et.data(), (int32_t)et.size(), count,
+                                                 ids.data(), w.data(), t.data()));
+  for (size_t i = 0; i < n; ++i)
+    if (ids[i * count] != 0)   // engine form: a row whose first id is 0 (DEFAULT_UINT64) is an empty result
+      for (int j = 0; j < count; ++j) out[i].emplace_back((NodeId)ids[i * count + j], w[i * count + j], t[i * count + j]);
+  return out;
+}
+
+// The same call with the semantics every tf_euler OP observes: the engine uniquifies the ids first (ID_UNIQUE,
+// euler/parser/compiler.cc:76-90), so duplicate ids in one call share one sampled row and consume one set of uniforms.
+inline IdWeightPairVec SampleNeighborUnique(const NodeIdVec& node_ids, const std::vector<int>& edge_types, int count) {
   const size_t n = node_ids.size();
   IdWeightPairVec out(n);
   if (n == 0 || count <= 0) return out;
@@ -167,6 +196,104 @@ inline bool GetEdgeType(const std::vector<std::string*> edge_types, std::vector<
     if (!GetEdgeType(*edge_types[i], &type_ids->at(i)) || type_ids->at(i) < 0) { type_ids->clear(); return false; }
   return true;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// euler::Graph / euler::Node (euler/core/graph/graph.h:41-93, node.h:63-110) for C++ code written against the classes
+// rather than the free functions.  The graph lives in HBM; a Node is a light proxy (id, type, weight) whose methods are
+// one-row calls into the same kernels.  Status mirrors euler/common/status.h's ok()/error_message().
+class Status {
+ public:
+  Status() : ok_(true) {}
+  explicit Status(const std::string& msg) : ok_(false), msg_(msg) {}
+  static Status OK() { return Status(); }
+  bool ok() const { return ok_; }
+  const std::string& error_message() const { return msg_; }
+ private:
+  bool ok_;
+  std::string msg_;
+};
+
+namespace common {
+typedef uint64_t NodeID;
+typedef std::tuple<NodeID, float, int32_t> IDWeightPair;
+}  // namespace common
+
+class Node {
+ public:
+  Node(common::NodeID id, float weight, int32_t type) : id_(id), weight_(weight), type_(type) {}
+  common::NodeID GetID() const { return id_; }
+  int32_t GetType() const { return type_; }
+  float GetWeight() const { return weight_; }
+  // node.cc:98-161 (count entries, or none)
+  std::vector<common::IDWeightPair> SampleNeighbor(const std::vector<int32_t>& edge_types, int32_t count) const {
+    return SampleNeighbor_(NodeIdVec{id_}, edge_types, count);
+  }
+  // node.cc:176-198
+  std::vector<common::IDWeightPair> GetFullNeighbor(const std::vector<int32_t>& edge_types) const {
+    return euler::GetFullNeighbor(NodeIdVec{id_}, std::vector<int>(edge_types.begin(), edge_types.end()))[0];
+  }
+  // node.cc:210-262: ordered by neighbor id
+  std::vector<common::IDWeightPair> GetSortedFullNeighbor(const std::vector<int32_t>& edge_types) const {
+    std::vector<common::IDWeightPair> v = GetFullNeighbor(edge_types);
+    std::stable_sort(v.begin(), v.end(), [](const common::IDWeightPair& a, const common::IDWeightPair& b) { return std::get<0>(a) < std::get<0>(b); });
+    return v;
+  }
+  // node.cc:264-316: the k heaviest, heaviest first
+  std::vector<common::IDWeightPair> GetTopKNeighbor(const std::vector<int32_t>& edge_types, int32_t k) const {
+    std::vector<common::IDWeightPair> v = GetFullNeighbor(edge_types);
+    std::stable_sort(v.begin(), v.end(), [](const common::IDWeightPair& a, const common::IDWeightPair& b) { return std::get<1>(a) > std::get<1>(b); });
+    if (k >= 0 && (size_t)k < v.size()) v.resize(k);
+    if (k <= 0) v.clear();
+    return v;
+  }
+ private:
+  static std::vector<common::IDWeightPair> SampleNeighbor_(const NodeIdVec& one, const std::vector<int32_t>& edge_types, int32_t count) {
+    return euler::SampleNeighbor(one, std::vector<int>(edge_types.begin(), edge_types.end()), count)[0];
+  }
+  common::NodeID id_;
+  float weight_;
+  int32_t type_;
+};
+
+class Graph {
+ public:
+  static Graph& Instance() {   // graph.h:64-67
+    static Graph instance;
+    return instance;
+  }
+  // graph.h:53-56.  sampler_type / load_data_type are accepted for source compatibility: the node sampler is built on first
+  // use and this path loads node data only.  `device` and `seed` are extensions with defaults.
+  Status Init(int shard_index, int shard_number, const std::string& sampler_type, const std::string& data_path,
+              const std::string& load_data_type, int device = 0, uint64_t seed = 1) {
+    (void)sampler_type; (void)load_data_type;
+    if (!InitGraph(data_path, shard_index, shard_number, device, seed)) return Status(std::string("Graph::Init: ") + eu_last_error());
+    std::lock_guard<std::mutex> l(mu_);
+    nodes_.clear();
+    return Status::OK();
+  }
+  // graph.h:75-79, graph.cc:221-275
+  std::vector<common::NodeID> SampleNode(int node_type, int count) const { return euler::SampleNode(std::vector<int>{node_type}, count); }
+  std::vector<common::NodeID> SampleNode(const std::vector<int>& node_types, int count) const { return euler::SampleNode(node_types, count); }
+  // graph.h:87-93: nullptr when the id is not a node.  The proxy stays valid until the next Init.
+  Node* GetNodeByID(common::NodeID id) const {
+    std::lock_guard<std::mutex> l(mu_);
+    auto it = nodes_.find(id);
+    if (it != nodes_.end()) return it->second.get();
+    int32_t type = 0;
+    float weight = 0.f;
+    const int64_t sid = (int64_t)id;
+    b200_detail::check(eu_get_node_type_host(b200_detail::ctx(), &sid, 1, &type));
+    if (type == std::numeric_limits<int32_t>::lowest()) return nullptr;
+    b200_detail::check(eu_get_node_weight_host(b200_detail::ctx(), &sid, 1, &weight));
+    Node* n = new Node(id, weight, type);
+    nodes_[id].reset(n);
+    return n;
+  }
+ private:
+  Graph() {}
+  mutable std::mutex mu_;
+  mutable std::unordered_map<common::NodeID, std::unique_ptr<Node>> nodes_;
+};
 
 // ---- declared by api.h, outside the accelerated path ("out of scope")
 inline bool EdgeExist(const EdgeId&) { b200_detail::out_of_scope("EdgeExist"); }

@@ -47,6 +47,32 @@ int main(int argc, char** argv) {
   const bool ok1 = euler::GetNodeType(std::string("no such type"), &t1);
   std::printf("names: %d %d %d %d\n", (int)ok0, t0, (int)ok1, t1);
 
+  // the op-level variant (ID_UNIQUE first: duplicates share a row)
+  print_pairs("unique", euler::SampleNeighborUnique({1, 2, 3, 99, 1, 6}, {0, 1}, count));
+
+  // euler::Graph / euler::Node (graph.h:41-93, node.h:63-110)
+  euler::Graph& gr = euler::Graph::Instance();
+  euler::Node* n1 = gr.GetNodeByID(1);
+  euler::Node* n99 = gr.GetNodeByID(99);
+  std::printf("graph_node: %d %llu %d %.9g %d\n", n1 != nullptr, n1 ? (unsigned long long)n1->GetID() : 0ull, n1 ? n1->GetType() : 0,
+              n1 ? (double)n1->GetWeight() : 0.0, n99 == nullptr);
+  if (n1) {
+    euler::IdWeightPairVec one(1);
+    one[0] = n1->SampleNeighbor({0, 1}, count);
+    print_pairs("node_sample", one);
+    one[0] = n1->GetFullNeighbor({0, 1});
+    print_pairs("node_full", one);
+    one[0] = n1->GetSortedFullNeighbor({0, 1});
+    print_pairs("node_sorted", one);
+    one[0] = n1->GetTopKNeighbor({0, 1}, 2);
+    print_pairs("node_topk", one);
+  }
+  std::printf("graph_sample_node:");
+  for (euler::NodeId id : gr.SampleNode(0, 6)) std::printf(" %llu", (unsigned long long)id);
+  std::printf("\n");
+  const euler::Status st = gr.Init(0, 1, "node", "/no/such/dir", "node");
+  std::printf("graph_init_bad: %d\n", (int)st.ok());
+
   try {
     euler::SampleEdge({0}, 1);
     std::printf("out_of_scope: no throw\n");

@@ -530,17 +530,23 @@ def test_cpp_api_adapter(tiny_dir):
             want += [str(int(ids[k])), "%.9g" % float(w[k]), str(int(t[k]))]
         assert got == want, (i, got, want)
         off += n
-    # sampled neighbors: engine stream seeded 4242, op semantics (duplicates share a row), empty vector for absent rows
-    po.seed(4242)
-    for key, nodes, et in [("sample", [1, 2, 3, 99, 1, 6], [0, 1]), ("sample2", [4, 5], [1])]:
-        o_ids, o_w, o_t = og.op_sample_neighbor(np.asarray(nodes, np.int64), et, 5, 0)
-        o_ids, o_w, o_t = o_ids.reshape(len(nodes), 5), o_w.reshape(len(nodes), 5), o_t.reshape(len(nodes), 5)
-        for i in range(len(nodes)):
+    # sampled neighbors: engine stream seeded 4242; euler::SampleNeighbor = api.cc:223-236 (every occurrence of an id draws
+    # independently, in order), empty vector for absent rows
+    rng = po.Rng(4242)
+
+    def fmt_rows(o_ids, o_w, o_t, n_rows, cnt, lens=None):
+        out = []
+        for i in range(n_rows):
             want = []
-            if o_ids[i, 0] != 0:
-                for j in range(5):
+            if (lens[i] if lens is not None else o_ids[i, 0] != 0):
+                for j in range(cnt):
                     want += [str(int(o_ids[i, j])), "%.9g" % float(o_w[i, j]), str(int(o_t[i, j]))]
-            assert kv["%s[%d]" % (key, i)] == want, (key, i)
+            out.append(want)
+        return out
+    for key, nodes, et in [("sample", [1, 2, 3, 99, 1, 6], [0, 1]), ("sample2", [4, 5], [1])]:
+        o_ids, o_w, o_t, o_len = og.sample_neighbor_api(np.asarray(nodes, np.uint64), et, 5, rng)
+        for i, want in enumerate(fmt_rows(o_ids, o_w, o_t, len(nodes), 5, o_len)):
+            assert kv["%s[%d]" % (key, i)] == want, (key, i, kv["%s[%d]" % (key, i)], want)
     # dense features: node 1 and 3 per slot, absent node -> empty vectors, unknown slot -> empty
     feat = g["feat"].reshape(len(g["ids"]), -1)
     rows = {int(i): r for r, i in enumerate(g["ids"])}
@@ -557,6 +563,30 @@ def test_cpp_api_adapter(tiny_dir):
                 assert len(vals) > 0
     assert len(kv["sample_node"]) == 8 and all(int(x) in rows for x in kv["sample_node"])
     assert kv["names"] == ["1", "-1", "0", "-1"]
+    # the op-level variant continues the same engine: sample_node drew 8 x 3 uniforms (a list of 2 types) in between
+    for _ in range(24):
+        rng.uniform()
+    po.set_state((rng.x, rng.draws))
+    nodes = [1, 2, 3, 99, 1, 6]
+    o_ids, o_w, o_t = og.op_sample_neighbor(np.asarray(nodes, np.int64), [0, 1], 5, 0)
+    for i, want in enumerate(fmt_rows(o_ids.reshape(6, 5), o_w.reshape(6, 5), o_t.reshape(6, 5), 6, 5)):
+        assert kv["unique[%d]" % i] == want, ("unique", i)
+    assert kv["unique[0]"] == kv["unique[4]"]          # duplicates share one row under the op semantics
+    st = po.get_state()
+    rng.x, rng.draws = st[0], st[1]
+    # euler::Graph / euler::Node
+    r1 = rows[1]
+    assert kv["graph_node"] == ["1", "1", str(int(g["node_type"][r1])), "%.9g" % float(g["node_w"][r1]), "1"]
+    o_ids, o_w, o_t, o_len = og.sample_neighbor_api(np.asarray([1], np.uint64), [0, 1], 5, rng)
+    assert kv["node_sample[0]"] == fmt_rows(o_ids, o_w, o_t, 1, 5, o_len)[0]
+    lens, f_ids, f_w, f_t = og.get_full_neighbor(np.asarray([1], np.uint64), [0, 1])
+    full = [(int(f_ids[k]), float(f_w[k]), int(f_t[k])) for k in range(int(lens[0]))]
+    flat = lambda v: [x for (a, b, c) in v for x in (str(a), "%.9g" % b, str(c))]  # noqa: E731
+    assert kv["node_full[0]"] == flat(full)
+    assert kv["node_sorted[0]"] == flat(sorted(full, key=lambda z: z[0]))
+    assert kv["node_topk[0]"] == flat(sorted(full, key=lambda z: -z[1])[:2])
+    assert len(kv["graph_sample_node"]) == 6 and all(type_of[int(x)] == 0 for x in kv["graph_sample_node"])
+    assert kv["graph_init_bad"] == ["0"]
     assert kv["out_of_scope"] == ["throws"]
 
 
@@ -675,3 +705,111 @@ def test_fanout_with_zero_count_leaves_the_dedup_tables_clean():
     ids2, _, _ = euler_b200.sample_fanout(seeds, [[0], [0]], [4, 3])
     o2, _, _ = og.op_sample_fanout(seeds, [[0], [0]], [4, 3])
     cases.eq(ids2[2].cpu().numpy(), o2[1], "fanout after a zero-count call")
+
+
+def test_sample_node_on_a_loaded_graph_follows_the_reference_map_order(tiny_dir):
+    """eu_graph_load replays the reference's node_map_ insert sequence into the same std::unordered_map, so the global node
+    sampler enumerates nodes in the reference's order: sample_node on Graph.load(dir) == the reference's own SampleNode on the
+    same directory under the same seed, all three type modes (graph.cc:221-275,333-370)."""
+    if not po.have_ref():
+        pytest.skip("oracle/_ref not built")
+    import euler_b200
+    rg = po.RefGraph.load(tiny_dir)          # the reference's own loader: same directory, same readdir order
+    gr = euler_b200.Graph.load(tiny_dir)
+    euler_b200.set_graph(gr, rng="minstd", seed=1)
+    for types, nt in (([0], 0), ([1], 1), ([-1], '-1'), ([0, 1], [0, 1])):
+        for s in (77, 12345):
+            rg.seed(s)
+            want = rg.sample_node(types, 200).astype(np.int64)
+            euler_b200.seed(s)
+            got = euler_b200.sample_node(200, nt).cpu().numpy()
+            cases.eq(got, want, "sample_node types=%s seed=%d on the loaded graph" % (types, s))
+
+
+# ------------------------------------------------------------------ next-1: sorted / top-k listings, gen_pair, raw api sampling
+def test_sorted_and_topk_neighbors_reference_vectors_and_random_graph():
+    """tiny graph: the reference's own expectations (tf_euler/python/euler_ops/neighbor_ops_test.py:73-110); random graph:
+    stable sort by id / by weight descending of the oracle's full listing."""
+    import euler_b200
+    z = graphs.load_tiny_csr()
+    euler_b200.set_graph(graphs.cuda_graph(z))
+    ptr, ids, w, t = euler_b200.get_sorted_full_neighbor([1, 2], [0, 1])
+    cases.eq(ptr.cpu().numpy(), np.array([0, 3, 5]), "sorted indptr")
+    cases.eq(ids.cpu().numpy(), np.array([2, 3, 4, 3, 5]), "sorted ids (neighbor_ops_test.py:73-84)")
+    assert np.allclose(w.cpu().numpy(), [2.0, 3.0, 4.0, 3.0, 5.0])
+    cases.eq(t.cpu().numpy(), np.array([0, 1, 0, 1, 1], np.int32), "sorted types")
+    k_ids, k_w, k_t = euler_b200.get_top_k_neighbor([1, 2], [0, 1], 2)
+    cases.eq(k_ids.cpu().numpy(), np.array([[4, 3], [5, 3]]), "top-k ids (neighbor_ops_test.py:102-110)")
+    assert np.allclose(k_w.cpu().numpy(), [[4.0, 3.0], [5.0, 3.0]])
+    cases.eq(k_t.cpu().numpy(), np.array([[0, 1], [1, 1]], np.int32), "top-k types")
+    g = graphs.random_graph(seed=301, n=3000, T=3, avg_deg=9, hub=700, dup_edges=True, empty_frac=0.1)
+    euler_b200.set_graph(graphs.cuda_graph(g))
+    og = graphs.oracle_graph(g)
+    nodes = g["ids"][np.random.RandomState(2).randint(0, 3000, size=500)].astype(np.int64)
+    nodes[::17] = 987654321
+    for et in ([0, 2], [1], [2, 0, 1]):
+        lens, f_ids, f_w, f_t = og.get_full_neighbor(nodes.astype(np.uint64), et)
+        ptr, ids, w, t = euler_b200.get_sorted_full_neighbor(nodes, et)
+        k_ids, k_w, k_t = euler_b200.get_top_k_neighbor(nodes, et, 7, default_node=-5)
+        off = 0
+        s_ids, s_w, s_t = [], [], []
+        want_k = np.full((len(nodes), 7), -5, np.int64); want_kw = np.zeros((len(nodes), 7), np.float32); want_kt = np.full((len(nodes), 7), -1, np.int32)
+        for i, n in enumerate(lens):
+            sl = slice(off, off + n)
+            o = np.argsort(f_ids[sl], kind="stable")
+            s_ids.append(f_ids[sl][o]); s_w.append(f_w[sl][o]); s_t.append(f_t[sl][o])
+            o2 = np.argsort(-f_w[sl], kind="stable")[:7]
+            want_k[i, :len(o2)] = f_ids[sl][o2]; want_kw[i, :len(o2)] = f_w[sl][o2]; want_kt[i, :len(o2)] = f_t[sl][o2]
+            off += n
+        cases.eq(ptr.cpu().numpy(), np.concatenate([[0], np.cumsum(lens)]), "sorted indptr %s" % et)
+        cases.eq(ids.cpu().numpy(), np.concatenate(s_ids).astype(np.int64), "sorted ids %s" % et)
+        cases.eq(w.cpu().numpy(), np.concatenate(s_w), "sorted weights %s" % et)
+        cases.eq(t.cpu().numpy(), np.concatenate(s_t), "sorted types %s" % et)
+        cases.eq(k_ids.cpu().numpy(), want_k, "top-k ids %s" % et)
+        cases.eq(k_w.cpu().numpy(), want_kw, "top-k weights %s" % et)
+        cases.eq(k_t.cpu().numpy(), want_kt, "top-k types %s" % et)
+
+
+@pytest.mark.parametrize("plen,lw,rw", [(6, 1, 1), (11, 2, 3), (5, 7, 0), (1, 2, 2), (81, 5, 5)])
+def test_gen_pair_matches_the_reference_loop(plen, lw, rw):
+    """literal restatement of tf_euler/kernels/gen_pair_op.cc:61-80 on the host vs the closed-form kernel"""
+    import euler_b200
+    g = graphs.random_graph(seed=5, n=50, T=1)
+    euler_b200.set_graph(graphs.cuda_graph(g))
+    paths = np.random.RandomState(plen).randint(1, 1000, size=(37, plen)).astype(np.int64)
+    want = []
+    for path in paths:
+        row = []
+        for j in range(plen):
+            k = 0
+            while j - k - 1 >= 0 and k < lw:
+                row += [path[j], path[j - k - 1]]; k += 1
+            k = 0
+            while j + k + 1 < plen and k < rw:
+                row += [path[j], path[j + k + 1]]; k += 1
+        want.append(row)
+    want = np.asarray(want, np.int64).reshape(37, -1, 2)
+    got = euler_b200.gen_pair(paths, lw, rw).cpu().numpy()
+    assert got.shape == want.shape, (got.shape, want.shape)
+    cases.eq(got, want, "gen_pair")
+
+
+def test_raw_api_sample_neighbor_draws_duplicates_independently():
+    """eu_sample_neighbor_raw == euler::SampleNeighbor (api.cc:223-236) on the oracle: no unique, serial draw order"""
+    import euler_b200
+    for T, et in ((1, [0]), (3, [0, 2]), (3, [0, 1, 2])):
+        g = graphs.random_graph(seed=410 + T, n=5000, T=T, avg_deg=8, hub=600, empty_frac=0.1, zero_w_frac=0.05)
+        euler_b200.set_graph(graphs.cuda_graph(g), rng="minstd", seed=55)
+        og = graphs.oracle_graph(g)
+        nodes = g["ids"][np.random.RandomState(3).randint(0, 5000, size=2000)].astype(np.int64)
+        nodes[::7] = nodes[0]
+        nodes[5::31] = 424242424242
+        rng = po.Rng(55)
+        for rep in range(2):
+            o_ids, o_w, o_t, o_len = og.sample_neighbor_api(nodes.astype(np.uint64), et, 6, rng)
+            ids, w, t = euler_b200.sample_neighbor_api(nodes, et, 6)
+            keep = (o_len > 0)[:, None]
+            cases.eq(ids.cpu().numpy(), np.where(keep, o_ids.astype(np.int64), 0), "raw ids T=%d rep=%d" % (T, rep))
+            cases.eq(w.cpu().numpy(), np.where(keep, o_w, 0).astype(np.float32), "raw weights")
+            cases.eq(t.cpu().numpy(), np.where(keep, o_t, -1).astype(np.int32), "raw types")
+        assert euler_b200.context().draws() == rng.draws
