@@ -147,6 +147,31 @@ __device__ __forceinline__ void philox_uniform2(unsigned long long id, uint32_t 
   u1 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
 }
 
+// ---------------------------------------------------------------------------------- TMA bulk copy (sm_90+/sm_100a)
+// 1-D bulk copy global -> shared through the TMA unit, completion signalled on an mbarrier (SASS: UBLKCP + SYNCS).  One
+// elected lane issues it and moves on; the consumers wait on the barrier's phase parity.  src, dst and bytes must be
+// multiples of 16.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy accesses to shared memory ordered before subsequent async-proxy (TMA) accesses of the same thread
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+
 // ---------------------------------------------------------------------------------- CDF pick
 // r for a pick in [begin,end] of a cumulative array (compact_weighted_collection.h:33-36):
 //   limit_begin = begin==first ? 0 : cum[begin-1]; r = u * (double)(limit_end - limit_begin) + limit_begin

@@ -349,20 +349,34 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
   const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   __shared__ uint32_t s_lanepow[32];  // A^(2k*lane)
   __shared__ uint32_t s_fpow[32];     // F^k, k < 32
-  if (!PHILOX) {
-    if (threadIdx.x < 32) {
-      s_lanepow[threadIdx.x] = a.lanepow[threadIdx.x];
-      uint32_t fp = 1, fb = a.F;
-      for (uint32_t e = threadIdx.x; e; e >>= 1) { if (e & 1) fp = modmul(fp, fb); fb = modmul(fb, fb); }
-      s_fpow[threadIdx.x] = fp;
-    }
-    __syncthreads();
-    // k_prepare (the only reader of this hop's dedup tables) has finished: wipe them
-    for (int64_t s = gtid; s < a.clear_n; s += (int64_t)gridDim.x * blockDim.x) { a.clear_tab[s].key = 0; a.clear_tab[s].row = kEmptyRow; }
-  }
+  // TMA-staged adjacency tiles: a row longer than the group's lanes but of at most kStageF * SG cumulative weights is copied
+  // into the group's slice of shared memory by ONE cp.async.bulk (the elected lane issues it right after the row bounds are
+  // known and the whole group goes on to derive its engine states; the draws then wait on the slice's mbarrier), and every
+  // inverse-CDF search of that row is a shared-memory binary search instead of an 8-ary descent through L2.
+  constexpr int kStageF = 16;
+  __shared__ __align__(128) float s_stage[256 * kStageF];
+  __shared__ __align__(8) unsigned long long s_bar[32];
   const int SG = 1 << a.sg_log;
   const int sl = lane & (SG - 1);                    // lane inside its group = draw index modulo SG
   const unsigned gmask = SG == 32 ? 0xffffffffu : (((1u << SG) - 1u) << (lane - sl));
+  const bool can_stage = a.sg_log >= 3;              // <= 32 groups per CTA, slices of >= 256 B
+  unsigned long long* const bar = &s_bar[can_stage ? (threadIdx.x >> a.sg_log) : 0];
+  float* const sm = s_stage + (threadIdx.x - sl) * kStageF;   // this group's slice: kStageF * SG floats, 16-byte aligned
+  const int64_t capg = (int64_t)SG * kStageF;
+  uint32_t phase = 0;                                // parity of the slice's barrier (uniform over the group)
+  if (can_stage && sl == 0) mbar_init(bar, 1);
+  if (!PHILOX && threadIdx.x < 32) {
+    s_lanepow[threadIdx.x] = a.lanepow[threadIdx.x];
+    uint32_t fp = 1, fb = a.F;
+    for (uint32_t e = threadIdx.x; e; e >>= 1) { if (e & 1) fp = modmul(fp, fb); fb = modmul(fb, fb); }
+    s_fpow[threadIdx.x] = fp;
+  }
+  fence_mbar_init();
+  __syncthreads();
+  if (!PHILOX) {
+    // k_prepare (the only reader of this hop's dedup tables) has finished: wipe them
+    for (int64_t s = gtid; s < a.clear_n; s += (int64_t)gridDim.x * blockDim.x) { a.clear_tab[s].key = 0; a.clear_tab[s].row = kEmptyRow; }
+  }
   const int32_t count = a.count;
   const int32_t T = g.T;
   const int64_t total = PHILOX ? a.gm.nb * a.gm.rows_b : (int64_t)__ldg(a.n_live);   // empty rows were finished by k_prepare
@@ -418,6 +432,17 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
     const bool small_row = rlen <= SG;
     float c = __int_as_float(0x7f800000);  // +inf
     if (small_row && sl < rlen) c = __ldg(g.cum_w + base + sl);
+    // mid row: stage [base - mis, base + rlen) rounded to 16 bytes (the copy starts at the 16-byte boundary below the row;
+    // arrays are allocated in 256-byte units, so the rounded end stays inside the allocation)
+    const int mis = (int)((reinterpret_cast<uintptr_t>(g.cum_w + base) & 15u) >> 2);
+    const bool mid_row = can_stage && !small_row && rlen + mis <= capg;   // uniform over the group (one row per group)
+    if (mid_row && sl == 0) {
+      const uint32_t bytes = (uint32_t)((((rlen + mis) << 2) + 15) & ~15ll);
+      fence_proxy_async_smem();        // the group's reads of the previous tile (ordered by its closing __syncwarp) before the TMA write
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_copy_g2s(sm, g.cum_w + base - mis, bytes, bar);
+    }
+    const float* const srow = sm + mis;   // srow[k] = cum_w[base + k]
 
     // mode 0: fixed group
     int64_t gb = 0, ge = 0;  // group [gb, ge] inclusive, global indices
@@ -455,6 +480,10 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
     const uint32_t salt = PHILOX ? (uint32_t)rng->calls : 0u;
     const unsigned long long pkey = PHILOX ? a.key ^ rng->key : 0ull;
 
+    if (mid_row) {   // the tile has landed?
+      while (!mbar_try_wait(bar, phase)) {}
+      phase ^= 1u;
+    }
     bool keep = true;
     bool bad = false;
     for (int32_t j0 = 0; j0 < count; j0 += SG) {
@@ -495,6 +524,14 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
         float lo_v = __shfl_sync(gmask, c, li2 > 0 ? li2 - 1 : 0, SG);
         m = base + li2;
         wgt = __fsub_rn(hi_v, li2 > 0 ? lo_v : 0.f);
+      } else if (mid_row) {
+        int lo = (int)(b - base), hi = (int)(e - base);   // first index in [lo, hi] with cum >= thr, else hi
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (srow[mid] >= thr) hi = mid; else lo = mid + 1;
+        }
+        m = base + lo;
+        wgt = __fsub_rn(srow[lo], lo > 0 ? srow[lo - 1] : 0.f);
       } else {
         m = b + upper_bound_clamped(g.cum_w + b, 0, (int32_t)(e - b), thr);
         float hi_v = __ldg(g.cum_w + m);
@@ -544,6 +581,7 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
         }
       }
     }
+    if (mid_row) __syncwarp(gmask);   // every lane is done with the tile before the group's next row overwrites it
   }
 }
 
