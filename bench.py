@@ -375,6 +375,9 @@ def run_ours(args):
     n_lanes = max(1, min(args.lanes, args.steps // G if args.steps >= G else 1))
     lanes = [Lane(eb, graph, args, counts, 12345 + i, torch, G) for i in range(n_lanes)]
     tail_lane = Lane(eb, graph, args, counts, 12345 + n_lanes, torch, tail) if tail else None
+    # the *_host calls are synchronous per caller thread: the e2e leg through them runs one thread per lane on HOST_LANES lanes
+    # = the reference's client thread pool (euler/client/query_proxy.cc:205-210: 8 threads) so that PCIe stays busy
+    HOST_LANES = 8
     raw_step = make_step(lib, args, counts, et)
     nb = args.warmup + args.steps
     n_seed_batches = -(-max(nb, 4 * G) // G) * G
@@ -420,6 +423,8 @@ def run_ours(args):
     main = torch.cuda.current_stream()
     all_lanes = lanes + ([tail_lane] if tail_lane else [])
 
+    host_lanes = []
+
     def run(n_steps, first, mode):
         """n_steps steps round-robin over the lanes; returns device ms (events on the main stream, lanes fork from / join
         into it).  mode: "dev" = seeds resident in HBM; "e2e" = device entry points + pinned H2D / D2H copies;
@@ -428,16 +433,21 @@ def run_ours(args):
         rem = n_steps % G
         use_tail = tail_lane is not None and rem == tail_lane.G
         n_groups = n_steps // G + (1 if rem else 0)     # an untimed (warm-up) remainder is rounded up to a full group
+        pool = lanes
+        if mode == "host":
+            while len(lanes) + len(host_lanes) < min(HOST_LANES, max(n_groups, len(lanes))):
+                host_lanes.append(Lane(eb, graph, args, counts, 22345 + len(host_lanes), torch, G))
+            pool = lanes + host_lanes
         work = []                                        # (lane, first seed batch, batches)
         for i in range(n_groups):
-            ln = lanes[i % len(lanes)]
+            ln = pool[i % len(pool)]
             g0, sd = group_seeds(first, i)
             if use_tail and i == n_groups - 1:
                 ln, sd = tail_lane, sd[:rem * args.batch]
             work.append((ln, g0, sd))
         torch.cuda.synchronize()
         ev0.record(main)
-        for ln in all_lanes:
+        for ln in all_lanes + host_lanes:
             ln.stream.wait_event(ev0)
         if mode == "host":
             def worker(ln):
@@ -445,7 +455,7 @@ def run_ours(args):
                     if l2 is ln:
                         ln.h_seeds.copy_(torch.from_numpy(host_seeds[g0:g0 + ln.G].reshape(-1)))
                         raw_step.host(ln)
-            ths = [threading.Thread(target=worker, args=(ln,)) for ln in all_lanes]
+            ths = [threading.Thread(target=worker, args=(ln,)) for ln in all_lanes + host_lanes]
             for t in ths:
                 t.start()
             for t in ths:
@@ -465,7 +475,7 @@ def run_ours(args):
                             ln.h_agg[l].copy_(ln.agg[l], non_blocking=True)
                     else:
                         step(ln, sd)
-        for ln in all_lanes:
+        for ln in all_lanes + host_lanes:
             main.wait_stream(ln.stream)
         ev1.record(main)
         torch.cuda.synchronize()
@@ -597,7 +607,7 @@ def run_ours(args):
         e2e = {"value": edges_step * args.steps / (ms_host * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": lanes[0].h2d_host,
                "d2h_bytes_per_step": lanes[0].d2h_host, "ms_per_step": ms_host / args.steps,
                "api": "eu_sample_fanout_batched_host + eu_get_dense_feature_host + eu_sage_mean_aggregate_host (HOST buffers in and out; "
-                      "one host thread per lane); PCIe-bound: %.0f MB D2H per step" % (lanes[0].d2h_host / 1e6),
+                      "one host thread per lane, %d lanes); PCIe-bound: %.0f MB D2H per step" % (len(lanes) + len(host_lanes), lanes[0].d2h_host / 1e6),
                "pcie_gbs": round((lanes[0].d2h_host + lanes[0].h2d_host) * args.steps / (ms_host * 1e-3) / 1e9, 1),
                "device_api_variant": e2e_dev}
     else:
@@ -625,7 +635,7 @@ def run_ours(args):
         "graph_build_s": round(t_graph, 2), "hbm_graph_bytes": graph.hbm_bytes,
     }
     if not args.no_cpu_baseline and rank == 0:
-        for ln_ in all_lanes:
+        for ln_ in all_lanes + host_lanes:
             del ln_.h_x, ln_.h_agg
         out["cpu_baseline"] = cpu_baseline(args, counts)
     emit(out)

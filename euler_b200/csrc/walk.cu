@@ -241,12 +241,13 @@ struct WarpWalk {
 // ---------------------------------------------------------------------------------------------
 // Exact node2vec step for BIG rows (deg > kWalkBig), split so that nothing latency-heavy sits inside the sequential part:
 //   k_walk_plan     one block: RNG engine states of the live walkers (the reference draws one uniform per live walker, in
-//                   walker order), the big / small work lists, offsets of the big rows in the weight scratch V
-//   k_walk_weights  fully parallel over (big walker, neighbor): BuildWeights' bias (:140-168) per element -- membership of
-//                   the child in the parent's sorted list by binary search, multiset rule as in WarpWalk -- written to V
-//   k_walk_prefix   CTA per big walker: the SEQUENTIAL f32 prefix of CompactWeightedCollection::Init (:82-97) evaluated
-//                   1024 elements per iteration without changing a single rounding (block_exact_prefix below), total ->
-//                   one uniform -> RandomSelect; then warp per small walker (WarpWalk, as before)
+//                   walker order), the work lists, offsets of every live walker's row in the weight scratch V
+//   k_walk_weights  fully parallel over (walker, neighbor): BuildWeights' bias (:140-168) per element -- membership of the
+//                   child in the parent's sorted list by binary search, multiset rule as in WarpWalk -- written to V.  No
+//                   walker streams its parent's list (a small row behind a 137K-edge parent cost 4300 dependent loads)
+//   k_walk_prefix   CTA per big walker (deg > kWalkBig): the SEQUENTIAL f32 prefix of CompactWeightedCollection::Init
+//                   (:82-97) evaluated 1024 elements per iteration without changing a single rounding (block_exact_prefix
+//                   below), total -> one uniform -> RandomSelect; warp per small walker: the same chain through shuffles
 //
 // block_exact_prefix: S_k = fl(S_{k-1} + v_k) for v_k >= 0.  While S stays in one binade (ulp u = 2^(e-23), S = M u with
 // 2^23 <= M < 2^24) and v_k's exponent does not exceed e, fl(S + v) = (M + a + c) u with a = floor(v / u) and c = 1 iff the
@@ -267,11 +268,13 @@ static constexpr int kPrefCk = 256;         // checkpoints kept per row
 
 struct WalkPlan {
   int32_t* deg;         // [B] length of the walker's child list (single type), 0 if dead
-  int32_t* big_list;    // [B] walkers on the V path, walker order
-  int32_t* small_list;  // [B] the rest of the live walkers
-  long long* voff;      // [B+1] V offset of big walker k (k = position in big_list)
-  int32_t* coff;        // [B+1] first k_walk_weights chunk of big walker k
-  unsigned int* ctr;    // [8]: 0 n_big, 1 n_small, 2 n_chunks, 3 big ticket, 4 small ticket
+  int32_t* live_list;   // [B] live walkers whose row fits in V, walker order (k_walk_weights maps chunks to them)
+  int32_t* coff;        // [B+1] first k_walk_weights chunk of live_list[k]
+  long long* voff;      // [B] V offset of walker i's row (by walker id)
+  int32_t* big_list;    // [B] walkers with deg > kWalkBig: one CTA each in k_walk_prefix
+  int32_t* small_list;  // [B] the other walkers with a V row: one warp each
+  int32_t* ovf_list;    // [B] live walkers whose row does not fit in V: the self-contained warp path (WarpWalk)
+  unsigned int* ctr;    // [8]: 0 n_big, 1 n_small, 2 n_chunks, 3 big ticket, 4 small ticket, 5 n_ovf, 6 ovf ticket, 7 n_fit
   float* V;
   long long capV;
 };
@@ -293,81 +296,64 @@ __global__ void __launch_bounds__(1024) k_walk_plan(int64_t B, const uint8_t* __
   __shared__ uint32_t s_prod[1024];
   __shared__ uint32_t s_cnt[1024];
   __shared__ uint32_t s_big[1024];
-  __shared__ uint32_t s_small[1024];
   __shared__ uint32_t s_chunks[1024];
   __shared__ unsigned long long s_el[1024];
+  __shared__ unsigned int s_fit, s_fitbig, s_fitchunks;
   const int t = threadIdx.x;
-  if (t == 0) wp.ctr[5] = 0;   // walkers demoted to the warp path because V is full
+  if (t == 0) { wp.ctr[5] = 0; s_fit = 0; s_fitbig = 0; s_fitchunks = 0; }
   const int64_t per = (B + 1023) / 1024;
   const int64_t b = min((int64_t)t * per, B), e = min(b + per, B);
-  uint32_t prod = 1, cnt = 0, nbig = 0, nsmall = 0, chunks = 0;
+  uint32_t prod = 1, cnt = 0, nbig = 0, chunks = 0;
   unsigned long long el = 0;
   for (int64_t i = b; i < e; ++i) {
     if (!live[i]) continue;
     prod = modmul(prod, F); ++cnt;
     const int32_t d = wp.deg[i];
-    if (d > kWalkBig) { ++nbig; el += (unsigned long long)d; chunks += (uint32_t)((d + kWalkChunk - 1) / kWalkChunk); }
-    else ++nsmall;
+    el += (unsigned long long)d;
+    chunks += (uint32_t)((d + kWalkChunk - 1) / kWalkChunk);
+    if (d > kWalkBig) ++nbig;
   }
-  s_prod[t] = prod; s_cnt[t] = cnt; s_big[t] = nbig; s_small[t] = nsmall; s_chunks[t] = chunks; s_el[t] = el;
+  s_prod[t] = prod; s_cnt[t] = cnt; s_big[t] = nbig; s_chunks[t] = chunks; s_el[t] = el;
   __syncthreads();
   for (int off = 1; off < 1024; off <<= 1) {   // inclusive Hillis-Steele scans (modmul is associative and commutative)
-    uint32_t v = 1, c = 0, g1 = 0, g2 = 0, g3 = 0; unsigned long long g4 = 0;
-    if (t >= off) { v = s_prod[t - off]; c = s_cnt[t - off]; g1 = s_big[t - off]; g2 = s_small[t - off]; g3 = s_chunks[t - off]; g4 = s_el[t - off]; }
+    uint32_t v = 1, c = 0, g1 = 0, g3 = 0; unsigned long long g4 = 0;
+    if (t >= off) { v = s_prod[t - off]; c = s_cnt[t - off]; g1 = s_big[t - off]; g3 = s_chunks[t - off]; g4 = s_el[t - off]; }
     __syncthreads();
-    if (t >= off) { s_prod[t] = modmul(s_prod[t], v); s_cnt[t] += c; s_big[t] += g1; s_small[t] += g2; s_chunks[t] += g3; s_el[t] += g4; }
+    if (t >= off) { s_prod[t] = modmul(s_prod[t], v); s_cnt[t] += c; s_big[t] += g1; s_chunks[t] += g3; s_el[t] += g4; }
     __syncthreads();
   }
   const uint32_t x0 = minstd ? rng->x : 0u;
   uint32_t run = minstd ? modmul(x0, t > 0 ? s_prod[t - 1] : 1u) : 0u;
-  uint32_t kb = t > 0 ? s_big[t - 1] : 0u, ks = t > 0 ? s_small[t - 1] : 0u, kc = t > 0 ? s_chunks[t - 1] : 0u;
+  uint32_t kl = t > 0 ? s_cnt[t - 1] : 0u, kb = t > 0 ? s_big[t - 1] : 0u, kc = t > 0 ? s_chunks[t - 1] : 0u;
   unsigned long long ke = t > 0 ? s_el[t - 1] : 0ull;
-  const uint32_t n_small_scan = s_small[1023];
+  unsigned int fit = 0, fitbig = 0, fitchunks = 0;
   for (int64_t i = b; i < e; ++i) {
     if (minstd) state[i] = run;
     if (!live[i]) continue;
     if (minstd) run = modmul(run, F);
     const int32_t d = wp.deg[i];
-    if (d > kWalkBig) {
-      if (ke + (unsigned long long)d <= (unsigned long long)wp.capV) {
-        wp.big_list[kb] = (int32_t)i; wp.voff[kb] = (long long)ke; wp.coff[kb] = (int32_t)kc;
-      } else {
-        // V is full (offsets are monotone, so this is a suffix of the big walkers): the warp path serves it
-        wp.small_list[n_small_scan + atomicAdd(&wp.ctr[5], 1u)] = (int32_t)i;
-      }
-      ++kb; ke += (unsigned long long)d; kc += (uint32_t)((d + kWalkChunk - 1) / kWalkChunk);
+    const uint32_t nch = (uint32_t)((d + kWalkChunk - 1) / kWalkChunk);
+    if (ke + (unsigned long long)d <= (unsigned long long)wp.capV) {
+      // V offsets are monotone in walker order, so the walkers that fit are a prefix of the live ones: their positions in
+      // the live / big / small lists are the scanned counts
+      wp.live_list[kl] = (int32_t)i; wp.coff[kl] = (int32_t)kc; wp.voff[i] = (long long)ke;
+      if (d > kWalkBig) { wp.big_list[kb] = (int32_t)i; ++fitbig; } else wp.small_list[kl - kb] = (int32_t)i;
+      ++fit; fitchunks += nch;
     } else {
-      wp.small_list[ks++] = (int32_t)i;
+      wp.ovf_list[atomicAdd(&wp.ctr[5], 1u)] = (int32_t)i;   // V is full: the self-contained warp path serves it
     }
+    ++kl; ke += (unsigned long long)d; kc += nch;
+    if (d > kWalkBig) ++kb;
   }
+  if (fit) { atomicAdd(&s_fit, fit); atomicAdd(&s_fitbig, fitbig); atomicAdd(&s_fitchunks, fitchunks); }
   __syncthreads();
-  if (t == 1023) {
-    // big walkers that fit: the prefix whose end offset is within capV -- recount from the scanned stretch ends
-    if (minstd) { rng->x = modmul(x0, s_prod[1023]); rng->draws += (unsigned long long)s_cnt[1023]; }
-  }
-  // n_big = big walkers whose V range fits.  Thread t knows how many of ITS big walkers fit; sum them.
-  __shared__ unsigned int s_fit, s_fitchunks;
-  if (t == 0) { s_fit = 0; s_fitchunks = 0; }
-  __syncthreads();
-  {
-    unsigned long long ke2 = t > 0 ? s_el[t - 1] : 0ull;
-    unsigned int fit = 0, fc = 0;
-    for (int64_t i = b; i < e; ++i) {
-      if (!live[i]) continue;
-      const int32_t d = wp.deg[i];
-      if (d > kWalkBig) {
-        if (ke2 + (unsigned long long)d <= (unsigned long long)wp.capV) { ++fit; fc += (uint32_t)((d + kWalkChunk - 1) / kWalkChunk); }
-        ke2 += (unsigned long long)d;
-      }
-    }
-    if (fit) { atomicAdd(&s_fit, fit); atomicAdd(&s_fitchunks, fc); }
-  }
-  __syncthreads();
+  if (t == 1023 && minstd) { rng->x = modmul(x0, s_prod[1023]); rng->draws += (unsigned long long)s_cnt[1023]; }
   if (t == 0) {
-    wp.ctr[0] = s_fit;
-    wp.ctr[1] = n_small_scan + (s_big[1023] - s_fit);
+    wp.ctr[0] = s_fitbig;
+    wp.ctr[1] = s_fit - s_fitbig;
     wp.ctr[2] = s_fitchunks;
-    wp.ctr[3] = 0; wp.ctr[4] = 0;
+    wp.ctr[3] = 0; wp.ctr[4] = 0; wp.ctr[6] = 0;
+    wp.ctr[7] = s_fit;
     wp.coff[s_fit] = (int32_t)s_fitchunks;
   }
 }
@@ -384,16 +370,16 @@ __device__ __forceinline__ int64_t lower_bound_ll(const unsigned long long* __re
 __global__ void __launch_bounds__(kWalkChunk) k_walk_weights(DevGraph g, int32_t ctype, int32_t ptype, float p, float q, WalkState s,
                                                              WalkPlan wp) {
   __shared__ int s_k;
-  const unsigned int n_chunks = wp.ctr[2], n_big = wp.ctr[0];
+  const unsigned int n_chunks = wp.ctr[2], n_fit = wp.ctr[7];
   for (unsigned int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-    if (threadIdx.x == 0) {   // big walker of chunk c: last k with coff[k] <= c
-      int lo = 0, hi = (int)n_big;
+    if (threadIdx.x == 0) {   // walker of chunk c: last k with coff[k] <= c
+      int lo = 0, hi = (int)n_fit;
       while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((unsigned int)wp.coff[mid] <= c) lo = mid; else hi = mid; }
       s_k = lo;
     }
     __syncthreads();
     const int k = s_k;
-    const int64_t i = wp.big_list[k];
+    const int64_t i = wp.live_list[k];
     const int64_t crow = s.cur_row[i];
     const int64_t cbase = g.grp_ptr[crow * g.T];
     const int64_t cb = g.grp_ptr[crow * g.T + ctype];
@@ -416,7 +402,7 @@ __global__ void __launch_bounds__(kWalkChunk) k_walk_weights(DevGraph g, int32_t
         shared = lb + m < pe && (long long)__ldg(g.nbr + lb + m) == cv;   // the parent holds more than m copies
       }
       if (!shared) w = cv != s.parent[i] ? __fdiv_rn(w, q) : __fdiv_rn(w, p);   // d_tx = 2 / d_tx = 0
-      wp.V[wp.voff[k] + off] = w;
+      wp.V[wp.voff[i] + off] = w;
     }
     __syncthreads();
   }
@@ -565,7 +551,7 @@ __global__ void __launch_bounds__(kPrefT) k_walk_prefix(DevGraph g, int64_t B, i
     if (k >= n_big) break;
     const int64_t i = wp.big_list[k];
     const int32_t n = wp.deg[i];
-    const float* V = wp.V + wp.voff[k];
+    const float* V = wp.V + wp.voff[i];
     if (t == 0) { sh.pos = 0; sh.S = 0.f; sh.n_ck = 0; sh.answer = -1; }
     const int ck_stride = 1 + (n / kPrefCH) / (kPrefCk / 2);
     block_exact_prefix(sh, V, n, false, true, ck_stride);
@@ -594,13 +580,53 @@ __global__ void __launch_bounds__(kPrefT) k_walk_prefix(DevGraph g, int64_t B, i
     }
     __syncthreads();
   }
-  // ---- small walkers: one warp each
+  // ---- small walkers (deg <= kWalkBig): one warp each over the row's biased weights in V.  The prefix is the plain
+  // left-to-right f32 chain evaluated through shuffles (<= 16 chunks of 32); pass 1 = total, pass 2 = select.
   while (true) {
     unsigned int k = 0;
     if (lane == 0) k = atomicAdd(&wp.ctr[4], 1u);
     k = __shfl_sync(0xffffffffu, k, 0);
     if (k >= n_small) break;
     const int64_t i = wp.small_list[k];
+    const int32_t n = wp.deg[i];
+    const float* V = wp.V + wp.voff[i];
+    float run = 0.f;
+    for (int32_t c0 = 0; c0 < n; c0 += 32) {
+      const float w = c0 + lane < n ? V[c0 + lane] : 0.f;
+      const int nv = min(32, n - c0);
+      for (int j = 0; j < nv; ++j) run = __fadd_rn(run, __shfl_sync(0xffffffffu, w, j));
+    }
+    double u, u2;
+    if (philox) philox_uniform2((unsigned long long)i, (uint32_t)step, 0x77616C6Bu, key, u, u2);
+    else { uint32_t x = state[i]; u = minstd_uniform(x); }
+    const double r = pick_r(u, 0.f, run);
+    int32_t ans = n - 1;                 // RandomSelect's fall-through: the last entry
+    run = 0.f;
+    for (int32_t c0 = 0; c0 < n; c0 += 32) {
+      const float w = c0 + lane < n ? V[c0 + lane] : 0.f;
+      const int nv = min(32, n - c0);
+      float mine = 0.f;
+      for (int j = 0; j < nv; ++j) { run = __fadd_rn(run, __shfl_sync(0xffffffffu, w, j)); if (lane == j) mine = run; }
+      const unsigned hit = __ballot_sync(0xffffffffu, lane < nv && (double)mine > r);
+      if (hit) { ans = c0 + __ffs(hit) - 1; break; }
+    }
+    if (lane == 0) {
+      const int64_t crow = s.cur_row[i];
+      const long long next = (long long)__ldg(g.nbr + g.grp_ptr[crow * g.T + ctype] + ans);
+      out[i * (L + 1) + step + 1] = next;
+      s.parent[i] = s.cur[i];
+      s.parent_row[i] = crow;
+      s.cur[i] = next;
+    }
+  }
+  // ---- walkers whose row did not fit in V: the self-contained warp path
+  const unsigned int n_ovf = wp.ctr[5];
+  while (true) {
+    unsigned int k = 0;
+    if (lane == 0) k = atomicAdd(&wp.ctr[6], 1u);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (k >= n_ovf) break;
+    const int64_t i = wp.ovf_list[k];
     const long long cur = s.cur[i];
     const int64_t crow = s.cur_row[i];
     const int64_t prow = s.parent_row[i];
@@ -693,13 +719,11 @@ extern "C" int64_t eu_gen_pair_count(int32_t path_len, int32_t left_win_size, in
 // tf_euler.gen_pair: paths i64[B, path_len] -> out i64[B, eu_gen_pair_count(...), 2]   (device pointers)
 extern "C" int eu_gen_pair(eu_ctx* c, const int64_t* paths, int64_t B, int32_t path_len, int32_t left_win_size, int32_t right_win_size,
                            int64_t* out) {
-  if (!c || B < 0 || path_len < 0 || left_win_size < 0 || right_win_size < 0 || (B > 0 && path_len > 0 && (!paths || !out))) {
-    set_error("eu_gen_pair: bad argument");
-    return EU_ERR_INVALID;
-  }
+  if (!c || B < 0 || path_len < 0 || left_win_size < 0 || right_win_size < 0) { set_error("eu_gen_pair: bad argument"); return EU_ERR_INVALID; }
   EU_CUDA(cudaSetDevice(c->g->device));
   const long long pc = eu_gen_pair_count(path_len, left_win_size, right_win_size);
-  if (B == 0 || path_len == 0 || pc == 0) return EU_OK;
+  if (B == 0 || path_len == 0 || pc == 0) return EU_OK;     // nothing to write (a path of one node has no pairs)
+  if (!paths || !out) { set_error("eu_gen_pair: null buffer"); return EU_ERR_INVALID; }
   k_gen_pair<<<(unsigned)ceil_div(B * (int64_t)path_len, 256), 256, 0, c->stream>>>((const long long*)paths, B, path_len, left_win_size,
                                                                                     right_win_size, pc, (long long*)out);
   EU_LAUNCHED();
@@ -737,7 +761,7 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
     return EU_OK;
   }
   // node2vec
-  const int64_t plan_bytes = B * (4 + 4 + 4) + (B + 1) * (8 + 4) + 64 + 256;
+  const int64_t plan_bytes = B * (4 + 4 + 4 + 4 + 4) + (B + 1) * (8 + 4) + 64 + 256;
   rc = ctx_misc(c, 256 + B * (8 + 8 + 8 + 8) + plan_bytes);
   if (rc) return rc;
   char* m = (char*)c->d_misc + 256;
@@ -749,8 +773,10 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
   WalkPlan wp{};
   wp.voff = (long long*)m; m += 8 * (B + 1);
   wp.deg = (int32_t*)m; m += 4 * B;
+  wp.live_list = (int32_t*)m; m += 4 * B;
   wp.big_list = (int32_t*)m; m += 4 * B;
   wp.small_list = (int32_t*)m; m += 4 * B;
+  wp.ovf_list = (int32_t*)m; m += 4 * B;
   wp.coff = (int32_t*)m; m += 4 * (B + 1);
   m = (char*)(((uintptr_t)m + 63) & ~(uintptr_t)63);
   wp.ctr = (unsigned int*)m;
