@@ -25,6 +25,8 @@ class GraphDesc(C.Structure):
         ("grp_ptr", C.c_void_p), ("nbr", C.c_void_p), ("cum_w", C.c_void_p), ("grp_cum", C.c_void_p),
         ("w", C.c_void_p), ("feat_dim", C.c_int32), ("feat", C.c_void_p),
         ("sampler_order", C.c_void_p), ("n_feat_slots", C.c_int32), ("feat_slot_dims", C.c_void_p),
+        ("n_u64_slots", C.c_int32), ("u64_ptr", C.c_void_p), ("u64_val", C.c_void_p),
+        ("n_bin_slots", C.c_int32), ("bin_ptr", C.c_void_p), ("bin_val", C.c_void_p),
     ]
 
 
@@ -54,6 +56,12 @@ SIGNATURES = {
     "eu_graph_node_type_id": (_I32, [_P, C.c_char_p]),
     "eu_graph_dense_feature_id": (_I32, [_P, C.c_char_p]),
     "eu_graph_dense_feature_dim": (_I32, [_P, _I32]),
+    "eu_graph_sparse_feature_id": (_I32, [_P, C.c_char_p]),
+    "eu_graph_binary_feature_id": (_I32, [_P, C.c_char_p]),
+    "eu_get_sparse_feature": (C.c_int, [_P, _P, _I64, _I32, _I64, _I64, _P, _P]),
+    "eu_get_sparse_feature_host": (C.c_int, [_P, _P, _I64, _I32, _I64, _I64, _P, _P, _P]),
+    "eu_get_binary_feature": (C.c_int, [_P, _P, _I64, _I32, _I64, _P, _P]),
+    "eu_get_binary_feature_host": (C.c_int, [_P, _P, _I64, _I32, _I64, _P, _P, _P]),
     "eu_ctx_create": (C.c_int, [_P, C.c_int, _U64, _P, C.POINTER(_P)]),
     "eu_ctx_destroy": (C.c_int, [_P]),
     "eu_ctx_set_stream": (C.c_int, [_P, _P]),

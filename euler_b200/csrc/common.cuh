@@ -46,6 +46,14 @@ struct DevGraph {
   int32_t n_slots;
   int32_t slot_off[EU_MAX_FEAT_SLOTS];
   int32_t slot_dim[EU_MAX_FEAT_SLOTS];
+  // ragged features (Node::uint64_features_ / binary_features_ with their *_idx_ ends, node.h): slot s of row r is
+  // [ptr[r*S+s], ptr[r*S+s+1]) of the value array; S = 0 when the graph has none
+  int32_t n_u64_slots;
+  const int64_t* u64_ptr;
+  const unsigned long long* u64_val;
+  int32_t n_bin_slots;
+  const int64_t* bin_ptr;
+  const unsigned char* bin_val;
 };
 
 __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long k) {

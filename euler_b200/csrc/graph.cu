@@ -396,6 +396,20 @@ int eu_graph_create(const eu_graph_desc* desc, int device, eu_graph** out) {
     }
     for (int s = 0; s < d.n_slots; ++s) g->dense_feature_names.push_back("feat" + std::to_string(s));
   }
+  if (desc->n_u64_slots > 0 && desc->u64_ptr) {
+    const int64_t S = desc->n_u64_slots;
+    d.n_u64_slots = (int32_t)S;
+    TRY(upload(g, &d.u64_ptr, desc->u64_ptr, n * S + 1));
+    TRY(upload(g, (const uint64_t**)&d.u64_val, desc->u64_val, desc->u64_ptr[n * S]));
+    for (int64_t k = 0; k < S; ++k) g->sparse_feature_names.push_back("u64_" + std::to_string(k));
+  }
+  if (desc->n_bin_slots > 0 && desc->bin_ptr) {
+    const int64_t S = desc->n_bin_slots;
+    d.n_bin_slots = (int32_t)S;
+    TRY(upload(g, &d.bin_ptr, desc->bin_ptr, n * S + 1));
+    TRY(upload(g, (const uint8_t**)&d.bin_val, desc->bin_val, desc->bin_ptr[n * S]));
+    for (int64_t k = 0; k < S; ++k) g->binary_feature_names.push_back("bin_" + std::to_string(k));
+  }
   // dense id range?
   bool dense = n > 0;
   for (int64_t r = 0; r < n && dense; ++r) dense = desc->ids[r] == desc->ids[0] + (uint64_t)r;
@@ -588,6 +602,18 @@ int32_t eu_graph_dense_feature_id(const eu_graph* g, const char* name) {
   if (!g || !name) return -1;
   for (size_t i = 0; i < g->dense_feature_names.size(); ++i)
     if (g->dense_feature_names[i] == name) return (int32_t)i;
+  return -1;
+}
+int32_t eu_graph_sparse_feature_id(const eu_graph* g, const char* name) {
+  if (!g || !name) return -1;
+  for (size_t i = 0; i < g->sparse_feature_names.size(); ++i)
+    if (g->sparse_feature_names[i] == name) return (int32_t)i;
+  return -1;
+}
+int32_t eu_graph_binary_feature_id(const eu_graph* g, const char* name) {
+  if (!g || !name) return -1;
+  for (size_t i = 0; i < g->binary_feature_names.size(); ++i)
+    if (g->binary_feature_names[i] == name) return (int32_t)i;
   return -1;
 }
 int32_t eu_graph_dense_feature_dim(const eu_graph* g, int32_t fid) {

@@ -63,6 +63,7 @@ struct eu_graph {
   std::vector<int64_t> sampler_order;  // optional explicit order (rows)
   std::vector<std::string> edge_type_names, node_type_names;
   std::vector<std::string> dense_feature_names;  // per slot, without the "dense_" prefix
+  std::vector<std::string> sparse_feature_names, binary_feature_names;   // per slot, without the "sparse_" / "binary_" prefix
 
   template <typename T>
   int alloc(T** p, int64_t count) {

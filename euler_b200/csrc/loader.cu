@@ -97,12 +97,15 @@ extern "C" int eu_graph_load(const char* data_path, int shard_index, int shard_n
   m.get<uint64_t>(); m.get<uint64_t>();
   int32_t partitions = m.get<int32_t>();
   std::map<int32_t, std::pair<std::string, int64_t>> dense;  // idx -> (name, dim)
+  std::map<int32_t, std::string> sparse, binary;               // idx -> name (kind 0 / kind 2)
   uint32_t nf = m.get<uint32_t>();
   for (uint32_t i = 0; i < nf && m.ok; ++i) {
     std::string name = m.str();
     int32_t kind = m.get<int32_t>(), idx = m.get<int32_t>();
     int64_t dim = m.get<int64_t>();
     if (kind == 1) dense[idx] = std::make_pair(name, dim);
+    else if (kind == 0) sparse[idx] = name;
+    else if (kind == 2) binary[idx] = name;
   }
   uint32_t ef = m.get<uint32_t>();
   for (uint32_t i = 0; i < ef && m.ok; ++i) { m.str(); m.get<int32_t>(); m.get<int32_t>(); m.get<int64_t>(); }
@@ -143,9 +146,15 @@ extern "C" int eu_graph_load(const char* data_path, int shard_index, int shard_n
   std::vector<int32_t> ntype;
   std::vector<float> nw, cum, gcum, feat;
   std::vector<int64_t> gptr(1, 0);
-  std::vector<int32_t> gi, ge, fe;
+  std::vector<int32_t> gi, ge, fe, ue, be;
   std::vector<float> gw, cw, fv;
   std::vector<uint64_t> nb, u64v;
+  const int32_t US = sparse.empty() ? 0 : sparse.rbegin()->first + 1;   // uint64 / binary feature slots (meta idx range)
+  const int32_t BS = binary.empty() ? 0 : binary.rbegin()->first + 1;
+  std::vector<int64_t> u64_ptr(1, 0), bin_ptr(1, 0);
+  std::vector<uint64_t> u64_all;
+  std::vector<uint8_t> bin_all;
+  std::string binv;
   for (const auto& fn : files) {
     if (!read_file(dir + "/Node/" + fn, &buf)) { set_error("cannot read %s", fn.c_str()); return EU_ERR_IO; }
     Reader f{buf.data(), buf.data() + buf.size()};
@@ -180,9 +189,28 @@ extern "C" int eu_graph_load(const char* data_path, int shard_index, int shard_n
       cum.insert(cum.end(), cw.begin(), cw.end());
       // in-neighbor block: not on this path (sample_neighbor / walks use out edges only)
       r.list(&gi); r.list(&gw); r.list(&ge); r.list(&nb); r.list(&cw);
-      r.list(&fe); r.list(&u64v);
+      r.list(&ue); r.list(&u64v);
       r.list(&fe); r.list(&fv);
+      r.list(&be); binv = r.str();
       if (!r.ok) { set_error("malformed feature block (id %llu)", (unsigned long long)ids.back()); return EU_ERR_IO; }
+      // ragged uint64 / binary features: slot s = [ends[s-1], ends[s]) of the node's value array (node.cc:353-364); slots the
+      // node does not carry are empty
+      for (int32_t s2 = 0; s2 < US; ++s2) {
+        if (s2 < (int32_t)ue.size()) {
+          const int32_t b = s2 == 0 ? 0 : ue[s2 - 1], e = ue[s2];
+          if (b < 0 || e < b || e > (int32_t)u64v.size()) { set_error("bad uint64 feature ends (id %llu)", (unsigned long long)ids.back()); return EU_ERR_IO; }
+          u64_all.insert(u64_all.end(), u64v.begin() + b, u64v.begin() + e);
+        }
+        u64_ptr.push_back((int64_t)u64_all.size());
+      }
+      for (int32_t s2 = 0; s2 < BS; ++s2) {
+        if (s2 < (int32_t)be.size()) {
+          const int32_t b = s2 == 0 ? 0 : be[s2 - 1], e = be[s2];
+          if (b < 0 || e < b || e > (int32_t)binv.size()) { set_error("bad binary feature ends (id %llu)", (unsigned long long)ids.back()); return EU_ERR_IO; }
+          bin_all.insert(bin_all.end(), binv.begin() + b, binv.begin() + e);
+        }
+        bin_ptr.push_back((int64_t)bin_all.size());
+      }
       // dense slots: zero-padded / clipped to the meta dim (get_dense_feature_op.cc:66-75 zero-fills)
       const size_t fbase = feat.size();
       feat.resize(fbase + width, 0.f);
@@ -226,6 +254,9 @@ extern "C" int eu_graph_load(const char* data_path, int shard_index, int shard_n
   d.feat_dim = width; d.feat = width > 0 ? feat.data() : nullptr;
   d.n_feat_slots = width > 0 ? n_slots : 0; d.feat_slot_dims = slot_dims.data();
   d.sampler_order = order.data();
+  uint64_t u64_dummy = 0; uint8_t bin_dummy = 0;
+  if (US > 0) { d.n_u64_slots = US; d.u64_ptr = u64_ptr.data(); d.u64_val = u64_all.empty() ? &u64_dummy : u64_all.data(); }
+  if (BS > 0) { d.n_bin_slots = BS; d.bin_ptr = bin_ptr.data(); d.bin_val = bin_all.empty() ? &bin_dummy : bin_all.data(); }
   int rc = eu_graph_create(&d, device, out);
   if (rc) return rc;
   eu_graph* g = *out;
@@ -239,5 +270,9 @@ extern "C" int eu_graph_load(const char* data_path, int shard_index, int shard_n
     if (nm.rfind("dense_", 0) == 0) nm = nm.substr(6);
     if (kv.first < d.n_feat_slots) g->dense_feature_names[kv.first] = nm;
   }
+  g->sparse_feature_names.assign(US, "");
+  for (auto& kv : sparse) { std::string nm = kv.second; if (nm.rfind("sparse_", 0) == 0) nm = nm.substr(7); g->sparse_feature_names[kv.first] = nm; }
+  g->binary_feature_names.assign(BS, "");
+  for (auto& kv : binary) { std::string nm = kv.second; if (nm.rfind("binary_", 0) == 0) nm = nm.substr(7); g->binary_feature_names[kv.first] = nm; }
   return EU_OK;
 }

@@ -13,6 +13,10 @@
 //     warp per OUTPUT row, its edges found by binary search, accumulated left to right -> the
 //     reference's summation order, bit-exact, no atomics;
 //   unsorted indices: vector atomics (red.global.add.v4.f32), order-free, within 1e-5 relative.
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "internal.h"
 
 namespace eu {
@@ -34,22 +38,25 @@ template <bool VEC>
 __global__ void __launch_bounds__(256) k_feature(DevGraph g, const unsigned long long* __restrict__ ids,
                                                  int64_t M, int32_t dim, int G, int32_t soff, int32_t sdim,
                                                  float* __restrict__ out) {
-  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  const int64_t i = tid >> (31 - __clz(G));   // G is a power of two
-  const int sub = (int)(tid & (G - 1));
-  if (i >= M) return;
-  const int64_t row = sdim > 0 ? lookup_row(g, ids[i]) : -1;
-  const int32_t fd = sdim;  // stored width of this slot
-  float* o = out + i * (int64_t)dim;
-  const float* f = row >= 0 ? g.feat + row * (int64_t)g.feat_dim + soff : nullptr;
-  if (VEC) {
-    for (int32_t d = sub * 4; d < dim; d += G * 4) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (f && d < fd) v = ldg4(f + d);  // VEC requires fd % 4 == 0 so a float4 never straddles fd
-      st4(o + d, v);
+  const int sh = 31 - __clz(G);   // G is a power of two
+  const int sub = (int)(threadIdx.x & (G - 1));
+  const int64_t stride = ((int64_t)gridDim.x * blockDim.x) >> sh;
+  // grid-stride over the rows: the launcher may cap the grid (EU_FEATURE_CTAS CTAs per SM) so that this HBM-bound copy leaves
+  // SM residency to the issue-bound sampling kernels of the other lanes
+  for (int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> sh; i < M; i += stride) {
+    const int64_t row = sdim > 0 ? lookup_row(g, ids[i]) : -1;
+    const int32_t fd = sdim;  // stored width of this slot
+    float* o = out + i * (int64_t)dim;
+    const float* f = row >= 0 ? g.feat + row * (int64_t)g.feat_dim + soff : nullptr;
+    if (VEC) {
+      for (int32_t d = sub * 4; d < dim; d += G * 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f && d < fd) v = ldg4(f + d);  // VEC requires fd % 4 == 0 so a float4 never straddles fd
+        st4(o + d, v);
+      }
+    } else {
+      for (int32_t d = sub; d < dim; d += G) o[d] = (f && d < fd) ? __ldg(f + d) : 0.f;
     }
-  } else {
-    for (int32_t d = sub; d < dim; d += G) o[d] = (f && d < fd) ? __ldg(f + d) : 0.f;
   }
 }
 
@@ -187,14 +194,15 @@ __global__ void k_mean_div(float* __restrict__ out, int64_t D, int64_t size, con
 // out[r,:] = (sum_j feat[row(ids[r*count+j]),:]) / (count + 1e-7), j ascending (== get_dense_feature
 // followed by scatter_mean over edge_src = repeat(range(rows), count)).  One warp per output row;
 // the `count` id->row lookups run in parallel across lanes, then NV float4 per lane are accumulated.
-template <int NV>
+template <int NV>   // NV float4 per lane: rows of up to NV * 128 floats (any width that is a multiple of 4)
 __global__ void __launch_bounds__(256) k_sage_mean(DevGraph g, const unsigned long long* __restrict__ ids,
                                                    int64_t rows, int32_t count, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
-  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  if (r >= rows) return;
-  constexpr int32_t fd = NV * 128;  // == g.feat_dim (checked by the launcher)
+  const int32_t fd = g.feat_dim;    // == dim, a multiple of 4, <= NV * 128 (checked by the launcher)
   const float* __restrict__ feat = g.feat + lane * 4;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  // grid-stride, one warp per output row (the launcher may cap the grid: EU_SAGE_CTAS CTAs per SM)
+  for (int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps) {
   float4 acc[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(256) k_sage_mean(DevGraph g, const unsigned lo
           const int32_t row = __shfl_sync(0xffffffffu, my, j);
           const float* p = feat + (int64_t)row * fd;
 #pragma unroll
-          for (int t = 0; t < NV; ++t) v[q][t] = ldg4(p + t * 128);
+          for (int t = 0; t < NV; ++t) v[q][t] = lane * 4 + t * 128 < fd ? ldg4(p + t * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
           n = q + 1;
         }
       }
@@ -238,7 +246,8 @@ __global__ void __launch_bounds__(256) k_sage_mean(DevGraph g, const unsigned lo
   for (int t = 0; t < NV; ++t) {
     float4 a = acc[t];
     a.x = __fdiv_rn(a.x, denom); a.y = __fdiv_rn(a.y, denom); a.z = __fdiv_rn(a.z, denom); a.w = __fdiv_rn(a.w, denom);
-    st4(o + t * 128, a);
+    if (lane * 4 + t * 128 < fd) st4(o + t * 128, a);
+  }
   }
 }
 
@@ -247,21 +256,32 @@ __global__ void __launch_bounds__(256) k_sage_mean_generic(DevGraph g, const uns
                                                            int64_t rows, int32_t count, int32_t dim,
                                                            float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
-  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-  if (r >= rows) return;
   const int32_t fd = g.feat_dim;
   const float denom = __fadd_rn((float)count, 1e-7f);
-  for (int32_t d = lane; d < dim; d += 32) {
-    float acc = 0.f;
-    for (int32_t j = 0; j < count; ++j) {
-      const int64_t row = lookup_row(g, __ldg(ids + r * count + j));
-      acc = __fadd_rn(acc, (row >= 0 && d < fd) ? __ldg(g.feat + row * (int64_t)fd + d) : 0.f);
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; r < rows; r += nwarps)
+    for (int32_t d = lane; d < dim; d += 32) {
+      float acc = 0.f;
+      for (int32_t j = 0; j < count; ++j) {
+        const int64_t row = lookup_row(g, __ldg(ids + r * count + j));
+        acc = __fadd_rn(acc, (row >= 0 && d < fd) ? __ldg(g.feat + row * (int64_t)fd + d) : 0.f);
+      }
+      out[r * (int64_t)dim + d] = __fdiv_rn(acc, denom);
     }
-    out[r * (int64_t)dim + d] = __fdiv_rn(acc, denom);
-  }
 }
 
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+// CTAs per SM of the HBM-bound row movers (0 = one CTA per 8 rows / as many as the rows need).  A capped, persistent grid keeps
+// the copy at HBM speed (a few warps per SM cover the bandwidth-delay product) while the issue-bound sampling kernels of the
+// other lanes stay resident beside it.
+static inline unsigned capped_grid(int64_t want_blocks, const char* env, int dflt) {
+  static int cached_sage = -1, cached_feat = -1;
+  int& cached = env[3] == 'S' ? cached_sage : cached_feat;
+  if (cached < 0) { const char* e = getenv(env); cached = e ? std::max(0, atoi(e)) : dflt; }
+  const int64_t cap = cached > 0 ? (int64_t)148 * cached : want_blocks;
+  return (unsigned)std::max<int64_t>(1, std::min(want_blocks, cap));
+}
 
 template <int OP>
 static int scatter(eu_ctx* c, const float* upd, int64_t D, const int32_t* idx, int64_t E, int64_t size,
@@ -321,7 +341,7 @@ int eu_get_dense_feature(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid
   const int32_t soff = have ? d.slot_off[fid] : 0, sdim = have ? d.slot_dim[fid] : 0;
   const bool vec = (dim % 4 == 0) && (d.feat_dim % 4 == 0) && (soff % 4 == 0) && (sdim % 4 == 0) && aligned16(out);
   const int G = vec ? lanes_per_row(dim) : (dim >= 32 ? 32 : 1);
-  const unsigned blocks = (unsigned)ceil_div(M * G, 256);
+  const unsigned blocks = capped_grid(ceil_div(M * G, 256), "EU_FEATURE_CTAS", 0);
   EuProfScope ps(c, "k_feature", M);
   if (vec) k_feature<true><<<blocks, 256, 0, c->stream>>>(d, (const unsigned long long*)nodes, M, dim, G, soff, sdim, out);
   else k_feature<false><<<blocks, 256, 0, c->stream>>>(d, (const unsigned long long*)nodes, M, dim, G, soff, sdim, out);
@@ -358,11 +378,15 @@ int eu_sage_mean_aggregate(eu_ctx* c, const int64_t* nbr_ids, int64_t rows, int3
   EU_CUDA(cudaSetDevice(c->g->device));
   if (rows == 0) return EU_OK;
   const DevGraph& d = c->g->d;
-  const unsigned blocks = (unsigned)ceil_div(rows * 32, 256);
+  const unsigned blocks = capped_grid(ceil_div(rows * 32, 256), "EU_SAGE_CTAS", 0);
   const unsigned long long* ids = (const unsigned long long*)nbr_ids;
   EuProfScope ps(c, "k_sage_mean", rows);
-  if (d.n < ((int64_t)1 << 31) && d.n_slots == 1 && dim == d.feat_dim && dim == 128 && aligned16(out)) k_sage_mean<1><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
-  else if (d.n < ((int64_t)1 << 31) && d.n_slots == 1 && dim == d.feat_dim && dim == 256 && aligned16(out)) k_sage_mean<2><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
+  // float4 path: one slot of the full stored width, a multiple of 4 floats up to 1024 (D = 64 of configs[4], 128, 256, ...)
+  const bool v4 = d.n < ((int64_t)1 << 31) && d.n_slots == 1 && dim == d.feat_dim && (dim & 3) == 0 && dim <= 1024 && aligned16(out) && aligned16(d.feat);
+  if (v4 && dim <= 128) k_sage_mean<1><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
+  else if (v4 && dim <= 256) k_sage_mean<2><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
+  else if (v4 && dim <= 512) k_sage_mean<4><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
+  else if (v4) k_sage_mean<8><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
   else k_sage_mean_generic<<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, dim, out);
   EU_LAUNCHED();
   return EU_OK;

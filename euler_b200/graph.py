@@ -33,7 +33,8 @@ class Graph:
     @classmethod
     def from_csr(cls, ids, grp_ptr, nbr, n_edge_types=1, cum_w=None, grp_cum=None, w=None,
                  node_type=None, node_w=None, n_node_types=1, feat=None, feat_slot_dims=None,
-                 sampler_order=None, device=0):
+                 sampler_order=None, device=0, u64_ptr=None, u64_val=None, n_u64_slots=0, bin_ptr=None, bin_val=None,
+                 n_bin_slots=0):
         ids = _np(ids, np.uint64)
         keep = [ids, _np(node_type, np.int32), _np(node_w, np.float32), _np(grp_ptr, np.int64),
                 _np(nbr, np.uint64), _np(cum_w, np.float32), _np(grp_cum, np.float32),
@@ -49,6 +50,11 @@ class Graph:
         d.sampler_order = _ptr(keep[9])
         d.n_feat_slots = 0 if feat_slot_dims is None else len(keep[10])
         d.feat_slot_dims = _ptr(keep[10])
+        keep += [_np(u64_ptr, np.int64), _np(u64_val, np.uint64), _np(bin_ptr, np.int64), _np(bin_val, np.uint8)]
+        if n_u64_slots and u64_ptr is not None:
+            d.n_u64_slots, d.u64_ptr, d.u64_val = int(n_u64_slots), _ptr(keep[11]), _ptr(keep[12] if len(keep[12]) else np.zeros(1, np.uint64))
+        if n_bin_slots and bin_ptr is not None:
+            d.n_bin_slots, d.bin_ptr, d.bin_val = int(n_bin_slots), _ptr(keep[13]), _ptr(keep[14] if len(keep[14]) else np.zeros(1, np.uint8))
         h = C.c_void_p()
         check(_lib.load().eu_graph_create(C.byref(d), device, C.byref(h)))
         return cls(h, device)
@@ -132,6 +138,12 @@ class Graph:
 
     def dense_feature_dim(self, fid):
         return _lib.load().eu_graph_dense_feature_dim(self._h, fid)
+
+    def sparse_feature_id(self, name):
+        return _lib.load().eu_graph_sparse_feature_id(self._h, str(name).encode())
+
+    def binary_feature_id(self, name):
+        return _lib.load().eu_graph_binary_feature_id(self._h, str(name).encode())
 
     def export(self, with_feat=True):
         """Copy the CSR back to host numpy arrays (used by tests / the CPU baseline arm)."""

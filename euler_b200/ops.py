@@ -246,6 +246,53 @@ def get_dense_feature(nodes, feature_names, dimensions, thread_num=1):
     return outs
 
 
+def _ragged(fn, nodes, fid, *mid):
+    """two-phase ragged fetch: lengths, then values"""
+    nodes = _t(nodes, torch.int64).reshape(-1)
+    n = nodes.numel()
+    ctx = _ctx_on_stream()
+    indptr = torch.empty(n + 1, dtype=torch.int64, device=nodes.device)
+    check(fn(ctx._h, nodes.data_ptr(), n, int(fid), *mid, 0, indptr.data_ptr(), None))
+    total = int(indptr[-1].item())
+    return nodes, n, ctx, indptr, total
+
+
+def get_sparse_feature(nodes, feature_names, default_values=None, thread_num=1):
+    """feature_ops.get_sparse_feature (feature_ops.py:57-73; kernel get_sparse_feature_op.cc:52-130).  Per feature the
+    reference returns a SparseTensor; here the same content as (indices i64[nnz, 2], values i64[nnz], dense_shape (N, max_len)):
+    row i lists the uint64 values of the node, a node without values gets the single entry (i, 0) = default value."""
+    g, lib = get_graph(), _lib.load()
+    names = [str(x) for x in feature_names]
+    defaults = [0] * len(names) if default_values is None else [int(x) for x in default_values]
+    outs = []
+    for name, dv in zip(names, defaults):
+        fid = g.sparse_feature_id(name)
+        nd, n, ctx, indptr, total = _ragged(lib.eu_get_sparse_feature, nodes, fid, dv)
+        vals = torch.empty(total, dtype=torch.int64, device=nd.device)
+        if total:
+            check(lib.eu_get_sparse_feature(ctx._h, nd.data_ptr(), n, int(fid), dv, total, indptr.data_ptr(), vals.data_ptr()))
+        lens = indptr[1:] - indptr[:-1]
+        rows = torch.repeat_interleave(torch.arange(n, device=nd.device), lens)
+        cols = torch.arange(total, device=nd.device) - indptr[:-1][rows]
+        outs.append((torch.stack([rows, cols], dim=1), vals, (n, int(lens.max().item()) if n else 0)))
+    return outs
+
+
+def get_binary_feature(nodes, feature_names, thread_num=1):
+    """feature_ops.get_binary_feature (feature_ops.py:158-171): per feature a list of N byte strings (b'' for absent nodes)."""
+    g, lib = get_graph(), _lib.load()
+    outs = []
+    for name in [str(x) for x in feature_names]:
+        fid = g.binary_feature_id(name)
+        nd, n, ctx, indptr, total = _ragged(lib.eu_get_binary_feature, nodes, fid)
+        buf = torch.empty(max(total, 1), dtype=torch.uint8, device=nd.device)
+        if total:
+            check(lib.eu_get_binary_feature(ctx._h, nd.data_ptr(), n, int(fid), total, indptr.data_ptr(), buf.data_ptr()))
+        raw, ptr = bytes(buf[:total].cpu().numpy().tobytes()), indptr.cpu().tolist()
+        outs.append([raw[ptr[i]:ptr[i + 1]] for i in range(n)])
+    return outs
+
+
 def get_full_neighbor(nodes, edge_types):
     """neighbor_ops.get_full_neighbor (tf_euler/python/euler_ops/neighbor_ops.py; kernel get_full_neighbor_op.cc over
     euler::GetFullNeighbor api.cc:208-221).  The reference returns three SparseTensors [N, max_degree] (ids, weights,

@@ -81,6 +81,14 @@ typedef struct {
    * n_feat_slots > 0, feat is [n, sum(feat_slot_dims)] and feat_dim must equal that sum */
   int32_t n_feat_slots;
   const int32_t* feat_slot_dims;
+  /* optional ragged features (Node::uint64_features_ / binary_features_, euler/core/graph/node.h): slot s of row r is
+   * [ptr[r*S+s], ptr[r*S+s+1]) of the value array; S = 0 / NULL = none */
+  int32_t n_u64_slots;
+  const int64_t* u64_ptr;   /* [n*S+1] */
+  const uint64_t* u64_val;
+  int32_t n_bin_slots;
+  const int64_t* bin_ptr;   /* [n*S+1] */
+  const uint8_t* bin_val;
 } eu_graph_desc;
 
 int eu_graph_create(const eu_graph_desc* desc, int device, eu_graph** out);
@@ -122,6 +130,9 @@ int32_t eu_graph_node_type_id(const eu_graph* g, const char* name);
  * -1 if unknown.  eu_graph_dense_feature_dim: stored width of a slot. */
 int32_t eu_graph_dense_feature_id(const eu_graph* g, const char* name);
 int32_t eu_graph_dense_feature_dim(const eu_graph* g, int32_t fid);
+/* slots of the uint64 ("sparse_"+name, get_sparse_feature_op.cc:75) and binary ("binary_"+name) features; -1 if unknown */
+int32_t eu_graph_sparse_feature_id(const eu_graph* g, const char* name);
+int32_t eu_graph_binary_feature_id(const eu_graph* g, const char* name);
 
 /* ------------------------------------------------------------------ contexts ----------------- */
 /* stream: a cudaStream_t (NULL = legacy default stream). */
@@ -193,6 +204,21 @@ int eu_get_dense_feature(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid
                          float* out);
 int eu_get_dense_feature_host(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid, int32_t dim,
                               float* out);
+/* tf_euler.get_sparse_feature, one feature (tf_euler/kernels/get_sparse_feature_op.cc:52-130 over Node::GetUint64Feature
+ * node.cc:366-379): the uint64 values of slot `fid` for every node, CSR-style: node i owns out_values[out_ptr[i], out_ptr[i+1]).
+ * A node without values (absent node, unknown slot, empty slot) owns exactly ONE entry = default_value (the kernel's
+ * SparseTensor gets {i, 0} -> default, :96-99).  cap = 0: lengths only (out_values may be NULL); only the first `cap`
+ * entries are written.  The SparseTensor of the reference is indices (i, k - out_ptr[i]), dense_shape [M, max row length]. */
+int eu_get_sparse_feature(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid, int64_t default_value, int64_t cap,
+                          int64_t* out_ptr, int64_t* out_values);
+int eu_get_sparse_feature_host(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid, int64_t default_value, int64_t cap,
+                               int64_t* out_ptr, int64_t* out_values, int64_t* total);
+/* tf_euler.get_binary_feature, one feature (tf_euler/kernels/get_binary_feature_op.cc over Node::GetBinaryFeature
+ * node.cc:396-409): the bytes of slot `fid` for every node, CSR-style (absent node / unknown slot: empty string). */
+int eu_get_binary_feature(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid, int64_t cap, int64_t* out_ptr, uint8_t* out_bytes);
+int eu_get_binary_feature_host(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid, int64_t cap, int64_t* out_ptr,
+                               uint8_t* out_bytes, int64_t* total);
+
 /* tf_euler.get_full_neighbor core (euler::GetFullNeighbor api.cc:208-221 over Node::GetFullNeighbor node.cc:176-198):
  * for every node the edges of each requested type, in the order the types are given, as (id, weight, type); a missing
  * node has an empty list.  CSR-style output: out_ptr i64[B+1] (device) -- entries of node i are

@@ -813,3 +813,28 @@ def test_raw_api_sample_neighbor_draws_duplicates_independently():
             cases.eq(w.cpu().numpy(), np.where(keep, o_w, 0).astype(np.float32), "raw weights")
             cases.eq(t.cpu().numpy(), np.where(keep, o_t, -1).astype(np.int32), "raw types")
         assert euler_b200.context().draws() == rng.draws
+
+
+def test_sparse_and_binary_features_reference_test_vectors(tiny_dir):
+    """the reference's own expectations on the tools/test_data graph (tf_euler/python/euler_ops/feature_ops_test.py:46-85):
+    sparse f1 / f2 of nodes [1, -1, 2, 3, 4] and binary f5 / f6 of nodes [1, 2], through Graph.load of the converter's files"""
+    import euler_b200
+    gr = euler_b200.Graph.load(tiny_dir)
+    euler_b200.set_graph(gr)
+    sp = euler_b200.get_sparse_feature([1, -1, 2, 3, 4], ['f1', 'f2'], None, 2)
+    want = [[[11, 12], [0, 0], [21, 22], [31, 32], [41, 42]], [[13, 14], [0, 0], [23, 24], [33, 34], [43, 44]]]
+    for (idx, vals, shape), w in zip(sp, want):
+        dense = np.zeros(shape, np.int64)
+        i = idx.cpu().numpy()
+        dense[i[:, 0], i[:, 1]] = vals.cpu().numpy()
+        cases.eq(dense, np.asarray(w, np.int64), "sparse feature (dense view)")
+        assert shape == (5, 2)
+    # the absent node (-1) owns exactly one entry (1, 0) = default value
+    idx, vals, _ = euler_b200.get_sparse_feature([1, -1], ['f1'], [77])[0]
+    cases.eq(idx.cpu().numpy(), np.array([[0, 0], [0, 1], [1, 0]]), "sparse indices")
+    cases.eq(vals.cpu().numpy(), np.array([11, 12, 77]), "sparse values with default")
+    assert euler_b200.get_binary_feature([1, 2], ['f5', 'f6'], 3) == [[b'1a', b'2a'], [b'1b', b'2b']]
+    assert euler_b200.get_binary_feature([99, 1], ['graph_label', 'nope']) == [[b'', b'1'], [b'', b'']]
+    # unknown sparse feature: every node gets the default entry
+    idx, vals, shape = euler_b200.get_sparse_feature([1, 2], ['nope'], [5])[0]
+    cases.eq(vals.cpu().numpy(), np.array([5, 5]), "unknown sparse feature")
