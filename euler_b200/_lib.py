@@ -44,6 +44,16 @@ SIGNATURES = {
     "eu_graph_create_rmat_hetero": (C.c_int, [_I64, _I64, _I32, _I32, C.c_double, C.c_double, C.c_double, _U64, _I32, _U64,
                                               C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "eu_graph_load": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "eu_graph_load_ex": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "eu_graph_set_edges": (C.c_int, [_P, _P]),
+    "eu_graph_num_edge_records": (_I64, [_P]),
+    "eu_graph_edge_dense_feature_id": (_I32, [_P, C.c_char_p]),
+    "eu_graph_edge_sparse_feature_id": (_I32, [_P, C.c_char_p]),
+    "eu_graph_edge_binary_feature_id": (_I32, [_P, C.c_char_p]),
+    "eu_sample_edge": (C.c_int, [_P, _I32, _P, _I32, _P]),
+    "eu_get_edge_dense_feature": (C.c_int, [_P, _P, _I64, _I32, _I32, _P]),
+    "eu_get_edge_sparse_feature": (C.c_int, [_P, _P, _I64, _I32, _I64, _I64, _P, _P]),
+    "eu_get_edge_binary_feature": (C.c_int, [_P, _P, _I64, _I32, _I64, _P, _P]),
     "eu_graph_destroy": (C.c_int, [_P]),
     "eu_graph_num_nodes": (_I64, [_P]),
     "eu_graph_num_edges": (_I64, [_P]),

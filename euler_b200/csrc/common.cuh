@@ -56,6 +56,33 @@ struct DevGraph {
   const unsigned char* bin_val;
 };
 
+// edge store (edges.cu): SoA edge arrays + (src, dst, type) -> row table + features with the node layout
+struct EdgeSlot {   // 32 B
+  unsigned long long src, dst;
+  int32_t type, pad;
+  long long row;    // -1 = free
+};
+struct DevEdges {
+  int64_t n;
+  const unsigned long long* src;
+  const unsigned long long* dst;
+  const int32_t* type;
+  const float* w;
+  const EdgeSlot* htab;
+  unsigned long long hmask;
+  int32_t feat_dim;
+  const float* feat;
+  int32_t n_slots;
+  int32_t slot_off[EU_MAX_FEAT_SLOTS];
+  int32_t slot_dim[EU_MAX_FEAT_SLOTS];
+  int32_t n_u64_slots;
+  const int64_t* u64_ptr;
+  const unsigned long long* u64_val;
+  int32_t n_bin_slots;
+  const int64_t* bin_ptr;
+  const unsigned char* bin_val;
+};
+
 __host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long k) {
   k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL; k ^= k >> 33;
   return k;

@@ -252,6 +252,10 @@ static float fwc_build(const std::vector<float>& w, std::vector<float>* prob,
   return s;
 }
 
+void fwc_build_public(const std::vector<float>& w, std::vector<float>* prob, std::vector<int32_t>* alias, float* sum) {
+  *sum = fwc_build(w, prob, alias);
+}
+
 // Graph::BuildGlobalSampler, euler/core/graph/graph.cc:333-370.
 int graph_build_sampler(eu_graph* g) {
   if (g->sampler_built) return EU_OK;

@@ -64,6 +64,12 @@ struct eu_graph {
   std::vector<std::string> edge_type_names, node_type_names;
   std::vector<std::string> dense_feature_names;  // per slot, without the "dense_" prefix
   std::vector<std::string> sparse_feature_names, binary_feature_names;   // per slot, without the "sparse_" / "binary_" prefix
+  // edges (eu_graph_set_edges): device store, per-type alias samplers in edge_map_ order, feature names
+  eu::DevEdges e{};
+  bool edges_set = false;
+  struct EdgeSampler { int64_t n = 0; const int64_t* order = nullptr; const float* prob = nullptr; const int32_t* alias = nullptr; float fwc_sum = 0.f; };
+  std::vector<EdgeSampler> edge_samplers;
+  std::vector<std::string> edge_dense_names, edge_sparse_names, edge_binary_names;
 
   template <typename T>
   int alloc(T** p, int64_t count) {

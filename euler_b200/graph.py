@@ -85,10 +85,11 @@ class Graph:
         return cls(h, device)
 
     @classmethod
-    def load(cls, data_path, shard_index=0, shard_number=1, device=0):
+    def load(cls, data_path, shard_index=0, shard_number=1, device=0, load_edges=True):
+        """Graph::Init (graph.h:53-56); load_edges=False = load_data_type 'node'"""
         h = C.c_void_p()
-        check(_lib.load().eu_graph_load(str(data_path).encode(), shard_index, shard_number, device,
-                                        C.byref(h)))
+        check(_lib.load().eu_graph_load_ex(str(data_path).encode(), shard_index, shard_number, device, int(load_edges),
+                                           C.byref(h)))
         return cls(h, device)
 
     def close(self):
@@ -144,6 +145,16 @@ class Graph:
 
     def binary_feature_id(self, name):
         return _lib.load().eu_graph_binary_feature_id(self._h, str(name).encode())
+
+    def edge_feature_id(self, kind, name):
+        """kind: 'dense' | 'sparse' | 'binary'"""
+        fn = getattr(_lib.load(), "eu_graph_edge_%s_feature_id" % kind)
+        return fn(self._h, str(name).encode())
+
+    @property
+    def num_edge_records(self):
+        """edges attached for sample_edge / edge features (0 when the graph was built without them)"""
+        return _lib.load().eu_graph_num_edge_records(self._h)
 
     def export(self, with_feat=True):
         """Copy the CSR back to host numpy arrays (used by tests / the CPU baseline arm)."""

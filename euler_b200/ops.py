@@ -293,6 +293,78 @@ def get_binary_feature(nodes, feature_names, thread_num=1):
     return outs
 
 
+def sample_edge(count, edge_type):
+    """sample_ops.sample_edge (tf_euler/python/euler_ops/sample_ops.py; kernel sample_edge_op.cc): i64[count, 3] rows of
+    (src, dst, type), drawn by edge weight among the edges of ONE type (several types return nothing in the reference)."""
+    types = get_edge_type_id(edge_type)
+    count = int(count)
+    out = torch.empty((count, 3), dtype=torch.int64, device=_dev())
+    ctx = _ctx_on_stream()
+    check(_lib.load().eu_sample_edge(ctx._h, count, types.ctypes.data, len(types), out.data_ptr()))
+    return out
+
+
+def _edges(edges):
+    e = _t(edges, torch.int64)
+    if e.dim() != 2 or e.shape[1] != 3:
+        raise EulerError("edges must be a matrix with shape [n, 3]")
+    return e.contiguous()
+
+
+def get_edge_dense_feature(edges, feature_names, dimensions, thread_num=1):
+    """feature_ops.get_edge_dense_feature: list of f32[E, dim] (zeros for unknown edges / features)"""
+    e = _edges(edges)
+    g, lib, outs = get_graph(), _lib.load(), []
+    ctx = _ctx_on_stream()
+    for name, dim in zip(feature_names, dimensions):
+        out = torch.empty((e.shape[0], int(dim)), dtype=torch.float32, device=e.device)
+        check(lib.eu_get_edge_dense_feature(ctx._h, e.data_ptr(), e.shape[0], g.edge_feature_id("dense", name), int(dim), out.data_ptr()))
+        outs.append(out)
+    return outs
+
+
+def get_edge_sparse_feature(edges, feature_names, default_values=None, thread_num=1):
+    """feature_ops.get_edge_sparse_feature: per feature (indices i64[nnz, 2], values i64[nnz], dense_shape)"""
+    e = _edges(edges)
+    g, lib, outs = get_graph(), _lib.load(), []
+    names = [str(x) for x in feature_names]
+    defaults = [0] * len(names) if default_values is None else [int(x) for x in default_values]
+    ctx = _ctx_on_stream()
+    n = e.shape[0]
+    for name, dv in zip(names, defaults):
+        fid = g.edge_feature_id("sparse", name)
+        indptr = torch.empty(n + 1, dtype=torch.int64, device=e.device)
+        check(lib.eu_get_edge_sparse_feature(ctx._h, e.data_ptr(), n, fid, dv, 0, indptr.data_ptr(), None))
+        total = int(indptr[-1].item())
+        vals = torch.empty(total, dtype=torch.int64, device=e.device)
+        if total:
+            check(lib.eu_get_edge_sparse_feature(ctx._h, e.data_ptr(), n, fid, dv, total, indptr.data_ptr(), vals.data_ptr()))
+        lens = indptr[1:] - indptr[:-1]
+        rows = torch.repeat_interleave(torch.arange(n, device=e.device), lens)
+        cols = torch.arange(total, device=e.device) - indptr[:-1][rows]
+        outs.append((torch.stack([rows, cols], dim=1), vals, (n, int(lens.max().item()) if n else 0)))
+    return outs
+
+
+def get_edge_binary_feature(edges, feature_names, thread_num=1):
+    """feature_ops.get_edge_binary_feature: per feature a list of E byte strings"""
+    e = _edges(edges)
+    g, lib, outs = get_graph(), _lib.load(), []
+    ctx = _ctx_on_stream()
+    n = e.shape[0]
+    for name in [str(x) for x in feature_names]:
+        fid = g.edge_feature_id("binary", name)
+        indptr = torch.empty(n + 1, dtype=torch.int64, device=e.device)
+        check(lib.eu_get_edge_binary_feature(ctx._h, e.data_ptr(), n, fid, 0, indptr.data_ptr(), None))
+        total = int(indptr[-1].item())
+        buf = torch.empty(max(total, 1), dtype=torch.uint8, device=e.device)
+        if total:
+            check(lib.eu_get_edge_binary_feature(ctx._h, e.data_ptr(), n, fid, total, indptr.data_ptr(), buf.data_ptr()))
+        raw, ptr = bytes(buf[:total].cpu().numpy().tobytes()), indptr.cpu().tolist()
+        outs.append([raw[ptr[i]:ptr[i + 1]] for i in range(n)])
+    return outs
+
+
 def get_full_neighbor(nodes, edge_types):
     """neighbor_ops.get_full_neighbor (tf_euler/python/euler_ops/neighbor_ops.py; kernel get_full_neighbor_op.cc over
     euler::GetFullNeighbor api.cc:208-221).  The reference returns three SparseTensors [N, max_degree] (ids, weights,

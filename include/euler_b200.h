@@ -113,6 +113,32 @@ int eu_graph_create_rmat_hetero(int64_t n_nodes, int64_t n_edges, int32_t n_edge
  * `shard_number` with the reference's file filter (graph.cc:90-98).  = Graph::Init, graph.h:53-56. */
 int eu_graph_load(const char* data_path, int shard_index, int shard_number, int device,
                   eu_graph** out);
+/* load_edges = 0: node data only (Graph::Init's load_data_type "node"); eu_graph_load = load_edges 1 ("all"): the Edge
+ * files, when the directory has them, feed eu_sample_edge and the edge feature ops. */
+int eu_graph_load_ex(const char* data_path, int shard_index, int shard_number, int device, int load_edges,
+                     eu_graph** out);
+/* Edge records (Edge files of the Euler format; euler/core/graph/edge.h): needed only by sample_edge and the edge feature ops.
+ * HOST arrays; features use the node layout (dense slots concatenated per edge, ragged uint64 / binary slots).
+ * sampler_order: edge rows in the order the reference's edge_map_ iterates (graph.cc:372-399); NULL = row order. */
+typedef struct {
+  int64_t n_edges;
+  const uint64_t* src;      /* [nE] */
+  const uint64_t* dst;      /* [nE] */
+  const int32_t* type;      /* [nE] */
+  const float* w;           /* [nE] or NULL (all 1.0) */
+  int32_t feat_dim;         /* total dense width, 0 = none */
+  const float* feat;        /* [nE * feat_dim] */
+  int32_t n_feat_slots;     /* 0 = one slot of feat_dim */
+  const int32_t* feat_slot_dims;
+  int32_t n_u64_slots; const int64_t* u64_ptr; const uint64_t* u64_val;
+  int32_t n_bin_slots; const int64_t* bin_ptr; const uint8_t* bin_val;
+  const int64_t* sampler_order;
+} eu_edge_desc;
+int eu_graph_set_edges(eu_graph* g, const eu_edge_desc* desc);
+int64_t eu_graph_num_edge_records(const eu_graph* g);
+int32_t eu_graph_edge_dense_feature_id(const eu_graph* g, const char* name);
+int32_t eu_graph_edge_sparse_feature_id(const eu_graph* g, const char* name);
+int32_t eu_graph_edge_binary_feature_id(const eu_graph* g, const char* name);
 int eu_graph_destroy(eu_graph* g);
 int64_t eu_graph_num_nodes(const eu_graph* g);
 int64_t eu_graph_num_edges(const eu_graph* g);
@@ -218,6 +244,18 @@ int eu_get_sparse_feature_host(eu_ctx* c, const int64_t* nodes, int64_t M, int32
 int eu_get_binary_feature(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid, int64_t cap, int64_t* out_ptr, uint8_t* out_bytes);
 int eu_get_binary_feature_host(eu_ctx* c, const int64_t* nodes, int64_t M, int32_t fid, int64_t cap, int64_t* out_ptr,
                                uint8_t* out_bytes, int64_t* total);
+
+/* tf_euler.sample_edge -- TF op SampleEdge (tf_euler/kernels/sample_edge_op.cc; Graph::SampleEdge graph.cc:277-301): `count`
+ * edges of ONE type drawn by the alias method over the edge weights, out i64[count,3] = (src, dst, type).  Several types or
+ * -1 return EU_ERR_STATE: the reference's edge_type_collection_ is never initialised and it returns nothing for them. */
+int eu_sample_edge(eu_ctx* c, int32_t count, const int32_t* types, int32_t n_types, int64_t* out);
+/* tf_euler.get_edge_dense_feature / _sparse_ / _binary_ (tf_euler/kernels/get_edge_*_feature_op.cc over
+ * euler::GetEdge*Feature api.cc:148-205): edges i64[E,3] = (src, dst, type); unknown edges give zeros / the default entry /
+ * the empty string.  Device pointers; the ragged variants follow eu_get_sparse_feature's two-call convention. */
+int eu_get_edge_dense_feature(eu_ctx* c, const int64_t* edges, int64_t E, int32_t fid, int32_t dim, float* out);
+int eu_get_edge_sparse_feature(eu_ctx* c, const int64_t* edges, int64_t E, int32_t fid, int64_t default_value, int64_t cap,
+                               int64_t* out_ptr, int64_t* out_values);
+int eu_get_edge_binary_feature(eu_ctx* c, const int64_t* edges, int64_t E, int32_t fid, int64_t cap, int64_t* out_ptr, uint8_t* out_bytes);
 
 /* tf_euler.get_full_neighbor core (euler::GetFullNeighbor api.cc:208-221 over Node::GetFullNeighbor node.cc:176-198):
  * for every node the edges of each requested type, in the order the types are given, as (id, weight, type); a missing

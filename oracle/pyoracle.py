@@ -407,6 +407,8 @@ def ref():
                                             C.c_void_p, C.c_void_p, C.c_void_p]
         R.ref_sample_node.restype = C.c_int64
         R.ref_sample_node.argtypes = [i32p, C.c_int32, C.c_int32, u64p]
+        R.ref_sample_edge.restype = C.c_int64
+        R.ref_sample_edge.argtypes = [i32p, C.c_int32, C.c_int32, u64p]
         R.ref_get_dense_feature.argtypes = [u64p, C.c_int64, C.c_int32, C.c_int32, f32p, i32p]
         R.ref_op_sample_neighbor.argtypes = [i64p, C.c_int64, i32p, C.c_int32, C.c_int32, C.c_int64,
                                              i64p, f32p, i32p]
@@ -526,6 +528,13 @@ class RefGraph:
         out = np.zeros(max(count, 1), np.uint64)
         m = ref().ref_sample_node(types, len(types), count, out)
         return out[:m]
+
+    def sample_edge(self, types, count):
+        """euler::SampleEdge: (n, 3) int64 array of (src, dst, type); n == 0 for several types (upstream quirk)"""
+        types = _arr(np.atleast_1d(types), np.int32)
+        out = np.zeros(max(count, 1) * 3, np.uint64)
+        m = ref().ref_sample_edge(types, len(types), count, out)
+        return out[:m * 3].astype(np.int64).reshape(m, 3)
 
     def get_dense_feature(self, ids, fid, dim):
         ids = _arr(ids, np.uint64)

@@ -277,6 +277,17 @@ int64_t ref_sample_node(const int32_t* types, int32_t n_types, int32_t count,
   return v.size();
 }
 
+// euler::SampleEdge (api.cc:39-44 -> Graph::SampleEdge graph.cc:277-331).  out: [count][3] = src, dst, type.
+// Returns the number of edges produced (0 for several types / -1: edge_type_collection_ is never initialised upstream).
+int64_t ref_sample_edge(const int32_t* types, int32_t n_types, int32_t count, uint64_t* out) {
+  std::vector<int> t(types, types + n_types);
+  auto v = euler::SampleEdge(t, count);
+  for (size_t i = 0; i < v.size(); ++i) {
+    out[i * 3] = std::get<0>(v[i]); out[i * 3 + 1] = std::get<1>(v[i]); out[i * 3 + 2] = (uint64_t)(int64_t)std::get<2>(v[i]);
+  }
+  return v.size();
+}
+
 // euler::GetNodeFloat32Feature (api.cc:63-78) for one feature slot, with the TF
 // kernel's zero fill (tf_euler/kernels/get_dense_feature_op.cc:66-75,108-115).
 // The TF kernel copies each row's TRUE length; here the copy is clipped to dim

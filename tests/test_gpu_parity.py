@@ -838,3 +838,37 @@ def test_sparse_and_binary_features_reference_test_vectors(tiny_dir):
     # unknown sparse feature: every node gets the default entry
     idx, vals, shape = euler_b200.get_sparse_feature([1, 2], ['nope'], [5])[0]
     cases.eq(vals.cpu().numpy(), np.array([5, 5]), "unknown sparse feature")
+
+
+# ------------------------------------------------------------------ next-4: edge sampling and edge features
+def test_edge_features_reference_test_vectors_and_sample_edge(tiny_dir):
+    """edge features: the reference's own expectations (tf_euler/python/euler_ops/feature_ops_test.py:62-140);
+    sample_edge: the reference's Graph::SampleEdge on the same directory under the same seed (one type; several types
+    return nothing upstream and are refused here)."""
+    import euler_b200
+    gr = euler_b200.Graph.load(tiny_dir)
+    assert gr.num_edge_records == 12
+    euler_b200.set_graph(gr, rng="minstd", seed=1)
+    edges = [[1, 2, 0], [2, 3, 1]]
+    sp = euler_b200.get_edge_sparse_feature(edges, ['f1', 'f2'], None)
+    for (idx, vals, shape), want in zip(sp, ([[121, 122], [231, 232]], [[123, 124], [233, 234]])):
+        dense = np.zeros(shape, np.int64)
+        i = idx.cpu().numpy()
+        dense[i[:, 0], i[:, 1]] = vals.cpu().numpy()
+        cases.eq(dense, np.asarray(want, np.int64), "edge sparse feature")
+    assert euler_b200.get_edge_binary_feature(edges, ['f5']) == [[b'12a', b'23a']]
+    f3, f4 = euler_b200.get_edge_dense_feature(edges + [[9, 9, 0]], ["f3", "f4"], [2, 3], 2)
+    assert np.allclose(f3.cpu().numpy(), [[12.1, 12.2], [23.1, 23.2], [0, 0]])
+    assert np.allclose(f4.cpu().numpy(), [[12.3, 12.4, 12.5], [23.3, 23.4, 23.5], [0, 0, 0]])
+    if po.have_ref():
+        rg = po.RefGraph.load(tiny_dir, "all", "all")
+        for t in (0, 1):
+            for s in (5, 777):
+                rg.seed(s)
+                want = rg.sample_edge([t], 64)
+                euler_b200.seed(s)
+                got = euler_b200.sample_edge(64, t).cpu().numpy()
+                cases.eq(got, want, "sample_edge type %d seed %d" % (t, s))
+                assert euler_b200.context().draws() == rg.draws()
+    with pytest.raises(euler_b200.EulerError):
+        euler_b200.sample_edge(4, [0, 1])
