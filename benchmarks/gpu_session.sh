@@ -7,7 +7,7 @@ for s in "$@"; do
   case $s in
     info) (nproc; free -g; lscpu | grep -E "Model name|Socket|NUMA node\(s\)"; nvidia-smi --query-gpu=name,memory.total --format=csv) > $out/info.txt 2>&1 ;;
     tests) (time timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -40) > $out/tests.txt 2>&1 ;;
-    tests_all) (time timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -60) > $out/tests.txt 2>&1 ;;
+    tests_all) (time timeout 900 python -m pytest tests -m gpu -q --timeout 180 --timeout-method=thread 2>&1 | tail -80) > $out/tests.txt 2>&1 ;;
     bench_c4) (time timeout 900 python bench.py --steps 20 --warmup 5 > $out/bench_c4.json 2> $out/bench_c4.err) > $out/bench_c4.time 2>&1 ;;
     bench_c4_nocpu) (time timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $out/bench_c4.json 2> $out/bench_c4.err) > $out/bench_c4.time 2>&1 ;;
     bench_c2) (time timeout 600 python bench.py --config c2 --steps 64 --warmup 16 --no-cpu-baseline > $out/bench_c2.json 2> $out/bench_c2.err) > $out/bench_c2.time 2>&1 ;;
