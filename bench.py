@@ -1000,6 +1000,41 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def host_mem_budget():
+    """bytes the CPU arms may hold at once: a quarter of what the container may use (cgroup limit when there is one, else
+    MemAvailable), never more than 64 GB.  Every reference thread builds the whole minibatch in std::vectors (3 GB per thread
+    at the headline config): unbounded, 128 threads would ask for ~400 GB and take the box down with them."""
+    limit = None
+    for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
+        try:
+            v = open(path).read().strip()
+            if v.isdigit() and int(v) < (1 << 60):
+                limit = int(v)
+                break
+        except Exception:
+            pass
+    avail = None
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                avail = int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    cands = [x for x in (limit, avail) if x]
+    base = min(cands) if cands else 32 << 30
+    return int(min(base // 4, 64 << 30))
+
+
+def cpu_threads_cap(args, counts, graph_bytes=0):
+    """largest thread count whose per-thread minibatch buffers fit the memory budget (see host_mem_budget)"""
+    rows = args.batch
+    for c in counts:
+        rows *= c
+    per_thread = int(rows * max(args.dim, 1) * 4 * 2.6) + (64 << 20)   # widest hop: feature matrix + the api's nested vectors + means
+    budget = max(host_mem_budget() - graph_bytes, 4 << 30)
+    return max(1, min(host_cores(), budget // per_thread))
+
+
 def cpu_graph(args):
     """The CPU arms' input: the same generator (oracle/rmat_gen.c restates euler_b200/csrc/graph.cu bit-exactly; nothing of
     the product is loaded), at the bench's size when the reference's in-memory graph can be built inside the time box, else
@@ -1054,7 +1089,11 @@ class CpuStep:
 
     def best_threads(self, cores):
         """the reference links jemalloc (CMakeLists.txt:13,41-43), absent here: with glibc malloc its
-        vector<vector<vector<float>>> feature path scales badly, so sweep thread counts and keep the best"""
+        vector<vector<vector<float>>> feature path scales badly, so sweep thread counts and keep the best.  The sweep never
+        exceeds the memory-derived cap (cpu_threads_cap)."""
+        cap = cpu_threads_cap(self.args, self.counts)
+        self.thread_cap = cap
+        cores = min(cores, cap)
         sweep, best = {}, (0.0, 1)
         for th in sorted({cores, max(1, cores // 2), max(1, cores // 4), min(cores, 16), min(cores, 8), 1}, reverse=True):
             self.step(th, 1)
@@ -1088,7 +1127,8 @@ def cpu_baseline(args, counts):
     iters = max(1, min(50, int(args.cpu_seconds / max(sec1, 1e-3))))
     sec, edges = cs.step(th, iters)
     one_sec, one_edges = cs.step(1, 1)
-    return {"value": edges / sec, "unit": "edges/s", "cores": th, "host_cores": cores, "kind": "reference" if rg is not None else "port",
+    return {"value": edges / sec, "unit": "edges/s", "cores": th, "host_cores": cores, "thread_cap_from_memory_budget": cs.thread_cap,
+            "kind": "reference" if rg is not None else "port",
             "sample": "best of a thread sweep: %d threads x %d batches of the same step (sample_fanout + dense features of every hop + "
                       "neighbor means), %.1f s" % (th, iters, sec),
             "one_thread_edges_per_s": one_edges / one_sec,
@@ -1313,7 +1353,8 @@ def cpu_walk_time(args, L, rg, og, threads, walkers):
 def cpu_walk_baseline(args, L, ex):
     rg, og = cpu_walk_graph(args, ex)
     cores = host_cores()
-    th = cores if rg is not None else 1     # the C restatement walks on one global engine: one thread
+    th = min(cores, 32) if rg is not None else 1     # the C restatement walks on one global engine: one thread; 32 bounds the
+    #                                                   per-thread neighbor-list vectors (hub rows) to a few GB in total
     sec, n = cpu_walk_time(args, L, rg, og, th, 8)
     walkers = max(8, min(256, int(8 * args.cpu_seconds / max(sec, 1e-3))))
     sec, n = cpu_walk_time(args, L, rg, og, th, walkers)
@@ -1331,7 +1372,7 @@ def run_walk_reference(args):
     L = int(args.fanout)
     rg, og = cpu_walk_graph(args, None)
     cores = host_cores()
-    th = cores if rg is not None else 1
+    th = min(cores, 32) if rg is not None else 1
     walkers = 16
     sec1, _ = cpu_walk_time(args, L, rg, og, th, walkers)
     steps = max(1, min(args.steps, int(120.0 / max(sec1, 1e-3)) - args.warmup))
@@ -1387,7 +1428,7 @@ def run_reference(args):
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 ids / f32 weights+features (f64 CDF compare)",
            "data": "synthetic", "config": workload_config(args, counts, args.gpus),
            "arm": {"step": "one bounded sample = %d host threads x %d batches each" % (th, PER_STEP), "cpu_graph": info,
-                   "threads_sweep_edges_per_s": sweep, "host_cores": cores},
+                   "threads_sweep_edges_per_s": sweep, "host_cores": cores, "thread_cap_from_memory_budget": cs.thread_cap},
            "agg_feat_gbs": (bts["agg"] + bts["self_feat"]) * (t_edges / bts["edges"]) / t_sec / 1e9,
            "sub_rates": sub,
            "cpu_baseline": {"value": v, "unit": "edges/s", "cores": th, "kind": "reference" if rg is not None else "port",

@@ -481,8 +481,9 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
     const unsigned long long pkey = PHILOX ? a.key ^ rng->key : 0ull;
 
     if (mid_row) {   // the tile has landed?  (bounded: a copy that never completes is a bug, not something to wait out)
-      for (unsigned spins = 0; !mbar_try_wait(bar, phase); ++spins)
-        if (spins > (1u << 26)) __trap();
+      const long long t0 = clock64();
+      while (!mbar_try_wait(bar, phase))
+        if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s
       phase ^= 1u;
     }
     bool keep = true;

@@ -434,6 +434,7 @@ __device__ void block_exact_prefix(PrefShared& sh, const float* __restrict__ V, 
     const float S = sh.S;
     if (record && t == 0 && (it % ck_stride) == 0 && sh.n_ck < kPrefCk) { sh.ck_pos[sh.n_ck] = pos; sh.ck_S[sh.n_ck] = S; ++sh.n_ck; }
     ++it;
+    if (it > n + 16) __trap();   // every iteration consumes at least one element: anything else is a bug, not a wait
     const int32_t n_it = min((int32_t)kPrefCH, n - pos);
     const uint32_t sb = __float_as_uint(S);
     const uint32_t eS = (sb >> 23) & 0xffu;
