@@ -426,6 +426,41 @@ def get_top_k_neighbor(nodes, edge_types, k, default_node=-1, condition=''):
     return ids, w, t
 
 
+def sample_neighbor_layerwise(nodes, edge_types, count, default_node=-1, weight_func=''):
+    """neighbor_ops.sample_neighbor_layerwise (neighbor_ops.py:72-77): nodes [batch, n] -> (neighbors i64[batch, count],
+    adj f32[batch, n, count]); adj is the dense view of the reference's SparseTensor (1.0 where neighbors[b, k] is a neighbor of
+    nodes[b, j]).  weight_func: '' or 'sqrt'."""
+    nd = _t(nodes, torch.int64)
+    if nd.dim() != 2:
+        raise EulerError("sample_neighbor_layerwise: nodes must be [batch, n]")
+    if weight_func not in ('', 'sqrt'):
+        raise EulerError("sample_neighbor_layerwise: weight_func must be '' or 'sqrt' (local_sample_layer_op.cc:93-101)")
+    nd = nd.contiguous()
+    batch, n = nd.shape
+    et = get_edge_type_id(edge_types)
+    out = torch.empty((batch, int(count)), dtype=torch.int64, device=nd.device)
+    adj = torch.empty((batch, n, int(count)), dtype=torch.float32, device=nd.device)
+    ctx = _ctx_on_stream()
+    check(_lib.load().eu_sample_neighbor_layerwise(ctx._h, nd.data_ptr(), batch, n, et.ctypes.data, len(et), int(count), default_node,
+                                                   1 if weight_func == 'sqrt' else 0, out.data_ptr(), adj.data_ptr()))
+    return out, adj
+
+
+def sparse_get_adj(nodes, nb_nodes, edge_types, n=-1, m=-1):
+    """neighbor_ops.sparse_get_adj (neighbor_ops.py:33-36): nodes [batch * n], nb_nodes [batch * m] (n / m = -1: one batch row)
+    -> f32[batch, n, m], the dense view of the reference's SparseTensor."""
+    nd = _t(nodes, torch.int64).reshape(-1).contiguous()
+    nb = _t(nb_nodes, torch.int64).reshape(-1).contiguous()
+    N = nd.numel() if n == -1 else int(n)
+    M = nb.numel() if m == -1 else int(m)
+    batch = nd.numel() // max(N, 1)
+    et = get_edge_type_id(edge_types)
+    adj = torch.empty((batch, N, M), dtype=torch.float32, device=nd.device)
+    ctx = _ctx_on_stream()
+    check(_lib.load().eu_sparse_get_adj(ctx._h, nd.data_ptr(), nb.data_ptr(), batch, N, M, et.ctypes.data, len(et), adj.data_ptr()))
+    return adj
+
+
 def gen_pair(paths, left_win_size, right_win_size):
     """walk_ops.gen_pair (tf_euler/kernels/gen_pair_op.cc): skip-gram pairs i64[B, n_pairs, 2] of walks i64[B, path_len]."""
     paths = _t(paths, torch.int64)

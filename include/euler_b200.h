@@ -281,6 +281,20 @@ int eu_get_sorted_full_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, cons
  * the stream once (scratch is sized from the listing length). */
 int eu_get_top_k_neighbor(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K, int32_t k,
                           int64_t default_node, int64_t* out_ids, float* out_w, int32_t* out_t);
+/* tf_euler.sample_neighbor_layerwise (neighbor_ops.py:72-77; tf_euler/kernels/sample_neighbor_layerwise_with_adj_op.cc:54-150 over
+ * API_LOCAL_SAMPLE_L, euler/core/kernels/local_sample_layer_op.cc:41-140): nodes i64[batch, n]; per batch row `count` neighbors
+ * drawn from the union of the rows' neighbor lists, candidates unique by (dst, type) with summed weights (weight_func 1 = sqrt),
+ * out_nb i64[batch, count] (default_node when the union is empty); out_adj (may be NULL) f32[batch, n, count] = 1.0 where
+ * out_nb[b, k] is a neighbor of nodes[b, j] -- the dense view of the op's SparseTensor.  Same candidate set, weights and
+ * distribution as the reference; the candidate ORDER (an unordered_map<string> artefact upstream) is (dst, type) here.
+ * Device pointers; synchronises (scratch is sized from the listing). */
+int eu_sample_neighbor_layerwise(eu_ctx* c, const int64_t* nodes, int64_t batch, int32_t n, const int32_t* etypes, int32_t K,
+                                 int32_t count, int64_t default_node, int32_t weight_func, int64_t* out_nb, float* out_adj);
+/* tf_euler.sparse_get_adj (neighbor_ops.py:33-36; euler/core/kernels/sparse_get_adj_op.cc:34-90): nodes i64[batch, N],
+ * nb_nodes i64[batch, M] -> out_adj f32[batch, N, M] = 1.0 where an edge nodes[b, j] -> nb_nodes[b, k] of a listed type exists
+ * (dense view of the SparseTensor). */
+int eu_sparse_get_adj(eu_ctx* c, const int64_t* nodes, const int64_t* nb_nodes, int64_t batch, int32_t N, int32_t M,
+                      const int32_t* etypes, int32_t K, float* out_adj);
 /* tf_euler.gen_pair (tf_euler/kernels/gen_pair_op.cc:41-100): skip-gram pairs of walks.  paths i64[B,path_len] ->
  * out i64[B, eu_gen_pair_count(path_len, lw, rw), 2] (device pointers). */
 int64_t eu_gen_pair_count(int32_t path_len, int32_t left_win_size, int32_t right_win_size);
