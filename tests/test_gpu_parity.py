@@ -872,3 +872,58 @@ def test_edge_features_reference_test_vectors_and_sample_edge(tiny_dir):
                 assert euler_b200.context().draws() == rg.draws()
     with pytest.raises(euler_b200.EulerError):
         euler_b200.sample_edge(4, [0, 1])
+
+
+# ------------------------------------------------------------------ next-3: layerwise sampling and batch adjacency
+@pytest.mark.parametrize("weight_func", ['', 'sqrt'])
+def test_layerwise_sampling_candidates_distribution_and_adj(weight_func):
+    """sample_neighbor_layerwise: the candidate set and every candidate's summed weight are the reference's
+    (local_sample_layer_op.cc:66-101, restated here from the oracle's full-neighbor listing); the draws must stay inside the
+    set, follow those weights (5-sigma band over 6000 draws per row), adj must equal membership exactly; rows without
+    candidates are default-filled.  The reference's own tests check the same properties (neighbor_ops_test.py:142-181)."""
+    import euler_b200
+    g = graphs.random_graph(seed=640, n=300, T=2, avg_deg=5, dup_edges=True, empty_frac=0.2)
+    euler_b200.set_graph(graphs.cuda_graph(g), rng="minstd", seed=3)
+    og = graphs.oracle_graph(g)
+    rs = np.random.RandomState(4)
+    batch, n, count = 6, 4, 6000
+    nodes = g["ids"][rs.randint(0, 300, size=(batch, n))].astype(np.int64)
+    nodes[2, :] = 10 ** 12            # a row of absent nodes: no candidates
+    nodes[3, 1] = nodes[3, 0]         # a repeated node: its edges count twice
+    et = [0, 1]
+    out, adj = euler_b200.sample_neighbor_layerwise(nodes, et, count, -7, weight_func)
+    out, adj = out.cpu().numpy(), adj.cpu().numpy()
+    lens, f_ids, f_w, f_t = og.get_full_neighbor(nodes.reshape(-1).astype(np.uint64), et)
+    ptr = np.concatenate([[0], np.cumsum(lens)])
+    for b in range(batch):
+        lo, hi = ptr[b * n], ptr[(b + 1) * n]
+        cand = {}
+        for k in range(lo, hi):
+            key = (int(f_ids[k]), int(f_t[k]))
+            cand[key] = np.float32(cand.get(key, np.float32(0)) + f_w[k]) if key in cand else np.float32(f_w[k])
+        if weight_func == 'sqrt':
+            cand = {k: np.float32(np.sqrt(v)) for k, v in cand.items()}
+        if not cand:
+            assert (out[b] == -7).all() and (adj[b] == 0).all()
+            continue
+        by_dst = {}
+        for (d, _), v in cand.items():
+            by_dst[d] = by_dst.get(d, 0.0) + float(v)
+        tot = sum(by_dst.values())
+        vals, cnts = np.unique(out[b], return_counts=True)
+        assert set(vals.tolist()) <= set(by_dst), "draws outside the candidate set"
+        for d, c in zip(vals, cnts):
+            p = by_dst[int(d)] / tot
+            assert abs(c - count * p) <= 5 * np.sqrt(count * p * (1 - p)) + 3, (b, d, c, count * p)
+        for j in range(n):
+            nbrs = set(int(x) for x in f_ids[ptr[b * n + j]:ptr[b * n + j + 1]])
+            want = np.array([1.0 if int(x) in nbrs else 0.0 for x in out[b]], np.float32)
+            cases.eq(adj[b, j], want, "adj row")
+    # sparse_get_adj: membership of given neighbor candidates
+    nb = g["ids"][rs.randint(0, 300, size=(batch, 7))].astype(np.int64)
+    nb[:, 0] = out[:, 0]
+    a2 = euler_b200.sparse_get_adj(nodes.reshape(-1), nb.reshape(-1), et, n, 7).cpu().numpy()
+    for b in range(batch):
+        for j in range(n):
+            nbrs = set(int(x) for x in f_ids[ptr[b * n + j]:ptr[b * n + j + 1]])
+            cases.eq(a2[b, j], np.array([1.0 if int(x) in nbrs else 0.0 for x in nb[b]], np.float32), "sparse_get_adj row")
