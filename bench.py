@@ -79,6 +79,8 @@ def parse():
     for k in ("nodes", "edges", "batch", "fanout", "dim"):
         if getattr(a, k) is None:
             setattr(a, k, cfg[k])
+    if a.config == "c3" and a.lanes == 4:
+        a.lanes = 8       # a walk is a chain of 80 dependent steps whose tail is one hub row: more batches in flight hide it
     a.label = cfg["label"] if all(getattr(a, k) == cfg[k] for k in ("nodes", "edges", "batch", "fanout", "dim")) else "custom"
     return a
 
@@ -1002,7 +1004,7 @@ def host_cores():
 
 def host_mem_budget():
     """bytes the CPU arms may hold at once: a quarter of what the container may use (cgroup limit when there is one, else
-    MemAvailable), never more than 64 GB.  Every reference thread builds the whole minibatch in std::vectors (3 GB per thread
+    MemAvailable), never more than 48 GB.  Every reference thread builds the whole minibatch in std::vectors (3 GB per thread
     at the headline config): unbounded, 128 threads would ask for ~400 GB and take the box down with them."""
     limit = None
     for path in ("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory/memory.limit_in_bytes"):
@@ -1022,7 +1024,7 @@ def host_mem_budget():
         pass
     cands = [x for x in (limit, avail) if x]
     base = min(cands) if cands else 32 << 30
-    return int(min(base // 4, 64 << 30))
+    return int(min(base // 4, 48 << 30))
 
 
 def cpu_threads_cap(args, counts, graph_bytes=0):
