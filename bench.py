@@ -1114,8 +1114,14 @@ def cpu_sub_rates(cs, args, counts, th, iters):
     s_sec, s_edges = cs.step(th, iters)
     agg_sec = max(s_sec - f_sec, 1e-9)
     batches = s_edges / bts["edges"]
-    return {"sampling_only_edges_per_s": f_edges / f_sec, "aggregation_only_gbs": (bts["agg"] + bts["self_feat"]) * batches / agg_sec / 1e9,
-            "how": "%d threads x %d batches: sampling-only loop timed alone; aggregation = full-step time minus sampling-only time" % (th, iters)}
+    out = {"sampling_only_edges_per_s": f_edges / f_sec, "aggregation_only_gbs": (bts["agg"] + bts["self_feat"]) * batches / agg_sec / 1e9,
+           "how": "%d threads x %d batches: sampling-only loop timed alone; aggregation = full-step time minus sampling-only time" % (th, iters)}
+    cores = host_cores()
+    if cores > th:    # the sampler alone needs little memory per thread: also time it on every host core (the north-star's 10x bar)
+        cs.fanout(cores, 1)
+        a_sec, a_edges = cs.fanout(cores, max(2, iters))
+        out["sampling_only_all_cores"] = {"edges_per_s": a_edges / a_sec, "cores": cores}
+    return out
 
 
 def cpu_baseline(args, counts):

@@ -18,6 +18,19 @@ for s in "$@"; do
     sharded2) (time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/run_sharded_gpu.py > $out/sharded2.txt 2>&1) > $out/sharded2.time 2>&1 ;;
     bench_n2) (time timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 2 --steps 20 --warmup 5 > $out/bench_n2.json 2> $out/bench_n2.err) > $out/bench_n2.time 2>&1 ;;
     bench_n2_sharded) (time timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29545 bench.py --gpus 2 --steps 20 --warmup 5 --features sharded > $out/bench_n2_sharded.json 2> $out/bench_n2_sharded.err) > $out/bench_n2_sharded.time 2>&1 ;;
+    ab) Q="--steps 40 --warmup 8 --no-cpu-baseline --no-e2e-host --no-gate"
+        run() { tag2=$1; shift; (env "$@" timeout 300 python bench.py $Q $EXTRA > $out/ab_$tag2.json 2> $out/ab_$tag2.err); }
+        EXTRA="" run c4_default X=1
+        EXTRA="" run c4_nostage EU_SAMPLE_STAGE=0
+        EXTRA="--lanes 8" run c4_lanes8 X=1
+        EXTRA="" run c4_part_a EU_SAGE_CTAS=3 EU_SAMPLE_CTAS=6
+        EXTRA="" run c4_part_b EU_SAGE_CTAS=2 EU_FEATURE_CTAS=2 EU_SAMPLE_CTAS=6
+        EXTRA="--lanes 8" run c4_part_c EU_SAGE_CTAS=2 EU_FEATURE_CTAS=2 EU_SAMPLE_CTAS=6
+        EXTRA="--config c2 --steps 128 --warmup 32" run c2_default X=1
+        EXTRA="--config c2 --steps 128 --warmup 32" run c2_nostage EU_SAMPLE_STAGE=0 ;;
+    walk_ab) (timeout 300 python bench.py --config c3 --steps 16 --warmup 4 --no-cpu-baseline > $out/walk_l8.json 2> $out/walk_l8.err)
+        (timeout 300 python bench.py --config c3 --steps 32 --warmup 4 --no-cpu-baseline --no-gate --lanes 16 > $out/walk_l16.json 2> $out/walk_l16.err)
+        (timeout 300 python bench.py --config c3 --steps 16 --warmup 4 --no-cpu-baseline --no-gate --rng philox > $out/walk_philox.json 2> $out/walk_philox.err) ;;
     *) echo "unknown step $s" ;;
   esac
   echo "== $s done rc=$?" >> $out/steps.log

@@ -194,11 +194,13 @@ __global__ void k_mean_div(float* __restrict__ out, int64_t D, int64_t size, con
 // out[r,:] = (sum_j feat[row(ids[r*count+j]),:]) / (count + 1e-7), j ascending (== get_dense_feature
 // followed by scatter_mean over edge_src = repeat(range(rows), count)).  One warp per output row;
 // the `count` id->row lookups run in parallel across lanes, then NV float4 per lane are accumulated.
-template <int NV>   // NV float4 per lane: rows of up to NV * 128 floats (any width that is a multiple of 4)
+// NV float4 per lane: rows of up to NV * 128 floats.  FULL: the width is exactly NV * 128 (128 / 256: no column guards, the
+// width is a compile-time constant); otherwise any multiple of 4 up to NV * 128 (e.g. 64 of configs[4]) with guarded columns.
+template <int NV, bool FULL>
 __global__ void __launch_bounds__(256) k_sage_mean(DevGraph g, const unsigned long long* __restrict__ ids,
                                                    int64_t rows, int32_t count, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
-  const int32_t fd = g.feat_dim;    // == dim, a multiple of 4, <= NV * 128 (checked by the launcher)
+  const int32_t fd = FULL ? NV * 128 : g.feat_dim;    // == dim, a multiple of 4, <= NV * 128 (checked by the launcher)
   const float* __restrict__ feat = g.feat + lane * 4;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   // grid-stride, one warp per output row (the launcher may cap the grid: EU_SAGE_CTAS CTAs per SM)
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(256) k_sage_mean(DevGraph g, const unsigned lo
           const int32_t row = __shfl_sync(0xffffffffu, my, j);
           const float* p = feat + (int64_t)row * fd;
 #pragma unroll
-          for (int t = 0; t < NV; ++t) v[q][t] = lane * 4 + t * 128 < fd ? ldg4(p + t * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int t = 0; t < NV; ++t) v[q][t] = (FULL || lane * 4 + t * 128 < fd) ? ldg4(p + t * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
           n = q + 1;
         }
       }
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(256) k_sage_mean(DevGraph g, const unsigned lo
   for (int t = 0; t < NV; ++t) {
     float4 a = acc[t];
     a.x = __fdiv_rn(a.x, denom); a.y = __fdiv_rn(a.y, denom); a.z = __fdiv_rn(a.z, denom); a.w = __fdiv_rn(a.w, denom);
-    if (lane * 4 + t * 128 < fd) st4(o + t * 128, a);
+    if (FULL || lane * 4 + t * 128 < fd) st4(o + t * 128, a);
   }
   }
 }
@@ -383,10 +385,12 @@ int eu_sage_mean_aggregate(eu_ctx* c, const int64_t* nbr_ids, int64_t rows, int3
   EuProfScope ps(c, "k_sage_mean", rows);
   // float4 path: one slot of the full stored width, a multiple of 4 floats up to 1024 (D = 64 of configs[4], 128, 256, ...)
   const bool v4 = d.n < ((int64_t)1 << 31) && d.n_slots == 1 && dim == d.feat_dim && (dim & 3) == 0 && dim <= 1024 && aligned16(out) && aligned16(d.feat);
-  if (v4 && dim <= 128) k_sage_mean<1><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
-  else if (v4 && dim <= 256) k_sage_mean<2><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
-  else if (v4 && dim <= 512) k_sage_mean<4><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
-  else if (v4) k_sage_mean<8><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
+  if (v4 && dim == 128) k_sage_mean<1, true><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
+  else if (v4 && dim == 256) k_sage_mean<2, true><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
+  else if (v4 && dim <= 128) k_sage_mean<1, false><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
+  else if (v4 && dim <= 256) k_sage_mean<2, false><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
+  else if (v4 && dim <= 512) k_sage_mean<4, false><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
+  else if (v4) k_sage_mean<8, false><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
   else k_sage_mean_generic<<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, dim, out);
   EU_LAUNCHED();
   return EU_OK;

@@ -310,6 +310,7 @@ struct SampleArgs {
   uint32_t lanepow[32];         // A^(2 * uniforms per draw * lane): a lane's jump from the row state
   uint32_t stride;              // A^(2 * uniforms per draw * SG)
   int sg_log;                   // log2 of the lanes per row (SG)
+  int stage;                    // 1: TMA-stage mid rows in shared memory (EU_SAMPLE_STAGE=0 turns it off for A/B runs)
   HashSlot* clear_tab;          // dedup tables of THIS hop (all batches), cleared here for the next user
   int64_t clear_n;
   HashSlot* next_tabs;          // dedup tables of the NEXT hop: this hop's engine ids are its seeds (or null)
@@ -359,7 +360,7 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
   const int SG = 1 << a.sg_log;
   const int sl = lane & (SG - 1);                    // lane inside its group = draw index modulo SG
   const unsigned gmask = SG == 32 ? 0xffffffffu : (((1u << SG) - 1u) << (lane - sl));
-  const bool can_stage = a.sg_log >= 3;              // <= 32 groups per CTA, slices of >= 256 B
+  const bool can_stage = a.sg_log >= 3 && a.stage;   // <= 32 groups per CTA, slices of >= 256 B
   unsigned long long* const bar = &s_bar[can_stage ? (threadIdx.x >> a.sg_log) : 0];
   float* const sm = s_stage + (threadIdx.x - sl) * kStageF;   // this group's slice: kStageF * SG floats, 16-byte aligned
   const int64_t capg = (int64_t)SG * kStageF;
@@ -719,6 +720,8 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
   }
   // persistent grid: 8 CTAs per SM stride over the (live) rows.  EU_SAMPLE_CTAS = CTAs per SM (1..8; 6 also relaxes the
   // register cap); read once (C++11 static initialisation is thread-safe: the ABI is re-entrant across ctxs)
+  static const int stage_rows = [] { const char* e = getenv("EU_SAMPLE_STAGE"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
+  a.stage = stage_rows;
   static const int grid_ctas = [] { const char* e = getenv("EU_SAMPLE_CTAS"); return e ? std::min(8, std::max(1, atoi(e))) : 8; }();
   const int ctas = grid_ctas == 6 ? 6 : 8;
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(ceil_div(rows * 32, (int64_t)(32 >> a.sg_log)), 256), 148 * grid_ctas);

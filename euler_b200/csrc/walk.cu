@@ -258,7 +258,8 @@ struct WarpWalk {
 // common only while S is within a few binades of the addends (the first dozens of elements of a row); a 137K-edge hub row
 // of the R-MAT graph takes 143 iterations instead of 137K dependent FADDs.  Checked against the plain sequential sum on
 // random, tie-heavy, zero-laden and wide-exponent inputs (the same arithmetic in Python) and by the oracle parity tests.
-static constexpr int kWalkBig = 512;        // rows longer than this take the V path
+static constexpr int kWalkBig = 512;        // rows longer than this get a 256-thread CTA (shorter ones a warp)
+static constexpr int kWalkHuge = 16384;     // rows longer than this get a 1024-thread CTA
 static constexpr int kWalkChunk = 256;      // elements per k_walk_weights chunk
 static constexpr int kPrefT = 256;          // threads of a k_walk_prefix CTA
 static constexpr int kPrefE = 4;            // elements per thread and iteration
@@ -271,10 +272,12 @@ struct WalkPlan {
   int32_t* live_list;   // [B] live walkers whose row fits in V, walker order (k_walk_weights maps chunks to them)
   int32_t* coff;        // [B+1] first k_walk_weights chunk of live_list[k]
   long long* voff;      // [B] V offset of walker i's row (by walker id)
-  int32_t* big_list;    // [B] walkers with deg > kWalkBig: one CTA each in k_walk_prefix
+  int32_t* huge_list;   // [B] walkers with deg > kWalkHuge: one 1024-thread CTA each
+  int32_t* big_list;    // [B] walkers with kWalkBig < deg <= kWalkHuge: one 256-thread CTA each
   int32_t* small_list;  // [B] the other walkers with a V row: one warp each
   int32_t* ovf_list;    // [B] live walkers whose row does not fit in V: the self-contained warp path (WarpWalk)
-  unsigned int* ctr;    // [8]: 0 n_big, 1 n_small, 2 n_chunks, 3 big ticket, 4 small ticket, 5 n_ovf, 6 ovf ticket, 7 n_fit
+  unsigned int* ctr;    // [16]: 0 n_big, 1 n_small, 2 n_chunks, 3 big ticket, 4 small ticket, 5 n_ovf, 6 ovf ticket, 7 n_fit,
+                        //       8 n_huge, 9 huge ticket
   float* V;
   long long capV;
 };
@@ -296,14 +299,15 @@ __global__ void __launch_bounds__(1024) k_walk_plan(int64_t B, const uint8_t* __
   __shared__ uint32_t s_prod[1024];
   __shared__ uint32_t s_cnt[1024];
   __shared__ uint32_t s_big[1024];
+  __shared__ uint32_t s_huge[1024];
   __shared__ uint32_t s_chunks[1024];
   __shared__ unsigned long long s_el[1024];
-  __shared__ unsigned int s_fit, s_fitbig, s_fitchunks;
+  __shared__ unsigned int s_fit, s_fitbig, s_fithuge, s_fitchunks;
   const int t = threadIdx.x;
-  if (t == 0) { wp.ctr[5] = 0; s_fit = 0; s_fitbig = 0; s_fitchunks = 0; }
+  if (t == 0) { wp.ctr[5] = 0; s_fit = 0; s_fitbig = 0; s_fithuge = 0; s_fitchunks = 0; }
   const int64_t per = (B + 1023) / 1024;
   const int64_t b = min((int64_t)t * per, B), e = min(b + per, B);
-  uint32_t prod = 1, cnt = 0, nbig = 0, chunks = 0;
+  uint32_t prod = 1, cnt = 0, nbig = 0, nhuge = 0, chunks = 0;
   unsigned long long el = 0;
   for (int64_t i = b; i < e; ++i) {
     if (!live[i]) continue;
@@ -311,22 +315,22 @@ __global__ void __launch_bounds__(1024) k_walk_plan(int64_t B, const uint8_t* __
     const int32_t d = wp.deg[i];
     el += (unsigned long long)d;
     chunks += (uint32_t)((d + kWalkChunk - 1) / kWalkChunk);
-    if (d > kWalkBig) ++nbig;
+    if (d > kWalkHuge) ++nhuge; else if (d > kWalkBig) ++nbig;
   }
-  s_prod[t] = prod; s_cnt[t] = cnt; s_big[t] = nbig; s_chunks[t] = chunks; s_el[t] = el;
+  s_prod[t] = prod; s_cnt[t] = cnt; s_big[t] = nbig; s_huge[t] = nhuge; s_chunks[t] = chunks; s_el[t] = el;
   __syncthreads();
   for (int off = 1; off < 1024; off <<= 1) {   // inclusive Hillis-Steele scans (modmul is associative and commutative)
-    uint32_t v = 1, c = 0, g1 = 0, g3 = 0; unsigned long long g4 = 0;
-    if (t >= off) { v = s_prod[t - off]; c = s_cnt[t - off]; g1 = s_big[t - off]; g3 = s_chunks[t - off]; g4 = s_el[t - off]; }
+    uint32_t v = 1, c = 0, g1 = 0, g2 = 0, g3 = 0; unsigned long long g4 = 0;
+    if (t >= off) { v = s_prod[t - off]; c = s_cnt[t - off]; g1 = s_big[t - off]; g2 = s_huge[t - off]; g3 = s_chunks[t - off]; g4 = s_el[t - off]; }
     __syncthreads();
-    if (t >= off) { s_prod[t] = modmul(s_prod[t], v); s_cnt[t] += c; s_big[t] += g1; s_chunks[t] += g3; s_el[t] += g4; }
+    if (t >= off) { s_prod[t] = modmul(s_prod[t], v); s_cnt[t] += c; s_big[t] += g1; s_huge[t] += g2; s_chunks[t] += g3; s_el[t] += g4; }
     __syncthreads();
   }
   const uint32_t x0 = minstd ? rng->x : 0u;
   uint32_t run = minstd ? modmul(x0, t > 0 ? s_prod[t - 1] : 1u) : 0u;
-  uint32_t kl = t > 0 ? s_cnt[t - 1] : 0u, kb = t > 0 ? s_big[t - 1] : 0u, kc = t > 0 ? s_chunks[t - 1] : 0u;
+  uint32_t kl = t > 0 ? s_cnt[t - 1] : 0u, kb = t > 0 ? s_big[t - 1] : 0u, kh = t > 0 ? s_huge[t - 1] : 0u, kc = t > 0 ? s_chunks[t - 1] : 0u;
   unsigned long long ke = t > 0 ? s_el[t - 1] : 0ull;
-  unsigned int fit = 0, fitbig = 0, fitchunks = 0;
+  unsigned int fit = 0, fitbig = 0, fithuge = 0, fitchunks = 0;
   for (int64_t i = b; i < e; ++i) {
     if (minstd) state[i] = run;
     if (!live[i]) continue;
@@ -337,23 +341,26 @@ __global__ void __launch_bounds__(1024) k_walk_plan(int64_t B, const uint8_t* __
       // V offsets are monotone in walker order, so the walkers that fit are a prefix of the live ones: their positions in
       // the live / big / small lists are the scanned counts
       wp.live_list[kl] = (int32_t)i; wp.coff[kl] = (int32_t)kc; wp.voff[i] = (long long)ke;
-      if (d > kWalkBig) { wp.big_list[kb] = (int32_t)i; ++fitbig; } else wp.small_list[kl - kb] = (int32_t)i;
+      if (d > kWalkHuge) { wp.huge_list[kh] = (int32_t)i; ++fithuge; }
+      else if (d > kWalkBig) { wp.big_list[kb] = (int32_t)i; ++fitbig; }
+      else wp.small_list[kl - kb - kh] = (int32_t)i;
       ++fit; fitchunks += nch;
     } else {
       wp.ovf_list[atomicAdd(&wp.ctr[5], 1u)] = (int32_t)i;   // V is full: the self-contained warp path serves it
     }
     ++kl; ke += (unsigned long long)d; kc += nch;
-    if (d > kWalkBig) ++kb;
+    if (d > kWalkHuge) ++kh; else if (d > kWalkBig) ++kb;
   }
-  if (fit) { atomicAdd(&s_fit, fit); atomicAdd(&s_fitbig, fitbig); atomicAdd(&s_fitchunks, fitchunks); }
+  if (fit) { atomicAdd(&s_fit, fit); atomicAdd(&s_fitbig, fitbig); atomicAdd(&s_fithuge, fithuge); atomicAdd(&s_fitchunks, fitchunks); }
   __syncthreads();
   if (t == 1023 && minstd) { rng->x = modmul(x0, s_prod[1023]); rng->draws += (unsigned long long)s_cnt[1023]; }
   if (t == 0) {
     wp.ctr[0] = s_fitbig;
-    wp.ctr[1] = s_fit - s_fitbig;
+    wp.ctr[1] = s_fit - s_fitbig - s_fithuge;
     wp.ctr[2] = s_fitchunks;
     wp.ctr[3] = 0; wp.ctr[4] = 0; wp.ctr[6] = 0;
     wp.ctr[7] = s_fit;
+    wp.ctr[8] = s_fithuge; wp.ctr[9] = 0;
     wp.coff[s_fit] = (int32_t)s_fitchunks;
   }
 }
@@ -408,9 +415,10 @@ __global__ void __launch_bounds__(kWalkChunk) k_walk_weights(DevGraph g, int32_t
   }
 }
 
+template <int T>
 struct PrefShared {
-  float v[kPrefCH];
-  unsigned int warp_tot[kPrefT / 32];
+  float v[T * kPrefE];
+  unsigned int warp_tot[T / 32];
   float ck_S[kPrefCk];
   int32_t ck_pos[kPrefCk];
   int n_ck;
@@ -424,7 +432,13 @@ struct PrefShared {
 
 // Runs the exact prefix over V[0, n) from (sh.pos, sh.S).  select: stop at the first k with (double)S_k > r and leave k in
 // sh.answer (-1 if none).  record: store a checkpoint every ck_stride iterations.  Returns with sh.S = S_{n-1} when !select.
-__device__ void block_exact_prefix(PrefShared& sh, const float* __restrict__ V, int32_t n, bool select, bool record, int ck_stride) {
+template <int T>
+__device__ void block_exact_prefix(PrefShared<T>& sh, const float* __restrict__ V, int32_t n, bool select, bool record, int ck_stride) {
+  constexpr int CH = T * kPrefE;   // elements per iteration
+  // software pipeline: the values of the NEXT iteration (assuming this one ends without an exception, i.e. at pos + CH) are
+  // requested before this iteration's scan, so their latency hides behind it; an exception moves pos elsewhere and they are dropped
+  float vn[kPrefE];
+  int32_t pre_pos = -1;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   int it = 0;
   while (true) {
@@ -435,7 +449,7 @@ __device__ void block_exact_prefix(PrefShared& sh, const float* __restrict__ V, 
     if (record && t == 0 && (it % ck_stride) == 0 && sh.n_ck < kPrefCk) { sh.ck_pos[sh.n_ck] = pos; sh.ck_S[sh.n_ck] = S; ++sh.n_ck; }
     ++it;
     if (it > n + 16) __trap();   // every iteration consumes at least one element: anything else is a bug, not a wait
-    const int32_t n_it = min((int32_t)kPrefCH, n - pos);
+    const int32_t n_it = min((int32_t)CH, n - pos);
     const uint32_t sb = __float_as_uint(S);
     const uint32_t eS = (sb >> 23) & 0xffu;
     const uint32_t M_in = eS ? ((sb & 0x7fffffu) | 0x800000u) : 0u;
@@ -448,12 +462,24 @@ __device__ void block_exact_prefix(PrefShared& sh, const float* __restrict__ V, 
     uint32_t inc[kPrefE];
     bool flg[kPrefE];
     uint32_t l = 0;
-    int myfirst = kPrefCH;
+    int myfirst = CH;
+    float vcur[kPrefE];
+    const bool have = pre_pos == pos;
 #pragma unroll
     for (int e = 0; e < kPrefE; ++e) {
       const int32_t k = t * kPrefE + e;
-      float v = 0.f;
-      if (k < n_it) v = V[pos + k];
+      vcur[e] = have ? vn[e] : (k < n_it ? V[pos + k] : 0.f);
+    }
+    pre_pos = pos + CH;
+#pragma unroll
+    for (int e = 0; e < kPrefE; ++e) {
+      const int32_t k2 = pre_pos + t * kPrefE + e;
+      vn[e] = k2 < n ? V[k2] : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < kPrefE; ++e) {
+      const int32_t k = t * kPrefE + e;
+      const float v = vcur[e];
       sh.v[k] = v;
       const uint32_t vb = __float_as_uint(v);
       uint32_t in = 0; bool f = false;
@@ -483,24 +509,24 @@ __device__ void block_exact_prefix(PrefShared& sh, const float* __restrict__ V, 
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += y; }
     if (lane == 31) sh.warp_tot[wid] = min(ws, 0x2000000u);   // anything >= 2^24 means "crossed": clamp so that sums stay in 32 bits
-    if (t == 0) { sh.first = kPrefCH; sh.hit = kPrefCH; }
+    if (t == 0) { sh.first = CH; sh.hit = CH; }
     __syncthreads();
     uint32_t base = M_in + (ws - l);
     for (int w2 = 0; w2 < wid; ++w2) base += sh.warp_tot[w2];
     uint32_t Mk = base, Mbefore = base;
-    int myhit = kPrefCH;
+    int myhit = CH;
 #pragma unroll
     for (int e = 0; e < kPrefE; ++e) {
       const int32_t k = t * kPrefE + e;
       const uint32_t prev = Mk;
       Mk += inc[e];
       if (k < n_it) {
-        if ((flg[e] || Mk >= 0x1000000u) && myfirst == kPrefCH) { myfirst = k; Mbefore = prev; }
-        if (select && Mk > Mthr && myhit == kPrefCH) myhit = k;
+        if ((flg[e] || Mk >= 0x1000000u) && myfirst == CH) { myfirst = k; Mbefore = prev; }
+        if (select && Mk > Mthr && myhit == CH) myhit = k;
       }
     }
-    if (myfirst < kPrefCH) atomicMin(&sh.first, myfirst);
-    if (myhit < kPrefCH) atomicMin(&sh.hit, myhit);
+    if (myfirst < CH) atomicMin(&sh.first, myfirst);
+    if (myhit < CH) atomicMin(&sh.hit, myhit);
     __syncthreads();
     const int f = sh.first, h = sh.hit;
     if (select && h < f) {   // every element before the first exception is final: the hit is real
@@ -535,26 +561,27 @@ __device__ void block_exact_prefix(PrefShared& sh, const float* __restrict__ V, 
   }
 }
 
-__global__ void __launch_bounds__(kPrefT) k_walk_prefix(DevGraph g, int64_t B, int32_t L, int32_t step, int32_t ctype, int32_t ptype,
-                                                        float p, float q, long long default_node, WalkState s,
-                                                        const uint8_t* __restrict__ live, const uint32_t* __restrict__ state,
-                                                        bool philox, unsigned long long key, WalkPlan wp, long long* __restrict__ out) {
-  __shared__ PrefShared sh;
+// CTA per walker of `list` (T threads, T * kPrefE elements per iteration): huge rows get 1024-thread CTAs, big rows 256
+template <int T>
+__global__ void __launch_bounds__(T) k_walk_prefix_cta(DevGraph g, int32_t L, int32_t step, int32_t ctype, WalkState s,
+                                                       const uint32_t* __restrict__ state, bool philox, unsigned long long key, WalkPlan wp,
+                                                       const int32_t* __restrict__ list, int n_idx, int ticket_idx,
+                                                       long long* __restrict__ out) {
+  __shared__ PrefShared<T> sh;
   __shared__ unsigned int s_tk;
-  const int t = threadIdx.x, lane = t & 31;
-  const unsigned int n_big = wp.ctr[0], n_small = wp.ctr[1];
-  // ---- big walkers: one CTA each
+  const int t = threadIdx.x;
+  const unsigned int n_list = wp.ctr[n_idx];
   while (true) {
-    if (t == 0) s_tk = atomicAdd(&wp.ctr[3], 1u);
+    if (t == 0) s_tk = atomicAdd(&wp.ctr[ticket_idx], 1u);
     __syncthreads();
     const unsigned int k = s_tk;
     __syncthreads();
-    if (k >= n_big) break;
-    const int64_t i = wp.big_list[k];
+    if (k >= n_list) break;
+    const int64_t i = list[k];
     const int32_t n = wp.deg[i];
     const float* V = wp.V + wp.voff[i];
     if (t == 0) { sh.pos = 0; sh.S = 0.f; sh.n_ck = 0; sh.answer = -1; }
-    const int ck_stride = 1 + (n / kPrefCH) / (kPrefCk / 2);
+    const int ck_stride = 1 + (n / (T * kPrefE)) / (kPrefCk / 2);
     block_exact_prefix(sh, V, n, false, true, ck_stride);
     if (t == 0) {
       const float total = sh.S;
@@ -581,6 +608,14 @@ __global__ void __launch_bounds__(kPrefT) k_walk_prefix(DevGraph g, int64_t B, i
     }
     __syncthreads();
   }
+}
+
+// warp per walker: rows of up to kWalkBig edges over V, then the walkers whose row did not fit in V (self-contained WarpWalk)
+__global__ void __launch_bounds__(256) k_walk_prefix_warp(DevGraph g, int32_t L, int32_t step, int32_t ctype, int32_t ptype, float p, float q,
+                                                          long long default_node, WalkState s, const uint32_t* __restrict__ state, bool philox,
+                                                          unsigned long long key, WalkPlan wp, long long* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int n_small = wp.ctr[1];
   // ---- small walkers (deg <= kWalkBig): one warp each over the row's biased weights in V.  The prefix is the plain
   // left-to-right f32 chain evaluated through shuffles (<= 16 chunks of 32); pass 1 = total, pass 2 = select.
   while (true) {
@@ -762,7 +797,7 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
     return EU_OK;
   }
   // node2vec
-  const int64_t plan_bytes = B * (4 + 4 + 4 + 4 + 4) + (B + 1) * (8 + 4) + 64 + 256;
+  const int64_t plan_bytes = B * (4 + 4 + 4 + 4 + 4 + 4) + (B + 1) * (8 + 4) + 128 + 256;
   rc = ctx_misc(c, 256 + B * (8 + 8 + 8 + 8) + plan_bytes);
   if (rc) return rc;
   char* m = (char*)c->d_misc + 256;
@@ -775,6 +810,7 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
   wp.voff = (long long*)m; m += 8 * (B + 1);
   wp.deg = (int32_t*)m; m += 4 * B;
   wp.live_list = (int32_t*)m; m += 4 * B;
+  wp.huge_list = (int32_t*)m; m += 4 * B;
   wp.big_list = (int32_t*)m; m += 4 * B;
   wp.small_list = (int32_t*)m; m += 4 * B;
   wp.ovf_list = (int32_t*)m; m += 4 * B;
@@ -813,9 +849,14 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
       { EuProfScope ps(c, "k_walk_weights", B);
         k_walk_weights<<<148 * 8, kWalkChunk, 0, s>>>(d, ctype, ptype, p, q, ws, wp); }
       EU_LAUNCHED();
-      { EuProfScope ps(c, "k_walk_prefix", B);
-        k_walk_prefix<<<148 * 4, kPrefT, 0, s>>>(d, B, L, l, ctype, ptype, p, q, default_node, ws, c->d_elig, c->d_state, philox, wkey, wp,
-                                               (long long*)out); }
+      { EuProfScope ps(c, "k_walk_prefix(huge rows, 1024-thread CTAs)", B);
+        k_walk_prefix_cta<1024><<<148, 1024, 0, s>>>(d, L, l, ctype, ws, c->d_state, philox, wkey, wp, wp.huge_list, 8, 9, (long long*)out); }
+      EU_LAUNCHED();
+      { EuProfScope ps(c, "k_walk_prefix(big rows, 256-thread CTAs)", B);
+        k_walk_prefix_cta<256><<<148 * 4, 256, 0, s>>>(d, L, l, ctype, ws, c->d_state, philox, wkey, wp, wp.big_list, 0, 3, (long long*)out); }
+      EU_LAUNCHED();
+      { EuProfScope ps(c, "k_walk_prefix(small rows, warps)", B);
+        k_walk_prefix_warp<<<148 * 4, 256, 0, s>>>(d, L, l, ctype, ptype, p, q, default_node, ws, c->d_state, philox, wkey, wp, (long long*)out); }
       EU_LAUNCHED();
       k_walk_dead<<<(unsigned)ceil_div(B, tb), tb, 0, s>>>(B, L, l, default_node, ws, c->d_elig, (long long*)out);
       EU_LAUNCHED();
