@@ -198,7 +198,7 @@ __global__ void k_mean_div(float* __restrict__ out, int64_t D, int64_t size, con
 // width is a compile-time constant); otherwise any multiple of 4 up to NV * 128 (e.g. 64 of configs[4]) with guarded columns.
 template <int NV, bool FULL>
 __global__ void __launch_bounds__(256) k_sage_mean(DevGraph g, const unsigned long long* __restrict__ ids,
-                                                   int64_t rows, int32_t count, float* __restrict__ out) {
+                                                   int64_t rows, int32_t count, bool mean, float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int32_t fd = FULL ? NV * 128 : g.feat_dim;    // == dim, a multiple of 4, <= NV * 128 (checked by the launcher)
   const float* __restrict__ feat = g.feat + lane * 4;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(256) k_sage_mean(DevGraph g, const unsigned lo
 #pragma unroll
   for (int t = 0; t < NV; ++t) {
     float4 a = acc[t];
-    a.x = __fdiv_rn(a.x, denom); a.y = __fdiv_rn(a.y, denom); a.z = __fdiv_rn(a.z, denom); a.w = __fdiv_rn(a.w, denom);
+    if (mean) { a.x = __fdiv_rn(a.x, denom); a.y = __fdiv_rn(a.y, denom); a.z = __fdiv_rn(a.z, denom); a.w = __fdiv_rn(a.w, denom); }
     if (FULL || lane * 4 + t * 128 < fd) st4(o + t * 128, a);
   }
   }
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) k_sage_mean(DevGraph g, const unsigned lo
 
 // generic width fallback: G lanes... one warp per row, scalar columns
 __global__ void __launch_bounds__(256) k_sage_mean_generic(DevGraph g, const unsigned long long* __restrict__ ids,
-                                                           int64_t rows, int32_t count, int32_t dim,
+                                                           int64_t rows, int32_t count, int32_t dim, bool mean,
                                                            float* __restrict__ out) {
   const int lane = threadIdx.x & 31;
   const int32_t fd = g.feat_dim;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(256) k_sage_mean_generic(DevGraph g, const uns
         const int64_t row = lookup_row(g, __ldg(ids + r * count + j));
         acc = __fadd_rn(acc, (row >= 0 && d < fd) ? __ldg(g.feat + row * (int64_t)fd + d) : 0.f);
       }
-      out[r * (int64_t)dim + d] = __fdiv_rn(acc, denom);
+      out[r * (int64_t)dim + d] = mean ? __fdiv_rn(acc, denom) : acc;
     }
 }
 
@@ -375,25 +375,35 @@ int eu_scatter_mean(eu_ctx* c, const float* u, int64_t D, const int32_t* idx, in
   return scatter<OP_MEAN>(c, u, D, idx, E, size, out);
 }
 
-int eu_sage_mean_aggregate(eu_ctx* c, const int64_t* nbr_ids, int64_t rows, int32_t count, int32_t dim, float* out) {
+static int fanout_aggregate(eu_ctx* c, const int64_t* nbr_ids, int64_t rows, int32_t count, int32_t dim, bool mean, float* out) {
   if (!c || rows < 0 || count < 0 || dim <= 0 || (rows > 0 && (!nbr_ids || !out))) { set_error("eu_sage_mean_aggregate: bad argument"); return EU_ERR_INVALID; }
   EU_CUDA(cudaSetDevice(c->g->device));
   if (rows == 0) return EU_OK;
   const DevGraph& d = c->g->d;
   const unsigned blocks = capped_grid(ceil_div(rows * 32, 256), "EU_SAGE_CTAS", 0);
   const unsigned long long* ids = (const unsigned long long*)nbr_ids;
-  EuProfScope ps(c, "k_sage_mean", rows);
+  EuProfScope ps(c, mean ? "k_sage_mean" : "k_sage_add", rows);
   // float4 path: one slot of the full stored width, a multiple of 4 floats up to 1024 (D = 64 of configs[4], 128, 256, ...)
   const bool v4 = d.n < ((int64_t)1 << 31) && d.n_slots == 1 && dim == d.feat_dim && (dim & 3) == 0 && dim <= 1024 && aligned16(out) && aligned16(d.feat);
-  if (v4 && dim == 128) k_sage_mean<1, true><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
-  else if (v4 && dim == 256) k_sage_mean<2, true><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
-  else if (v4 && dim <= 128) k_sage_mean<1, false><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
-  else if (v4 && dim <= 256) k_sage_mean<2, false><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
-  else if (v4 && dim <= 512) k_sage_mean<4, false><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
-  else if (v4) k_sage_mean<8, false><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, out);
-  else k_sage_mean_generic<<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, dim, out);
+  if (v4 && dim == 128) k_sage_mean<1, true><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, mean, out);
+  else if (v4 && dim == 256) k_sage_mean<2, true><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, mean, out);
+  else if (v4 && dim <= 128) k_sage_mean<1, false><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, mean, out);
+  else if (v4 && dim <= 256) k_sage_mean<2, false><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, mean, out);
+  else if (v4 && dim <= 512) k_sage_mean<4, false><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, mean, out);
+  else if (v4) k_sage_mean<8, false><<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, mean, out);
+  else k_sage_mean_generic<<<blocks, 256, 0, c->stream>>>(d, ids, rows, count, dim, mean, out);
   EU_LAUNCHED();
   return EU_OK;
+}
+
+
+int eu_sage_mean_aggregate(eu_ctx* c, const int64_t* nbr_ids, int64_t rows, int32_t count, int32_t dim, float* out) {
+  return fanout_aggregate(c, nbr_ids, rows, count, dim, true, out);
+}
+// the scatter_add variant over the same fixed-fanout blocks (aggr='add': GCN / the per-relation sums of configs[4]):
+// get_dense_feature + scatter_add over edge_src = repeat(range(rows), count), fused
+int eu_sage_add_aggregate(eu_ctx* c, const int64_t* nbr_ids, int64_t rows, int32_t count, int32_t dim, float* out) {
+  return fanout_aggregate(c, nbr_ids, rows, count, dim, false, out);
 }
 
 }  // extern "C"

@@ -927,3 +927,69 @@ def test_layerwise_sampling_candidates_distribution_and_adj(weight_func):
         for j in range(n):
             nbrs = set(int(x) for x in f_ids[ptr[b * n + j]:ptr[b * n + j + 1]])
             cases.eq(a2[b, j], np.array([1.0 if int(x) in nbrs else 0.0 for x in nb[b]], np.float32), "sparse_get_adj row")
+
+
+# ------------------------------------------------------------------ a-13: GCN / RGCN / SAGE aggregation blocks
+@pytest.mark.parametrize("D", [64, 128])
+def test_gcn_relation_and_sage_blocks_vs_literal_restatement(D):
+    """euler_b200/convolution.py (GCNConv / RelationConv / SAGEConv message passing over the mp ops) against numpy
+    restatements of gcn_conv.py:32-55, relation_conv.py:53-70, sage_conv.py:33-38 on a SageDataFlow-shaped block (sorted,
+    fixed-fanout edge_src + appended self loops) and on an unsorted edge list; 1e-5 relative (north_star float tolerance)."""
+    import euler_b200  # noqa: F401
+    from euler_b200 import convolution as conv
+    g = graphs.random_graph(seed=5, n=50, T=1)
+    euler_b200.set_graph(graphs.cuda_graph(g))
+    rs = np.random.RandomState(D)
+    n0, n1, fan = 200, 700, 6
+    src = np.repeat(np.arange(n0), fan)
+    dst = rs.randint(0, n1, size=n0 * fan)
+    loops = np.arange(n0)                                  # add_self_loops (neighbor_dataflow.py:98-100)
+    blocks = {"sorted+self-loops": (np.concatenate([src, loops]), np.concatenate([dst, loops])),
+              "unsorted": (rs.randint(0, n0, size=900), rs.randint(0, n1, size=900))}
+    x1 = rs.randn(n1, D).astype(np.float32)
+    R, dim = 5, 32
+    mat = rs.randn(R, dim, D).astype(np.float32) * 0.1
+    for name, (e0, e1) in blocks.items():
+        ei = torch.from_numpy(np.stack([e0, e1])).cuda()
+        X = torch.from_numpy(x1).cuda()
+        # GCN
+        deg0 = np.bincount(e0, minlength=n0).astype(np.float64)
+        deg1 = np.bincount(e1, minlength=n1).astype(np.float64)
+        with np.errstate(divide="ignore"):
+            w = (deg0[e0] ** -0.5) * (deg1[e1] ** -0.5)
+        want = np.zeros((n0, D), np.float64)
+        np.add.at(want, e0, w[:, None] * x1[e1].astype(np.float64))
+        got = conv.gcn_aggregate((None, X), ei, (n0, n1)).cpu().numpy()
+        has = deg0 > 0
+        assert np.allclose(got[has], want[has], rtol=RTOL, atol=1e-5), "gcn block " + name
+        # SAGE mean
+        s = np.zeros((n0, D), np.float64)
+        np.add.at(s, e0, x1[e1].astype(np.float64))
+        want = s / (deg0[:, None] + 1e-7)
+        got = conv.sage_aggregate((None, X), ei, (n0, n1)).cpu().numpy()
+        assert np.allclose(got, want, rtol=RTOL, atol=1e-5), "sage block " + name
+        # Relation (RGCN): per-edge relation matrix, then mean
+        attr = rs.randint(0, R, size=len(e0))
+        msg = np.einsum("eij,ej->ei", mat[attr].astype(np.float64), x1[e1].astype(np.float64))
+        s = np.zeros((n0, dim), np.float64)
+        np.add.at(s, e0, msg)
+        want = s / (deg0[:, None] + 1e-7)
+        got = conv.relation_aggregate((None, X), ei, (n0, n1), torch.from_numpy(attr).cuda(), torch.from_numpy(mat).cuda()).cpu().numpy()
+        assert np.allclose(got, want, rtol=1e-4, atol=1e-4), "relation block " + name
+
+
+def test_fused_add_aggregate_equals_scatter_add_composition():
+    """eu_sage_add_aggregate (aggr='add' over a fixed-fanout block, D = 64 of configs[4]) == get_dense_feature + scatter_add"""
+    import euler_b200
+    from euler_b200 import _lib
+    g = graphs.random_graph(seed=77, n=3000, T=2, avg_deg=5, feat_dim=64)
+    euler_b200.set_graph(graphs.cuda_graph(g))
+    ids = g["ids"][np.random.RandomState(3).randint(0, 3000, size=512 * 10)].astype(np.int64)
+    ids[::9] = -1
+    d_ids = torch.from_numpy(ids).cuda()
+    out = torch.empty((512, 64), dtype=torch.float32, device="cuda")
+    ctx = euler_b200.context()
+    _lib.check(_lib.load().eu_sage_add_aggregate(ctx._h, d_ids.data_ptr(), 512, 10, 64, out.data_ptr()))
+    feat = euler_b200.get_dense_feature(d_ids, [0], [64])[0]
+    want = euler_b200.scatter_add(feat, torch.arange(512, dtype=torch.int32, device="cuda").repeat_interleave(10), 512)
+    cases.eq(out.cpu().numpy(), want.cpu().numpy(), "fused add aggregate")
