@@ -39,7 +39,10 @@ CONFIGS = {
     "c2": dict(nodes=10_000_000, edges=100_000_000, batch=1024, fanout="25,10", dim=128, label="BASELINE configs[1]"),
     # node2vec biased walk (deepwalk / line example path): metric = walker-steps/s
     "c3": dict(nodes=10_000_000, edges=100_000_000, batch=4096, fanout="80", dim=0, label="BASELINE configs[2]"),
+    # heterogeneous graph (3 node types / 5 edge types): per-edge-type SampleNeighbor + RGCN scatter_add aggregation
+    "c5": dict(nodes=50_000_000, edges=400_000_000, batch=8192, fanout="10", dim=64, label="BASELINE configs[4]"),
 }
+C5_ETYPES, C5_NTYPES, C5_SEED = 5, 3, 44
 CPU_GRAPH_MAX_NODES = 10_000_000   # the CPU arms build the reference's unordered_map<NodeID,Node*> graph: bounded so the arm fits the driver's time box
 GRAPH_SEED, FEAT_SEED = 42, 7
 
@@ -1402,6 +1405,146 @@ def run_walk_reference(args):
           "e2e": {"value": v, "unit": "walker-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
+# ----------------------------------------------------------------------------- config c5: per-relation sampling + scatter_add
+def c5_config(args, count, n_gpus):
+    return {"workload": "%s: synthetic heterogeneous R-MAT graph %dM nodes/%dM edges, %d node types / %d edge types, per-edge-type "
+                        "sample_neighbor count=%d batch=%d + dense features (dim %d) summed per relation (scatter_add), %d GPU(s)"
+                        % (args.label, args.nodes // 10**6, args.edges // 10**6, C5_NTYPES, C5_ETYPES, count, args.batch, args.dim, n_gpus),
+            "nodes": args.nodes, "edges": args.edges, "batch": args.batch, "count": count, "feat_dim": args.dim, "edge_types": C5_ETYPES,
+            "rng": args.rng, "l2_policy": "inputs larger than L2 (graph >> 126 MB, fresh random seeds every step)"}
+
+
+def run_c5(args):
+    """A step = for every edge type t: sample_neighbor(seeds, [t], count) and the per-relation feature sum of the sampled
+    neighbors (get_dense_feature + scatter_add over the fixed-fanout block, fused).  metric = sampled edges/s (T * B * count / step)."""
+    import torch
+    import euler_b200 as eb
+    from euler_b200 import _lib
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    lib = _lib.load()
+    T, count, B, D = C5_ETYPES, int(args.fanout), args.batch, args.dim
+    t0 = time.time()
+    graph = eb.Graph.rmat_hetero(args.nodes, args.edges, T, C5_NTYPES, seed=C5_SEED, feat_dim=D, feat_seed=FEAT_SEED, device=local)
+    torch.cuda.synchronize()
+    t_graph = time.time() - t0
+    G = max(1, min(8, -(-args.steps // max(args.lanes, 1))))
+    cs = np.asarray([count], np.int32)
+    P1 = ctypes.c_void_p * 1
+
+    class CL:
+        pass
+    lanes = []
+    for i in range(max(1, min(args.lanes, args.steps // G if args.steps >= G else 1))):
+        ln = CL()
+        ln.stream = torch.cuda.Stream()
+        ln.ctx = eb.Context(graph, args.rng, 555 + i, ln.stream.cuda_stream)
+        ln.seeds_of = [9000 + 100 * i + b for b in range(G)]
+        ln.ctx.set_engines(G, ln.seeds_of)
+        ln.ctx.reserve(G * B * count)
+        ln.d_seeds = torch.empty(G * B, dtype=torch.int64, device="cuda")
+        ln.ids = [torch.empty(G * B * count, dtype=torch.int64, device="cuda") for _ in range(T)]
+        ln.w = [torch.empty(G * B * count, dtype=torch.float32, device="cuda") for _ in range(T)]
+        ln.ty = [torch.empty(G * B * count, dtype=torch.int32, device="cuda") for _ in range(T)]
+        ln.agg = [torch.empty((G * B, D), dtype=torch.float32, device="cuda") for _ in range(T)]
+        lanes.append(ln)
+
+    def raw(ln):
+        rc = 0
+        for t in range(T):
+            et = np.asarray([[t]], np.int32)
+            rc |= lib.eu_sample_fanout_batched(ln.ctx._h, ln.d_seeds.data_ptr(), G, B, et.ctypes.data, 1, cs.ctypes.data, 1, -1,
+                                               P1(ln.ids[t].data_ptr()), P1(ln.w[t].data_ptr()), P1(ln.ty[t].data_ptr()))
+            rc |= lib.eu_sage_add_aggregate(ln.ctx._h, ln.ids[t].data_ptr(), G * B, count, D, ln.agg[t].data_ptr())
+        if rc:
+            raise RuntimeError(lib.eu_last_error().decode())
+    n_sb = max(-(-(args.warmup + args.steps) // G), 8)
+    host_seeds = np.stack([np.random.RandomState(7000 + i).randint(1, args.nodes + 1, size=G * B) for i in range(n_sb)]).astype(np.int64)
+    dev_seeds = torch.from_numpy(host_seeds).cuda()
+    gate = {"passed": None, "skipped": "--no-gate"}
+    if not args.no_gate and args.rng == "minstd":
+        from oracle import pyoracle as po
+        tg = time.time()
+        ex = graph.export(with_feat=False)
+        og = po.OracleGraph(ex["ids"], ex["node_type"], ex["node_w"], T, ex["grp_ptr"], ex["nbr"], ex["cum_w"], ex["grp_cum"])
+        ln = lanes[0]
+        ln.ctx.set_engines(G, ln.seeds_of)
+        with torch.cuda.stream(ln.stream):
+            ln.d_seeds.copy_(dev_seeds[0])
+            raw(ln)
+        ln.stream.synchronize()
+        # the engines run relation after relation: batch b's engine serves type 0, then type 1, ... of batch b
+        for b in range(G):
+            po.seed(ln.seeds_of[b])
+            sd = host_seeds[0][b * B:(b + 1) * B]
+            for t in range(T):
+                o_ids, o_w, o_t = og.op_sample_neighbor(sd, [t], count, -1)
+                sl = slice(b * B * count, (b + 1) * B * count)
+                for nm, got, want in (("ids", ln.ids[t], o_ids), ("weights", ln.w[t], o_w), ("types", ln.ty[t], o_t)):
+                    if not np.array_equal(got[sl].cpu().numpy(), want.reshape(-1)):
+                        raise SystemExit("PARITY GATE FAILED: %s of relation %d, batch %d differ from the oracle" % (nm, t, b))
+                if b == 0:
+                    feat = po.rmat_feat_rows(o_ids.reshape(-1), args.nodes, D, FEAT_SEED)
+                    want = po.scatter_add(feat, np.repeat(np.arange(B, dtype=np.int32), count), B)
+                    if not np.array_equal(ln.agg[t][:B].cpu().numpy(), want):
+                        raise SystemExit("PARITY GATE FAILED: relation %d feature sums differ from the oracle's scatter_add" % t)
+        ln.ctx.set_engines(G, ln.seeds_of)
+        gate = {"passed": True, "batches": G, "relations": T, "seconds": round(time.time() - tg, 2),
+                "what": "per-relation sample_neighbor of %d batches bit-exact vs the oracle on the exported CSR; per-relation feature sums of "
+                        "batch 0 bit-exact vs oracle scatter_add over oracle/rmat_gen.c rows" % G}
+        del og, ex
+    use_graphs = not args.no_graphs
+    for ln in lanes:
+        with torch.cuda.stream(ln.stream):
+            ln.d_seeds.copy_(dev_seeds[0])
+            raw(ln)
+        ln.stream.synchronize()
+        if use_graphs:
+            l0 = lib.eu_launch_count()
+            ln.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ln.graph, stream=ln.stream):
+                raw(ln)
+            ln.launches = lib.eu_launch_count() - l0
+    main = torch.cuda.current_stream()
+
+    def run(n_steps, first):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ev0.record(main)
+        for ln in lanes:
+            ln.stream.wait_event(ev0)
+        for i in range(-(-n_steps // G)):
+            ln = lanes[i % len(lanes)]
+            with torch.cuda.stream(ln.stream):
+                ln.d_seeds.copy_(dev_seeds[(first // G + i) % n_sb], non_blocking=True)
+                ln.graph.replay() if use_graphs else raw(ln)
+        for ln in lanes:
+            main.wait_stream(ln.stream)
+        ev1.record(main)
+        torch.cuda.synchronize()
+        return ev0.elapsed_time(ev1)
+    steps = -(-args.steps // G) * G
+    run(max(args.warmup, G), 0)
+    clocks = Clocks(local)
+    clocks.start()
+    time.sleep(0.3)
+    w0 = time.time()
+    ms = run(steps, args.warmup)
+    w1 = time.time()
+    clk = clocks.stop(w0, w1)
+    edges = T * B * count
+    valid = float(np.mean([(lanes[0].ids[t] != -1).float().mean().item() for t in range(T)]))
+    agg_bytes = T * (B * count * 8 + valid * B * count * 4 * D + B * 4 * D)
+    out = {"metric": "sampled_edges_per_sec", "value": edges * steps / (ms * 1e-3), "unit": "edges/s", "n_gpus": 1, "steps": steps,
+           "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "u64 ids / f32 weights+features (f64 CDF compare)", "data": "synthetic", "config": c5_config(args, count, 1),
+           "arm": {"lanes_in_flight": len(lanes), "steps_per_launch_group": G, "cuda_graphs": use_graphs, "graph_hbm_gb": round(graph.hbm_bytes / 1e9, 1)},
+           "parity_gate": gate, "agg_feat_gbs": agg_bytes * steps / (ms * 1e-3) / 1e9, "valid_edge_fraction": round(valid, 4),
+           "gpu_launches": int(sum(getattr(x, "launches", 0) for x in lanes) / len(lanes) * (steps // G)) if use_graphs else None,
+           "clocks": clk, "graph_build_s": round(t_graph, 2)}
+    emit(out)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the same step on the host cores.  Loads nothing of the
     product: the input graph comes from oracle/rmat_gen.c."""
@@ -1462,6 +1605,10 @@ if __name__ == "__main__":
     a = parse()
     if a.config == "c3":
         run_walk_reference(a) if a.impl == "reference" else run_walk(a)
+    elif a.config == "c5" and a.impl == "ours":
+        run_c5(a)
+    elif a.config == "c5":
+        emit({"impl": "reference", "unavailable": "config c5 is a secondary (extras) line: its CPU arm is not wired; the headline, c2 and c3 have one"})
     elif a.impl == "reference":
         run_reference(a)
     else:

@@ -31,6 +31,7 @@ for s in "$@"; do
     walk_ab) (timeout 300 python bench.py --config c3 --steps 16 --warmup 4 --no-cpu-baseline > $out/walk_l8.json 2> $out/walk_l8.err)
         (timeout 300 python bench.py --config c3 --steps 32 --warmup 4 --no-cpu-baseline --no-gate --lanes 16 > $out/walk_l16.json 2> $out/walk_l16.err)
         (timeout 300 python bench.py --config c3 --steps 16 --warmup 4 --no-cpu-baseline --no-gate --rng philox > $out/walk_philox.json 2> $out/walk_philox.err) ;;
+    c5) (time timeout 600 python bench.py --config c5 --steps 32 --warmup 8 > $out/c5.json 2> $out/c5.err) > $out/c5.time 2>&1 ;;
     *) echo "unknown step $s" ;;
   esac
   echo "== $s done rc=$?" >> $out/steps.log
