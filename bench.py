@@ -539,7 +539,7 @@ def run_ours(args):
     lib.eu_ctx_profile(ln.ctx._h, 0)
     kernels = []
     for line in buf.value.decode().strip().splitlines():
-        nm, rows, n, ms_tot = line.split(",")
+        nm, rows, n, ms_tot = line.rsplit(",", 3)
         kernels.append({"kernel": nm, "rows": int(rows), "launches_per_step": int(n) / (args.breakdown_iters * G),
                         "ms_per_launch": float(ms_tot) / int(n), "ms_per_step": float(ms_tot) / (args.breakdown_iters * G)})
     kernels.sort(key=lambda k: -k["ms_per_step"])
@@ -918,7 +918,7 @@ def run_sharded(args, world, rank, local):
         lib.eu_ctx_profile_read(hctx._h, buf, len(buf))
         lib.eu_ctx_profile(hctx._h, 0)
         for line in buf.value.decode().strip().splitlines():
-            nm, rows_, cnt_, ms_tot = line.split(",")
+            nm, rows_, cnt_, ms_tot = line.rsplit(",", 3)
             prof["%s[rows=%s]" % (nm, rows_)] = round(float(ms_tot) / reps / G, 4)
     all_prof = [None] * world
     dist.all_gather_object(all_prof, prof)
@@ -1297,7 +1297,7 @@ def run_walk(args):
     lib.eu_ctx_profile(ln.ctx._h, 0)
     prof = {}
     for line in buf.value.decode().strip().splitlines():
-        nm, rows_, cnt_, ms_tot = line.split(",")
+        nm, rows_, cnt_, ms_tot = line.rsplit(",", 3)
         prof[nm] = round(float(ms_tot), 4)
     peaks = {}
     try:

@@ -31,6 +31,11 @@ for s in "$@"; do
     walk_ab) (timeout 300 python bench.py --config c3 --steps 16 --warmup 4 --no-cpu-baseline > $out/walk_l8.json 2> $out/walk_l8.err)
         (timeout 300 python bench.py --config c3 --steps 32 --warmup 4 --no-cpu-baseline --no-gate --lanes 16 > $out/walk_l16.json 2> $out/walk_l16.err)
         (timeout 300 python bench.py --config c3 --steps 16 --warmup 4 --no-cpu-baseline --no-gate --rng philox > $out/walk_philox.json 2> $out/walk_philox.err) ;;
+    tune) Q="--steps 40 --warmup 8 --no-cpu-baseline --no-e2e-host --no-gate --lanes 8"
+        for cfg in "3 2 6" "3 3 5" "2 2 5" "4 2 4" "3 2 5" "2 3 6" "2 2 8"; do
+          set -- $cfg
+          (EU_SAGE_CTAS=$1 EU_FEATURE_CTAS=$2 EU_SAMPLE_CTAS=$3 timeout 300 python bench.py $Q > $out/tune_$1_$2_$3.json 2> $out/tune_$1_$2_$3.err)
+        done ;;
     c5) (time timeout 600 python bench.py --config c5 --steps 32 --warmup 8 > $out/c5.json 2> $out/c5.err) > $out/c5.time 2>&1 ;;
     *) echo "unknown step $s" ;;
   esac

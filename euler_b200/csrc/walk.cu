@@ -849,13 +849,13 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
       { EuProfScope ps(c, "k_walk_weights", B);
         k_walk_weights<<<148 * 8, kWalkChunk, 0, s>>>(d, ctype, ptype, p, q, ws, wp); }
       EU_LAUNCHED();
-      { EuProfScope ps(c, "k_walk_prefix(huge rows, 1024-thread CTAs)", B);
+      { EuProfScope ps(c, "k_walk_prefix_cta<1024>", B);
         k_walk_prefix_cta<1024><<<148, 1024, 0, s>>>(d, L, l, ctype, ws, c->d_state, philox, wkey, wp, wp.huge_list, 8, 9, (long long*)out); }
       EU_LAUNCHED();
-      { EuProfScope ps(c, "k_walk_prefix(big rows, 256-thread CTAs)", B);
+      { EuProfScope ps(c, "k_walk_prefix_cta<256>", B);
         k_walk_prefix_cta<256><<<148 * 4, 256, 0, s>>>(d, L, l, ctype, ws, c->d_state, philox, wkey, wp, wp.big_list, 0, 3, (long long*)out); }
       EU_LAUNCHED();
-      { EuProfScope ps(c, "k_walk_prefix(small rows, warps)", B);
+      { EuProfScope ps(c, "k_walk_prefix_warp", B);
         k_walk_prefix_warp<<<148 * 4, 256, 0, s>>>(d, L, l, ctype, ptype, p, q, default_node, ws, c->d_state, philox, wkey, wp, (long long*)out); }
       EU_LAUNCHED();
       k_walk_dead<<<(unsigned)ceil_div(B, tb), tb, 0, s>>>(B, L, l, default_node, ws, c->d_elig, (long long*)out);
