@@ -646,6 +646,30 @@ def run_ours(args):
     emit(out)
 
 
+def nvlink_counters(index):
+    """cumulative NVLink data bytes (tx, rx) of GPU `index` from the driver's own link counters
+    (`nvidia-smi nvlink -gt d`: per link "Data Tx: N KiB" / "Data Rx: N KiB"); None when the tool cannot report them"""
+    try:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+        txt = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(phys)], capture_output=True, text=True, timeout=20).stdout
+        tx = rx = 0
+        seen = False
+        for line in txt.splitlines():
+            line = line.strip()
+            if "Data Tx:" in line or "Data Rx:" in line:
+                val = line.split(":")[-1].strip().split()
+                n = int(val[0]) * {"KiB": 1024, "MiB": 1 << 20, "GiB": 1 << 30, "B": 1}.get(val[1] if len(val) > 1 else "KiB", 1024)
+                if "Data Tx:" in line:
+                    tx += n
+                else:
+                    rx += n
+                seen = True
+        return (tx, rx) if seen else None
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------- sharded arm (N > 1)
 def sharded_gate(args, counts, graph, rank, world, torch, dist):
     """N > 1 parity gate: one seeded batch per rank through the peer-memory exchange (csrc/p2p.cu) vs the SAME sharded
@@ -890,9 +914,11 @@ def run_sharded(args, world, rank, local):
     clocks = Clocks(local)
     clocks.start()
     time.sleep(0.3)
+    nv0 = nvlink_counters(local) if rank == 0 else None
     w0 = time.time()
     ms = run(args.steps, args.warmup, False)
     w1 = time.time()
+    nv1 = nvlink_counters(local) if rank == 0 else None
     clk = clocks.stop(w0, w1)
     run(G * min(len(lanes), 2), 0, True)
     ms_e2e = run(args.steps, args.warmup, True)
@@ -952,14 +978,16 @@ def run_sharded(args, world, rank, local):
     else:
         a2a_bytes += remote * sum(n) * (12 + 4 * D)
     if rank == 0:
-        traffic, traffic_src = None, None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
-            ent = tj.get(args.config, {}).get("nvlink", {}).get(str(world))
-            if ent and args.label != "custom":
-                traffic, traffic_src = ent["nvlink_bytes_per_step_per_rank"], ent.get("source")
-        except Exception:
-            pass
+        traffic, traffic_src, link = None, None, None
+        if nv0 and nv1:
+            # measured on the wire: the driver's NVLink data counters of rank 0's GPU around the timed region (KiB granularity;
+            # the peer exchange is the only NVLink user in that window)
+            tx, rx = nv1[0] - nv0[0], nv1[1] - nv0[1]
+            traffic = int((tx + rx) / args.steps)
+            traffic_src = "nvidia-smi nvlink -gt d on rank 0's GPU, (tx + rx) delta over the timed region / steps"
+            link = {"tx_bytes_per_step": int(tx / args.steps), "rx_bytes_per_step": int(rx / args.steps),
+                    "tx_gbs": round(tx / (ms * 1e-3) / 1e9, 2), "rx_gbs": round(rx / (ms * 1e-3) / 1e9, 2),
+                    "frac_of_770_gbs_per_direction": round(max(tx, rx) / (ms * 1e-3) / 1e9 / 770.0, 4)}
         out = {
             "metric": "sampled_edges_per_sec", "value": edges_step * args.steps / (ms * 1e-3), "unit": "edges/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -982,7 +1010,7 @@ def run_sharded(args, world, rank, local):
                          "achieved": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9, 2), "peak": 770.0, "unit": "GB/s",
                          "frac": round(a2a_bytes / (ms / args.steps * 1e-3) / 1e9 / 770.0, 4), "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "B200_PROFILING.md measured peer copy 770 GB/s per direction",
-                         "algorithmic_bytes_per_step_per_rank": int(a2a_bytes),
+                         "algorithmic_bytes_per_step_per_rank": int(a2a_bytes), "nvlink_measured": link,
                          "note": "achieved = algorithmic exchange bytes per rank per step / whole step time (the exchange overlaps the local "
                                  "kernels of the other lanes and is not timed alone)"},
             "graph_build_s": round(t_graph, 2),
