@@ -166,6 +166,8 @@ int eu_ctx_destroy(eu_ctx* c) {
   cudaFree(c->d_rng); cudaFree(c->d_dedup); cudaFree(c->d_first); cudaFree(c->d_rowof);
   cudaFree(c->d_elig); cudaFree(c->d_state); cudaFree(c->d_emask); cudaFree(c->d_woff); cudaFree(c->d_blkpre); cudaFree(c->d_blkmul); cudaFree(c->d_live); cudaFree(c->d_nlive); cudaFree(c->d_front[0]); cudaFree(c->d_front[1]);
   cudaFree(c->d_misc); cudaFree(c->d_stage); cudaFree(c->d_walkv);
+  for (int i = 0; i < 2; ++i) { if (c->aux[i]) cudaStreamDestroy(c->aux[i]); if (c->ev_join[i]) cudaEventDestroy(c->ev_join[i]); }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->h_pin) cudaFreeHost(c->h_pin);
   delete c;
   return EU_OK;

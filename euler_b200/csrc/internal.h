@@ -126,6 +126,10 @@ struct eu_ctx {
   int64_t misc_bytes = 0;
   float* d_walkv = nullptr;          // node2vec: biased weights of the big rows of one step (walk.cu)
   long long walkv_cap = 0;
+  // node2vec: the three prefix kernels of a step (huge / big / small rows) are independent -> forked onto two auxiliary
+  // streams and joined back (event fork/join: capturable in a CUDA graph)
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   // pinned staging for *_host calls
   void* h_pin = nullptr;
   int64_t pin_bytes = 0;

@@ -264,7 +264,8 @@ static constexpr int kWalkChunk = 256;      // elements per k_walk_weights chunk
 static constexpr int kPrefT = 256;          // threads of a k_walk_prefix CTA
 static constexpr int kPrefE = 4;            // elements per thread and iteration
 static constexpr int kPrefCH = kPrefT * kPrefE;
-static constexpr int kPrefSer = 32;         // elements redone serially after an exception
+static constexpr int kPrefSer = 96;         // elements redone serially after an exception (4 cycles each: far cheaper than an iteration)
+static constexpr int kPrefHead = 768;       // elements of a row summed serially before the first parallel iteration
 static constexpr int kPrefCk = 256;         // checkpoints kept per row
 
 struct WalkPlan {
@@ -450,6 +451,26 @@ __device__ void block_exact_prefix(PrefShared<T>& sh, const float* __restrict__ 
     ++it;
     if (it > n + 16) __trap();   // every iteration consumes at least one element: anything else is a bug, not a wait
     const int32_t n_it = min((int32_t)CH, n - pos);
+    if (pos == 0) {
+      // Head of the row: while S is within a few binades of the addends nearly every element is an exception (ties, binade
+      // steps), so the first kPrefHead elements are summed the plain way by one thread out of shared memory -- 4 cycles per
+      // element, ~1.5 us in all, instead of a dozen exception iterations.
+      const int32_t nh = min(n_it, (int32_t)kPrefHead);
+      for (int32_t k = t; k < nh; k += T) sh.v[k] = V[k];
+      __syncthreads();
+      if (t == 0) {
+        float Sc = S;
+        int32_t k = 0, ans = -1;
+        for (; k < nh; ++k) {
+          Sc = __fadd_rn(Sc, sh.v[k]);
+          if (select && (double)Sc > sh.r) { ans = k; ++k; break; }
+        }
+        sh.S = Sc;
+        sh.pos = k;
+        if (ans >= 0) sh.answer = ans;
+      }
+      continue;
+    }
     const uint32_t sb = __float_as_uint(S);
     const uint32_t eS = (sb >> 23) & 0xffu;
     const uint32_t M_in = eS ? ((sb & 0x7fffffu) | 0x800000u) : 0u;
@@ -839,6 +860,14 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
         c->walkv_cap = want;
       }
       wp.V = c->d_walkv; wp.capV = c->walkv_cap;
+      if (!c->aux[0]) {
+        if ((rc = refuse_growth_in_capture(c, "the node2vec auxiliary streams"))) return rc;
+        for (int i = 0; i < 2; ++i) {
+          EU_CUDA(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+          EU_CUDA(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+        }
+        EU_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+      }
       const int32_t ctype = cet.v[0], ptype = pet.K == 1 ? pet.v[0] : -1;
       { EuProfScope ps(c, "k_walk_deg", B);
         k_walk_deg<<<(unsigned)ceil_div(B, tb), tb, 0, s>>>(d, B, ctype, ws, c->d_elig, wp.deg); }
@@ -849,15 +878,33 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
       { EuProfScope ps(c, "k_walk_weights", B);
         k_walk_weights<<<148 * 8, kWalkChunk, 0, s>>>(d, ctype, ptype, p, q, ws, wp); }
       EU_LAUNCHED();
-      { EuProfScope ps(c, "k_walk_prefix_cta<1024>", B);
-        k_walk_prefix_cta<1024><<<148, 1024, 0, s>>>(d, L, l, ctype, ws, c->d_state, philox, wkey, wp, wp.huge_list, 8, 9, (long long*)out); }
-      EU_LAUNCHED();
-      { EuProfScope ps(c, "k_walk_prefix_cta<256>", B);
-        k_walk_prefix_cta<256><<<148 * 4, 256, 0, s>>>(d, L, l, ctype, ws, c->d_state, philox, wkey, wp, wp.big_list, 0, 3, (long long*)out); }
-      EU_LAUNCHED();
-      { EuProfScope ps(c, "k_walk_prefix_warp", B);
-        k_walk_prefix_warp<<<148 * 4, 256, 0, s>>>(d, L, l, ctype, ptype, p, q, default_node, ws, c->d_state, philox, wkey, wp, (long long*)out); }
-      EU_LAUNCHED();
+      if (c->prof) {   // per-kernel timing: one after the other on the ctx stream
+        { EuProfScope ps(c, "k_walk_prefix_cta<1024>", B);
+          k_walk_prefix_cta<1024><<<148, 1024, 0, s>>>(d, L, l, ctype, ws, c->d_state, philox, wkey, wp, wp.huge_list, 8, 9, (long long*)out); }
+        EU_LAUNCHED();
+        { EuProfScope ps(c, "k_walk_prefix_cta<256>", B);
+          k_walk_prefix_cta<256><<<148 * 4, 256, 0, s>>>(d, L, l, ctype, ws, c->d_state, philox, wkey, wp, wp.big_list, 0, 3, (long long*)out); }
+        EU_LAUNCHED();
+        { EuProfScope ps(c, "k_walk_prefix_warp", B);
+          k_walk_prefix_warp<<<148 * 4, 256, 0, s>>>(d, L, l, ctype, ptype, p, q, default_node, ws, c->d_state, philox, wkey, wp, (long long*)out); }
+        EU_LAUNCHED();
+      } else {
+        // the three are independent (disjoint walkers): fork onto two auxiliary streams, join back -- a step then costs its
+        // longest list, not the sum
+        EU_CUDA(cudaEventRecord(c->ev_fork, s));
+        EU_CUDA(cudaStreamWaitEvent(c->aux[0], c->ev_fork, 0));
+        EU_CUDA(cudaStreamWaitEvent(c->aux[1], c->ev_fork, 0));
+        k_walk_prefix_cta<1024><<<148, 1024, 0, c->aux[0]>>>(d, L, l, ctype, ws, c->d_state, philox, wkey, wp, wp.huge_list, 8, 9, (long long*)out);
+        EU_LAUNCHED();
+        k_walk_prefix_cta<256><<<148 * 4, 256, 0, c->aux[1]>>>(d, L, l, ctype, ws, c->d_state, philox, wkey, wp, wp.big_list, 0, 3, (long long*)out);
+        EU_LAUNCHED();
+        k_walk_prefix_warp<<<148 * 4, 256, 0, s>>>(d, L, l, ctype, ptype, p, q, default_node, ws, c->d_state, philox, wkey, wp, (long long*)out);
+        EU_LAUNCHED();
+        EU_CUDA(cudaEventRecord(c->ev_join[0], c->aux[0]));
+        EU_CUDA(cudaEventRecord(c->ev_join[1], c->aux[1]));
+        EU_CUDA(cudaStreamWaitEvent(s, c->ev_join[0], 0));
+        EU_CUDA(cudaStreamWaitEvent(s, c->ev_join[1], 0));
+      }
       k_walk_dead<<<(unsigned)ceil_div(B, tb), tb, 0, s>>>(B, L, l, default_node, ws, c->d_elig, (long long*)out);
       EU_LAUNCHED();
     } else {
