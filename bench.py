@@ -607,6 +607,15 @@ def run_ours(args):
             "algorithmic_bytes_per_launch": dom["algorithmic_bytes_per_launch"], "kernel_ms": round(dom["ms_per_launch"], 5),
             "valid_edge_fraction_per_hop": [round(v, 4) for v in valid_frac],
             "all_kernels": kernels}
+    # the step as a whole: the kernels of different lanes overlap (each on its SM share), so the sum of their algorithmic bytes over the
+    # timed step is the figure that says how close the PATH is to the HBM roof; the per-kernel lines above are each kernel timed alone
+    step_alg = sum(k["algorithmic_bytes_per_launch"] * k["launches_per_step"] for k in kernels)
+    step_gbs = step_alg / (ms / args.steps * 1e-3) / 1e9
+    roof["step"] = {"algorithmic_bytes_per_step": int(step_alg), "achieved": round(step_gbs, 1), "frac": round(step_gbs / peak, 4),
+                    "how": "sum of every kernel's algorithmic bytes per step / timed ms_per_step (all lanes in flight)"}
+    if any(os.environ.get(k) not in (None, "0") for k in SM_SHARE):
+        roof["note"] += "; per-kernel times are single-lane on the kernel's SM share (%s), not a full-GPU grid" % ", ".join(
+            "%s=%s" % (k, os.environ.get(k)) for k in SM_SHARE)
     # aggregated-feature bytes per step with the measured valid fractions (default slots read no row)
     agg_bytes = 0
     for l in range(Lh):
@@ -778,6 +787,7 @@ def run_sharded(args, world, rank, local):
 
     class SLane:
         pass
+    E2E_LANES = 4
     lanes = []
     for i in range(n_lanes + (1 if tail else 0)):
         ln = SLane()
@@ -805,10 +815,11 @@ def run_sharded(args, world, rank, local):
         ln.ids = [ln.idbuf[offs[l + 1]:offs[l + 2]] for l in range(L)]
         ln.agg = [torch.empty((G * n[l], D), dtype=torch.float32, device="cuda") for l in range(L)]
         ln.x = torch.empty((G * n_self, D), dtype=torch.float32, device="cuda")
-        ln.h_seeds = torch.empty((G, B), dtype=torch.int64).pin_memory()
-        ln.h_ids = [torch.empty(G * x, dtype=torch.int64).pin_memory() for x in n[1:]]
-        ln.h_x = torch.empty((G * n_self, D), dtype=torch.float32).pin_memory()
-        ln.h_agg = [torch.empty((G * n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
+        if i < E2E_LANES or i >= n_lanes:   # pinned host side of the e2e pass: PCIe-bound, 4 lanes (+ the tail) saturate the link
+            ln.h_seeds = torch.empty((G, B), dtype=torch.int64).pin_memory()
+            ln.h_ids = [torch.empty(G * x, dtype=torch.int64).pin_memory() for x in n[1:]]
+            ln.h_x = torch.empty((G * n_self, D), dtype=torch.float32).pin_memory()
+            ln.h_agg = [torch.empty((G * n[l], D), dtype=torch.float32).pin_memory() for l in range(L)]
         G = G_main
         lanes.append(ln)
     tail_lane = lanes.pop() if tail else None
@@ -893,14 +904,15 @@ def run_sharded(args, world, rank, local):
         n_groups = n_steps // G + (1 if rem else 0)     # an untimed (warm-up) remainder is rounded up to a full group
         for ln in all_lanes:
             ln.stream.wait_event(ev0)
+        pool = lanes[:E2E_LANES] if e2e else lanes
         for i in range(n_groups):
-            ln = lanes[i % len(lanes)]
+            ln = pool[i % len(pool)]
             if use_tail and i == n_groups - 1:
                 ln = tail_lane
             sd = (first // G + i) % n_seed_groups
             with torch.cuda.stream(ln.stream):
                 if e2e:
-                    ln.stream.synchronize() if i >= len(lanes) else None
+                    ln.stream.synchronize() if i >= len(pool) else None
                     ln.h_seeds.copy_(torch.from_numpy(host_seeds[sd][:ln.G]))
                     ln.d_seeds.copy_(ln.h_seeds, non_blocking=True)
                     step(ln)
@@ -1244,16 +1256,19 @@ def run_walk(args):
 
     class WLane:
         pass
-    lanes = []
-    for i in range(max(1, args.lanes)):
-        ln = WLane()
-        ln.stream = torch.cuda.Stream()
-        ln.ctx = eb.Context(graph, args.rng, 777 + i, ln.stream.cuda_stream)
-        ln.d_seeds = torch.empty(B, dtype=torch.int64, device="cuda")
-        ln.out = torch.empty((B, L + 1), dtype=torch.int64, device="cuda")
-        ln.h_seeds = torch.empty(B, dtype=torch.int64).pin_memory()
-        ln.h_out = torch.empty((B, L + 1), dtype=torch.int64).pin_memory()
-        lanes.append(ln)
+    def make_lanes(rng, count):
+        made = []
+        for i in range(max(1, count)):
+            ln = WLane()
+            ln.stream = torch.cuda.Stream()
+            ln.ctx = eb.Context(graph, rng, 777 + i, ln.stream.cuda_stream)
+            ln.d_seeds = torch.empty(B, dtype=torch.int64, device="cuda")
+            ln.out = torch.empty((B, L + 1), dtype=torch.int64, device="cuda")
+            ln.h_seeds = torch.empty(B, dtype=torch.int64).pin_memory()
+            ln.h_out = torch.empty((B, L + 1), dtype=torch.int64).pin_memory()
+            made.append(ln)
+        return made
+    lanes = make_lanes(args.rng, args.lanes)
     n_sb = max(args.warmup + args.steps, 8)
     host_seeds = np.stack([np.random.RandomState(3000 + i).randint(1, args.nodes + 1, size=B) for i in range(n_sb)]).astype(np.int64)
     dev_seeds = torch.from_numpy(host_seeds).cuda()
@@ -1263,20 +1278,23 @@ def run_walk(args):
         if rc:
             raise RuntimeError(lib.eu_last_error().decode())
     use_graphs = not args.no_graphs
-    for ln in lanes:
-        with torch.cuda.stream(ln.stream):
-            ln.d_seeds.copy_(dev_seeds[0])
-            raw(ln)
-        ln.stream.synchronize()
-        if use_graphs:
-            l_before = lib.eu_launch_count()
-            ln.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(ln.graph, stream=ln.stream):
+
+    def prime(made):
+        for ln in made:
+            with torch.cuda.stream(ln.stream):
+                ln.d_seeds.copy_(dev_seeds[0])
                 raw(ln)
-            ln.launches = lib.eu_launch_count() - l_before
+            ln.stream.synchronize()
+            if use_graphs:
+                l_before = lib.eu_launch_count()
+                ln.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ln.graph, stream=ln.stream):
+                    raw(ln)
+                ln.launches = lib.eu_launch_count() - l_before
+    prime(lanes)
     main = torch.cuda.current_stream()
 
-    def run(n_steps, first, mode):
+    def run(n_steps, first, mode, lanes=lanes):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         ev0.record(main)
@@ -1352,7 +1370,8 @@ def run_walk(args):
            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "u64 ids / f32 weights (sequential f32 prefix, f64 compare)", "data": "synthetic", "config": walk_config(args, L, 1),
            "arm": {"lanes_in_flight": len(lanes), "cuda_graphs": use_graphs, "graph_hbm_gb": round(graph.hbm_bytes / 1e9, 1),
-                   "mode": "exact (bit-exact with the reference's serial engine stream and sequential f32 prefix)" if args.rng == "minstd" else "philox"},
+                   "mode": "exact (bit-exact with the reference's serial engine stream and sequential f32 prefix)" if args.rng == "minstd"
+                           else "philox throughput mode (rejection-sampled steps, k_walk_fast)"},
            "parity_gate": gate,
            "e2e": {"value": ws * args.steps / (ms_host * 1e-3), "unit": "walker-steps/s", "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 8 * B * (L + 1),
                    "ms_per_step": ms_host / args.steps, "api": "eu_random_walk_host (HOST buffers in and out), one host thread per lane"},
@@ -1366,6 +1385,18 @@ def run_walk(args):
                                 "rows are L2-resident, so this is an algorithmic rate"},
            "kernel_ms_per_batch_single_lane": dict(sorted(prof.items(), key=lambda kv: -kv[1])),
            "graph_build_s": round(t_graph, 2)}
+    if args.rng == "minstd":
+        # the throughput engine beside the exact one ("fast mode ... report both"): EU_RNG_PHILOX takes a node2vec
+        # step by rejection (propose from the stored CDF, accept with bias / max bias): same distribution, O(log deg) per step
+        flanes = make_lanes("philox", max(args.lanes, 16))
+        prime(flanes)
+        fsteps = max(args.steps, 4 * len(flanes))
+        run(len(flanes), 0, "dev", flanes)
+        ms_f = run(fsteps, 0, "dev", flanes)
+        out["fast_mode"] = {"value": ws * fsteps / (ms_f * 1e-3), "unit": "walker-steps/s", "ms_per_step": ms_f / fsteps, "steps": fsteps,
+                            "lanes_in_flight": len(flanes), "rng": "philox",
+                            "what": "k_walk_fast: rejection-sampled node2vec steps (distribution-exact, not stream-exact), one thread per "
+                                    "walker for all %d steps; checked by a chi-square test against the exact transition weights" % L}
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_walk_baseline(args, L, ex)
     emit(out)

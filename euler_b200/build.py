@@ -46,8 +46,10 @@ def build(force=False, verbose=False):
         ok &= p.returncode == 0
     if not ok:
         raise RuntimeError("nvcc failed")
-    cmd = [nvcc, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = SO + ".tmp.%d" % os.getpid()      # link beside the target, then rename: a reader never sees a half-written library
+    cmd = [nvcc, "-shared", "-o", tmp] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     subprocess.check_call(cmd)
+    os.replace(tmp, SO)
     return SO
 
 

@@ -709,6 +709,101 @@ __global__ void __launch_bounds__(256) k_walk_prefix_warp(DevGraph g, int32_t L,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------- fast mode
+// EU_RNG_PHILOX ("throughput mode": same algorithm and distribution, counter-based stream): a node2vec step by REJECTION
+// instead of the O(deg) biased prefix.  The target is P(j) ~ w_j * b_j with b_j in {1/p, 1, 1/q} (BuildWeights,
+// random_walk_op.cc:140-168); propose j ~ w_j by one inverse-CDF search in the row's stored cumulative weights, accept with
+// probability b_j / max(b): O(log deg(cur) + log deg(prev)) per try, expected tries <= max(b) / min(b) (4 at p=0.5, q=2).
+// A walker no longer depends on any other walker, so one thread carries it through every step of the launch; after kFastTries
+// rejections (extreme p/q) the thread evaluates the biased row exactly.  Multi-edges follow the reference's multiset rule: the
+// m-th copy of id v in the child list is "shared" iff the parent's list holds more than m copies of v.
+static constexpr int kFastSteps = 96;
+static constexpr int kFastTries = 96;
+struct FastTypes {
+  int32_t prev;                 // edge type of the step before the first one of this launch (-1 = empty parent list)
+  int32_t v[kFastSteps];
+};
+
+__device__ __forceinline__ double fast_bias(const DevGraph& g, int64_t cb, int64_t j, long long cv, int64_t pb, int64_t pe, long long parent,
+                                            double bp, double bq) {
+  int64_t m = 0;
+  while (j - 1 - m >= cb && (long long)__ldg(g.nbr + j - 1 - m) == cv) ++m;
+  if (pe > pb) {
+    const int64_t lb = lower_bound_ll(g.nbr, pb, pe, cv);
+    if (lb + m < pe && (long long)__ldg(g.nbr + lb + m) == cv) return 1.0;
+  }
+  return cv != parent ? bq : bp;
+}
+
+__global__ void k_walk_fast_done(EuRngState* rng) { rng->calls += 1; }
+
+__global__ void __launch_bounds__(128) k_walk_fast(DevGraph g, int64_t B, int32_t L, int32_t l0, int32_t nl, FastTypes ft, float p, float q,
+                                                   long long default_node, WalkState s, unsigned long long key, const EuRngState* __restrict__ rng,
+                                                   long long* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  key ^= rng->calls * 0x9E3779B97F4A7C15ull;       // a new stream per call (device-side counter: CUDA-graph replays advance too)
+  long long cur = s.cur[i], parent = s.parent[i];
+  int64_t prow = s.parent_row[i];
+  const double bp = 1.0 / (double)p, bq = 1.0 / (double)q;
+  const double bmax = fmax(1.0, fmax(bp, bq));
+  int32_t ptype = ft.prev;
+  for (int32_t k = 0; k < nl; ++k) {
+    const int32_t step = l0 + k, ctype = ft.v[k];
+    const int64_t crow = lookup_row(g, (unsigned long long)cur);
+    int64_t cb = 0, ce = 0, cbase = 0;
+    if (crow >= 0 && ctype >= 0 && ctype < g.T) {
+      cbase = g.grp_ptr[crow * g.T];
+      cb = g.grp_ptr[crow * g.T + ctype];
+      ce = g.grp_ptr[crow * g.T + ctype + 1];
+    }
+    long long next = default_node;
+    if (ce > cb) {
+      int64_t pb = 0, pe = 0;
+      if (prow >= 0 && ptype >= 0 && ptype < g.T) { pb = g.grp_ptr[prow * g.T + ptype]; pe = g.grp_ptr[prow * g.T + ptype + 1]; }
+      const double lo = cb == cbase ? 0.0 : (double)__ldg(g.cum_w + cb - 1);
+      const double hi = (double)__ldg(g.cum_w + ce - 1);
+      int64_t pick = ce - 1;                       // RandomSelect's fall-through (a row of zero weights): the last entry
+      if (hi > lo) {
+        bool done = false;
+        for (int a = 0; a < kFastTries && !done; ++a) {
+          double u, u2;
+          philox_uniform2((unsigned long long)i, (uint32_t)step, 0x66617374u + (uint32_t)a, key, u, u2);
+          const double r = lo + u * (hi - lo);
+          int64_t x = cb, y = ce - 1;              // first j with cum_w[j] > r, clamped to the last entry
+          while (x < y) { const int64_t mid = x + ((y - x) >> 1); if ((double)__ldg(g.cum_w + mid) > r) y = mid; else x = mid + 1; }
+          const long long cv = (long long)__ldg(g.nbr + x);
+          if (u2 * bmax < fast_bias(g, cb, x, cv, pb, pe, parent, bp, bq)) { pick = x; done = true; }
+        }
+        if (!done) {
+          // exact evaluation of the biased row (two passes, f64 accumulation)
+          double tot = 0.0;
+          for (int64_t j = cb; j < ce; ++j) {
+            const double w = (double)__ldg(g.cum_w + j) - (j == cbase ? 0.0 : (double)__ldg(g.cum_w + j - 1));
+            tot += w * fast_bias(g, cb, j, (long long)__ldg(g.nbr + j), pb, pe, parent, bp, bq);
+          }
+          double u, u2;
+          philox_uniform2((unsigned long long)i, (uint32_t)step, 0x66617374u + (uint32_t)kFastTries, key, u, u2);
+          const double r = u * tot;
+          double run = 0.0;
+          for (int64_t j = cb; j < ce; ++j) {
+            const double w = (double)__ldg(g.cum_w + j) - (j == cbase ? 0.0 : (double)__ldg(g.cum_w + j - 1));
+            run += w * fast_bias(g, cb, j, (long long)__ldg(g.nbr + j), pb, pe, parent, bp, bq);
+            if (run > r) { pick = j; break; }
+          }
+        }
+      }
+      next = (long long)__ldg(g.nbr + pick);
+    }
+    out[i * (L + 1) + step + 1] = next;
+    parent = cur;
+    prow = crow;                                   // dead walkers keep the bookkeeping of the live ones (k_walk_dead)
+    cur = next;
+    ptype = ctype;
+  }
+  s.cur[i] = cur; s.parent[i] = parent; s.parent_row[i] = prow;
+}
+
 // dead walkers: default_node forever (:232-241); parent bookkeeping as for the live ones
 __global__ void k_walk_dead(int64_t B, int32_t L, int32_t step, long long default_node, WalkState s, const uint8_t* __restrict__ live,
                             long long* __restrict__ out) {
@@ -844,6 +939,21 @@ extern "C" int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const 
   pet.K = 0;
   const bool philox = c->rng == EU_RNG_PHILOX;
   const unsigned long long wkey = c->seed ^ 0x6E32766563ull;
+  if (philox && K == 1 && d.adj_sorted && !getenv("EU_WALK_FAST_OFF")) {
+    // throughput mode: rejection steps, every walker independent, kFastSteps steps per launch
+    for (int l0 = 0; l0 < L; l0 += kFastSteps) {
+      FastTypes ft{};
+      ft.prev = l0 == 0 ? -1 : etypes[l0 - 1];
+      const int nl = std::min(kFastSteps, L - l0);
+      for (int k = 0; k < nl; ++k) ft.v[k] = etypes[l0 + k];
+      EuProfScope ps(c, "k_walk_fast", B);
+      k_walk_fast<<<(unsigned)ceil_div(B, 128), 128, 0, s>>>(d, B, L, l0, nl, ft, p, q, default_node, ws, wkey, c->d_rng, (long long*)out);
+      EU_LAUNCHED();
+    }
+    k_walk_fast_done<<<1, 1, 0, s>>>(c->d_rng);
+    EU_LAUNCHED();
+    return EU_OK;
+  }
   for (int l = 0; l < L; ++l) {
     ETypes2 cet{};
     cet.K = K;

@@ -395,6 +395,96 @@ def test_philox_mode_semantics_and_distribution():
     assert chi2 < 2.0 * len(exp) + 100, chi2
 
 
+def _node2vec_weights(cids, cw, pids, parent_id, p, q):
+    """literal restatement of BuildWeights (tf_euler/kernels/random_walk_op.cc:140-168): two-pointer merge of the child list
+    against the parent's list, f64"""
+    out = np.array(cw, np.float64)
+    j = k = 0
+    while j < len(cids) and k < len(pids):
+        if cids[j] < pids[k]:
+            out[j] /= (q if cids[j] != parent_id else p)
+            j += 1
+        elif cids[j] == pids[k]:
+            j += 1
+            k += 1
+        else:
+            k += 1
+    while j < len(cids):
+        out[j] /= (q if cids[j] != parent_id else p)
+        j += 1
+    return out
+
+
+def test_philox_node2vec_fast_mode_distribution():
+    """EU_RNG_PHILOX takes node2vec steps by rejection (k_walk_fast): every step is a real edge, dead walkers go to the
+    default node, calls differ, and the transition frequencies match the exact biased weights (chi-square), multi-edges
+    and the walker's own parent included."""
+    import euler_b200
+    g = graphs.random_graph(seed=83, n=60, T=1, avg_deg=14, empty_frac=0.05)
+    gr = graphs.cuda_graph(g)
+    euler_b200.set_graph(gr, rng="philox", seed=3)
+    ids, ptr, nbr, w = g["ids"].astype(np.int64), g["grp_ptr"], g["nbr"].astype(np.int64), g["w"].astype(np.float64)
+    row = {int(v): r for r, v in enumerate(ids)}
+    p, q = 0.5, 2.0
+    deg = np.diff(ptr)
+    a = int(ids[int(np.argmax(deg))])
+    N = 400_000
+    wk = euler_b200.random_walk(np.full(N, a, np.int64), [[0], [0]], p, q, -1).cpu().numpy()
+    wk2 = euler_b200.random_walk(np.full(N, a, np.int64), [[0], [0]], p, q, -1).cpu().numpy()
+    assert not np.array_equal(wk, wk2)
+    assert (wk[:, 0] == a).all()
+
+    def chi2(obs_ids, cand, weights):
+        exp = {}
+        for v, x in zip(cand.tolist(), weights.tolist()):
+            exp[v] = exp.get(v, 0.0) + x
+        tot = sum(exp.values())
+        uniq, cnt = np.unique(obs_ids, return_counts=True)
+        assert set(uniq.tolist()) <= {v for v, x in exp.items() if x > 0}
+        got = dict(zip(uniq.tolist(), cnt.tolist()))
+        n = obs_ids.size
+        stat = sum((got.get(v, 0) - n * x / tot) ** 2 / (n * x / tot) for v, x in exp.items() if x > 0)
+        dof = sum(1 for x in exp.values() if x > 0) - 1
+        return stat, dof
+    ra = row[a]
+    ca, wa = nbr[ptr[ra]:ptr[ra + 1]], w[ptr[ra]:ptr[ra + 1]]
+    st, dof = chi2(wk[:, 1], ca, _node2vec_weights(ca, wa, [], a, p, q))     # step 0: empty parent list, parent = the start node
+    assert st < dof + 6 * np.sqrt(2 * dof) + 10, (st, dof)
+    checked = 0
+    for b in np.unique(wk[:, 1]):
+        sel = wk[wk[:, 1] == b]
+        rb = row[int(b)]
+        cb, wb = nbr[ptr[rb]:ptr[rb + 1]], w[ptr[rb]:ptr[rb + 1]]
+        if len(cb) == 0:
+            assert (sel[:, 2] == -1).all()
+            continue
+        if len(sel) < 20000:
+            continue
+        st, dof = chi2(sel[:, 2], cb, _node2vec_weights(cb, wb, ca, a, p, q))
+        assert st < dof + 6 * np.sqrt(2 * dof) + 10, (int(b), st, dof)
+        checked += 1
+    assert checked >= 3
+    # long walks (two launches of the step loop), unknown / dead seeds
+    seeds = np.concatenate([ids[:50], [10 ** 12, 0]]).astype(np.int64)
+    L = 130
+    lw = euler_b200.random_walk(seeds, [[0]] * L, 0.25, 4.0, -1).cpu().numpy()
+    assert (lw[-2:, 1:] == -1).all()
+    edges = set()
+    for r in range(len(ids)):
+        for v in nbr[ptr[r]:ptr[r + 1]]:
+            edges.add((int(ids[r]), int(v)))
+    for i in range(50):
+        for t in range(L):
+            u, v = int(lw[i, t]), int(lw[i, t + 1])
+            if u == -1:
+                assert v == -1
+            elif v == -1:
+                assert deg[row[u]] == 0
+            else:
+                assert (u, v) in edges
+
+
+
 # ------------------------------------------------------------------ large-size properties
 def test_rmat_large_properties():
     """RMAT 2M nodes / 20M edges generated on the device: structure invariants, and at BASELINE's
