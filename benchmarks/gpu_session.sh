@@ -16,9 +16,11 @@ for s in "$@"; do
     ncu_walk) (timeout 900 ncu --set full --import-source on -k regex:k_walk_prefix --launch-skip 30 -c 2 -f -o $out/walk_prefix python bench.py --config c3 --steps 1 --warmup 1 --no-cpu-baseline --no-gate --no-graphs --lanes 1 > $out/ncu_walk.json 2> $out/ncu_walk.err; ncu -i $out/walk_prefix.ncu-rep --page source --csv > $out/walk_prefix_source.csv 2>/dev/null; ncu -i $out/walk_prefix.ncu-rep --page raw --csv > $out/walk_prefix_raw.csv 2>/dev/null) ;;
     launches_c4) (timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/launches_c4.csv python bench.py --steps 8 --warmup 4 --no-cpu-baseline --no-e2e-host --no-gate > $out/launches_c4.json 2> $out/launches_c4.err) ;;
     ncu_c4) (timeout 1200 ncu --set full --import-source on --clock-control none -k regex:"k_sage_mean|k_feature|k_sample|k_prepare" --launch-skip 18 -c 9 -f -o $out/c4_top python bench.py --steps 3 --warmup 3 --lanes 1 --no-graphs --no-cpu-baseline --no-e2e-host --no-gate > $out/ncu_c4.json 2> $out/ncu_c4.err; ncu -i $out/c4_top.ncu-rep --page raw --csv > $out/c4_top_raw.csv 2>/dev/null) ;;
-    sharded2) (time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/run_sharded_gpu.py > $out/sharded2.txt 2>&1) > $out/sharded2.time 2>&1 ;;
-    bench_n2) (time timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 2 --steps 20 --warmup 5 > $out/bench_n2.json 2> $out/bench_n2.err) > $out/bench_n2.time 2>&1 ;;
-    bench_n2_sharded) (time timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29545 bench.py --gpus 2 --steps 20 --warmup 5 --features sharded > $out/bench_n2_sharded.json 2> $out/bench_n2_sharded.err) > $out/bench_n2_sharded.time 2>&1 ;;
+    sharded2) (time EU_SYM_TIMEOUT_S=10 timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/run_sharded_gpu.py > $out/sharded2.txt 2>&1) > $out/sharded2.time 2>&1 ;;
+    bench_n2) (time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29544 bench.py --gpus 2 --steps 20 --warmup 5 > $out/bench_n2.json 2> $out/bench_n2.err) > $out/bench_n2.time 2>&1 ;;
+    bench_n2_sharded) (time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29545 bench.py --gpus 2 --steps 20 --warmup 5 --features sharded > $out/bench_n2_sharded.json 2> $out/bench_n2_sharded.err) > $out/bench_n2_sharded.time 2>&1 ;;
+    bench_g*) N=${s#bench_g}; (time timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29546 bench.py --gpus $N --steps 20 --warmup 5 > $out/bench_g$N.json 2> $out/bench_g$N.err) > $out/bench_g$N.time 2>&1 ;;
+    ref_g*) N=${s#ref_g}; (time timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29547 bench.py --impl reference --gpus $N --steps 20 --warmup 5 > $out/ref_g$N.json 2> $out/ref_g$N.err) > $out/ref_g$N.time 2>&1 ;;
     ab) Q="--steps 40 --warmup 8 --no-cpu-baseline --no-e2e-host --no-gate"
         run() { tag2=$1; shift; (env "$@" timeout 300 python bench.py $Q $EXTRA > $out/ab_$tag2.json 2> $out/ab_$tag2.err); }
         EXTRA="" run c4_default X=1

@@ -219,7 +219,10 @@ int eu_sample_node(eu_ctx* c, int32_t count, const int32_t* types, int32_t n_typ
 int eu_sample_node_host(eu_ctx* c, int32_t count, const int32_t* types, int32_t n_types,
                         int64_t* out);
 /* tf_euler.random_walk -- TF op RandomWalk (tf_euler/ops/walk_ops.cc:77-107, kernel
- * tf_euler/kernels/random_walk_op.cc:83-289).  etypes i32[L,K] (host); out i64[B,L+1]. */
+ * tf_euler/kernels/random_walk_op.cc:83-289).  etypes i32[L,K] (host); out i64[B,L+1].
+ * EU_RNG_MINSTD: the reference's walks bit for bit (serial engine stream, sequential f32 prefix of the biased weights).
+ * EU_RNG_PHILOX with one edge type per step on sorted adjacency: node2vec steps by rejection sampling (propose from the
+ * stored CDF, accept with bias / max bias) -- the same transition distribution at O(log deg) per step. */
 int eu_random_walk(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes, int32_t K,
                    int32_t L, float p, float q, int64_t default_node, int64_t* out);
 int eu_random_walk_host(eu_ctx* c, const int64_t* nodes, int64_t B, const int32_t* etypes,
