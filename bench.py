@@ -1042,6 +1042,44 @@ def run_sharded(args, world, rank, local):
         }
         if use_graphs:
             out["arm"]["launch"] = "one CUDA graph replay per launch group; gpu_launches counts this library's kernels inside the replays"
+        if peer and replicated:
+            # With the feature table replicated the exchange is ~2 % of a rank's bytes: a rank's step is bounded by the same local
+            # HBM-bound kernels as at N=1.  Headline roofline = that kernel; the link figures move to roofline["nvlink"].
+            try:
+                vf = [float((lanes[0].ids[l] != -1).float().mean().item()) for l in range(L)]
+            except Exception:
+                vf = [1.0] * L
+            peaks = {}
+            try:
+                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            peak = float(peaks.get("hbm_gbs", 6650.0))
+            hbm_step = 0.0
+            for l in range(L):
+                c_ = counts[l]
+                hbm_step += n[l] * c_ * 8 + vf[l] * n[l] * c_ * 4 * D + n[l] * 4 * D                      # k_sage_mean
+                hbm_step += n[l] * 8 + (1.0 if l == 0 else vf[l - 1]) * n[l] * 4 * D + n[l] * 4 * D        # k_feature
+                hbm_step += n[l] * 40 + vf[l] * n[l] * c_ * 48 + (1 - vf[l]) * n[l] * c_ * 16 + n[l] * 52  # k_sample + k_prepare (owner side)
+            link_roof = out["roofline"]
+            rows_dom = G * n[L - 1]
+            dom_ms = prof.get("k_sage_mean[rows=%d]" % rows_dom)
+            roof = {"bound": "hbm", "peak": peak, "unit": "GB/s", "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650 (B200_PROFILING.md)",
+                    "valid_edge_fraction_per_hop": [round(v, 4) for v in vf]}
+            if dom_ms:
+                dom_bytes = rows_dom * counts[L - 1] * 8 + vf[L - 1] * rows_dom * counts[L - 1] * 4 * D + rows_dom * 4 * D
+                ach = dom_bytes / (dom_ms * G * 1e-3) / 1e9
+                roof.update({"kernel": "k_sage_mean over %d rows (largest share of a rank's step; timed alone on its SM share, max over ranks)" % rows_dom,
+                             "achieved": round(ach, 1), "frac": round(ach / peak, 4), "algorithmic_bytes_per_launch": int(dom_bytes),
+                             "kernel_ms": round(dom_ms * G, 5)})
+            step_gbs = hbm_step / (ms / args.steps * 1e-3) / 1e9
+            roof["step"] = {"algorithmic_bytes_per_step_per_rank": int(hbm_step + a2a_bytes), "achieved": round(step_gbs, 1),
+                            "frac": round(step_gbs / peak, 4),
+                            "how": "a rank's local algorithmic HBM bytes per step / timed ms_per_step (all lanes in flight, max over ranks)"}
+            roof["nvlink"] = link_roof
+            roof["traffic_nvlink_bytes_per_step"] = traffic
+            out["roofline"] = roof
         emit(out)
     if peer:
         for ln in all_lanes:

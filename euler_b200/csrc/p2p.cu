@@ -140,15 +140,17 @@ __global__ void __launch_bounds__(256) k_sym_reply_sample(char* const* __restric
   if (threadIdx.x == 0) s_err = ld_volatile_i32(&mine->error);
   __syncthreads();
   if (s_err) return;   // poisoned exchange: no replies, no flags
-  const int64_t slots = (int64_t)nb * N * rows_b * count;
-  for (int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; tid < slots; tid += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t row = tid / count;            // row (g, p) of the owner's compact input
-    const int32_t j = (int32_t)(tid - row * count);
-    const int64_t cap_b = (int64_t)N * rows_b;
-    const int g = (int)(row / cap_b);
-    const int32_t p = (int32_t)(row - (int64_t)g * cap_b);
+  // per batch g only the bo[N] rows the owner really received (its input is compact; the arrays are strided for the worst case)
+  const int64_t cap_b = (int64_t)N * rows_b;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (int g = 0; g < nb; ++g) {
     const int32_t* bo = boff + g * (N + 1);
-    if (p < bo[N]) {
+    const uint32_t live = (uint32_t)bo[N] * (uint32_t)count;       // < 2^31: rows and count are bounded by the region's capacity
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < live; t += stride) {
+      const int32_t p = (int32_t)(t / (uint32_t)count);
+      const int32_t j = (int32_t)(t - (uint32_t)p * (uint32_t)count);
+      const int64_t row = (int64_t)g * cap_b + p;
+      const int64_t tid = row * count + j;
       const int s = src_of(bo, N, p);
       const int64_t dst = (int64_t)src[(int64_t)s * lay.cap + seg_lo[s * (nb + 1) + g] + (p - bo[s])] * count + j;   // requester's flat slot [g][pos][j]
       const long long id = r_ids[tid];

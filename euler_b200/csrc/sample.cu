@@ -63,18 +63,19 @@ __device__ __forceinline__ void dedup_insert_one(HashSlot* tab, unsigned long lo
   }
 }
 
+// grid (blocks per batch, nb): a block past the batch's real row count (sharded owner inputs are sized for the worst case)
+// leaves at once
 __global__ void k_dedup_insert(HashSlot* tabs, Geom gm, const unsigned long long* __restrict__ seeds) {
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= gm.nb * gm.rows_b) return;
-  const int b = (int)(i / gm.rows_b);
-  const int64_t li = i - b * gm.rows_b;
-  if (gm.rows_act && li >= gm.rows_act[b]) return;
-  const unsigned long long id = seeds[i];
+  const int b = blockIdx.y;
+  const int64_t li = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t rows_here = gm.rows_act ? (int64_t)gm.rows_act[b] : gm.rows_b;
+  if (li >= rows_here) return;
+  const unsigned long long id = seeds[b * gm.rows_b + li];
   // Warp-aggregate: frontiers are full of runs of equal ids (a default row is `count` zeros, hubs repeat)
-  // and equal ids hammer one slot.  The lowest lane of each (batch, id) group carries the group's minimum
+  // and equal ids hammer one slot.  The lowest lane of each id group carries the group's minimum
   // index, so only it touches the table.
   const unsigned act = __activemask();
-  const unsigned peers = __match_any_sync(act, id) & __match_any_sync(act, b);
+  const unsigned peers = __match_any_sync(act, id);
   if ((threadIdx.x & 31) != __ffs(peers) - 1) return;
   dedup_insert_one(tabs + (int64_t)b * (gm.cap_b + 1), (unsigned long long)gm.cap_b - 1, id, li);
 }
@@ -160,6 +161,10 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSl
   bool e = false;      // eligible FIRST occurrence: takes a slot of the serial draw order
   bool own = false;    // this row samples (its id is eligible, whether or not it is the first occurrence)
   const int64_t rows_here = gm.rows_act ? (int64_t)gm.rows_act[b] : gm.rows_b;
+  // blocks past the batch's real rows (worst-case-sized sharded owner inputs) neither scan nor take a ticket: the launch
+  // costs its live rows, not its capacity.  Block 0 always stays (it advances the engine of an empty batch).
+  const uint32_t nblk_act = (uint32_t)max((int64_t)1, (rows_here + kPrepBlock - 1) / kPrepBlock);
+  if (blockIdx.x >= nblk_act) return;
   if (li < rows_here) {
     const int64_t w = b * gm.rows_b + li;
     const unsigned long long id = seeds[w];
@@ -210,7 +215,7 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSl
     for (int k = 0; k < kPrepBlock / 32; ++k) tot += s_w[k];
     bp[blockIdx.x] = tot;
     __threadfence();
-    s_last = atomicAdd(&rng->blocks_done, 1u) == gridDim.x - 1;
+    s_last = atomicAdd(&rng->blocks_done, 1u) == nblk_act - 1;
   }
   __syncthreads();
   if (!s_last) return;
@@ -218,9 +223,9 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSl
   __threadfence();
   __shared__ uint32_t s_scan[kPrepBlock];
   uint32_t carry = 0;
-  for (uint32_t base = 0; base < gridDim.x; base += kPrepBlock) {
+  for (uint32_t base = 0; base < nblk_act; base += kPrepBlock) {
     const uint32_t k = base + threadIdx.x;
-    const uint32_t v = k < gridDim.x ? __ldcg(bp + k) : 0u;  // written by other blocks: read at L2
+    const uint32_t v = k < nblk_act ? __ldcg(bp + k) : 0u;  // written by other blocks: read at L2
     s_scan[threadIdx.x] = v;
     __syncthreads();
     for (int off = 1; off < kPrepBlock; off <<= 1) {
@@ -229,7 +234,7 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSl
       s_scan[threadIdx.x] += t;
       __syncthreads();
     }
-    if (k < gridDim.x) {
+    if (k < nblk_act) {
       uint32_t pre = carry + s_scan[threadIdx.x] - v;   // eligible rows in earlier blocks of the batch
       bp[k] = pre;
       uint32_t fp = 1, fb = F;
@@ -748,7 +753,7 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
   if (raw && (pre_inserted || insert_next)) { set_error("hop: raw mode does not chain"); return EU_ERR_INVALID; }
   if (!pre_inserted && !raw) {
     EuProfScope ps(c, "k_dedup_insert", rows);
-    k_dedup_insert<<<(unsigned)ceil_div(rows, tb), tb, 0, s>>>(tabs, gm, seeds);
+    k_dedup_insert<<<dim3((unsigned)ceil_div(gm.rows_b, tb), (unsigned)nb), tb, 0, s>>>(tabs, gm, seeds);
     EU_LAUNCHED();
   }
   const unsigned long long upr = (unsigned long long)count * (a.mode == 0 ? 1 : 2);
