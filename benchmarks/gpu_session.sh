@@ -21,6 +21,15 @@ for s in "$@"; do
     bench_n2_sharded) (time timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29545 bench.py --gpus 2 --steps 20 --warmup 5 --features sharded > $out/bench_n2_sharded.json 2> $out/bench_n2_sharded.err) > $out/bench_n2_sharded.time 2>&1 ;;
     bench_g*) N=${s#bench_g}; (time timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29546 bench.py --gpus $N --steps 20 --warmup 5 > $out/bench_g$N.json 2> $out/bench_g$N.err) > $out/bench_g$N.time 2>&1 ;;
     ref_g*) N=${s#ref_g}; (time timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29547 bench.py --impl reference --gpus $N --steps 20 --warmup 5 > $out/ref_g$N.json 2> $out/ref_g$N.err) > $out/ref_g$N.time 2>&1 ;;
+    lanes_g*) N=${s#lanes_g}
+        for LN in 10 20; do
+          (timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29548 bench.py --gpus $N --steps 20 --warmup 5 --lanes $LN --no-gate > $out/lanes_g${N}_$LN.json 2> $out/lanes_g${N}_$LN.err)
+        done ;;
+    lanes_n1) for LN in 10 20; do
+          (timeout 300 python bench.py --steps 20 --warmup 5 --lanes $LN --no-cpu-baseline --no-e2e-host --no-gate > $out/lanes_n1_$LN.json 2> $out/lanes_n1_$LN.err)
+        done ;;
+    sharded1) (EU_BENCH_FORCE_SHARDED=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29549 bench.py --gpus 1 --steps 20 --warmup 5 --no-gate > $out/sharded1.json 2> $out/sharded1.err) ;;
+    launches_sharded1) (EU_BENCH_FORCE_SHARDED=1 MASTER_ADDR=127.0.0.1 MASTER_PORT=29550 RANK=0 WORLD_SIZE=1 LOCAL_RANK=0 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --clock-control none --launch-skip 150 -c 260 --csv --log-file $out/launches_sharded1.csv python bench.py --gpus 1 --steps 6 --warmup 3 --lanes 1 --no-graphs --no-gate > $out/launches_sharded1.json 2> $out/launches_sharded1.err) ;;
     ab) Q="--steps 40 --warmup 8 --no-cpu-baseline --no-e2e-host --no-gate"
         run() { tag2=$1; shift; (env "$@" timeout 300 python bench.py $Q $EXTRA > $out/ab_$tag2.json 2> $out/ab_$tag2.err); }
         EXTRA="" run c4_default X=1
