@@ -157,6 +157,27 @@ __device__ __forceinline__ double minstd_uniform(uint32_t& x) {
   return ret;
 }
 
+// ---------------------------------------------------------------------------------- per-call seed dedup table
+// tab[h] = {id+1, min index}.  key 0 = free.
+__device__ __forceinline__ void dedup_insert_one(HashSlot* tab, unsigned long long mask, unsigned long long id,
+                                                 int64_t i) {
+  const unsigned long long tag = id + 1;
+  if (tag == 0ull) {  // id == 2^64-1 (e.g. default_node -1 fed back as a seed): dedicated slot [mask+1]
+    atomicMin(&tab[mask + 1].row, (unsigned long long)i);
+    return;
+  }
+  unsigned long long h = mix64(id) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS(&tab[h].key, 0ull, tag);
+    if (prev == 0ull || prev == tag) {
+      atomicMin(&tab[h].row, (unsigned long long)i);
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+
 // ---------------------------------------------------------------------------------- philox4x32-10
 __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;

@@ -103,25 +103,26 @@ __global__ void __launch_bounds__(256) k_sym_wait_in(char* base, char* const* pb
 
 // ---- owner: the sampleNB input of batch g = the requests of source 0..N-1 for that batch, back to back (compact: the
 // kernels of hop() learn the real row count of every batch from act[g]; nothing is zero-padded)  ->  pad[g][0 .. act[g])
-__device__ __forceinline__ int src_of(const int32_t* __restrict__ bo /* [N+1] */, int N, int32_t p) {
-  int s = 0;
-  while (s + 1 < N && p >= bo[s + 1]) ++s;
-  return s;
-}
-
 __global__ void __launch_bounds__(256) k_sym_gather_pad(const char* base, SymLayout lay, int N, int nb, int64_t rows_b,
                                                         const int32_t* __restrict__ seg_lo, const int32_t* __restrict__ boff,
-                                                        unsigned long long* __restrict__ pad) {
+                                                        unsigned long long* __restrict__ pad, HashSlot* tabs, int64_t tab_cap) {
+  // per batch g only the bo[N] requests that really arrived; each is also entered into the hop's dedup table (exact-RNG
+  // mode: tabs != null), so the owner's sampleNB needs no insert pass of its own
   const unsigned long long* ids = reinterpret_cast<const unsigned long long*>(base + lay.off_inbox_ids);
   const int64_t cap_b = (int64_t)N * rows_b;
-  const int64_t total = (int64_t)nb * cap_b;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i / cap_b);
-    const int32_t p = (int32_t)(i - (int64_t)g * cap_b);
+  const int32_t stride = (int32_t)(gridDim.x * blockDim.x);
+  for (int g = 0; g < nb; ++g) {
     const int32_t* bo = boff + g * (N + 1);
-    if (p >= bo[N]) continue;
-    const int s = src_of(bo, N, p);
-    pad[i] = ids[(int64_t)s * lay.cap + seg_lo[s * (nb + 1) + g] + (p - bo[s])];
+    const int32_t live = bo[N];
+    for (int32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < live; p += stride) {
+      const int s = src_of(bo, N, p);
+      const unsigned long long id = ids[(int64_t)s * lay.cap + seg_lo[s * (nb + 1) + g] + (p - bo[s])];
+      pad[(int64_t)g * cap_b + p] = id;
+      if (tabs) {
+        const unsigned peers = __match_any_sync(__activemask(), id);       // runs of equal ids: the lowest lane carries the minimum index
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) dedup_insert_one(tabs + (int64_t)g * (tab_cap + 1), (unsigned long long)tab_cap - 1, id, p);
+      }
+    }
   }
 }
 
@@ -597,10 +598,37 @@ int eu_sym_sample_hop_batched(eu_sym* s, const int64_t* seeds, int32_t nb, int64
   if (rc) return rc;
   { EuProfScope ps(c, "k_sym_wait_in", total); k_sym_wait_in<<<1, 256, 0, st>>>(s->base, s->d_peers, L, N, nb, rows, (int)total, s->d_seglo, s->d_boff, s->d_act); }
   EU_LAUNCHED();
-  { EuProfScope ps(c, "k_sym_gather_pad", prow); k_sym_gather_pad<<<sym_grid(prow), 256, 0, st>>>(s->base, L, N, nb, rows, s->d_seglo, s->d_boff, s->d_pad); }
+  // exact-RNG mode: the gather also enters the requests into the hop's dedup table (set 0; hop() wipes it), so the scratch is
+  // reserved here, before the table is touched
+  const bool will_sample = count > 0 && rows > 0;
+  HashSlot* tabs = nullptr;
+  int64_t tab_cap = 0;
+  if (will_sample && c->rng == EU_RNG_MINSTD) {
+    rc = ctx_reserve(c, hop_scratch_rows(nb, (int64_t)N * rows), hop_table_slots(nb, (int64_t)N * rows));
+    if (rc) return rc;
+    tabs = c->d_dedup;
+    tab_cap = hop_table_cap((int64_t)N * rows);
+  }
+  { EuProfScope ps(c, "k_sym_gather_pad", prow); k_sym_gather_pad<<<sym_grid(total), 256, 0, st>>>(s->base, L, N, nb, rows, s->d_seglo, s->d_boff, s->d_pad, tabs, tab_cap); }
   EU_LAUNCHED();
-  if (count > 0 && rows > 0) {
-    rc = hop(c, s->d_pad, (int64_t)N * rows, etypes, K, count, /*default_node=*/0, nullptr, s->d_rids, s->d_rw, s->d_rt, 0, false, false, nb, s->d_act);
+  // EU_SYM_FUSED_REPLY (default on): the owner's k_prepare / k_sample write every result straight into the requester's arrays
+  // and the last CTA of k_sample raises the reply flags -- no result arrays, no reply pass.  0 = the separate reply kernel.
+  static const int fused_reply = [] { const char* e = getenv("EU_SYM_FUSED_REPLY"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
+  if (will_sample && fused_reply) {
+    SymRedirect rd{};
+    rd.on = 1; rd.me = s->rank; rd.N = N; rd.nb = nb; rd.want_packed = want_packed != 0;
+    rd.pb_tab = s->d_peers;
+    rd.cap = L.cap; rd.off_inbox_src = L.off_inbox_src; rd.off_eng = L.off_eng; rd.off_ids = L.off_ids; rd.off_w = L.off_w; rd.off_t = L.off_t;
+    rd.seg_lo = s->d_seglo; rd.boff = s->d_boff;
+    rc = hop(c, s->d_pad, (int64_t)N * rows, etypes, K, count, default_node, nullptr, nullptr, nullptr, nullptr, 0, /*pre_inserted=*/tabs != nullptr, false, nb,
+             s->d_act, false, &rd);
+    if (rc) return rc;
+    { EuProfScope ps(c, "k_sym_wait", total); k_sym_wait<<<1, 32, 0, st>>>(s->base, s->d_peers, L, N); }
+    EU_LAUNCHED();
+    return EU_OK;
+  }
+  if (will_sample) {
+    rc = hop(c, s->d_pad, (int64_t)N * rows, etypes, K, count, /*default_node=*/0, nullptr, s->d_rids, s->d_rw, s->d_rt, 0, /*pre_inserted=*/tabs != nullptr, false, nb, s->d_act);
     if (rc) return rc;
   }
   { EuProfScope ps(c, "k_sym_reply_sample", prow);
