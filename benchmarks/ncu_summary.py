@@ -64,7 +64,7 @@ def main():
         ent = tj.setdefault(cfg, {}).setdefault("kernels", {})
         seen = {}
         for d in rs:
-            nm = d["kernel"].split("<")[0].replace("eu::", "")
+            nm = d["kernel"].split("<")[0].replace("void ", "").replace("eu::", "").strip()
             if nm not in rows_by_kernel:
                 continue
             i = seen.get(nm, 0)
