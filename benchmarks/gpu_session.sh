@@ -30,10 +30,8 @@ for s in "$@"; do
         done ;;
     sharded1) (EU_BENCH_FORCE_SHARDED=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29549 bench.py --gpus 1 --steps 20 --warmup 5 --no-gate > $out/sharded1.json 2> $out/sharded1.err) ;;
     launches_sharded1) (EU_BENCH_FORCE_SHARDED=1 MASTER_ADDR=127.0.0.1 MASTER_PORT=29550 RANK=0 WORLD_SIZE=1 LOCAL_RANK=0 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --clock-control none --launch-skip 150 -c 260 --csv --log-file $out/launches_sharded1.csv python bench.py --gpus 1 --steps 6 --warmup 3 --lanes 1 --no-graphs --no-gate > $out/launches_sharded1.json 2> $out/launches_sharded1.err) ;;
-    sharded2_nofuse) (time EU_SYM_FUSED_REPLY=0 EU_SYM_TIMEOUT_S=10 timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29534 tests/run_sharded_gpu.py > $out/sharded2_nofuse.txt 2>&1) > $out/sharded2_nofuse.time 2>&1 ;;
     g2_ab) run2() { tag2=$1; shift; (env "$@" timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus 2 --steps 20 --warmup 5 $EXTRA > $out/g2_$tag2.json 2> $out/g2_$tag2.err); }
-        EXTRA="" run2 fused X=1
-        EXTRA="" run2 nofuse EU_SYM_FUSED_REPLY=0
+        EXTRA="" run2 default X=1
         EXTRA="--no-gate" run2 symctas4 EU_SYM_CTAS=4
         EXTRA="--no-gate" run2 sample6 EU_SAMPLE_CTAS=6
         EXTRA="--no-gate" run2 sym2_sample6 EU_SYM_CTAS=2 EU_SAMPLE_CTAS=6

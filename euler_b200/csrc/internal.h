@@ -157,7 +157,6 @@ struct EuProfScope {
 
 namespace eu {
 int ctx_reserve(eu_ctx* c, int64_t rows, int64_t table_slots);
-struct SymRedirect;   // sym.cuh: owner-side results written straight into the requesters' arrays
 int64_t hop_scratch_rows(int nb, int64_t rows_b);
 int64_t hop_table_slots(int nb, int64_t rows_b);
 int64_t hop_table_cap(int64_t rows_b);   // dedup slots per batch (region stride = cap + 1)
@@ -171,5 +170,5 @@ int launch_state_scan(eu_ctx* c, int64_t rows, unsigned long long uniforms_per_r
 int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows, const int32_t* etypes, int32_t K,
         int32_t count, int64_t default_node, unsigned long long* eng_ids, int64_t* out_ids,
         float* out_w, int32_t* out_t, int hop_index, bool pre_inserted, bool insert_next, int nb,
-        const int32_t* rows_act = nullptr, bool raw = false, const struct SymRedirect* redirect = nullptr);
+        const int32_t* rows_act = nullptr, bool raw = false);
 }  // namespace eu

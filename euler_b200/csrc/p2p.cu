@@ -103,6 +103,12 @@ __global__ void __launch_bounds__(256) k_sym_wait_in(char* base, char* const* pb
 
 // ---- owner: the sampleNB input of batch g = the requests of source 0..N-1 for that batch, back to back (compact: the
 // kernels of hop() learn the real row count of every batch from act[g]; nothing is zero-padded)  ->  pad[g][0 .. act[g])
+__device__ __forceinline__ int src_of(const int32_t* __restrict__ bo /* [N+1] */, int N, int32_t p) {
+  int s = 0;
+  while (s + 1 < N && p >= bo[s + 1]) ++s;
+  return s;
+}
+
 __global__ void __launch_bounds__(256) k_sym_gather_pad(const char* base, SymLayout lay, int N, int nb, int64_t rows_b,
                                                         const int32_t* __restrict__ seg_lo, const int32_t* __restrict__ boff,
                                                         unsigned long long* __restrict__ pad, HashSlot* tabs, int64_t tab_cap) {
@@ -611,22 +617,8 @@ int eu_sym_sample_hop_batched(eu_sym* s, const int64_t* seeds, int32_t nb, int64
   }
   { EuProfScope ps(c, "k_sym_gather_pad", prow); k_sym_gather_pad<<<sym_grid(total), 256, 0, st>>>(s->base, L, N, nb, rows, s->d_seglo, s->d_boff, s->d_pad, tabs, tab_cap); }
   EU_LAUNCHED();
-  // EU_SYM_FUSED_REPLY (default on): the owner's k_prepare / k_sample write every result straight into the requester's arrays
-  // and the last CTA of k_sample raises the reply flags -- no result arrays, no reply pass.  0 = the separate reply kernel.
-  static const int fused_reply = [] { const char* e = getenv("EU_SYM_FUSED_REPLY"); return e ? (atoi(e) != 0 ? 1 : 0) : 1; }();
-  if (will_sample && fused_reply) {
-    SymRedirect rd{};
-    rd.on = 1; rd.me = s->rank; rd.N = N; rd.nb = nb; rd.want_packed = want_packed != 0;
-    rd.pb_tab = s->d_peers;
-    rd.cap = L.cap; rd.off_inbox_src = L.off_inbox_src; rd.off_eng = L.off_eng; rd.off_ids = L.off_ids; rd.off_w = L.off_w; rd.off_t = L.off_t;
-    rd.seg_lo = s->d_seglo; rd.boff = s->d_boff;
-    rc = hop(c, s->d_pad, (int64_t)N * rows, etypes, K, count, default_node, nullptr, nullptr, nullptr, nullptr, 0, /*pre_inserted=*/tabs != nullptr, false, nb,
-             s->d_act, false, &rd);
-    if (rc) return rc;
-    { EuProfScope ps(c, "k_sym_wait", total); k_sym_wait<<<1, 32, 0, st>>>(s->base, s->d_peers, L, N); }
-    EU_LAUNCHED();
-    return EU_OK;
-  }
+  // (Tried and dropped: k_prepare / k_sample writing their results straight into the requesters' arrays.  The sampler's 8-byte
+  // scattered NVLink stores stalled it -- 37 -> 109 us per step at N=2 -- where this reply pass copies coalesced rows.)
   if (will_sample) {
     rc = hop(c, s->d_pad, (int64_t)N * rows, etypes, K, count, /*default_node=*/0, nullptr, s->d_rids, s->d_rw, s->d_rt, 0, /*pre_inserted=*/tabs != nullptr, false, nb, s->d_act);
     if (rc) return rc;

@@ -22,7 +22,6 @@
 #include <stdlib.h>
 
 #include "internal.h"
-#include "sym.cuh"
 
 namespace eu {
 
@@ -117,7 +116,6 @@ struct PrepOut {
   int64_t next_cap_b;
   int32_t* live;           // [nb*rows_b] global indices of rows that sample
   unsigned int* n_live;    // their number (zeroed before the launch)
-  SymRedirect rd;          // rd.on: results go to the requesters' arrays (sharded owner side), not to the pointers above
 };
 
 // ---------------------------------------------------------------------------- 2. prepare
@@ -162,14 +160,11 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSl
     if (own) {
       rowof[ii] = row;
     } else {
-      RowOut ro;
-      if (po.rd.on) ro = sym_row_out(po.rd, b, (int32_t)li, po.count);
-      else { ro.eng = po.eng_ids; ro.ids = po.out_ids; ro.w = po.out_w; ro.t = po.out_t; ro.ob = w * (int64_t)po.count; }
+      const int64_t ob = w * (int64_t)po.count;
       for (int32_t j = 0; j < po.count; ++j) {
-        if (ro.eng) ro.eng[ro.ob + j] = 0ull;
-        if (ro.ids) { ro.ids[ro.ob + j] = po.default_node; ro.w[ro.ob + j] = 0.f; ro.t[ro.ob + j] = -1; }
+        if (po.eng_ids) po.eng_ids[ob + j] = 0ull;
+        if (po.out_ids) { po.out_ids[ob + j] = po.default_node; po.out_w[ob + j] = 0.f; po.out_t[ob + j] = -1; }
       }
-      if (po.rd.on) __threadfence_system();   // peer stores of this row ordered before the kernel's end (k_sample raises the flags)
       if (po.next_tabs)  // its `count` zeros enter the next hop's dedup table with their minimum index
         dedup_insert_one(po.next_tabs + (int64_t)b * (po.next_cap_b + 1), (unsigned long long)po.next_cap_b - 1, 0ull,
                          li * (int64_t)po.count);
@@ -314,7 +309,6 @@ struct SampleArgs {
   long long* out_ids;           // [nb*rows_b*count] TF-packed; may be null
   float* out_w;
   int32_t* out_t;
-  SymRedirect rd;               // k_sample<.., REDIR = true>: outputs per row through sym_row_out instead
 };
 
 // shuffle binary search over the SG lane-resident values c of a lane group (non-decreasing, +inf padded):
@@ -336,14 +330,8 @@ __device__ __forceinline__ int lane_upper_bound(float c, int lo, int hi, float t
 // rows, and a persistent grid strides over the live rows: with fanout 10 two rows share a warp (the kernel is
 // issue-bound, profiles/r01_*: every instruction a lane group spares is throughput), and the per-block set-up
 // (jump tables, table wipe, parameter loads) is paid once per CTA instead of once per 8 rows.
-template <bool PHILOX, int CTAS, bool REDIR = false>
+template <bool PHILOX, int CTAS>
 __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) {
-  if (REDIR) {   // a poisoned exchange (p2p.cu) has no valid request layout: write nothing, raise nothing
-    __shared__ int s_err;
-    if (threadIdx.x == 0) s_err = ld_volatile_i32(&hdr_of(a.rd.pb_tab[a.rd.me])->error);
-    __syncthreads();
-    if (s_err) return;
-  }
   const int lane = threadIdx.x & 31;
   const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   __shared__ uint32_t s_lanepow[32];  // A^(2k*lane)
@@ -388,9 +376,7 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
     const int bidx = (int)(w / a.gm.rows_b);
     const int64_t li = w - bidx * a.gm.rows_b;
     if (PHILOX && a.gm.rows_act && li >= a.gm.rows_act[bidx]) continue;   // rows past the batch's real count do not exist
-    RowOut ro;
-    if (REDIR) ro = sym_row_out(a.rd, bidx, (int32_t)li, count);
-    else { ro.eng = a.eng_ids; ro.ids = a.out_ids; ro.w = a.out_w; ro.t = a.out_t; ro.ob = w * (int64_t)count; }
+    const int64_t obase = w * (int64_t)count;
     const EuRngState* rng = a.rngs + bidx;
     HashSlot* ntab = a.next_tabs ? a.next_tabs + (int64_t)bidx * (a.next_cap_b + 1) : nullptr;
     const unsigned long long nmask = (unsigned long long)a.next_cap_b - 1;
@@ -419,8 +405,8 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
     }
     if (!ok) {
       for (int32_t j = sl; j < count; j += SG) {
-        if (ro.eng) ro.eng[ro.ob + j] = 0ull;
-        if (ro.ids) { ro.ids[ro.ob + j] = a.default_node; ro.w[ro.ob + j] = 0.f; ro.t[ro.ob + j] = -1; }
+        if (a.eng_ids) a.eng_ids[obase + j] = 0ull;
+        if (a.out_ids) { a.out_ids[obase + j] = a.default_node; a.out_w[obase + j] = 0.f; a.out_t[obase + j] = -1; }
       }
       if (!PHILOX && ntab && sl == 0) dedup_insert_one(ntab, nmask, 0ull, nbase);  // `count` zeros
       continue;
@@ -548,12 +534,11 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
         keep = first_id != 0ull;
       }
       if (active) {
-        // the exchange's requester-side frontier carries 0 for a row TF packing drops (k_sym_reply_sample did the same)
-        if (ro.eng) ro.eng[ro.ob + j] = REDIR && !keep ? 0ull : nid;
-        if (ro.ids) {
-          ro.ids[ro.ob + j] = keep ? (long long)nid : a.default_node;
-          ro.w[ro.ob + j] = keep ? wgt : 0.f;
-          ro.t[ro.ob + j] = keep ? etype : -1;
+        if (a.eng_ids) a.eng_ids[obase + j] = nid;
+        if (a.out_ids) {
+          a.out_ids[obase + j] = keep ? (long long)nid : a.default_node;
+          a.out_w[obase + j] = keep ? wgt : 0.f;
+          a.out_t[obase + j] = keep ? etype : -1;
         }
       }
       if (!PHILOX && ntab && a.mode == 0) {
@@ -567,8 +552,8 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
     }
     if (__any_sync(gmask, bad)) {
       for (int32_t j = sl; j < count; j += SG) {
-        if (ro.eng) ro.eng[ro.ob + j] = 0ull;
-        if (ro.ids) { ro.ids[ro.ob + j] = a.default_node; ro.w[ro.ob + j] = 0.f; ro.t[ro.ob + j] = -1; }
+        if (a.eng_ids) a.eng_ids[obase + j] = 0ull;
+        if (a.out_ids) { a.out_ids[obase + j] = a.default_node; a.out_w[obase + j] = 0.f; a.out_t[obase + j] = -1; }
       }
     }
     if (!PHILOX && ntab && a.mode != 0) {
@@ -577,7 +562,7 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
       for (int32_t j0 = 0; j0 < count; j0 += SG) {
         const int32_t j = j0 + sl;
         const bool active = j < count;
-        const unsigned long long nid = active ? ro.eng[ro.ob + j] : 0ull;
+        const unsigned long long nid = active ? a.eng_ids[obase + j] : 0ull;
         const unsigned act = __ballot_sync(gmask, active);
         if (active) {
           const unsigned peers = __match_any_sync(act, nid);
@@ -586,19 +571,6 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
       }
     }
     if (mid_row) __syncwarp(gmask);   // every lane is done with the tile before the group's next row overwrites it
-  }
-  if (REDIR) {
-    // publish: one system fence per CTA (it waits for the NVLink acks of the CTA's stores), the last CTA raises flagB at every
-    // requester -- what k_sym_reply_sample did after its copy pass
-    __shared__ bool s_last;
-    SymHeader* mine = hdr_of(a.rd.pb_tab[a.rd.me]);
-    __syncthreads();
-    if (threadIdx.x == 0) { __threadfence_system(); s_last = atomicAdd(&mine->done, 1u) == gridDim.x - 1; }
-    __syncthreads();
-    if (!s_last) return;
-    if ((int)threadIdx.x < a.rd.N) __threadfence_system();
-    if (threadIdx.x == 0) mine->done = 0;
-    if ((int)threadIdx.x < a.rd.N) st_release_sys(&hdr_of(a.rd.pb_tab[threadIdx.x])->flagB[a.rd.me], mine->epoch);
   }
 }
 
@@ -710,7 +682,7 @@ int64_t hop_table_cap(int64_t rows_b) { return make_geom(1, rows_b).cap_b; }
 int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_t* etypes,
         int32_t K, int32_t count, int64_t default_node, unsigned long long* eng_ids,
         int64_t* out_ids, float* out_w, int32_t* out_t, int hop_index, bool pre_inserted, bool insert_next, int nb,
-        const int32_t* rows_act, bool raw, const SymRedirect* redirect) {
+        const int32_t* rows_act, bool raw) {
   const int64_t rows = rows_b * nb;
   if (rows == 0 || count == 0) return EU_OK;
   if (nb < 1 || nb > c->n_eng) { set_error("hop: %d batches but the ctx has %d engines", nb, c->n_eng); return EU_ERR_INVALID; }
@@ -725,7 +697,6 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
   a.seeds = seeds; a.gm = gm; a.count = count; a.default_node = default_node;
   a.eng_ids = eng_ids; a.out_ids = (long long*)out_ids; a.out_w = out_w; a.out_t = out_t;
   a.rngs = c->d_rng;
-  if (redirect) a.rd = *redirect;
   // lanes per row: the smallest power of two that holds a row's draws (and the type-pick table of modes 1/2)
   {
     int need = std::min<int>(count, 32);
@@ -743,9 +714,7 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
   const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(ceil_div(rows * 32, (int64_t)(32 >> a.sg_log)), 256), 148 * grid_ctas);
   if (c->rng == EU_RNG_PHILOX) {
     a.key = c->seed;
-    { EuProfScope ps(c, "k_sample<philox>", rows);
-      if (redirect) k_sample<true, 6, true><<<blocks, 256, 0, s>>>(d, a);
-      else if (ctas == 6) k_sample<true, 6><<<blocks, 256, 0, s>>>(d, a); else k_sample<true, 8><<<blocks, 256, 0, s>>>(d, a); }
+    { EuProfScope ps(c, "k_sample<philox>", rows); if (ctas == 6) k_sample<true, 6><<<blocks, 256, 0, s>>>(d, a); else k_sample<true, 8><<<blocks, 256, 0, s>>>(d, a); }
     EU_LAUNCHED();
     k_bump_calls<<<1, 64, 0, s>>>(c->d_rng, nb);
     EU_LAUNCHED();
@@ -775,7 +744,6 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
     PrepOut po{};
     po.eng_ids = eng_ids; po.out_ids = (long long*)out_ids; po.out_w = out_w; po.out_t = out_t;
     po.count = count; po.default_node = default_node;
-    if (redirect) po.rd = *redirect;
     if (chain) { po.next_tabs = ntabs; po.next_cap_b = ng.cap_b; }
     po.live = c->d_live; po.n_live = c->d_nlive;
     EU_CUDA(cudaMemsetAsync(c->d_nlive, 0, sizeof(unsigned int), s));
@@ -795,9 +763,7 @@ int hop(eu_ctx* c, const unsigned long long* seeds, int64_t rows_b, const int32_
     a.next_tabs = ntabs;
     a.next_cap_b = ng.cap_b;
   }
-  { EuProfScope ps(c, "k_sample<minstd>", rows);
-    if (redirect) k_sample<false, 6, true><<<blocks, 256, 0, s>>>(d, a);
-    else if (ctas == 6) k_sample<false, 6><<<blocks, 256, 0, s>>>(d, a); else k_sample<false, 8><<<blocks, 256, 0, s>>>(d, a); }
+  { EuProfScope ps(c, "k_sample<minstd>", rows); if (ctas == 6) k_sample<false, 6><<<blocks, 256, 0, s>>>(d, a); else k_sample<false, 8><<<blocks, 256, 0, s>>>(d, a); }
   EU_LAUNCHED();
   return EU_OK;
 }
