@@ -178,6 +178,17 @@ __device__ __forceinline__ void dedup_insert_one(HashSlot* tab, unsigned long lo
 }
 
 
+// Slots a batch's dedup region really uses: the power of two >= 2 * live rows (>= 64), at most the region's capacity.  A
+// sharded owner sizes its regions for the worst case (every request of every rank) and learns the live count on the device:
+// inserting, probing and wiping with this mask keeps the table -- and its wipe -- proportional to the rows that exist.
+__device__ __forceinline__ int64_t dedup_cap_eff(int64_t cap_b, const int32_t* __restrict__ rows_act, int b) {
+  if (!rows_act) return cap_b;
+  const long long r2 = 2ll * (long long)rows_act[b];
+  int64_t cap = 64;
+  if (r2 > 64) cap = (int64_t)1 << (64 - __clzll(r2 - 1));
+  return cap < cap_b ? cap : cap_b;
+}
+
 // ---------------------------------------------------------------------------------- philox4x32-10
 __device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;

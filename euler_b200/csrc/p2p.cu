@@ -119,14 +119,15 @@ __global__ void __launch_bounds__(256) k_sym_gather_pad(const char* base, SymLay
   const int32_t stride = (int32_t)(gridDim.x * blockDim.x);
   for (int g = 0; g < nb; ++g) {
     const int32_t* bo = boff + g * (N + 1);
-    const int32_t live = bo[N];
+    const int32_t live = bo[N];                                            // == the rows_act[g] hop() is given (k_sym_wait_in)
+    const unsigned long long mask = (unsigned long long)dedup_cap_eff(tab_cap, &live, 0) - 1;
     for (int32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < live; p += stride) {
       const int s = src_of(bo, N, p);
       const unsigned long long id = ids[(int64_t)s * lay.cap + seg_lo[s * (nb + 1) + g] + (p - bo[s])];
       pad[(int64_t)g * cap_b + p] = id;
       if (tabs) {
         const unsigned peers = __match_any_sync(__activemask(), id);       // runs of equal ids: the lowest lane carries the minimum index
-        if ((threadIdx.x & 31) == __ffs(peers) - 1) dedup_insert_one(tabs + (int64_t)g * (tab_cap + 1), (unsigned long long)tab_cap - 1, id, p);
+        if ((threadIdx.x & 31) == __ffs(peers) - 1) dedup_insert_one(tabs + (int64_t)g * (tab_cap + 1), mask, id, p);
       }
     }
   }

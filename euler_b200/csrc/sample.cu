@@ -58,7 +58,7 @@ __global__ void k_dedup_insert(HashSlot* tabs, Geom gm, const unsigned long long
   const unsigned act = __activemask();
   const unsigned peers = __match_any_sync(act, id);
   if ((threadIdx.x & 31) != __ffs(peers) - 1) return;
-  dedup_insert_one(tabs + (int64_t)b * (gm.cap_b + 1), (unsigned long long)gm.cap_b - 1, id, li);
+  dedup_insert_one(tabs + (int64_t)b * (gm.cap_b + 1), (unsigned long long)dedup_cap_eff(gm.cap_b, gm.rows_act, b) - 1, id, li);
 }
 
 __device__ __forceinline__ int64_t dedup_first(const HashSlot* tab, unsigned long long mask,
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(kPrepBlock) k_prepare(DevGraph g, const HashSl
     const int64_t w = b * gm.rows_b + li;
     const unsigned long long id = seeds[w];
     // raw mode (tabs == null): euler::SampleNeighbor draws every occurrence of an id independently (api.cc:223-236)
-    const int64_t f = tabs ? dedup_first(tabs + (int64_t)b * (gm.cap_b + 1), (unsigned long long)gm.cap_b - 1, id) : li;
+    const int64_t f = tabs ? dedup_first(tabs + (int64_t)b * (gm.cap_b + 1), (unsigned long long)dedup_cap_eff(gm.cap_b, gm.rows_act, b) - 1, id) : li;
     first[ii] = (int32_t)f;
     // A duplicate has the same id, hence the same graph row and eligibility as its first occurrence: every row
     // resolves its own, so rows that cannot sample are finished right here and never reach k_sample.
@@ -362,7 +362,15 @@ __global__ void __launch_bounds__(256, CTAS) k_sample(DevGraph g, SampleArgs a) 
   __syncthreads();
   if (!PHILOX) {
     // k_prepare (the only reader of this hop's dedup tables) has finished: wipe them
-    for (int64_t s = gtid; s < a.clear_n; s += (int64_t)gridDim.x * blockDim.x) { a.clear_tab[s].key = 0; a.clear_tab[s].row = kEmptyRow; }
+    if (!a.gm.rows_act) {
+      for (int64_t s = gtid; s < a.clear_n; s += (int64_t)gridDim.x * blockDim.x) { a.clear_tab[s].key = 0; a.clear_tab[s].row = kEmptyRow; }
+    } else if (a.clear_n) {   // worst-case-sized regions (sharded owner): only the slots the live rows could touch
+      for (int b = 0; b < a.gm.nb; ++b) {
+        HashSlot* tab = a.clear_tab + (int64_t)b * (a.gm.cap_b + 1);
+        const int64_t n = dedup_cap_eff(a.gm.cap_b, a.gm.rows_act, b) + 1;
+        for (int64_t s = gtid; s < n; s += (int64_t)gridDim.x * blockDim.x) { tab[s].key = 0; tab[s].row = kEmptyRow; }
+      }
+    }
   }
   const int32_t count = a.count;
   const int32_t T = g.T;
