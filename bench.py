@@ -509,11 +509,20 @@ def run_ours(args):
     if use_graphs:
         launches = int(per_step_launches * args.steps)  # kernels of ours inside the replayed graphs
     clk = clocks.stop(w0, w1)
-    run(min(args.warmup, 2 * G), 0, "e2e")
+    # end-to-end passes: warm EVERY lane the timed pass will use (a lane's first *_host call grows its pinned staging and device
+    # scratch -- cudaHostAlloc / cudaMalloc of hundreds of MB, which one box in round 2 took 40 ms per step to do inside the timed
+    # region), and the tail lane, before timing
+    n_timed_groups = -(-args.steps // G)
+    run(G * max(min(n_timed_groups, len(lanes)), 1), 0, "e2e")
+    if tail_lane:
+        run(tail, 0, "e2e")
     ms_e2e = run(args.steps, args.warmup, "e2e")
     ms_host = None
     if not args.no_e2e_host:
-        run(min(args.warmup, 2 * G), 0, "host")
+        for _ in range(2):
+            run(G * max(min(HOST_LANES, max(n_timed_groups, len(lanes))), 1), 0, "host")
+        if tail_lane:
+            run(tail, 0, "host")
         ms_host = run(args.steps, args.warmup, "host")
     edges_step = bts["edges"]
     value = edges_step * args.steps / (ms * 1e-3)
@@ -944,7 +953,9 @@ def run_sharded(args, world, rank, local):
     w1 = time.time()
     nv1 = nvlink_counters(local) if rank == 0 else None
     clk = clocks.stop(w0, w1)
-    run(G * min(len(lanes), 2), 0, True)
+    run(G * min(len(lanes), E2E_LANES), 0, True)
+    if tail_lane:
+        run(tail, 0, True)
     ms_e2e = run(args.steps, args.warmup, True)
     err = max(ln.sg.error() for ln in all_lanes) if peer else 0
     if err:
@@ -1369,7 +1380,7 @@ def run_walk(args):
     ms = run(args.steps, args.warmup, "dev")
     w1 = time.time()
     clk = clocks.stop(w0, w1)
-    run(2, 0, "host")
+    run(len(lanes), 0, "host")     # every lane's first *_host call grows its staging buffers: not inside the timed region
     ms_host = run(args.steps, args.warmup, "host")
     # measured sum of degrees: per walker-step 12 * deg(cur) + 8 * deg(prev) + 32 bytes
     ln = lanes[0]

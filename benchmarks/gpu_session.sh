@@ -36,6 +36,7 @@ for s in "$@"; do
         EXTRA="--no-gate" run2 sample6 EU_SAMPLE_CTAS=6
         EXTRA="--no-gate" run2 sym2_sample6 EU_SYM_CTAS=2 EU_SAMPLE_CTAS=6
         EXTRA="--no-gate --features sharded" run2 shardedfeat X=1 ;;
+    smoke) (time timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $out/smoke.txt 2>&1) > $out/smoke.time 2>&1 ;;
     ab) Q="--steps 40 --warmup 8 --no-cpu-baseline --no-e2e-host --no-gate"
         run() { tag2=$1; shift; (env "$@" timeout 300 python bench.py $Q $EXTRA > $out/ab_$tag2.json 2> $out/ab_$tag2.err); }
         EXTRA="" run c4_default X=1
