@@ -37,6 +37,8 @@ for s in "$@"; do
         EXTRA="--no-gate" run2 sym2_sample6 EU_SYM_CTAS=2 EU_SAMPLE_CTAS=6
         EXTRA="--no-gate --features sharded" run2 shardedfeat X=1 ;;
     smoke) (time timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $out/smoke.txt 2>&1) > $out/smoke.time 2>&1 ;;
+    g2_noise) run2() { tag2=$1; shift; (env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29552 bench.py --gpus 2 --steps 20 --warmup 5 --no-gate > $out/g2n_$tag2.json 2> $out/g2n_$tag2.err); }
+        run2 default_a X=1; run2 knob_a EU_SYM_CTAS=2 EU_SAMPLE_CTAS=6; run2 default_b X=1; run2 knob_b EU_SYM_CTAS=2 EU_SAMPLE_CTAS=6 ;;
     ab) Q="--steps 40 --warmup 8 --no-cpu-baseline --no-e2e-host --no-gate"
         run() { tag2=$1; shift; (env "$@" timeout 300 python bench.py $Q $EXTRA > $out/ab_$tag2.json 2> $out/ab_$tag2.err); }
         EXTRA="" run c4_default X=1
