@@ -216,29 +216,30 @@ static int upload(eu_graph* g, const T** dst, const T* src, int64_t count) {
   return EU_OK;
 }
 
-// AliasMethod::Init, euler/common/alias_method.cc:23-63 -- same float/double operation order.
+// Walker alias tables.  RESTATEMENT of AliasMethod::Init (euler/common/alias_method.cc:23-63): the tables must be bit-identical to
+// the reference's (the global sampler's draws index them), so the pairing order (two LIFO stacks, light entry first) and every
+// f32 / f64 operation -- p = w * n in f32, the donor's remainder (w_heavy + w_light) in f32 then minus the f64 mean, rounded back
+// to f32, the > comparison against the f64 mean -- are the reference's; nothing else of that file is used.
 static void alias_build(const std::vector<float>& weights, std::vector<float>* prob,
                         std::vector<int32_t>* alias) {
-  size_t n = weights.size();
+  const size_t n = weights.size();
   prob->assign(n, 0.f);
   alias->assign(n, 0);
-  std::vector<int64_t> small, large;
-  std::vector<float> w(weights);
-  double avg = 1 / static_cast<double>(n);
-  for (size_t i = 0; i < n; i++) {
-    if (w[i] > avg) large.push_back(i); else small.push_back(i);
+  std::vector<float> rem(weights);                 // what is left of each entry's normalised weight
+  const double mean = 1 / static_cast<double>(n);
+  std::vector<int64_t> light, heavy;               // LIFO: the reference pops the most recently pushed index
+  for (size_t i = 0; i < n; i++) (rem[i] > mean ? heavy : light).push_back((int64_t)i);
+  while (!heavy.empty() && !light.empty()) {
+    const int64_t lo = light.back(); light.pop_back();
+    const int64_t hi = heavy.back(); heavy.pop_back();
+    (*prob)[lo] = rem[lo] * (float)n;
+    (*alias)[lo] = (int32_t)hi;
+    const float both = rem[hi] + rem[lo];
+    rem[hi] = (float)((double)both - mean);
+    (rem[hi] > mean ? heavy : light).push_back(hi);
   }
-  while (!large.empty() && !small.empty()) {
-    int64_t less = small.back(); small.pop_back();
-    int64_t more = large.back(); large.pop_back();
-    (*prob)[less] = w[less] * (float)n;
-    (*alias)[less] = (int32_t)more;
-    float t = w[more] + w[less];
-    w[more] = (float)((double)t - avg);
-    if (w[more] > avg) large.push_back(more); else small.push_back(more);
-  }
-  while (!small.empty()) { (*prob)[small.back()] = 1.0f; small.pop_back(); }
-  while (!large.empty()) { (*prob)[large.back()] = 1.0f; large.pop_back(); }
+  for (int64_t i : light) (*prob)[i] = 1.0f;       // leftovers of either stack keep their own slot
+  for (int64_t i : heavy) (*prob)[i] = 1.0f;
 }
 
 // FastWeightedCollection::Init (fast_weighted_collection.h:54-74): f32 sum, f32 divide, alias.
