@@ -257,6 +257,19 @@ void fwc_build_public(const std::vector<float>& w, std::vector<float>* prob, std
   *sum = fwc_build(w, prob, alias);
 }
 
+}  // namespace eu
+extern "C" int eu_build_alias_table(const float* weights, int64_t n, float* prob, int32_t* alias, float* sum) {
+  if (n < 0 || (n > 0 && (!weights || !prob || !alias))) { eu::set_error("eu_build_alias_table: bad argument"); return EU_ERR_INVALID; }
+  std::vector<float> w(weights, weights + n), p;
+  std::vector<int32_t> a;
+  float s = 0.f;
+  eu::fwc_build_public(w, &p, &a, &s);
+  for (int64_t i = 0; i < n; ++i) { prob[i] = p[i]; alias[i] = a[i]; }
+  if (sum) *sum = s;
+  return EU_OK;
+}
+namespace eu {
+
 // Graph::BuildGlobalSampler, euler/core/graph/graph.cc:333-370.
 int graph_build_sampler(eu_graph* g) {
   if (g->sampler_built) return EU_OK;

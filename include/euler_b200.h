@@ -143,6 +143,11 @@ int eu_graph_destroy(eu_graph* g);
 int64_t eu_graph_num_nodes(const eu_graph* g);
 int64_t eu_graph_num_edges(const eu_graph* g);
 int32_t eu_graph_num_edge_types(const eu_graph* g);
+/* Host-only helper (no GPU needed): the sampler tables eu_graph_create / eu_graph_load build for the global node and edge samplers --
+ * FastWeightedCollection::Init + AliasMethod::Init (euler/common/fast_weighted_collection.h:54-74, alias_method.cc:23-63):
+ * weights f32[n] -> prob f32[n], alias i32[n], *sum = the f32 weight sum.  Exposed so the tables can be checked bit for bit
+ * against the reference's without a device. */
+int eu_build_alias_table(const float* weights, int64_t n, float* prob, int32_t* alias, float* sum);
 int32_t eu_graph_num_node_types(const eu_graph* g);
 int32_t eu_graph_feat_dim(const eu_graph* g);
 int64_t eu_graph_hbm_bytes(const eu_graph* g);

@@ -90,3 +90,34 @@ def test_cpp_api_adapter_compiles_and_links():
     if not torch.cuda.is_available():
         r = subprocess.run([exe, os.path.join(root, "tests", "golden", "tiny_euler")], capture_output=True, text=True)
         assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+def test_alias_tables_match_the_reference_on_the_host():
+    """eu_build_alias_table (host-only): the tables the global node / edge samplers are built from are bit-identical to the
+    oracle's restatement of AliasMethod::Init / FastWeightedCollection::Init and, when oracle/_ref is built, to the
+    reference's own AliasMethod (euler/common/alias_method.cc:23-63)."""
+    import ctypes as C
+    import numpy as np
+    from euler_b200 import _lib
+    from oracle import pyoracle as po
+    lib = _lib.load()
+    ol = po.lib()
+    rng = np.random.RandomState(11)
+    for rep in range(300):
+        n = int(rng.randint(1, 400))
+        w = (rng.randint(0, 1000, size=n) / np.float32(7)).astype(np.float32)
+        w[rng.rand(n) < 0.2] = 0
+        if w.sum() == 0:
+            w[0] = 1
+        prob, alias = np.empty(n, np.float32), np.empty(n, np.int32)
+        s = C.c_float(0)
+        assert lib.eu_build_alias_table(w.ctypes.data, n, prob.ctypes.data, alias.ctypes.data, C.addressof(s)) == 0
+        p2, a2 = np.empty(n, np.float32), np.empty(n, np.int64)
+        s2 = C.c_float(0)
+        ol.eo_fwc_build(w, n, p2, a2, C.byref(s2))
+        assert prob.tobytes() == p2.tobytes() and np.array_equal(alias, a2) and s.value == s2.value, rep
+        if po.have_ref():
+            norm = (w / np.float32(s2.value)).astype(np.float32)   # FastWeightedCollection normalises in f32 before AliasMethod
+            p3, a3 = np.empty(n, np.float32), np.empty(n, np.int64)
+            po.ref().ref_alias_build(norm, n, p3, a3)
+            assert prob.tobytes() == p3.tobytes() and np.array_equal(alias, a3), rep
