@@ -245,9 +245,17 @@ static int load_edge_files(eu_graph* g, const std::string& dir, int shard_index,
 
 using namespace eu;
 
-extern "C" int eu_graph_load_ex(const char* data_path, int shard_index, int shard_number, int device, int load_edges,
-                                eu_graph** out) {
-  if (!data_path || !out || shard_number <= 0 || shard_index < 0 || shard_index >= shard_number) {
+// what eu_graph_load_inspect reports (host-only: the parse and the sampler-order replay, no device)
+struct LoadInspect {
+  int64_t n_nodes = 0, n_edges = 0;
+  int32_t n_edge_types = 0, n_node_types = 0;
+  std::vector<int64_t> order_ids;
+  std::vector<int32_t> order_types;
+};
+
+static int load_impl(const char* data_path, int shard_index, int shard_number, int device, int load_edges, eu_graph** out,
+                     LoadInspect* inspect) {
+  if (!data_path || (!out && !inspect) || shard_number <= 0 || shard_index < 0 || shard_index >= shard_number) {
     set_error("eu_graph_load: bad argument (shard %d of %d)", shard_index, shard_number);
     return EU_ERR_INVALID;
   }
@@ -429,6 +437,14 @@ extern "C" int eu_graph_load_ex(const char* data_path, int shard_index, int shar
   uint64_t u64_dummy = 0; uint8_t bin_dummy = 0;
   if (US > 0) { d.n_u64_slots = US; d.u64_ptr = u64_ptr.data(); d.u64_val = u64_all.empty() ? &u64_dummy : u64_all.data(); }
   if (BS > 0) { d.n_bin_slots = BS; d.bin_ptr = bin_ptr.data(); d.bin_val = bin_all.empty() ? &bin_dummy : bin_all.data(); }
+  if (inspect) {   // everything above is host work: report it and stop before the upload
+    inspect->n_nodes = d.n_nodes;
+    inspect->n_edges = (int64_t)nbr.size();
+    inspect->n_edge_types = d.n_edge_types;
+    inspect->n_node_types = d.n_node_types;
+    for (int64_t r : order) { inspect->order_ids.push_back((int64_t)ids[r]); inspect->order_types.push_back(ntype[r]); }
+    return EU_OK;
+  }
   int rc = eu_graph_create(&d, device, out);
   if (rc) return rc;
   eu_graph* g = *out;
@@ -449,6 +465,30 @@ extern "C" int eu_graph_load_ex(const char* data_path, int shard_index, int shar
   if (load_edges) {
     rc = load_edge_files(g, dir, shard_index, shard_number, e_dense, e_sparse, e_binary);
     if (rc) { eu_graph_destroy(g); *out = nullptr; return rc; }
+  }
+  return EU_OK;
+}
+
+extern "C" int eu_graph_load_ex(const char* data_path, int shard_index, int shard_number, int device, int load_edges,
+                                eu_graph** out) {
+  if (!out) { set_error("eu_graph_load: bad argument (null out)"); return EU_ERR_INVALID; }
+  return load_impl(data_path, shard_index, shard_number, device, load_edges, out, nullptr);
+}
+
+extern "C" int eu_graph_load_inspect(const char* data_path, int shard_index, int shard_number, int64_t* n_nodes, int64_t* n_edges,
+                                     int32_t* n_edge_types, int32_t* n_node_types, int64_t cap, int64_t* order_ids,
+                                     int32_t* order_types) {
+  LoadInspect li;
+  const int rc = load_impl(data_path, shard_index, shard_number, 0, 0, nullptr, &li);
+  if (rc) return rc;
+  if (n_nodes) *n_nodes = li.n_nodes;
+  if (n_edges) *n_edges = li.n_edges;
+  if (n_edge_types) *n_edge_types = li.n_edge_types;
+  if (n_node_types) *n_node_types = li.n_node_types;
+  const int64_t n = std::min<int64_t>(cap, (int64_t)li.order_ids.size());
+  for (int64_t i = 0; i < n; ++i) {
+    if (order_ids) order_ids[i] = li.order_ids[i];
+    if (order_types) order_types[i] = li.order_types[i];
   }
   return EU_OK;
 }

@@ -143,6 +143,11 @@ int eu_graph_destroy(eu_graph* g);
 int64_t eu_graph_num_nodes(const eu_graph* g);
 int64_t eu_graph_num_edges(const eu_graph* g);
 int32_t eu_graph_num_edge_types(const eu_graph* g);
+/* Host-only (no GPU needed): parse an Euler 2.0 data directory exactly as eu_graph_load does -- same file filter, same record
+ * decoding, same replay of the reference's node_map_ iteration order (euler/core/graph/graph.cc:349-354) -- and report what would
+ * be uploaded: counts and, for the first `cap` entries, node ids and types in GLOBAL SAMPLER ORDER.  Any out pointer may be NULL. */
+int eu_graph_load_inspect(const char* data_path, int shard_index, int shard_number, int64_t* n_nodes, int64_t* n_edges,
+                          int32_t* n_edge_types, int32_t* n_node_types, int64_t cap, int64_t* order_ids, int32_t* order_types);
 /* Host-only helper (no GPU needed): the sampler tables eu_graph_create / eu_graph_load build for the global node and edge samplers --
  * FastWeightedCollection::Init + AliasMethod::Init (euler/common/fast_weighted_collection.h:54-74, alias_method.cc:23-63):
  * weights f32[n] -> prob f32[n], alias i32[n], *sum = the f32 weight sum.  Exposed so the tables can be checked bit for bit

@@ -121,3 +121,40 @@ def test_alias_tables_match_the_reference_on_the_host():
             p3, a3 = np.empty(n, np.float32), np.empty(n, np.int64)
             po.ref().ref_alias_build(norm, n, p3, a3)
             assert prob.tobytes() == p3.tobytes() and np.array_equal(alias, a3), rep
+
+
+def test_loader_replays_the_reference_sampler_order_on_the_host():
+    """eu_graph_load_inspect (host-only parse of an Euler 2.0 directory): node / edge counts of the converter's files and the
+    global-sampler enumeration order == the reference's own loader on the same directory (its unordered_map<NodeID, Node*>
+    iteration order, euler/core/graph/graph.cc:349-354), per node type."""
+    import ctypes as C
+    import os
+    import numpy as np
+    import pytest
+    from euler_b200 import _lib
+    from oracle import pyoracle as po
+    lib = _lib.load()
+    tiny = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tiny_euler")
+    nn, ne = C.c_int64(0), C.c_int64(0)
+    T, NT = C.c_int32(0), C.c_int32(0)
+    assert lib.eu_graph_load_inspect(tiny.encode(), 0, 1, C.addressof(nn), C.addressof(ne), C.addressof(T), C.addressof(NT), 0, None, None) == 0
+    assert (nn.value, T.value, NT.value) == (6, 2, 2) and ne.value > 0       # the reference's 6-node test graph (tf_euler/python/euler_ops/testdata)
+    ids, types = np.zeros(nn.value, np.int64), np.zeros(nn.value, np.int32)
+    assert lib.eu_graph_load_inspect(tiny.encode(), 0, 1, None, None, None, None, nn.value, ids.ctypes.data, types.ctypes.data) == 0
+    assert sorted(ids.tolist()) == [1, 2, 3, 4, 5, 6]
+    # sharded load: shard s of 2 sees the partitions p with p % 2 == s (graph_builder.cc:230-246); together they see every node
+    seen = []
+    for s in range(2):
+        n_s = C.c_int64(0)
+        assert lib.eu_graph_load_inspect(tiny.encode(), s, 2, C.addressof(n_s), None, None, None, 0, None, None) == 0
+        part = np.zeros(n_s.value, np.int64)
+        lib.eu_graph_load_inspect(tiny.encode(), s, 2, None, None, None, None, n_s.value, part.ctypes.data, None)
+        seen += part.tolist()
+    assert sorted(seen) == [1, 2, 3, 4, 5, 6]
+    assert lib.eu_graph_load_inspect(b"/nonexistent/dir", 0, 1, None, None, None, None, 0, None, None) != 0
+    if not po.have_ref():
+        pytest.skip("oracle/_ref not built: the order is compared with the reference's loader only where it exists")
+    rg = po.RefGraph.load(tiny)
+    for t in range(NT.value):
+        ref_ids = rg.sampler_tables(t)[0]
+        assert np.array_equal(ids[types == t].astype(np.uint64), ref_ids), (t, ids, types, ref_ids)
