@@ -158,3 +158,15 @@ def test_loader_replays_the_reference_sampler_order_on_the_host():
     for t in range(NT.value):
         ref_ids = rg.sampler_tables(t)[0]
         assert np.array_equal(ids[types == t].astype(np.uint64), ref_ids), (t, ids, types, ref_ids)
+
+
+def test_gen_pair_count_is_the_reference_formula():
+    """eu_gen_pair_count (host): pairs per path of tf_euler gen_pair (tf_euler/kernels/gen_pair_op.cc:41-60) == the number of
+    (j, k) with k in [j - left, j + right] inside the path, k != j -- counted literally."""
+    from euler_b200 import _lib
+    lib = _lib.load()
+    for plen in range(0, 12):
+        for lw in range(0, 6):
+            for rw in range(0, 6):
+                want = sum(1 for j in range(plen) for k in range(j - lw, j + rw + 1) if k != j and 0 <= k < plen)
+                assert lib.eu_gen_pair_count(plen, lw, rw) == want, (plen, lw, rw)
