@@ -91,18 +91,27 @@ def _worker(rank, world, port, q):
         q.put((rank, traceback.format_exc()))
 
 
-def test_sharded_fanout_and_features_world2_gloo():
+def _run_world(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    ps = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in ps:
         p.start()
-    got = [q.get(timeout=120) for _ in ps]
+    got = [q.get(timeout=180) for _ in ps]
     for p in ps:
         p.join(timeout=30)
     for r, msg in got:
         assert msg == "ok", "rank %d:\n%s" % (r, msg)
+
+
+def test_sharded_fanout_and_features_world2_gloo():
+    _run_world(2)
+
+
+def test_sharded_fanout_and_features_world3_gloo():
+    """a shard count that is not a power of two: owner = (id % P) % 3, uneven segments"""
+    _run_world(3)
 
 
 def test_partition_is_a_partition():
